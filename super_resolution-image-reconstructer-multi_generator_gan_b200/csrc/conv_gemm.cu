@@ -1,0 +1,457 @@
+// Strip implicit-GEMM convolution for sm_100a: TMA -> shared (128B swizzle) -> tcgen05.mma -> TMEM -> epilogue.
+//
+// GEMM view: M = 128 output pixels (a TH x TW tile), N = 64 (or 32) output channels, K = 64 input channels per
+// (strip, tap) k-block.  For every column shift s ("strip") the producer loads ONE box of (TH + span) input rows
+// x TW pixels x 64 channels; the taps that share that column shift read it at different row offsets, so each
+// input element crosses L2->SM  n_strips times instead of n_strips*n_taps times.  Because TW % 8 == 0 every tap's
+// A operand starts on a 1024-byte swizzle-atom boundary: canonical K-major SWIZZLE_128B descriptors throughout.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// Persistent CTAs; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace srg {
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+const char* last_error() { return g_err; }
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------- device parameters
+struct ConvKParams {
+  CUtensorMap in_map[kMaxInMaps];
+  CUtensorMap w_map;
+  int N, H, W, TH, TW;
+  int tiles_h, tiles_w, tiles_total;
+  int tile_step_w;  // TW, or TW-8 for the fold9 epilogue
+  int tile_w_org;   // 0, or -4 for fold9
+  int n_chunks, chunks_per_view;
+  int n_strips, n_taps, strip_rows, strip_dh;
+  int strip_dw[kMaxStrips];
+  int tap_row[kMaxTaps];
+  int cout_total, n_blocks, ctas_per_block;
+  int resident, n_stages;
+  uint32_t strip_bytes, stage_bytes, w_resident_bytes;
+  const float* bias;
+  int act;
+  float slope;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* mask_src;
+  void* out;
+  int out_mode;
+};
+
+constexpr int kThreads = 192;
+constexpr int kFoldPad = 33;
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint8_t* w_smem = smem;                                 // resident weights (may be empty)
+  uint8_t* stages = smem + p.w_resident_bytes;            // n_stages * stage_bytes
+  uint8_t* tail = stages + size_t(p.n_stages) * p.stage_bytes;
+  float* fold_buf = reinterpret_cast<float*>(tail);       // 128*33 floats (fold9 only)
+  uint8_t* tail2 = tail + (p.out_mode == OUT_FOLD9_NCHW ? 128 * kFoldPad * 4 : 0);
+  float* s_bias = reinterpret_cast<float*>(tail2);        // BLOCK_N floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail2 + 256);
+  uint64_t* full = bars;                                  // [n_stages]
+  uint64_t* empty = bars + 8;                             // [n_stages]
+  uint64_t* wfull = bars + 16;
+  uint64_t* tfull = bars + 17;                            // [2]
+  uint64_t* tempty = bars + 19;                           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+  const int nblk = blockIdx.x % p.n_blocks;
+  const int tile0 = blockIdx.x / p.n_blocks;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  constexpr uint32_t kBTile = BLOCK_N * 128;              // bytes of one weight k-block
+  const int kb_total = p.n_chunks * p.n_strips * p.n_taps;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(wfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+    for (int v = 0; v < kMaxInMaps; ++v) tma_prefetch_desc(&p.in_map[v]);
+    tma_prefetch_desc(&p.w_map);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (t < BLOCK_N) {
+      float b = 0.f;
+      if (p.bias != nullptr && p.out_mode != OUT_FOLD9_NCHW) b = p.bias[nblk * BLOCK_N + t];
+      s_bias[t] = b;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================================================== TMA producer
+    if (lane == 0) {
+      if (p.resident) {
+        mbar_expect_tx(wfull, uint32_t(kb_total) * kBTile);
+        for (int kb = 0; kb < kb_total; ++kb)
+          tma_load_2d(w_smem + size_t(kb) * kBTile, &p.w_map, wfull, 0, kb * p.cout_total + nblk * BLOCK_N);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * p.TH;
+        const int w0 = (rem % p.tiles_w) * p.tile_step_w + p.tile_w_org;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const int view = c / p.chunks_per_view;
+          const int coff = (c - view * p.chunks_per_view) * 64;
+          for (int s = 0; s < p.n_strips; ++s) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* dst = stages + size_t(stage) * p.stage_bytes;
+            mbar_expect_tx(&full[stage], p.resident ? p.strip_bytes : p.stage_bytes);
+            tma_load_4d(dst, &p.in_map[view], &full[stage], coff, w0 + p.strip_dw[s], h0 + p.strip_dh, n);
+            if (!p.resident) {
+              const int kb0 = (c * p.n_strips + s) * p.n_taps;
+              for (int r = 0; r < p.n_taps; ++r)
+                tma_load_2d(dst + p.strip_bytes + size_t(r) * kBTile, &p.w_map, &full[stage], 0,
+                            (kb0 + r) * p.cout_total + nblk * BLOCK_N);
+            }
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+    if (p.resident) mbar_wait(wfull, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
+      uint32_t accumulate = 0;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        for (int s = 0; s < p.n_strips; ++s) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_stage = smem_u32(stages + size_t(stage) * p.stage_bytes);
+            const int kb0 = (c * p.n_strips + s) * p.n_taps;
+            for (int r = 0; r < p.n_taps; ++r) {
+              const uint32_t a_addr = a_stage + uint32_t(p.tap_row[r] * p.TW) * 128u;
+              const uint32_t b_addr = p.resident ? smem_u32(w_smem) + uint32_t(kb0 + r) * kBTile
+                                                 : a_stage + p.strip_bytes + uint32_t(r) * kBTile;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 1024, 0),
+                          make_smem_desc_sw128(b_addr + k * 32, 1024, 0), idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            umma_commit(&empty[stage]);
+          }
+          __syncwarp();
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (lane == 0) umma_commit(&tfull[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // =================================================================== epilogue
+    const int q = warp & 3;            // TMEM lane quadrant this warp may read
+    const int m = q * 32 + lane;       // GEMM row == pixel within the tile
+    const int th = m / p.TW;
+    const int tw = m - th * p.TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int h = (rem / p.tiles_w) * p.TH + th;
+      const int w = (rem % p.tiles_w) * p.tile_step_w + p.tile_w_org + tw;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
+
+      if constexpr (BLOCK_N == 32) {
+        // fold9: P[pixel][s*3+co] -> out[co][h][w] = bias + sum_s P[(h, w+s-4)][s*3+co]
+        uint32_t v[32];
+        tmem_ld32(t_addr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&tempty[acc]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) fold_buf[m * kFoldPad + j] = __uint_as_float(v[j]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tw >= 4 && tw < p.TW - 4 && h < p.H && w >= 0 && w < p.W) {
+          float o0 = p.bias ? p.bias[0] : 0.f, o1 = p.bias ? p.bias[1] : 0.f, o2 = p.bias ? p.bias[2] : 0.f;
+#pragma unroll
+          for (int s = 0; s < 9; ++s) {
+            const float* row = fold_buf + (m + s - 4) * kFoldPad + s * 3;
+            o0 += row[0];
+            o1 += row[1];
+            o2 += row[2];
+          }
+          float* o = reinterpret_cast<float*>(p.out);
+          const size_t plane = size_t(p.H) * p.W;
+          const size_t base = (size_t(n) * 3) * plane + size_t(h) * p.W + w;
+          o[base] = o0;
+          o[base + plane] = o1;
+          o[base + 2 * plane] = o2;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      } else {
+        const bool valid = (h < p.H) && (w < p.W);
+        size_t pix;
+        if (p.out_mode == OUT_PIXEL_SHUFFLE) {
+          pix = ((size_t(n) * (2 * p.H) + (2 * h + (nblk >> 1))) * (2 * p.W) + (2 * w + (nblk & 1))) * 64;
+        } else {
+          pix = ((size_t(n) * p.H + h) * p.W + w) * p.cout_total + size_t(nblk) * BLOCK_N;
+        }
+        __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out) + pix;
+#pragma unroll
+        for (int half = 0; half < BLOCK_N / 32; ++half) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + half * 32, v);
+          tmem_ld_wait();
+          if (half == BLOCK_N / 32 - 1) {
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+          }
+          if (valid) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(v[j]) + s_bias[half * 32 + j];
+              if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+              else if (p.act == ACT_LRELU) x = x > 0.f ? x : x * p.slope;
+              f[j] = x;
+            }
+            if (p.residual != nullptr) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix + half * 32);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 r = __ldg(rp + g);
+                f[g * 8 + 0] += bf16_lo(r.x); f[g * 8 + 1] += bf16_hi(r.x);
+                f[g * 8 + 2] += bf16_lo(r.y); f[g * 8 + 3] += bf16_hi(r.y);
+                f[g * 8 + 4] += bf16_lo(r.z); f[g * 8 + 5] += bf16_hi(r.z);
+                f[g * 8 + 6] += bf16_lo(r.w); f[g * 8 + 7] += bf16_hi(r.w);
+              }
+            }
+            if (p.mask_src != nullptr) {
+              const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + pix + half * 32);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 r = __ldg(mp + g);
+                // bf16 > 0  <=>  sign bit clear and magnitude nonzero
+                const uint32_t ws[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!(bf16_lo(ws[e]) > 0.f)) f[g * 8 + 2 * e] = 0.f;
+                  if (!(bf16_hi(ws[e]) > 0.f)) f[g * 8 + 2 * e + 1] = 0.f;
+                }
+              }
+            }
+            uint4* op = reinterpret_cast<uint4*>(optr + half * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 o;
+              o.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]);
+              o.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
+              o.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]);
+              o.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
+              op[g] = o;
+            }
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
+}
+
+// ----------------------------------------------------------- host launcher
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || sym == nullptr) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+int encode_map_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return -100;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu box %u,%u)", int(r), rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return -101;
+  }
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
+  if (a.TH * a.TW != 128 || a.TW % 8 != 0) { set_error("conv_gemm: tile must be 128 pixels with TW%%8==0"); return -1; }
+  if (a.block_n != 64 && a.block_n != 32) { set_error("conv_gemm: block_n must be 32 or 64"); return -2; }
+  if (a.cout_total % a.block_n != 0) { set_error("conv_gemm: cout_total %% block_n != 0"); return -3; }
+  if (a.n_views < 1 || a.n_views > kMaxInMaps) { set_error("conv_gemm: bad n_views"); return -4; }
+  if (a.n_strips < 1 || a.n_strips > kMaxStrips || a.n_taps < 1 || a.n_taps > kMaxTaps) {
+    set_error("conv_gemm: bad strip/tap count"); return -5;
+  }
+  if ((a.out_mode == OUT_FOLD9_NCHW) != (a.block_n == 32)) { set_error("conv_gemm: fold9 <=> block_n 32"); return -6; }
+  if (a.strip_rows > 256 || a.TW > 256) { set_error("conv_gemm: TMA box too large"); return -7; }
+
+  ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a.N; p.H = a.H; p.W = a.W; p.TH = a.TH; p.TW = a.TW;
+  const bool fold = a.out_mode == OUT_FOLD9_NCHW;
+  p.tile_step_w = fold ? a.TW - 8 : a.TW;
+  p.tile_w_org = fold ? -4 : 0;
+  p.tiles_h = (a.H + a.TH - 1) / a.TH;
+  p.tiles_w = (a.W + p.tile_step_w - 1) / p.tile_step_w;
+  p.tiles_total = a.N * p.tiles_h * p.tiles_w;
+  int total_ch = 0;
+  for (int v = 0; v < a.n_views; ++v) {
+    if (a.views[v].channels % 64 != 0 || a.views[v].channels != a.views[0].channels) {
+      set_error("conv_gemm: view channels must be equal multiples of 64"); return -8;
+    }
+    total_ch += a.views[v].channels;
+  }
+  p.n_chunks = total_ch / 64;
+  p.chunks_per_view = a.views[0].channels / 64;
+  p.n_strips = a.n_strips; p.n_taps = a.n_taps; p.strip_rows = a.strip_rows; p.strip_dh = a.strip_dh;
+  for (int s = 0; s < a.n_strips; ++s) p.strip_dw[s] = a.strip_dw[s];
+  for (int r = 0; r < a.n_taps; ++r) {
+    if (a.tap_row[r] < 0 || a.tap_row[r] + a.TH > a.strip_rows) { set_error("conv_gemm: tap row outside strip"); return -9; }
+    p.tap_row[r] = a.tap_row[r];
+  }
+  p.cout_total = a.cout_total;
+  p.n_blocks = a.cout_total / a.block_n;
+  const int sms = num_sms();
+  p.ctas_per_block = sms / p.n_blocks;
+  if (p.ctas_per_block < 1) p.ctas_per_block = 1;
+  if (p.ctas_per_block > p.tiles_total) p.ctas_per_block = p.tiles_total;
+  if (p.tiles_total == 0) return 0;
+
+  const uint32_t btile = uint32_t(a.block_n) * 128u;
+  const int kb_total = p.n_chunks * a.n_strips * a.n_taps;
+  p.strip_bytes = uint32_t(a.strip_rows) * a.TW * 128u;
+  const uint32_t w_all = uint32_t(kb_total) * btile;
+  const uint32_t tail_bytes = (fold ? 128 * kFoldPad * 4 : 0) + 256 + 256;
+  const uint32_t budget = 227 * 1024 - 1024 - tail_bytes;
+  p.resident = (w_all + 2 * p.strip_bytes <= budget) ? 1 : 0;
+  p.w_resident_bytes = p.resident ? w_all : 0;
+  p.stage_bytes = p.strip_bytes + (p.resident ? 0 : uint32_t(a.n_taps) * btile);
+  int stages = int((budget - p.w_resident_bytes) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) { set_error("conv_gemm: shared memory too small for 2 stages (stage %u B)", p.stage_bytes); return -10; }
+  p.n_stages = stages;
+  const size_t smem_bytes = 1024 + p.w_resident_bytes + size_t(stages) * p.stage_bytes + tail_bytes;
+
+  for (int v = 0; v < a.n_views; ++v) {
+    const InView& iv = a.views[v];
+    uint64_t dims[4] = {uint64_t(iv.channels), uint64_t(a.in_W), uint64_t(a.in_H), uint64_t(a.N)};
+    uint64_t strides[3] = {uint64_t(iv.stride_w) * 2, uint64_t(iv.stride_h) * 2, uint64_t(iv.stride_n) * 2};
+    uint32_t box[4] = {64, uint32_t(a.TW), uint32_t(a.strip_rows), 1};
+    int rc = encode_map_bf16(&p.in_map[v], iv.ptr, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  for (int v = a.n_views; v < kMaxInMaps; ++v) p.in_map[v] = p.in_map[0];
+  {
+    uint64_t dims[2] = {64, uint64_t(kb_total) * a.cout_total};
+    uint64_t strides[1] = {128};
+    uint32_t box[2] = {64, uint32_t(a.block_n)};
+    int rc = encode_map_bf16(&p.w_map, a.weights, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  p.bias = a.bias; p.act = a.act; p.slope = a.slope;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual);
+  p.mask_src = reinterpret_cast<const __nv_bfloat16*>(a.mask_src);
+  p.out = a.out; p.out_mode = a.out_mode;
+
+  const dim3 grid(p.ctas_per_block * p.n_blocks);
+  cudaError_t e;
+  if (a.block_n == 64) {
+    static bool attr64 = false;
+    if (!attr64) {
+      e = cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+      attr64 = true;
+    }
+    conv_gemm_kernel<64><<<grid, kThreads, smem_bytes, stream>>>(p);
+  } else {
+    static bool attr32 = false;
+    if (!attr32) {
+      e = cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+      attr32 = true;
+    }
+    conv_gemm_kernel<32><<<grid, kThreads, smem_bytes, stream>>>(p);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("conv_gemm launch: %s", cudaGetErrorString(e)); return int(e); }
+  return 0;
+}
+
+}  // namespace srg

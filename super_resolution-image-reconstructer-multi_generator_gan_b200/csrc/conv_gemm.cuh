@@ -1,0 +1,67 @@
+// Host-side description of one "strip" implicit-GEMM convolution launch (internal; the public
+// C ABI in include/srgan_b200.h is a thin layer above this).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace srg {
+
+constexpr int kMaxStrips = 9;
+constexpr int kMaxTaps = 9;
+constexpr int kMaxInMaps = 4;
+
+enum ConvAct : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
+enum ConvOutMode : int {
+  OUT_NHWC = 0,          // bf16 [N,H,W,cout_total]
+  OUT_PIXEL_SHUFFLE = 1, // bf16 [N,2H,2W,64]; GEMM n-block q=(i,j) -> pixel (2h+i, 2w+j)
+  OUT_FOLD9_NCHW = 2,    // fp32 [N,3,H,W]; GEMM n = s*3+co partial sums, shift-accumulated over s (9x9, Cout=3)
+};
+
+// One view of the (NHWC bf16) input that a K-chunk is loaded from. A plain tensor uses one view;
+// the pixel-unshuffled gradient of an up-conv uses four strided views of the HR tensor.
+struct InView {
+  const void* ptr;       // base address (16-byte aligned)
+  int64_t stride_w;      // in elements, multiple of 8
+  int64_t stride_h;
+  int64_t stride_n;
+  int channels;          // channels visible through this view (multiple of 64)
+};
+
+struct ConvGemmArgs {
+  // logical output grid (stride-1 conv: same grid as the input views)
+  int N, H, W;
+  int TH, TW;            // pixel tile, TH*TW == 128, TW % 8 == 0
+  // input
+  int n_views;
+  InView views[kMaxInMaps];
+  int in_H, in_W;        // extents of the input views (rows/cols outside are zero)
+  // taps: n_strips column shifts, each with n_taps row offsets
+  int n_strips, n_taps;
+  int strip_dw[kMaxStrips];  // column offset of strip s relative to the tile origin
+  int strip_dh;              // row offset of every strip's first row relative to the tile origin
+  int strip_rows;            // rows loaded per strip (TH + vertical span)
+  int tap_row[kMaxTaps];     // first strip row used by tap r
+  // packed weights: bf16 [n_chunks*n_strips*n_taps][cout_total][64], k-block index ((c*S+s)*R+r)
+  const void* weights;
+  int cout_total;            // multiple of block_n
+  int block_n;               // 32 (fold9 only) or 64
+  // epilogue
+  const float* bias;         // [cout_total] (GEMM n order) or nullptr; OUT_FOLD9: [3]
+  int act;
+  float slope;
+  const void* residual;      // bf16, same layout as out (OUT_NHWC only), added after activation
+  const void* mask_src;      // bf16, same layout as out: out = (mask_src > 0) ? out : 0  (ReLU backward)
+  void* out;
+  int out_mode;
+  // fold9: tile columns overlap; valid output columns per tile = TW-8
+};
+
+// Returns 0 on success, cudaError_t (>0) or a negative argument-check code otherwise.
+int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream);
+
+const char* last_error();
+void set_error(const char* fmt, ...);
+
+}  // namespace srg

@@ -1,0 +1,295 @@
+// Standalone GPU probe for the strip implicit-GEMM conv kernel (developer tool, not part of the product path).
+// Builds random problems, runs launch_conv_gemm and compares with a scalar CPU evaluation of the same packed-GEMM
+// definition.  Usage: conv_probe [timing_iters]
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../super_resolution-image-reconstructer-multi_generator_gan_b200/csrc/conv_gemm.cuh"
+
+using namespace srg;
+
+static uint32_t rng_state = 12345u;
+static float frand() {
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return ((rng_state >> 8) & 0xFFFF) / 65536.0f - 0.5f;
+}
+static uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  uint32_t r = u + 0x7FFF + ((u >> 16) & 1);
+  return uint16_t(r >> 16);
+}
+static float bf2f(uint16_t h) {
+  uint32_t u = uint32_t(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+#define CK(x)                                                                  \
+  do {                                                                         \
+    cudaError_t e_ = (x);                                                      \
+    if (e_ != cudaSuccess) {                                                   \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                 \
+    }                                                                          \
+  } while (0)
+
+struct Problem {
+  const char* name;
+  int N, H, W, TH, TW;
+  int n_views, view_ch;      // input = n_views views of view_ch channels; stored as one [N,H,W,n_views*view_ch] tensor
+  bool strided_views;        // views are the 4 pixel-shuffle phases of an HR tensor [N,2H,2W,64]
+  int n_strips, n_taps, strip_rows, strip_dh;
+  int strip_dw[9], tap_row[9];
+  int cout_total, block_n;
+  bool bias;
+  int act;
+  bool residual, mask;
+  int out_mode;
+};
+
+static int run(const Problem& pr, int timing_iters) {
+  const int Cin = pr.n_views * pr.view_ch;
+  const int n_chunks = Cin / 64;
+  const int KB = n_chunks * pr.n_strips * pr.n_taps;
+  // input tensor, logical [N][H][W][Cin] (bf16)
+  std::vector<uint16_t> x(size_t(pr.N) * pr.H * pr.W * Cin);
+  for (auto& v : x) v = f2bf(frand());
+  // physical layout
+  std::vector<uint16_t> xphys(x.size());
+  if (pr.strided_views) {
+    // HR tensor [N][2H][2W][64]; view q=(i,j): pixel (2h+i, 2w+j)
+    for (int n = 0; n < pr.N; ++n)
+      for (int h = 0; h < pr.H; ++h)
+        for (int w = 0; w < pr.W; ++w)
+          for (int c = 0; c < Cin; ++c) {
+            int q = c / 64, ch = c % 64, i = q >> 1, j = q & 1;
+            size_t dst = ((size_t(n) * 2 * pr.H + 2 * h + i) * 2 * pr.W + 2 * w + j) * 64 + ch;
+            xphys[dst] = x[((size_t(n) * pr.H + h) * pr.W + w) * Cin + c];
+          }
+  } else {
+    xphys = x;
+  }
+  std::vector<uint16_t> wp(size_t(KB) * pr.cout_total * 64);
+  for (auto& v : wp) v = f2bf(frand() * 0.25f);
+  std::vector<float> bias(pr.cout_total);
+  for (auto& v : bias) v = frand();
+  const bool fold = pr.out_mode == OUT_FOLD9_NCHW;
+  const bool ps = pr.out_mode == OUT_PIXEL_SHUFFLE;
+  const size_t out_elems = fold ? size_t(pr.N) * 3 * pr.H * pr.W : size_t(pr.N) * pr.H * pr.W * pr.cout_total;
+  std::vector<uint16_t> res(out_elems), msk(out_elems);
+  for (auto& v : res) v = f2bf(frand());
+  for (auto& v : msk) v = f2bf(frand());
+
+  void *dx, *dw, *dout, *dres, *dmsk;
+  float* dbias;
+  CK(cudaMalloc(&dx, xphys.size() * 2));
+  CK(cudaMalloc(&dw, wp.size() * 2));
+  CK(cudaMalloc(&dout, out_elems * 4));
+  CK(cudaMalloc(&dres, out_elems * 2));
+  CK(cudaMalloc(&dmsk, out_elems * 2));
+  CK(cudaMalloc(&dbias, bias.size() * 4));
+  CK(cudaMemcpy(dx, xphys.data(), xphys.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dres, res.data(), out_elems * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dmsk, msk.data(), out_elems * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dbias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0xFF, out_elems * 4));
+
+  ConvGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = pr.N; a.H = pr.H; a.W = pr.W; a.TH = pr.TH; a.TW = pr.TW;
+  a.n_views = pr.n_views;
+  for (int v = 0; v < pr.n_views; ++v) {
+    if (pr.strided_views) {
+      int i = v >> 1, j = v & 1;
+      a.views[v].ptr = (uint16_t*)dx + (size_t(i) * 2 * pr.W + j) * 64;
+      a.views[v].stride_w = 128;
+      a.views[v].stride_h = int64_t(4) * pr.W * 64;
+      a.views[v].stride_n = int64_t(4) * pr.H * pr.W * 64;
+    } else {
+      a.views[v].ptr = (uint16_t*)dx + size_t(v) * pr.view_ch;
+      a.views[v].stride_w = Cin;
+      a.views[v].stride_h = int64_t(pr.W) * Cin;
+      a.views[v].stride_n = int64_t(pr.H) * pr.W * Cin;
+    }
+    a.views[v].channels = pr.view_ch;
+  }
+  a.in_H = pr.H; a.in_W = pr.W;
+  a.n_strips = pr.n_strips; a.n_taps = pr.n_taps; a.strip_rows = pr.strip_rows; a.strip_dh = pr.strip_dh;
+  for (int s = 0; s < pr.n_strips; ++s) a.strip_dw[s] = pr.strip_dw[s];
+  for (int r = 0; r < pr.n_taps; ++r) a.tap_row[r] = pr.tap_row[r];
+  a.weights = dw; a.cout_total = pr.cout_total; a.block_n = pr.block_n;
+  a.bias = pr.bias ? dbias : nullptr; a.act = pr.act; a.slope = 0.2f;
+  a.residual = pr.residual ? dres : nullptr; a.mask_src = pr.mask ? dmsk : nullptr;
+  a.out = dout; a.out_mode = pr.out_mode;
+
+  int rc = launch_conv_gemm(a, 0);
+  if (rc != 0) { printf("[%s] launch rc=%d err=%s\n", pr.name, rc, last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("[%s] kernel failed: %s\n", pr.name, cudaGetErrorString(e)); exit(3); }
+
+  std::vector<uint8_t> outraw(out_elems * 4);
+  CK(cudaMemcpy(outraw.data(), dout, out_elems * 4, cudaMemcpyDeviceToHost));
+
+  // CPU reference on a sample of pixels (all pixels when small)
+  const size_t npix = size_t(pr.N) * pr.H * pr.W;
+  const size_t stride = npix > 6000 ? npix / 3000 : 1;
+  double max_err = 0, max_ref = 0;
+  size_t checked = 0, bad = 0;
+  auto in_at = [&](int n, int h, int w, int c) -> float {
+    if (h < 0 || h >= pr.H || w < 0 || w >= pr.W) return 0.f;
+    return bf2f(x[((size_t(n) * pr.H + h) * pr.W + w) * Cin + c]);
+  };
+  auto gemm_at = [&](int n, int h, int w, int co) -> float {  // sum over all k-blocks
+    double acc = 0;
+    for (int c = 0; c < n_chunks; ++c)
+      for (int s = 0; s < pr.n_strips; ++s)
+        for (int r = 0; r < pr.n_taps; ++r) {
+          const int kb = (c * pr.n_strips + s) * pr.n_taps + r;
+          const int hh = h + pr.strip_dh + pr.tap_row[r], ww = w + pr.strip_dw[s];
+          if (hh < 0 || hh >= pr.H || ww < 0 || ww >= pr.W) continue;
+          const uint16_t* wrow = &wp[(size_t(kb) * pr.cout_total + co) * 64];
+          const uint16_t* xrow = &x[((size_t(n) * pr.H + hh) * pr.W + ww) * Cin + c * 64];
+          for (int k = 0; k < 64; ++k) acc += double(bf2f(xrow[k])) * bf2f(wrow[k]);
+        }
+    return float(acc);
+  };
+  (void)in_at;
+  for (size_t pi = 0; pi < npix; pi += stride) {
+    const int n = int(pi / (size_t(pr.H) * pr.W));
+    const int h = int((pi / pr.W) % pr.H);
+    const int w = int(pi % pr.W);
+    if (fold) {
+      for (int co = 0; co < 3; ++co) {
+        double ref = pr.bias ? bias[co] : 0.0;
+        for (int s = 0; s < 9; ++s) {
+          const int ww = w + s - 4;
+          if (ww < 0 || ww >= pr.W) continue;
+          ref += gemm_at(n, h, ww, s * 3 + co);
+        }
+        const float got = reinterpret_cast<float*>(outraw.data())[((size_t(n) * 3 + co) * pr.H + h) * pr.W + w];
+        const double err = fabs(got - ref);
+        if (err > max_err) max_err = err;
+        if (fabs(ref) > max_ref) max_ref = fabs(ref);
+        if (!(err <= 0.02 + 0.01 * fabs(ref))) ++bad;
+        ++checked;
+      }
+    } else {
+      for (int co = 0; co < pr.cout_total; ++co) {
+        float ref = gemm_at(n, h, w, co);
+        if (pr.bias) ref += bias[co];
+        if (pr.act == ACT_RELU) ref = ref > 0 ? ref : 0;
+        if (pr.act == ACT_LRELU) ref = ref > 0 ? ref : 0.2f * ref;
+        size_t oidx;
+        if (ps) {
+          const int q = co / 64, ch = co % 64, i = q >> 1, j = q & 1;
+          oidx = ((size_t(n) * 2 * pr.H + 2 * h + i) * 2 * pr.W + 2 * w + j) * 64 + ch;
+        } else {
+          oidx = ((size_t(n) * pr.H + h) * pr.W + w) * pr.cout_total + co;
+        }
+        if (pr.residual) ref += bf2f(res[oidx]);
+        if (pr.mask && !(bf2f(msk[oidx]) > 0.f)) ref = 0;
+        const float got = bf2f(reinterpret_cast<uint16_t*>(outraw.data())[oidx]);
+        const double err = fabs(got - ref);
+        if (err > max_err) max_err = err;
+        if (fabs(ref) > max_ref) max_ref = fabs(ref);
+        if (!(err <= 0.02 + 0.01 * fabs(ref))) ++bad;
+        ++checked;
+      }
+    }
+  }
+  printf("[%s] checked=%zu bad=%zu max_abs_err=%.5f max_ref=%.3f %s\n", pr.name, checked, bad, max_err, max_ref,
+         bad == 0 ? "OK" : "FAIL");
+
+  if (timing_iters > 0) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) launch_conv_gemm(a, 0);
+    cudaEventRecord(e0);
+    for (int i = 0; i < timing_iters; ++i) launch_conv_gemm(a, 0);
+    cudaEventRecord(e1);
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * npix * double(KB) * 64 * pr.cout_total;
+    printf("[%s] %.3f us/launch  %.1f TFLOP/s (MMA work incl. padding)\n", pr.name, ms * 1000 / timing_iters,
+           flops / (ms / timing_iters * 1e-3) / 1e12);
+  }
+  cudaFree(dx); cudaFree(dw); cudaFree(dout); cudaFree(dres); cudaFree(dmsk); cudaFree(dbias);
+  return bad == 0 ? 0 : 1;
+}
+
+static Problem conv3x3(const char* name, int N, int H, int W, int cout, bool ps) {
+  Problem p;
+  memset(&p, 0, sizeof(p));
+  p.name = name; p.N = N; p.H = H; p.W = W; p.TH = 16; p.TW = 8;
+  p.n_views = 1; p.view_ch = 64;
+  p.n_strips = 3; p.n_taps = 3; p.strip_rows = 18; p.strip_dh = -1;
+  for (int s = 0; s < 3; ++s) p.strip_dw[s] = s - 1;
+  for (int r = 0; r < 3; ++r) p.tap_row[r] = r;
+  p.cout_total = cout; p.block_n = 64; p.bias = true; p.act = ACT_NONE;
+  p.out_mode = ps ? OUT_PIXEL_SHUFFLE : OUT_NHWC;
+  return p;
+}
+
+int main(int argc, char** argv) {
+  const int iters = argc > 1 ? atoi(argv[1]) : 0;
+  int fails = 0;
+  {  // 1x1 "plain GEMM" sanity: one strip, one tap
+    Problem p = conv3x3("gemm1x1", 1, 16, 8, 64, false);
+    p.n_strips = 1; p.n_taps = 1; p.strip_rows = 16; p.strip_dh = 0; p.strip_dw[0] = 0; p.tap_row[0] = 0;
+    p.bias = false;
+    fails += run(p, 0);
+  }
+  fails += run(conv3x3("c3x3_small", 2, 32, 24, 64, false), 0);
+  fails += run(conv3x3("c3x3_ragged", 3, 40, 20, 64, false), 0);
+  {
+    Problem p = conv3x3("c3x3_epi", 2, 32, 16, 64, false);
+    p.act = ACT_LRELU; p.residual = true; p.mask = true;
+    fails += run(p, 0);
+  }
+  {
+    Problem p = conv3x3("c3x3_relu_ps", 2, 32, 16, 256, true);
+    p.act = ACT_RELU;
+    fails += run(p, 0);
+  }
+  {  // Cin = 256 through four strided pixel-shuffle views, weights streamed
+    Problem p = conv3x3("c3x3_cin256_views", 2, 32, 16, 64, false);
+    p.n_views = 4; p.strided_views = true;
+    fails += run(p, 0);
+  }
+  {  // 9x9-as-5-row-pairs on a 64-channel unfolded buffer
+    Problem p = conv3x3("c9_pairs", 2, 32, 16, 64, false);
+    p.n_strips = 1; p.n_taps = 5; p.strip_rows = 16 + 8; p.strip_dh = -3; p.strip_dw[0] = 0;
+    for (int r = 0; r < 5; ++r) p.tap_row[r] = 2 * r;
+    p.act = ACT_LRELU;
+    fails += run(p, 0);
+  }
+  {  // conv3: 9x9, Cout=3, horizontal taps folded into N=27(+5)
+    Problem p = conv3x3("fold9", 2, 24, 56, 32, false);
+    p.TH = 4; p.TW = 32;
+    p.n_strips = 1; p.n_taps = 9; p.strip_rows = 4 + 8; p.strip_dh = -4; p.strip_dw[0] = 0;
+    for (int r = 0; r < 9; ++r) p.tap_row[r] = r;
+    p.block_n = 32; p.out_mode = OUT_FOLD9_NCHW;
+    fails += run(p, 0);
+  }
+  if (iters > 0) {
+    fails += run(conv3x3("perf_trunk_16x96x96", 16, 96, 96, 64, false), iters);
+    Problem p = conv3x3("perf_up3_16x192x192", 16, 192, 192, 256, true);
+    p.act = ACT_RELU;
+    fails += run(p, iters);
+    Problem f = conv3x3("perf_fold9_16x384x384", 16, 384, 384, 32, false);
+    f.TH = 4; f.TW = 32; f.n_strips = 1; f.n_taps = 9; f.strip_rows = 12; f.strip_dh = -4; f.strip_dw[0] = 0;
+    for (int r = 0; r < 9; ++r) f.tap_row[r] = r;
+    f.block_n = 32; f.out_mode = OUT_FOLD9_NCHW;
+    fails += run(f, iters);
+  }
+  printf("PROBE %s (%d failing cases)\n", fails == 0 ? "PASS" : "FAIL", fails);
+  return fails == 0 ? 0 : 1;
+}
