@@ -31,12 +31,14 @@ void set_error(const char* fmt, ...) {
 struct ConvKParams {
   CUtensorMap in_map[kMaxInMaps];
   CUtensorMap w_map;
+  CUtensorMap out_map[4];  // NHWC: [0]; pixel shuffle: one strided view of the HR tensor per n-block
+  CUtensorMap aux_map;     // residual / mask tensor (same geometry as out_map[0])
   int N, H, W, TH, TW;
   int tiles_h, tiles_w, tiles_total;
   int tile_step_w;  // TW, or TW-8 for the fold9 epilogue
   int tile_w_org;   // 0, or -4 for fold9
   int n_chunks, chunks_per_view;
-  int n_strips, n_taps, strip_rows, strip_dh;
+  int n_strips, strip_rows, strip_dh;
   int strip_dw[kMaxStrips];
   int tap_row[kMaxTaps];
   int cout_total, n_blocks, ctas_per_block;
@@ -45,28 +47,40 @@ struct ConvKParams {
   const float* bias;
   int act;
   float slope;
-  const __nv_bfloat16* residual;
-  const __nv_bfloat16* mask_src;
-  void* out;
+  int aux_mode;  // 0 none, 1 add (residual), 2 mask (zero where aux <= 0)
+  void* out;     // fold9 only (fp32 NCHW)
   int out_mode;
+  long long* prof;  // optional per-CTA role timers (debug)
 };
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;       // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiThreads = 256;
 constexpr int kFoldPad = 33;
+constexpr uint32_t kTileOutBytes = 128 * 128;  // 128 pixels x 64 bf16
 
-template <int BLOCK_N>
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x, float slope) {
+  if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == ACT_LRELU) return x > 0.f ? x : x * slope;
+  return x;
+}
+
+template <int BLOCK_N, int NT>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
+  constexpr bool kFold = (BLOCK_N == 32);
 
   uint8_t* w_smem = smem;                                 // resident weights (may be empty)
   uint8_t* stages = smem + p.w_resident_bytes;            // n_stages * stage_bytes
-  uint8_t* tail = stages + size_t(p.n_stages) * p.stage_bytes;
+  uint8_t* out_stage = stages + size_t(p.n_stages) * p.stage_bytes;      // 2 x 16 KB (not fold9)
+  uint8_t* aux_stage = out_stage + (kFold ? 0 : 2 * kTileOutBytes);      // 2 x 16 KB (aux_mode != 0)
+  uint8_t* tail = aux_stage + (p.aux_mode ? 2 * kTileOutBytes : 0);
   float* fold_buf = reinterpret_cast<float*>(tail);       // 128*33 floats (fold9 only)
-  uint8_t* tail2 = tail + (p.out_mode == OUT_FOLD9_NCHW ? 128 * kFoldPad * 4 : 0);
+  uint8_t* tail2 = tail + (kFold ? 128 * kFoldPad * 4 : 0);
   float* s_bias = reinterpret_cast<float*>(tail2);        // BLOCK_N floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail2 + 256);
   uint64_t* full = bars;                                  // [n_stages]
@@ -74,13 +88,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* wfull = bars + 16;
   uint64_t* tfull = bars + 17;                            // [2]
   uint64_t* tempty = bars + 19;                           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* auxfull = bars + 21;                          // [2]
+  uint64_t* auxempty = bars + 23;                         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
   const int nblk = blockIdx.x % p.n_blocks;
   const int tile0 = blockIdx.x / p.n_blocks;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   constexpr uint32_t kBTile = BLOCK_N * 128;              // bytes of one weight k-block
-  const int kb_total = p.n_chunks * p.n_strips * p.n_taps;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  constexpr int kEpiActive = kFold ? 128 : kEpiThreads;   // epilogue threads that touch TMEM
+  const int kb_total = p.n_chunks * p.n_strips * NT;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.n_stages; ++i) {
@@ -90,18 +108,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     mbar_init(wfull, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], kEpiActive);
+      mbar_init(&auxfull[i], 1);
+      mbar_init(&auxempty[i], kEpiActive);
     }
     fence_barrier_init();
     for (int v = 0; v < kMaxInMaps; ++v) tma_prefetch_desc(&p.in_map[v]);
     tma_prefetch_desc(&p.w_map);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   if (warp >= 2) {
     const int t = threadIdx.x - 64;
     if (t < BLOCK_N) {
       float b = 0.f;
-      if (p.bias != nullptr && p.out_mode != OUT_FOLD9_NCHW) b = p.bias[nblk * BLOCK_N + t];
+      if (p.bias != nullptr && !kFold) b = p.bias[nblk * BLOCK_N + t];
       s_bias[t] = b;
     }
   }
@@ -109,33 +129,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long prof_acc[4] = {0, 0, 0, 0};
+  const long long t_start = clock64();
 
   if (warp == 0) {
     // =============================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       if (p.resident) {
         mbar_expect_tx(wfull, uint32_t(kb_total) * kBTile);
         for (int kb = 0; kb < kb_total; ++kb)
           tma_load_2d(w_smem + size_t(kb) * kBTile, &p.w_map, wfull, 0, kb * p.cout_total + nblk * BLOCK_N);
       }
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, ab = 0;
+      uint32_t phase = 0, aux_phase = 0;
       for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
         const int n = tile / tiles_per_img;
         const int rem = tile - n * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * p.TH;
         const int w0 = (rem % p.tiles_w) * p.tile_step_w + p.tile_w_org;
+        if (p.aux_mode) {
+          mbar_wait(&auxempty[ab], aux_phase ^ 1);
+          mbar_expect_tx(&auxfull[ab], kTileOutBytes);
+          tma_load_4d(aux_stage + ab * kTileOutBytes, &p.aux_map, &auxfull[ab], nblk * BLOCK_N, w0, h0, n);
+          ab ^= 1;
+          if (ab == 0) aux_phase ^= 1;
+        }
         for (int c = 0; c < p.n_chunks; ++c) {
           const int view = c / p.chunks_per_view;
           const int coff = (c - view * p.chunks_per_view) * 64;
           for (int s = 0; s < p.n_strips; ++s) {
-            mbar_wait(&empty[stage], phase ^ 1);
+            { long long t0_ = clock64(); mbar_wait(&empty[stage], phase ^ 1); prof_acc[0] += clock64() - t0_; }
             uint8_t* dst = stages + size_t(stage) * p.stage_bytes;
             mbar_expect_tx(&full[stage], p.resident ? p.strip_bytes : p.stage_bytes);
             tma_load_4d(dst, &p.in_map[view], &full[stage], coff, w0 + p.strip_dw[s], h0 + p.strip_dh, n);
             if (!p.resident) {
-              const int kb0 = (c * p.n_strips + s) * p.n_taps;
-              for (int r = 0; r < p.n_taps; ++r)
+              const int kb0 = (c * p.n_strips + s) * NT;
+              for (int r = 0; r < NT; ++r)
                 tma_load_2d(dst + p.strip_bytes + size_t(r) * kBTile, &p.w_map, &full[stage], 0,
                             (kb0 + r) * p.cout_total + nblk * BLOCK_N);
             }
@@ -146,73 +175,87 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
+    // The whole warp runs this loop with warp-uniform values; only `leader` issues tcgen05 instructions.
     constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+    const uint64_t desc_hi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+    uint32_t tap_off[NT];
+#pragma unroll
+    for (int r = 0; r < NT; ++r) tap_off[r] = uint32_t(p.tap_row[r] * p.TW) * 8u;  // bytes >> 4
+    const uint32_t stage0_lo = smem_u32(stages) >> 4;
+    const uint32_t stage_lo_stride = p.stage_bytes >> 4;
+    const uint32_t w_lo = smem_u32(w_smem) >> 4;
+    const uint32_t strip_lo = p.strip_bytes >> 4;
     if (p.resident) mbar_wait(wfull, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      { long long t0_ = clock64(); mbar_wait(&tempty[acc], acc_phase ^ 1); prof_acc[1] += clock64() - t0_; }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
       uint32_t accumulate = 0;
+      uint32_t kb = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
         for (int s = 0; s < p.n_strips; ++s) {
-          mbar_wait(&full[stage], phase);
+          { long long t0_ = clock64(); mbar_wait(&full[stage], phase); prof_acc[2] += clock64() - t0_; }
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_stage = smem_u32(stages + size_t(stage) * p.stage_bytes);
-            const int kb0 = (c * p.n_strips + s) * p.n_taps;
-            for (int r = 0; r < p.n_taps; ++r) {
-              const uint32_t a_addr = a_stage + uint32_t(p.tap_row[r] * p.TW) * 128u;
-              const uint32_t b_addr = p.resident ? smem_u32(w_smem) + uint32_t(kb0 + r) * kBTile
-                                                 : a_stage + p.strip_bytes + uint32_t(r) * kBTile;
+          const uint32_t a_lo = stage0_lo + uint32_t(stage) * stage_lo_stride;
+          const uint32_t b_lo = p.resident ? w_lo + kb * (kBTile >> 4) : a_lo + strip_lo;
+          if (elect_one()) {
+#pragma unroll
+            for (int r = 0; r < NT; ++r) {
+              const uint64_t adesc = desc_hi | uint64_t(a_lo + tap_off[r]);
+              const uint64_t bdesc = desc_hi | uint64_t(b_lo + uint32_t(r) * (kBTile >> 4));
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_bf16(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 1024, 0),
-                          make_smem_desc_sw128(b_addr + k * 32, 1024, 0), idesc, accumulate);
+                umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, accumulate);
                 accumulate = 1;
               }
             }
             umma_commit(&empty[stage]);
           }
           __syncwarp();
+          accumulate = 1;
+          kb += NT;
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (lane == 0) umma_commit(&tfull[acc]);
+      if (elect_one()) umma_commit(&tfull[acc]);
       __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else {
+  } else if (!kFold || warp < 6) {
     // =================================================================== epilogue
     const int q = warp & 3;            // TMEM lane quadrant this warp may read
     const int m = q * 32 + lane;       // GEMM row == pixel within the tile
-    const int th = m / p.TW;
-    const int tw = m - th * p.TW;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const int hf = (warp - 2) >> 2;    // which 32-column half of the 64-wide tile (0 for fold9)
+    const int etid = threadIdx.x - 64;
+    int acc = 0, ob = 0, ab = 0;
+    uint32_t acc_phase = 0, aux_phase = 0;
     for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
-      const int h = (rem / p.tiles_w) * p.TH + th;
-      const int w = (rem % p.tiles_w) * p.tile_step_w + p.tile_w_org + tw;
-      mbar_wait(&tfull[acc], acc_phase);
+      const int h0 = (rem / p.tiles_w) * p.TH;
+      const int w0 = (rem % p.tiles_w) * p.tile_step_w + p.tile_w_org;
+      { long long t0_ = clock64(); mbar_wait(&tfull[acc], acc_phase); prof_acc[3] += clock64() - t0_; }
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N + hf * 32);
+      uint32_t v[32];
+      tmem_ld32(t_addr, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
 
-      if constexpr (BLOCK_N == 32) {
+      if constexpr (kFold) {
         // fold9: P[pixel][s*3+co] -> out[co][h][w] = bias + sum_s P[(h, w+s-4)][s*3+co]
-        uint32_t v[32];
-        tmem_ld32(t_addr, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&tempty[acc]);
+        const int th = m / p.TW;
+        const int tw = m - th * p.TW;
+        const int h = h0 + th, w = w0 + tw;
 #pragma unroll
         for (int j = 0; j < 32; ++j) fold_buf[m * kFoldPad + j] = __uint_as_float(v[j]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        named_bar_sync(1, 128);
         if (tw >= 4 && tw < p.TW - 4 && h < p.H && w >= 0 && w < p.W) {
           float o0 = p.bias ? p.bias[0] : 0.f, o1 = p.bias ? p.bias[1] : 0.f, o2 = p.bias ? p.bias[2] : 0.f;
 #pragma unroll
@@ -229,80 +272,89 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           o[base + plane] = o1;
           o[base + 2 * plane] = o2;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        named_bar_sync(2, 128);
       } else {
-        const bool valid = (h < p.H) && (w < p.W);
-        size_t pix;
-        if (p.out_mode == OUT_PIXEL_SHUFFLE) {
-          pix = ((size_t(n) * (2 * p.H) + (2 * h + (nblk >> 1))) * (2 * p.W) + (2 * w + (nblk & 1))) * 64;
-        } else {
-          pix = ((size_t(n) * p.H + h) * p.W + w) * p.cout_total + size_t(nblk) * BLOCK_N;
-        }
-        __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out) + pix;
+        float f[32];
+        {
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + hf * 32);
 #pragma unroll
-        for (int half = 0; half < BLOCK_N / 32; ++half) {
-          uint32_t v[32];
-          tmem_ld32(t_addr + half * 32, v);
-          tmem_ld_wait();
-          if (half == BLOCK_N / 32 - 1) {
-            tc_fence_before();
-            mbar_arrive(&tempty[acc]);
-          }
-          if (valid) {
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(v[j]) + s_bias[half * 32 + j];
-              if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
-              else if (p.act == ACT_LRELU) x = x > 0.f ? x : x * p.slope;
-              f[j] = x;
-            }
-            if (p.residual != nullptr) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix + half * 32);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 r = __ldg(rp + g);
-                f[g * 8 + 0] += bf16_lo(r.x); f[g * 8 + 1] += bf16_hi(r.x);
-                f[g * 8 + 2] += bf16_lo(r.y); f[g * 8 + 3] += bf16_hi(r.y);
-                f[g * 8 + 4] += bf16_lo(r.z); f[g * 8 + 5] += bf16_hi(r.z);
-                f[g * 8 + 6] += bf16_lo(r.w); f[g * 8 + 7] += bf16_hi(r.w);
-              }
-            }
-            if (p.mask_src != nullptr) {
-              const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + pix + half * 32);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 r = __ldg(mp + g);
-                // bf16 > 0  <=>  sign bit clear and magnitude nonzero
-                const uint32_t ws[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  if (!(bf16_lo(ws[e]) > 0.f)) f[g * 8 + 2 * e] = 0.f;
-                  if (!(bf16_hi(ws[e]) > 0.f)) f[g * 8 + 2 * e + 1] = 0.f;
-                }
-              }
-            }
-            uint4* op = reinterpret_cast<uint4*>(optr + half * 32);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 o;
-              o.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]);
-              o.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
-              o.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]);
-              o.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
-              op[g] = o;
-            }
+          for (int g = 0; g < 8; ++g) {
+            const float4 b = bp[g];
+            f[4 * g + 0] = __uint_as_float(v[4 * g + 0]) + b.x;
+            f[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b.y;
+            f[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b.z;
+            f[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b.w;
           }
         }
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = apply_act<ACT_RELU>(f[j], 0.f);
+        } else if (p.act == ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = apply_act<ACT_LRELU>(f[j], p.slope);
+        }
+        const uint32_t row_off = uint32_t(m) * 128u;
+        const uint32_t sw = uint32_t(m & 7);
+        if (p.aux_mode) {
+          mbar_wait(&auxfull[ab], aux_phase);
+          const uint8_t* ap = aux_stage + ab * kTileOutBytes + row_off;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 r = *reinterpret_cast<const uint4*>(ap + (((uint32_t(hf * 4 + g)) ^ sw) << 4));
+            const uint32_t ws[4] = {r.x, r.y, r.z, r.w};
+            if (p.aux_mode == 1) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                f[g * 8 + 2 * e] += bf16_lo(ws[e]);
+                f[g * 8 + 2 * e + 1] += bf16_hi(ws[e]);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (!(bf16_lo(ws[e]) > 0.f)) f[g * 8 + 2 * e] = 0.f;
+                if (!(bf16_hi(ws[e]) > 0.f)) f[g * 8 + 2 * e + 1] = 0.f;
+              }
+            }
+          }
+          mbar_arrive(&auxempty[ab]);
+          ab ^= 1;
+          if (ab == 0) aux_phase ^= 1;
+        }
+        // stage the bf16 tile in shared memory (128B-swizzled rows) and hand it to the TMA store engine
+        if (etid == 0) tma_store_wait_read<1>();      // the store that used this buffer two tiles ago has drained
+        named_bar_sync(1, kEpiThreads);
+        uint8_t* op = out_stage + ob * kTileOutBytes + row_off;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]);
+          o.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
+          o.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]);
+          o.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(op + (((uint32_t(hf * 4 + g)) ^ sw) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, kEpiThreads);
+        if (etid == 0) {
+          const bool ps = p.out_mode == OUT_PIXEL_SHUFFLE;
+          tma_store_4d(&p.out_map[ps ? nblk : 0], out_stage + ob * kTileOutBytes, ps ? 0 : nblk * BLOCK_N, w0, h0, n);
+          tma_store_commit();
+        }
+        ob ^= 1;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (!kFold && etid == 0) tma_store_wait_all<0>();
   }
 
+  if (p.prof != nullptr && lane == 0 && (warp <= 2)) {
+    long long* d = p.prof + (size_t(blockIdx.x) * 3 + warp) * 6;
+    d[0] = prof_acc[0]; d[1] = prof_acc[1]; d[2] = prof_acc[2]; d[3] = prof_acc[3]; d[4] = clock64() - t_start; d[5] = t_start;
+  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ----------------------------------------------------------- host launcher
@@ -351,6 +403,21 @@ static int num_sms() {
   return g_num_sms;
 }
 
+template <int BLOCK_N, int NT>
+static int launch_instance(const ConvKParams& p, dim3 grid, size_t smem_bytes, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    attr_set = true;
+  }
+  conv_gemm_kernel<BLOCK_N, NT><<<grid, kThreads, smem_bytes, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("conv_gemm launch: %s", cudaGetErrorString(e)); return int(e); }
+  return 0;
+}
+
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   if (a.TH * a.TW != 128 || a.TW % 8 != 0) { set_error("conv_gemm: tile must be 128 pixels with TW%%8==0"); return -1; }
   if (a.block_n != 64 && a.block_n != 32) { set_error("conv_gemm: block_n must be 32 or 64"); return -2; }
@@ -359,13 +426,17 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   if (a.n_strips < 1 || a.n_strips > kMaxStrips || a.n_taps < 1 || a.n_taps > kMaxTaps) {
     set_error("conv_gemm: bad strip/tap count"); return -5;
   }
-  if ((a.out_mode == OUT_FOLD9_NCHW) != (a.block_n == 32)) { set_error("conv_gemm: fold9 <=> block_n 32"); return -6; }
+  const bool fold = a.out_mode == OUT_FOLD9_NCHW;
+  if (fold != (a.block_n == 32)) { set_error("conv_gemm: fold9 <=> block_n 32"); return -6; }
   if (a.strip_rows > 256 || a.TW > 256) { set_error("conv_gemm: TMA box too large"); return -7; }
+  if (a.residual != nullptr && a.mask_src != nullptr) { set_error("conv_gemm: residual and mask are exclusive"); return -11; }
+  const bool has_aux = a.residual != nullptr || a.mask_src != nullptr;
+  if (has_aux && a.out_mode != OUT_NHWC) { set_error("conv_gemm: residual/mask need OUT_NHWC"); return -12; }
+  if (a.out_mode == OUT_PIXEL_SHUFFLE && a.cout_total != 256) { set_error("conv_gemm: pixel shuffle needs cout 256"); return -13; }
 
   ConvKParams p;
   memset(&p, 0, sizeof(p));
   p.N = a.N; p.H = a.H; p.W = a.W; p.TH = a.TH; p.TW = a.TW;
-  const bool fold = a.out_mode == OUT_FOLD9_NCHW;
   p.tile_step_w = fold ? a.TW - 8 : a.TW;
   p.tile_w_org = fold ? -4 : 0;
   p.tiles_h = (a.H + a.TH - 1) / a.TH;
@@ -380,7 +451,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   }
   p.n_chunks = total_ch / 64;
   p.chunks_per_view = a.views[0].channels / 64;
-  p.n_strips = a.n_strips; p.n_taps = a.n_taps; p.strip_rows = a.strip_rows; p.strip_dh = a.strip_dh;
+  p.n_strips = a.n_strips; p.strip_rows = a.strip_rows; p.strip_dh = a.strip_dh;
   for (int s = 0; s < a.n_strips; ++s) p.strip_dw[s] = a.strip_dw[s];
   for (int r = 0; r < a.n_taps; ++r) {
     if (a.tap_row[r] < 0 || a.tap_row[r] + a.TH > a.strip_rows) { set_error("conv_gemm: tap row outside strip"); return -9; }
@@ -398,16 +469,17 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   const int kb_total = p.n_chunks * a.n_strips * a.n_taps;
   p.strip_bytes = uint32_t(a.strip_rows) * a.TW * 128u;
   const uint32_t w_all = uint32_t(kb_total) * btile;
-  const uint32_t tail_bytes = (fold ? 128 * kFoldPad * 4 : 0) + 256 + 256;
-  const uint32_t budget = 227 * 1024 - 1024 - tail_bytes;
-  p.resident = (w_all + 2 * p.strip_bytes <= budget) ? 1 : 0;
+  p.aux_mode = a.residual ? 1 : (a.mask_src ? 2 : 0);
+  const uint32_t fixed_bytes = (fold ? 128 * kFoldPad * 4 : 2 * kTileOutBytes) + (has_aux ? 2 * kTileOutBytes : 0) + 256 + 256;
+  const uint32_t budget = 227 * 1024 - 1024 - fixed_bytes;
+  p.resident = (w_all + 3 * p.strip_bytes <= budget) ? 1 : 0;
   p.w_resident_bytes = p.resident ? w_all : 0;
   p.stage_bytes = p.strip_bytes + (p.resident ? 0 : uint32_t(a.n_taps) * btile);
   int stages = int((budget - p.w_resident_bytes) / p.stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("conv_gemm: shared memory too small for 2 stages (stage %u B)", p.stage_bytes); return -10; }
   p.n_stages = stages;
-  const size_t smem_bytes = 1024 + p.w_resident_bytes + size_t(stages) * p.stage_bytes + tail_bytes;
+  const size_t smem_bytes = 1024 + p.w_resident_bytes + size_t(stages) * p.stage_bytes + fixed_bytes;
 
   for (int v = 0; v < a.n_views; ++v) {
     const InView& iv = a.views[v];
@@ -425,33 +497,52 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     int rc = encode_map_bf16(&p.w_map, a.weights, 2, dims, strides, box);
     if (rc) return rc;
   }
+  if (!fold) {
+    uint32_t box[4] = {64, uint32_t(a.TW), uint32_t(a.TH), 1};
+    if (a.out_mode == OUT_PIXEL_SHUFFLE) {
+      // view q=(i,j) of the HR tensor [N,2H,2W,64]: pixel (2h+i, 2w+j)
+      for (int q = 0; q < 4; ++q) {
+        const int i = q >> 1, j = q & 1;
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a.out) + (size_t(i) * 2 * a.W + j) * 64;
+        uint64_t dims[4] = {64, uint64_t(a.W), uint64_t(a.H), uint64_t(a.N)};
+        uint64_t strides[3] = {128 * 2, uint64_t(4) * a.W * 64 * 2, uint64_t(4) * a.H * a.W * 64 * 2};
+        int rc = encode_map_bf16(&p.out_map[q], base, 4, dims, strides, box);
+        if (rc) return rc;
+      }
+    } else {
+      uint64_t dims[4] = {uint64_t(a.cout_total), uint64_t(a.W), uint64_t(a.H), uint64_t(a.N)};
+      uint64_t strides[3] = {uint64_t(a.cout_total) * 2, uint64_t(a.W) * a.cout_total * 2,
+                             uint64_t(a.H) * a.W * a.cout_total * 2};
+      int rc = encode_map_bf16(&p.out_map[0], a.out, 4, dims, strides, box);
+      if (rc) return rc;
+      for (int q = 1; q < 4; ++q) p.out_map[q] = p.out_map[0];
+      if (has_aux) {
+        rc = encode_map_bf16(&p.aux_map, a.residual ? a.residual : a.mask_src, 4, dims, strides, box);
+        if (rc) return rc;
+      }
+    }
+    if (!has_aux) p.aux_map = p.out_map[0];
+  } else {
+    for (int q = 0; q < 4; ++q) p.out_map[q] = p.in_map[0];
+    p.aux_map = p.in_map[0];
+  }
   p.bias = a.bias; p.act = a.act; p.slope = a.slope;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual);
-  p.mask_src = reinterpret_cast<const __nv_bfloat16*>(a.mask_src);
   p.out = a.out; p.out_mode = a.out_mode;
+  p.prof = reinterpret_cast<long long*>(a.prof);
 
   const dim3 grid(p.ctas_per_block * p.n_blocks);
-  cudaError_t e;
-  if (a.block_n == 64) {
-    static bool attr64 = false;
-    if (!attr64) {
-      e = cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
-      attr64 = true;
-    }
-    conv_gemm_kernel<64><<<grid, kThreads, smem_bytes, stream>>>(p);
-  } else {
-    static bool attr32 = false;
-    if (!attr32) {
-      e = cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
-      attr32 = true;
-    }
-    conv_gemm_kernel<32><<<grid, kThreads, smem_bytes, stream>>>(p);
+  if (fold) {
+    if (a.n_taps != 9) { set_error("conv_gemm: fold9 needs 9 row taps"); return -14; }
+    return launch_instance<32, 9>(p, grid, smem_bytes, stream);
   }
-  e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error("conv_gemm launch: %s", cudaGetErrorString(e)); return int(e); }
-  return 0;
+  switch (a.n_taps) {
+    case 1: return launch_instance<64, 1>(p, grid, smem_bytes, stream);
+    case 2: return launch_instance<64, 2>(p, grid, smem_bytes, stream);
+    case 3: return launch_instance<64, 3>(p, grid, smem_bytes, stream);
+    case 4: return launch_instance<64, 4>(p, grid, smem_bytes, stream);
+    case 5: return launch_instance<64, 5>(p, grid, smem_bytes, stream);
+    default: set_error("conv_gemm: unsupported tap count %d", a.n_taps); return -15;
+  }
 }
 
 }  // namespace srg

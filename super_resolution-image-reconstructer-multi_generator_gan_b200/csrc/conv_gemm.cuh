@@ -55,6 +55,7 @@ struct ConvGemmArgs {
   const void* mask_src;      // bf16, same layout as out: out = (mask_src > 0) ? out : 0  (ReLU backward)
   void* out;
   int out_mode;
+  void* prof;                // optional debug timers: int64 [grid][3][6]
   // fold9: tile columns overlap; valid output columns per tile = TW-8
 };
 

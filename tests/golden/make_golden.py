@@ -1,0 +1,146 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference
+(/root/reference/src) on fixed seeds.  Run in the build container only (the reference does not
+travel to the GPU box):
+
+    python tests/golden/make_golden.py
+
+Off-path imports that are absent here (skimage, matplotlib) are replaced by empty stand-in modules
+before ``src.train`` is imported; ``torch.cuda.empty_cache`` is neutralised on CPU.
+Nothing in the reference is edited or copied.
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    for name in ("skimage", "skimage.metrics", "matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["skimage.metrics"].structural_similarity = None
+    sys.modules["skimage.metrics"].peak_signal_noise_ratio = None
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.path.insert(0, REF)
+    torch.cuda.empty_cache = lambda: None
+    import src.models as models
+    import src.train as train
+    import src.utils as utils
+    return models, train, utils
+
+
+def checksum(sd):
+    return {k: [float(v.double().sum()), float(v.double().abs().sum())] for k, v in sd.items()
+            if v.dtype.is_floating_point}
+
+
+def main():
+    torch.set_num_threads(8)
+    models, train, utils = import_reference()
+    out = {}
+
+    # ---- 1. tiny generator: forward (eval + train), loss, grads ---------------------------------
+    torch.manual_seed(1)
+    g = models.SRResNet()
+    init_ck = checksum(g.state_dict())
+    lr = torch.rand(2, 3, 16, 24)
+    hr = torch.rand(2, 3, 64, 96)
+    g.eval()
+    with torch.no_grad():
+        y_eval = g(lr)
+    g.train()
+    y_train = g(lr)
+    crit = utils.ReconstructionLoss()
+    com, tv = crit(hr, y_train)
+    (com + tv).backward()
+    grads = {k: p.grad for k, p in g.named_parameters()}
+    sel = ["conv1.weight", "conv1.bias", "residual_blocks.0.conv1.weight", "residual_blocks.0.bn1.weight",
+           "residual_blocks.0.bn1.bias", "residual_blocks.7.conv2.weight", "residual_blocks.15.bn2.weight",
+           "conv2.weight", "upsample.0.weight", "upsample.3.weight", "upsample.3.bias", "conv3.weight",
+           "conv3.bias"]
+    np.savez_compressed(
+        os.path.join(HERE, "generator_tiny.npz"),
+        y_eval=y_eval.numpy(), y_train=y_train.detach().numpy(),
+        com=np.float64(com.item()), tv=np.float64(tv.item()),
+        bn_rm=g.residual_blocks[0].bn1.running_mean.numpy(), bn_rv=g.residual_blocks[0].bn1.running_var.numpy(),
+        **{"grad/" + k: grads[k].numpy() for k in sel},
+    )
+    out["generator_tiny"] = {
+        "seed": 1, "lr_shape": [2, 3, 16, 24], "hr_shape": [2, 3, 64, 96], "init_checksum": init_ck,
+        "grad_norms": {k: float(v.double().norm()) for k, v in grads.items()},
+    }
+
+    # ---- 2. ReconstructionLoss value + gradient ---------------------------------------------------
+    torch.manual_seed(2)
+    hr2 = torch.rand(2, 3, 20, 28)
+    sr2 = (hr2 + 0.1 * torch.randn(2, 3, 20, 28)).requires_grad_(True)
+    e, t = utils.ReconstructionLoss()(hr2, sr2)
+    (e + t).backward()
+    np.savez_compressed(os.path.join(HERE, "recon_loss.npz"), hr=hr2.numpy(), sr=sr2.detach().numpy(),
+                        edge=np.float64(e.item()), tv=np.float64(t.item()), grad=sr2.grad.numpy())
+
+    # ---- 3. cfg1 anchors: 4 x train_generator as-is -----------------------------------
+    torch.manual_seed(0)
+    g = models.SRResNet()
+    d = models.Discriminator()
+    lr = torch.rand(8, 3, 64, 64)
+    hr = torch.rand(8, 3, 256, 256)
+    g.eval()
+    with torch.no_grad():
+        y = g(lr)
+    anchors = {"eval_sum": float(y.double().sum()), "eval_mean_abs": float(y.double().abs().mean()),
+               "eval_y0000": float(y[0, 0, 0, 0]), "steps": []}
+    crit = utils.ReconstructionLoss()
+    opt = torch.optim.Adam(g.parameters(), lr=1e-4)
+    for _ in range(4):
+        anchors["steps"].append(list(train.train_generator(g, d, lr, hr, None, crit, opt)))
+    torch.autograd.set_detect_anomaly(False)
+    out["cfg1_anchors"] = anchors
+
+    # ---- 4. discriminator at its smallest valid geometry (428 x 684) + one D step -----------------
+    torch.manual_seed(3)
+    d = models.Discriminator()
+    out["discriminator_init_checksum"] = checksum(d.state_dict())
+    x = torch.rand(1, 3, 428, 684)
+    with torch.no_grad():
+        yd = d(x)
+    np.savez_compressed(os.path.join(HERE, "discriminator_min.npz"), y=yd.numpy(),
+                        x_sum=np.float64(x.double().sum()))
+    torch.manual_seed(4)
+    g = models.SRResNet()
+    d = models.Discriminator()
+    lr = torch.rand(1, 3, 107, 171)
+    hr = torch.rand(1, 3, 428, 684)
+    d_opt = torch.optim.Adam(d.parameters(), lr=5e-5)
+    d_losses = [train.train_discriminator(d, g, hr, lr, d_opt) for _ in range(2)]
+    torch.autograd.set_detect_anomaly(False)
+    out["d_step"] = {"seed": 4, "lr_shape": [1, 3, 107, 171], "hr_shape": [1, 3, 428, 684], "d_losses": d_losses,
+                     "d_param_checksum_after": checksum(d.state_dict())}
+
+    # ---- 5. GAN-mode generator term (src/train.py:184-192, commented lines restated by the caller) --
+    torch.manual_seed(5)
+    g = models.SRResNet()
+    d = models.Discriminator()
+    g.train(); d.eval()
+    sr = g(lr)
+    fake = d(sr)
+    with torch.no_grad():
+        real = d(hr)
+    com, tv = utils.ReconstructionLoss()(hr, sr)
+    g_d = torch.mean(torch.tanh(real - fake))
+    (com + tv + g_d).backward()
+    out["gan_mode"] = {"seed": 5, "com": com.item(), "tv": tv.item(), "g_d": g_d.item(),
+                       "grad_norms": {k: float(p.grad.double().norm()) for k, p in g.named_parameters()}}
+
+    with open(os.path.join(HERE, "golden.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

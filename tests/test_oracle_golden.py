@@ -1,0 +1,128 @@
+"""Pins the CPU oracle (oracle/srgan_oracle.py) to outputs of the unmodified reference recorded in
+tests/golden/ (made by tests/golden/make_golden.py).  CPU-only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import srgan_oracle as O
+
+
+@pytest.fixture(scope="module")
+def gj(golden_dir):
+    with open(os.path.join(golden_dir, "golden.json")) as f:
+        return json.load(f)
+
+
+def _check_init(sd, ck):
+    for k, (s, a) in ck.items():
+        v = sd[k].double()
+        assert abs(float(v.sum()) - s) <= 1e-9 * max(1.0, abs(a)), k
+        assert abs(float(v.abs().sum()) - a) <= 1e-9 * max(1.0, abs(a)), k
+
+
+def test_seeded_init_matches_reference(gj):
+    _check_init(O.init_srresnet_state(1), gj["generator_tiny"]["init_checksum"])
+    _check_init(O.init_discriminator_state(3), gj["discriminator_init_checksum"])
+
+
+def test_generator_forward_loss_grads(gj, golden_dir):
+    z = np.load(os.path.join(golden_dir, "generator_tiny.npz"))
+    sd = O.init_srresnet_state(1)
+    lr = torch.rand(2, 3, 16, 24)
+    hr = torch.rand(2, 3, 64, 96)
+    with torch.no_grad():
+        y_eval = O.srresnet_forward(sd, lr, training=False)
+    np.testing.assert_allclose(y_eval.numpy(), z["y_eval"], rtol=0, atol=2e-6)
+    losses, grads, sr = O.generator_loss_and_grads(sd, lr, hr)
+    np.testing.assert_allclose(sr.numpy(), z["y_train"], rtol=0, atol=5e-6)
+    assert abs(losses[1] - float(z["com"])) < 1e-6 and abs(losses[2] - float(z["tv"])) < 1e-7
+    np.testing.assert_allclose(sd["residual_blocks.0.bn1.running_mean"].numpy(), z["bn_rm"], atol=1e-7)
+    np.testing.assert_allclose(sd["residual_blocks.0.bn1.running_var"].numpy(), z["bn_rv"], atol=1e-7)
+    for k in z.files:
+        if k.startswith("grad/"):
+            ref = z[k]
+            got = grads[k[5:]].numpy()
+            assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-6) + 1e-9, k
+    for k, n in gj["generator_tiny"]["grad_norms"].items():
+        assert abs(float(grads[k].double().norm()) - n) <= 2e-5 * max(n, 1e-9) + 1e-10, k
+
+
+def test_reconstruction_loss_value_and_closed_form_grad(golden_dir):
+    z = np.load(os.path.join(golden_dir, "recon_loss.npz"))
+    hr, sr = torch.from_numpy(z["hr"]), torch.from_numpy(z["sr"])
+    e, t = O.reconstruction_loss(hr, sr)
+    assert abs(float(e) - float(z["edge"])) < 1e-7 and abs(float(t) - float(z["tv"])) < 1e-8
+    g = O.reconstruction_loss_grad(hr, sr)
+    np.testing.assert_allclose(g.numpy(), z["grad"], rtol=0, atol=1e-9)
+
+
+def test_discriminator_forward_and_size_rule(golden_dir):
+    z = np.load(os.path.join(golden_dir, "discriminator_min.npz"))
+    sd = O.init_discriminator_state(3)
+    x = torch.rand(1, 3, 428, 684)
+    assert abs(float(x.double().sum()) - float(z["x_sum"])) < 1e-6
+    with torch.no_grad():
+        y = O.discriminator_forward(sd, x)
+    np.testing.assert_allclose(y.numpy(), z["y"], rtol=0, atol=5e-6)
+    assert O.discriminator_output_hw(512, 1024) == (1, 3)
+    assert O.discriminator_output_hw(684, 684) == (2, 2)
+    for bad in ((384, 384), (512, 512), (256, 256), (427, 1024)):
+        with pytest.raises(RuntimeError):
+            O.discriminator_output_hw(*bad)
+
+
+def test_cfg1_anchors_four_generator_steps(gj):
+    a = gj["cfg1_anchors"]
+    sd = O.init_srresnet_state(0)
+    O.init_discriminator_state  # D is constructed after G in the reference and consumes RNG before the data
+    torch.manual_seed(0)
+    sd = O.init_srresnet_state(0)
+    _ = O._conv_init(64, 3, 8), O._conv_init(128, 64, 4), O._conv_init(256, 128, 4), O._conv_init(512, 256, 4)
+    lr = torch.rand(8, 3, 64, 64)
+    hr = torch.rand(8, 3, 256, 256)
+    with torch.no_grad():
+        y = O.srresnet_forward(sd, lr, training=False)
+    assert abs(float(y.double().sum()) - a["eval_sum"]) < 1e-2
+    assert abs(float(y[0, 0, 0, 0]) - a["eval_y0000"]) < 1e-6
+    keys = O.trainable_keys(sd)
+    opt = O.AdamState([sd[k] for k in keys], lr=1e-4)
+    for ref in a["steps"][:2]:
+        got = O.train_generator_step(sd, opt, lr, hr)
+        for g, r in zip(got[:3], ref[:3]):
+            assert abs(g - r) <= 2e-5 * abs(r) + 1e-8, (got, ref)
+
+
+def test_discriminator_step_and_gan_mode(gj):
+    dj = gj["d_step"]
+    torch.manual_seed(4)
+    g_sd = O.init_srresnet_state(4)
+    d_sd = {}
+    d_sd["model.0.weight"], d_sd["model.0.bias"] = O._conv_init(64, 3, 8)
+    d_sd["model.4.weight"], d_sd["model.4.bias"] = O._conv_init(128, 64, 4)
+    d_sd["model.8.weight"], d_sd["model.8.bias"] = O._conv_init(256, 128, 4)
+    d_sd["model.12.weight"], d_sd["model.12.bias"] = O._conv_init(512, 256, 4)
+    lr = torch.rand(*dj["lr_shape"])
+    hr = torch.rand(*dj["hr_shape"])
+    keys = O.trainable_keys(d_sd)
+    opt = O.AdamState([d_sd[k] for k in keys], lr=5e-5)
+    for ref in dj["d_losses"]:
+        got = O.train_discriminator_step(d_sd, opt, g_sd, hr, lr)
+        assert abs(got - ref) <= 1e-4 * abs(ref) + 1e-6, (got, ref)
+    for k, (s, a) in dj["d_param_checksum_after"].items():
+        assert abs(float(d_sd[k].double().abs().sum()) - a) <= 1e-5 * a, k
+
+    gm = gj["gan_mode"]
+    torch.manual_seed(5)
+    g_sd = O.init_srresnet_state(5)
+    d_sd = {}
+    d_sd["model.0.weight"], d_sd["model.0.bias"] = O._conv_init(64, 3, 8)
+    d_sd["model.4.weight"], d_sd["model.4.bias"] = O._conv_init(128, 64, 4)
+    d_sd["model.8.weight"], d_sd["model.8.bias"] = O._conv_init(256, 128, 4)
+    d_sd["model.12.weight"], d_sd["model.12.bias"] = O._conv_init(512, 256, 4)
+    losses, grads, _ = O.generator_loss_and_grads(g_sd, lr, hr, d_sd=d_sd, gan_mode=True)
+    assert abs(losses[1] - gm["com"]) < 1e-6 and abs(losses[3] - gm["g_d"]) < 1e-6
+    for k, n in gm["grad_norms"].items():
+        assert abs(float(grads[k].double().norm()) - n) <= 1e-4 * n + 1e-9, k

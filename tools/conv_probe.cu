@@ -207,6 +207,20 @@ static int run(const Problem& pr, int timing_iters) {
          bad == 0 ? "OK" : "FAIL");
 
   if (timing_iters > 0) {
+    long long* dprof;
+    CK(cudaMalloc(&dprof, 1024 * 18 * 8));
+    CK(cudaMemset(dprof, 0, 1024 * 18 * 8));
+    a.prof = dprof;
+    launch_conv_gemm(a, 0);
+    CK(cudaDeviceSynchronize());
+    a.prof = nullptr;
+    std::vector<long long> hp(1024 * 18);
+    CK(cudaMemcpy(hp.data(), dprof, hp.size() * 8, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < 148; b += 49)
+      printf("  cta %d: producer wait_empty=%lld total=%lld | mma wait_tempty=%lld wait_full=%lld total=%lld | epi wait_tfull=%lld total=%lld\n", b,
+             hp[(b * 3 + 0) * 6 + 0], hp[(b * 3 + 0) * 6 + 4], hp[(b * 3 + 1) * 6 + 1], hp[(b * 3 + 1) * 6 + 2], hp[(b * 3 + 1) * 6 + 4],
+             hp[(b * 3 + 2) * 6 + 3], hp[(b * 3 + 2) * 6 + 4]);
+    cudaFree(dprof);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -250,9 +264,12 @@ int main(int argc, char** argv) {
   fails += run(conv3x3("c3x3_small", 2, 32, 24, 64, false), 0);
   fails += run(conv3x3("c3x3_ragged", 3, 40, 20, 64, false), 0);
   {
-    Problem p = conv3x3("c3x3_epi", 2, 32, 16, 64, false);
-    p.act = ACT_LRELU; p.residual = true; p.mask = true;
+    Problem p = conv3x3("c3x3_lrelu_res", 2, 32, 16, 64, false);
+    p.act = ACT_LRELU; p.residual = true;
     fails += run(p, 0);
+    Problem m = conv3x3("c3x3_mask_ragged", 2, 24, 20, 64, false);
+    m.mask = true;
+    fails += run(m, 0);
   }
   {
     Problem p = conv3x3("c3x3_relu_ps", 2, 32, 16, 256, true);
