@@ -362,7 +362,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeTiledFn get_encode_fn() {
+static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (fn) return fn;
   void* sym = nullptr;

@@ -62,6 +62,27 @@ struct ConvGemmArgs {
 // Returns 0 on success, cudaError_t (>0) or a negative argument-check code otherwise.
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream);
 
+// Weight gradient: D_t[ci][co] = sum_p x[p + shift_t][ci] * dy[p][co] for every tap t = s*n_taps + r
+// (strip-major), taps paired (2i, 2i+1) into 128-row accumulators.  Partials layout:
+// [splits][n_blocks][n_pairs][128][64] fp32 with row = (t & 1)*64 + ci, column = co within the n-block.
+struct WgradArgs {
+  int N, H, W;               // output-gradient grid
+  int TH, TW;
+  InView x;                  // 64-channel input view (rows/cols outside in_H/in_W read as zero)
+  int in_H, in_W;
+  int dy_views;              // 1: one NHWC tensor with n_blocks*64 channels; 4: one 64-channel view per n-block
+  InView dy[4];
+  int n_blocks;
+  int n_strips, n_taps, strip_rows, strip_dh;
+  int strip_dw[kMaxStrips];
+  int tap_row[kMaxTaps];
+  float* partials;
+};
+int wgrad_partials_floats(const WgradArgs& a, int* splits_out);
+int launch_wgrad_gemm(const WgradArgs& a, cudaStream_t stream);
+int launch_wgrad_reduce(const float* partials, const int* idx, float* out, int n_out, int splits, size_t split_stride,
+                        int accumulate_into, cudaStream_t stream);
+
 const char* last_error();
 void set_error(const char* fmt, ...);
 

@@ -1,0 +1,259 @@
+// Weight-gradient implicit GEMM for sm_100a.
+//
+//   D_t[ci][co] = sum over pixels p of  x[p + shift_t][ci] * dy[p][co]          (one 64x64 block per tap t)
+//
+// The reduction (GEMM K) dimension is the pixel index, so both operands are "MN-major": a shared-memory row is
+// one pixel's 64 channels (128 bytes, 128B-swizzled by TMA), exactly the tiles the forward kernel loads.  Two taps
+// are paired into one M=128 MMA: the A descriptor's leading-dimension byte offset is the distance between the two
+// taps' row-shifted views of the same input strips.  Every CTA keeps all tap accumulators resident in TMEM across
+// its pixel tiles (split-K over CTAs) and writes one fp32 partial block at the end; wgrad_reduce_kernel sums the
+// partials in a fixed order (deterministic) and scatters them into the OIHW gradient through an index map.
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+
+#include <string.h>
+
+namespace srg {
+
+int encode_map_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+
+struct WgradKParams {
+  CUtensorMap x_map;       // input activations (strips)
+  CUtensorMap dy_map[4];   // output gradients: one view per n-block
+  int N, H, W, TH, TW;
+  int tiles_h, tiles_w, tiles_total;
+  int n_strips, n_taps, strip_rows, strip_dh;   // n_taps = taps per strip
+  int strip_dw[kMaxStrips];
+  int tap_row[kMaxTaps];
+  int n_pairs;             // ceil(n_strips*n_taps / 2)
+  int n_blocks, splits;    // grid = n_blocks * splits
+  int dy_c0_step;          // channel offset per n-block inside dy_map (0 when each n-block has its own view)
+  uint32_t strip_bytes, stage_bytes;
+  int n_stages;
+  float* partials;         // [splits][n_blocks][n_pairs][128][64]
+};
+
+constexpr int kWgThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+constexpr uint32_t kDyBytes = 128 * 128;
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+
+  uint8_t* stages = smem;  // n_stages * stage_bytes; stage = [dy tile 16 KB][strip 0][strip 1]...
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + size_t(p.n_stages) * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 4;
+  uint64_t* done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int nblk = blockIdx.x % p.n_blocks;
+  const int split = blockIdx.x / p.n_blocks;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.x_map);
+    tma_prefetch_desc(&p.dy_map[nblk]);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = split; tile < p.tiles_total; tile += p.splits) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * p.TH;
+        const int w0 = (rem % p.tiles_w) * p.TW;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* dst = stages + size_t(stage) * p.stage_bytes;
+        mbar_expect_tx(&full[stage], p.stage_bytes);
+        tma_load_4d(dst, &p.dy_map[nblk], &full[stage], nblk * p.dy_c0_step, w0, h0, n);
+        for (int s = 0; s < p.n_strips; ++s)
+          tma_load_4d(dst + kDyBytes + size_t(s) * p.strip_bytes, &p.x_map, &full[stage], 0, w0 + p.strip_dw[s],
+                      h0 + p.strip_dh, n);
+        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+    const uint64_t hi_common = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+    const int total_taps = p.n_strips * p.n_taps;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (int tile = split; tile < p.tiles_total; tile += p.splits) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t base = smem_u32(stages + size_t(stage) * p.stage_bytes);
+      const uint32_t b_lo = base >> 4;
+      if (elect_one()) {
+        for (int pr = 0; pr < p.n_pairs; ++pr) {
+          const int t0 = 2 * pr, t1 = (2 * pr + 1 < total_taps) ? 2 * pr + 1 : 2 * pr;
+          const uint32_t a0 = base + kDyBytes + uint32_t(t0 / p.n_taps) * p.strip_bytes +
+                              uint32_t(p.tap_row[t0 % p.n_taps] * p.TW) * 128u;
+          const uint32_t a1 = base + kDyBytes + uint32_t(t1 / p.n_taps) * p.strip_bytes +
+                              uint32_t(p.tap_row[t1 % p.n_taps] * p.TW) * 128u;
+          const uint32_t lbo = (t1 == t0) ? 1024u : (a1 - a0);   // unpaired last tap: second half is junk
+          const uint64_t adesc = hi_common | (uint64_t((lbo >> 4) & 0x3FFF) << 16) | uint64_t(a0 >> 4);
+          const uint64_t bdesc = hi_common | uint64_t(b_lo);
+          const uint32_t d_tmem = tmem_base + uint32_t(pr * 64);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // 16 pixels (= 2048 bytes of rows) per MMA
+            umma_bf16(d_tmem, adesc + uint64_t(128 * k), bdesc + uint64_t(128 * k), idesc, (k > 0) ? 1u : accumulate);
+        }
+        umma_commit(&empty[stage]);
+      }
+      __syncwarp();
+      accumulate = 1;
+      if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
+  } else {
+    // epilogue: once per CTA
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const bool any = split < p.tiles_total;
+    float* dst = p.partials + ((size_t(split) * p.n_blocks + nblk) * p.n_pairs) * 128 * 64;
+    for (int pr = 0; pr < p.n_pairs; ++pr) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(pr * 64 + half * 32), v);
+        tmem_ld_wait();
+        float4* o = reinterpret_cast<float4*>(dst + (size_t(pr) * 128 + m) * 64 + half * 32);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 f;
+          f.x = any ? __uint_as_float(v[4 * g + 0]) : 0.f;
+          f.y = any ? __uint_as_float(v[4 * g + 1]) : 0.f;
+          f.z = any ? __uint_as_float(v[4 * g + 2]) : 0.f;
+          f.w = any ? __uint_as_float(v[4 * g + 3]) : 0.f;
+          o[g] = f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// out[e] = sum_s partials[s][idx[e]]  (idx < 0 -> 0).  Fixed summation order => run-to-run deterministic.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partials, const int* __restrict__ idx,
+                                    float* __restrict__ out, int n_out, int splits, size_t split_stride,
+                                    int accumulate_into) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_out) return;
+  const int j = idx[e];
+  float acc = 0.f;
+  if (j >= 0) {
+    const float* p = partials + j;
+    for (int s = 0; s < splits; ++s) acc += p[size_t(s) * split_stride];
+  }
+  out[e] = accumulate_into ? out[e] + acc : acc;
+}
+
+int wgrad_partials_floats(const WgradArgs& a, int* splits_out) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int tiles = a.N * ((a.H + a.TH - 1) / a.TH) * ((a.W + a.TW - 1) / a.TW);
+  int splits = sms / a.n_blocks;
+  if (splits < 1) splits = 1;
+  if (splits > tiles) splits = tiles;
+  if (splits_out) *splits_out = splits;
+  const int n_pairs = (a.n_strips * a.n_taps + 1) / 2;
+  return splits * a.n_blocks * n_pairs * 128 * 64;
+}
+
+int launch_wgrad_gemm(const WgradArgs& a, cudaStream_t stream) {
+  if (a.TH * a.TW != 128 || a.TW % 8 != 0) { set_error("wgrad: tile must be 128 pixels with TW%%8==0"); return -1; }
+  if (a.n_blocks < 1 || a.n_blocks > 4) { set_error("wgrad: n_blocks must be 1..4"); return -2; }
+  const int total_taps = a.n_strips * a.n_taps;
+  if (total_taps < 1 || a.n_strips > kMaxStrips || a.n_taps > kMaxTaps) { set_error("wgrad: bad tap count"); return -3; }
+  WgradKParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a.N; p.H = a.H; p.W = a.W; p.TH = a.TH; p.TW = a.TW;
+  p.tiles_h = (a.H + a.TH - 1) / a.TH;
+  p.tiles_w = (a.W + a.TW - 1) / a.TW;
+  p.tiles_total = a.N * p.tiles_h * p.tiles_w;
+  if (p.tiles_total == 0) return 0;
+  p.n_strips = a.n_strips; p.n_taps = a.n_taps; p.strip_rows = a.strip_rows; p.strip_dh = a.strip_dh;
+  for (int s = 0; s < a.n_strips; ++s) p.strip_dw[s] = a.strip_dw[s];
+  for (int r = 0; r < a.n_taps; ++r) {
+    if (a.tap_row[r] < 0 || a.tap_row[r] + a.TH > a.strip_rows) { set_error("wgrad: tap row outside strip"); return -4; }
+    p.tap_row[r] = a.tap_row[r];
+  }
+  p.n_pairs = (total_taps + 1) / 2;
+  if (p.n_pairs * 64 > 512) { set_error("wgrad: too many taps for TMEM"); return -5; }
+  p.n_blocks = a.n_blocks;
+  int splits = 0;
+  wgrad_partials_floats(a, &splits);
+  p.splits = splits;
+  p.strip_bytes = uint32_t(a.strip_rows) * a.TW * 128u;
+  p.stage_bytes = kDyBytes + uint32_t(a.n_strips) * p.strip_bytes;
+  int stages = int((227u * 1024u - 2048u) / p.stage_bytes);
+  if (stages > 4) stages = 4;
+  if (stages < 1) { set_error("wgrad: stage does not fit in shared memory (%u B)", p.stage_bytes); return -6; }
+  p.n_stages = stages;
+  p.partials = a.partials;
+  p.dy_c0_step = a.dy_views == 1 ? 64 : 0;
+
+  {
+    uint64_t dims[4] = {64, uint64_t(a.in_W), uint64_t(a.in_H), uint64_t(a.N)};
+    uint64_t strides[3] = {uint64_t(a.x.stride_w) * 2, uint64_t(a.x.stride_h) * 2, uint64_t(a.x.stride_n) * 2};
+    uint32_t box[4] = {64, uint32_t(a.TW), uint32_t(a.strip_rows), 1};
+    int rc = encode_map_bf16(&p.x_map, a.x.ptr, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  for (int v = 0; v < 4; ++v) {
+    const InView& dv = a.dy[v < a.dy_views ? v : 0];
+    uint64_t dims[4] = {uint64_t(dv.channels), uint64_t(a.W), uint64_t(a.H), uint64_t(a.N)};
+    uint64_t strides[3] = {uint64_t(dv.stride_w) * 2, uint64_t(dv.stride_h) * 2, uint64_t(dv.stride_n) * 2};
+    uint32_t box[4] = {64, uint32_t(a.TW), uint32_t(a.TH), 1};
+    int rc = encode_map_bf16(&p.dy_map[v], dv.ptr, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    attr = true;
+  }
+  const size_t smem_bytes = 1024 + size_t(stages) * p.stage_bytes + 256;
+  wgrad_gemm_kernel<<<p.n_blocks * p.splits, kWgThreads, smem_bytes, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("wgrad launch: %s", cudaGetErrorString(e)); return int(e); }
+  return 0;
+}
+
+int launch_wgrad_reduce(const float* partials, const int* idx, float* out, int n_out, int splits, size_t split_stride,
+                        int accumulate_into, cudaStream_t stream) {
+  if (n_out <= 0) return 0;
+  wgrad_reduce_kernel<<<(n_out + 255) / 256, 256, 0, stream>>>(partials, idx, out, n_out, splits, split_stride,
+                                                              accumulate_into);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("wgrad_reduce launch: %s", cudaGetErrorString(e)); return int(e); }
+  return 0;
+}
+
+}  // namespace srg

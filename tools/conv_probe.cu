@@ -252,9 +252,116 @@ static Problem conv3x3(const char* name, int N, int H, int W, int cout, bool ps)
   return p;
 }
 
+
+// ------------------------------------------------------------------ wgrad probe
+static int run_wgrad(const char* name, int N, int H, int W, int n_strips, int n_taps, int strip_rows, int strip_dh,
+                     const int* strip_dw, const int* tap_row, int n_blocks, bool strided_dy, int iters) {
+  const int Cout = n_blocks * 64;
+  std::vector<uint16_t> x(size_t(N) * H * W * 64), dy(size_t(N) * H * W * Cout);
+  for (auto& v : x) v = f2bf(frand());
+  for (auto& v : dy) v = f2bf(frand());
+  std::vector<uint16_t> dyphys(dy.size());
+  if (strided_dy) {
+    for (int n = 0; n < N; ++n) for (int h = 0; h < H; ++h) for (int w = 0; w < W; ++w) for (int c = 0; c < Cout; ++c) {
+      int q = c / 64, ch = c % 64, i = q >> 1, j = q & 1;
+      dyphys[((size_t(n) * 2 * H + 2 * h + i) * 2 * W + 2 * w + j) * 64 + ch] = dy[((size_t(n) * H + h) * W + w) * Cout + c];
+    }
+  } else dyphys = dy;
+  void *dx, *ddy; float* dpart; float* dout; int* didx;
+  CK(cudaMalloc(&dx, x.size() * 2)); CK(cudaMalloc(&ddy, dy.size() * 2));
+  CK(cudaMemcpy(dx, x.data(), x.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ddy, dyphys.data(), dy.size() * 2, cudaMemcpyHostToDevice));
+  WgradArgs a; memset(&a, 0, sizeof(a));
+  a.N = N; a.H = H; a.W = W; a.TH = 16; a.TW = 8;
+  a.x.ptr = dx; a.x.stride_w = 64; a.x.stride_h = int64_t(W) * 64; a.x.stride_n = int64_t(H) * W * 64; a.x.channels = 64;
+  a.in_H = H; a.in_W = W;
+  if (strided_dy) {
+    a.dy_views = 4;
+    for (int v = 0; v < 4; ++v) {
+      int i = v >> 1, j = v & 1;
+      a.dy[v].ptr = (uint16_t*)ddy + (size_t(i) * 2 * W + j) * 64;
+      a.dy[v].stride_w = 128; a.dy[v].stride_h = int64_t(4) * W * 64; a.dy[v].stride_n = int64_t(4) * H * W * 64; a.dy[v].channels = 64;
+    }
+  } else {
+    a.dy_views = 1;
+    a.dy[0].ptr = ddy; a.dy[0].stride_w = Cout; a.dy[0].stride_h = int64_t(W) * Cout; a.dy[0].stride_n = int64_t(H) * W * Cout; a.dy[0].channels = Cout;
+  }
+  a.n_blocks = n_blocks; a.n_strips = n_strips; a.n_taps = n_taps; a.strip_rows = strip_rows; a.strip_dh = strip_dh;
+  for (int s = 0; s < n_strips; ++s) a.strip_dw[s] = strip_dw[s];
+  for (int r = 0; r < n_taps; ++r) a.tap_row[r] = tap_row[r];
+  int splits = 0;
+  const int pf = wgrad_partials_floats(a, &splits);
+  CK(cudaMalloc(&dpart, size_t(pf) * 4));
+  a.partials = dpart;
+  const int T = n_strips * n_taps, n_pairs = (T + 1) / 2;
+  // index map: out[t][ci][co_total]
+  const int n_out = T * 64 * Cout;
+  std::vector<int> idx(n_out);
+  for (int t = 0; t < T; ++t) for (int ci = 0; ci < 64; ++ci) for (int co = 0; co < Cout; ++co) {
+    const int nb = co / 64, pr = t / 2, row = (t & 1) * 64 + ci;
+    idx[(t * 64 + ci) * Cout + co] = ((nb * n_pairs + pr) * 128 + row) * 64 + (co % 64);
+  }
+  CK(cudaMalloc(&didx, n_out * 4)); CK(cudaMalloc(&dout, n_out * 4));
+  CK(cudaMemcpy(didx, idx.data(), n_out * 4, cudaMemcpyHostToDevice));
+  int rc = launch_wgrad_gemm(a, 0);
+  if (rc) { printf("[%s] launch rc=%d %s\n", name, rc, last_error()); return 1; }
+  rc = launch_wgrad_reduce(dpart, didx, dout, n_out, splits, size_t(n_blocks) * n_pairs * 128 * 64, 0, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess || rc) { printf("[%s] kernel failed: %s\n", name, cudaGetErrorString(e)); exit(3); }
+  std::vector<float> out(n_out);
+  CK(cudaMemcpy(out.data(), dout, n_out * 4, cudaMemcpyDeviceToHost));
+  // CPU reference on a sample of (t, ci, co)
+  double max_err = 0, max_ref = 0; size_t bad = 0, checked = 0;
+  for (int t = 0; t < T; ++t) {
+    const int s = t / n_taps, r = t % n_taps;
+    const int dh = strip_dh + tap_row[r], dw = strip_dw[s];
+    for (int ci = (t * 7) % 5; ci < 64; ci += 13) for (int co = (t * 3) % 7; co < Cout; co += 29) {
+      double acc = 0;
+      for (int n = 0; n < N; ++n) for (int h = 0; h < H; ++h) {
+        const int hh = h + dh; if (hh < 0 || hh >= H) continue;
+        for (int w = 0; w < W; ++w) {
+          const int ww = w + dw; if (ww < 0 || ww >= W) continue;
+          acc += double(bf2f(x[((size_t(n) * H + hh) * W + ww) * 64 + ci])) * bf2f(dy[((size_t(n) * H + h) * W + w) * Cout + co]);
+        }
+      }
+      const double got = out[(t * 64 + ci) * Cout + co];
+      const double err = fabs(got - acc);
+      if (err > max_err) max_err = err;
+      if (fabs(acc) > max_ref) max_ref = fabs(acc);
+      if (!(err <= 1e-2 + 2e-3 * fabs(acc))) ++bad;
+      ++checked;
+    }
+  }
+  printf("[%s] checked=%zu bad=%zu max_abs_err=%.5f max_ref=%.3f %s\n", name, checked, bad, max_err, max_ref, bad == 0 ? "OK" : "FAIL");
+  if (iters > 0) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) { launch_wgrad_gemm(a, 0); launch_wgrad_reduce(dpart, didx, dout, n_out, splits, size_t(n_blocks) * n_pairs * 128 * 64, 0, 0); }
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) { launch_wgrad_gemm(a, 0); launch_wgrad_reduce(dpart, didx, dout, n_out, splits, size_t(n_blocks) * n_pairs * 128 * 64, 0, 0); }
+    cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * N * H * W * double(T) * 64 * Cout;
+    printf("[%s] %.3f us/launch (gemm+reduce)  %.1f TFLOP/s useful\n", name, ms * 1000 / iters, flops / (ms / iters * 1e-3) / 1e12);
+  }
+  cudaFree(dx); cudaFree(ddy); cudaFree(dpart); cudaFree(dout); cudaFree(didx);
+  return bad == 0 ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 0;
   int fails = 0;
+  {
+    const int dw3[3] = {-1, 0, 1}, tr3[3] = {0, 1, 2};
+    fails += run_wgrad("wg3x3_small", 2, 32, 24, 3, 3, 18, -1, dw3, tr3, 1, false, 0);
+    fails += run_wgrad("wg3x3_ragged", 3, 40, 20, 3, 3, 18, -1, dw3, tr3, 1, false, 0);
+    fails += run_wgrad("wg3x3_cout256_ps", 2, 32, 16, 3, 3, 18, -1, dw3, tr3, 4, true, 0);
+    const int dw1[1] = {0}, tr5[5] = {0, 2, 4, 6, 8};
+    fails += run_wgrad("wg9_pairs", 2, 32, 16, 1, 5, 24, -3, dw1, tr5, 1, false, 0);
+    if (iters > 0) {
+      fails += run_wgrad("perf_wg_trunk_16x96x96", 16, 96, 96, 3, 3, 18, -1, dw3, tr3, 1, false, iters);
+      fails += run_wgrad("perf_wg_up3_16x192x192", 16, 192, 192, 3, 3, 18, -1, dw3, tr3, 4, true, iters);
+    }
+  }
   {  // 1x1 "plain GEMM" sanity: one strip, one tap
     Problem p = conv3x3("gemm1x1", 1, 16, 8, 64, false);
     p.n_strips = 1; p.n_taps = 1; p.strip_rows = 16; p.strip_dh = 0; p.strip_dw[0] = 0; p.tap_row[0] = 0;
