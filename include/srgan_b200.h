@@ -1,0 +1,113 @@
+/* srgan_b200.h -- C ABI of the B200-native SR-GAN hot path (libsrgan_b200.so).
+ *
+ * The reference (angelowxx/Super_resolution-Image-Reconstructer-Multi_Generator_GAN) has no FFI of its own: its
+ * hot path is Python calling PyTorch ATen ops.  Each entry point below therefore replaces a *range of reference
+ * Python lines*, cited per function (paths relative to the reference root).  The Python host side in
+ * super_resolution-image-reconstructer-multi_generator_gan_b200/ binds these with ctypes and re-exposes the
+ * reference's nn.Module / train-step interface.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a positive cudaError_t or a negative argument-check code otherwise; it
+ *    never throws, exits or synchronises.  srg_last_error() returns a thread-local description of the last failure.
+ *  - all pointers are DEVICE pointers unless stated otherwise; the caller owns every buffer; work is enqueued on
+ *    `stream` (a cudaStream_t passed as void*), nothing is allocated on the hot path.
+ *  - images are NCHW fp32 (the reference's tensors); parameters / gradients / Adam moments are flat fp32 buffers
+ *    whose element offsets are reported by srg_generator_param_info().
+ */
+#ifndef SRGAN_B200_H_
+#define SRGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRG_ABI_VERSION 1
+
+int srg_abi_version(void);
+const char* srg_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Generator engine: SRResNet (src/models.py:44-87) built from ResidualBlock (src/models.py:10-25).
+ * N x 3 x H x W fp32 in  ->  N x 3 x (H << n_up) x (W << n_up) fp32 out; n_up = int(upscale_factor // 2) stages.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct srg_generator srg_generator_t;
+
+/* replaces SRResNet.__init__ (src/models.py:53-78): fixes geometry, builds weight-packing and scatter maps. */
+int srg_generator_create(srg_generator_t** out, int N, int H, int W, int num_residuals, int num_upsample_stages);
+void srg_generator_destroy(srg_generator_t* g);
+
+/* parameter table in the reference's parameters() order / state_dict keys */
+int srg_generator_num_params(const srg_generator_t* g);
+int64_t srg_generator_param_elems(const srg_generator_t* g); /* length of the flat fp32 param / grad buffers */
+int srg_generator_param_info(const srg_generator_t* g, int i, char* name, int name_cap, int64_t* offset,
+                             int64_t* numel, int* ndim, int* shape4);
+/* BatchNorm running_mean / running_var table (flat fp32 buffer) */
+int srg_generator_num_buffers(const srg_generator_t* g);
+int64_t srg_generator_buffer_elems(const srg_generator_t* g);
+int srg_generator_buffer_info(const srg_generator_t* g, int i, char* name, int name_cap, int64_t* offset,
+                              int64_t* numel);
+
+size_t srg_generator_workspace_bytes(const srg_generator_t* g, int training);
+/* binds caller-owned memory; `workspace` must be 1024-byte aligned; `grads` may be NULL when training == 0 */
+int srg_generator_bind(srg_generator_t* g, float* params, float* grads, float* bn_buffers, void* workspace,
+                       size_t workspace_bytes, int training);
+/* fp32 master weights -> packed bf16 GEMM operands; call after every optimizer step / load_state_dict */
+int srg_generator_pack(srg_generator_t* g, void* stream);
+/* replaces SRResNet.forward (src/models.py:80-87); training != 0 uses batch statistics (and keeps the
+ * activations backward needs), update_running != 0 updates running_mean/var (momentum 0.1, unbiased var). */
+int srg_generator_forward(srg_generator_t* g, const float* lr_nchw, float* sr_nchw, int training, int update_running,
+                          void* stream);
+/* replaces autograd through SRResNet inside g_loss.backward() (src/train.py:195): d(loss)/d(sr) in, every
+ * parameter gradient out (written to the bound flat `grads`; biases feeding a training-mode BatchNorm get 0). */
+int srg_generator_backward(srg_generator_t* g, const float* dsr_nchw, void* stream);
+
+/* named intermediates inside the workspace (per-layer parity checks): dtype 0 = bf16 NHWC, dims = N,H,W,C */
+int srg_generator_num_tensors(const srg_generator_t* g);
+int srg_generator_tensor_info(const srg_generator_t* g, int i, char* name, int name_cap, int64_t* byte_offset,
+                              int* dims4, int* dtype);
+long long srg_generator_launch_count(const srg_generator_t* g); /* kernels enqueued so far */
+
+/* SyncBatchNorm hook: called between the local per-channel sums and the BatchNorm finalize in forward and
+ * backward with a device buffer of `n` doubles to be summed in place across `world` ranks on `stream`. */
+typedef int (*srg_allreduce_f64_fn)(void* ctx, double* buf, int n, void* stream);
+int srg_generator_set_allreduce(srg_generator_t* g, srg_allreduce_f64_fn fn, void* ctx, int world);
+
+/* NCCL-backed implementation of the hook (libnccl is resolved with dlopen at first use). */
+int srg_nccl_unique_id(void* out128); /* host buffer, 128 bytes */
+int srg_nccl_init(const void* unique_id128, int world, int rank);
+int srg_nccl_allreduce_f64(void* ctx, double* buf, int n, void* stream);
+int srg_nccl_allreduce_f32(float* buf, int64_t n, void* stream);
+int srg_generator_use_nccl(srg_generator_t* g);
+void srg_nccl_shutdown(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Losses and optimiser
+ * ------------------------------------------------------------------------------------------------------------- */
+/* replaces ReconstructionLoss.forward (src/utils.py:173-241; called at src/train.py:189):
+ * losses2[0] = edge-weighted L1 ("com_loss"), losses2[1] = Laplacian TV loss.  e_buf / g_buf: fp32 scratch of hr's
+ * size, kept (with `scratch`) for the backward call. */
+size_t srg_recon_loss_scratch_bytes(void);
+int srg_recon_loss_forward(const float* hr_nchw, const float* sr_nchw, int N, int C, int H, int W, void* scratch,
+                           size_t scratch_bytes, float* e_buf, float* g_buf, float* losses2, void* stream);
+/* replaces autograd through ReconstructionLoss inside g_loss.backward() (src/train.py:195):
+ * grad_sr = (w_edge * d losses2[0]/d sr + w_tv * d losses2[1]/d sr) * grad_scale, where w_edge / w_tv are optional
+ * DEVICE scalars (NULL = 1; the reference's objective is com_loss + tv_loss, src/train.py:192). */
+int srg_recon_loss_backward(const float* hr_nchw, const float* sr_nchw, int N, int C, int H, int W, const void* scratch,
+                            const float* e_buf, const float* g_buf, const float* w_edge, const float* w_tv,
+                            float* grad_sr, float grad_scale, void* stream);
+/* replaces mean(tanh(fake - real)) / mean(tanh(real - fake)) (src/train.py:218, :190):
+ * out[0] = mean(tanh(sign * (a - b))); da / db (may be NULL) receive the gradients times grad_scale. */
+int srg_tanh_mean(const float* a, const float* b, int64_t n, float sign, void* scratch, size_t scratch_bytes,
+                  float* out1, float* da, float* db, float grad_scale, void* stream);
+/* replaces torch.optim.Adam.step with default betas/eps, no weight decay (src/train.py:61-62,196,223) on flat
+ * buffers; `step` is the 1-based step count; gradients are multiplied by grad_scale first (1/world for DDP mean). */
+int srg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRGAN_B200_H_ */

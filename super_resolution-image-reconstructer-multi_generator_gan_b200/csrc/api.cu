@@ -1,0 +1,210 @@
+// C ABI of libsrgan_b200.so (declared in include/srgan_b200.h): thin wrappers over the internal launchers.
+#include "../../include/srgan_b200.h"
+
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "conv_gemm.cuh"
+#include "elementwise.cuh"
+#include "generator.cuh"
+
+using namespace srg;
+
+namespace {
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline GeneratorEngine* G(srg_generator_t* g) { return reinterpret_cast<GeneratorEngine*>(g); }
+inline const GeneratorEngine* G(const srg_generator_t* g) { return reinterpret_cast<const GeneratorEngine*>(g); }
+void copy_name(const std::string& s, char* dst, int cap) {
+  if (dst == nullptr || cap <= 0) return;
+  snprintf(dst, size_t(cap), "%s", s.c_str());
+}
+
+// ---- NCCL through dlopen (the library torch bundles is already mapped in a training process) -------------------
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+typedef int (*GetUniqueIdFn)(NcclId*);
+typedef int (*CommInitRankFn)(NcclComm*, int, NcclId, int);
+typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*CommDestroyFn)(NcclComm);
+typedef const char* (*GetErrorStringFn)(int);
+struct NcclApi {
+  void* handle = nullptr;
+  GetUniqueIdFn get_unique_id = nullptr;
+  CommInitRankFn comm_init_rank = nullptr;
+  AllReduceFn all_reduce = nullptr;
+  CommDestroyFn comm_destroy = nullptr;
+  GetErrorStringFn error_string = nullptr;
+  NcclComm comm = nullptr;
+  int world = 1;
+} g_nccl;
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
+
+int nccl_load() {
+  if (g_nccl.handle) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) { set_error("dlopen(libnccl.so.2) failed: %s", dlerror()); return -40; }
+  g_nccl.get_unique_id = reinterpret_cast<GetUniqueIdFn>(dlsym(g_nccl.handle, "ncclGetUniqueId"));
+  g_nccl.comm_init_rank = reinterpret_cast<CommInitRankFn>(dlsym(g_nccl.handle, "ncclCommInitRank"));
+  g_nccl.all_reduce = reinterpret_cast<AllReduceFn>(dlsym(g_nccl.handle, "ncclAllReduce"));
+  g_nccl.comm_destroy = reinterpret_cast<CommDestroyFn>(dlsym(g_nccl.handle, "ncclCommDestroy"));
+  g_nccl.error_string = reinterpret_cast<GetErrorStringFn>(dlsym(g_nccl.handle, "ncclGetErrorString"));
+  if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.all_reduce || !g_nccl.comm_destroy) {
+    set_error("libnccl is missing a required symbol");
+    return -41;
+  }
+  return 0;
+}
+int nccl_check(int rc, const char* what) {
+  if (rc == 0) return 0;
+  set_error("%s: NCCL error %d (%s)", what, rc, g_nccl.error_string ? g_nccl.error_string(rc) : "?");
+  return -42;
+}
+}  // namespace
+
+extern "C" {
+
+int srg_abi_version(void) { return SRG_ABI_VERSION; }
+const char* srg_last_error(void) { return last_error(); }
+
+int srg_generator_create(srg_generator_t** out, int N, int H, int W, int num_residuals, int num_upsample_stages) {
+  if (out == nullptr) { set_error("srg_generator_create: null out"); return -1; }
+  GeneratorEngine* g = generator_create(N, H, W, num_residuals, num_upsample_stages);
+  if (g == nullptr) return -2;
+  *out = reinterpret_cast<srg_generator_t*>(g);
+  return 0;
+}
+void srg_generator_destroy(srg_generator_t* g) { delete G(g); }
+
+int srg_generator_num_params(const srg_generator_t* g) { return int(G(g)->params.size()); }
+int64_t srg_generator_param_elems(const srg_generator_t* g) { return G(g)->param_elems; }
+int srg_generator_param_info(const srg_generator_t* g, int i, char* name, int name_cap, int64_t* offset, int64_t* numel,
+                             int* ndim, int* shape4) {
+  const GeneratorEngine* e = G(g);
+  if (i < 0 || i >= int(e->params.size())) { set_error("param index out of range"); return -3; }
+  const ParamInfo& p = e->params[size_t(i)];
+  copy_name(p.name, name, name_cap);
+  if (offset) *offset = p.offset;
+  if (numel) *numel = p.numel;
+  if (ndim) *ndim = p.ndim;
+  if (shape4) for (int k = 0; k < 4; ++k) shape4[k] = p.shape[k];
+  return 0;
+}
+int srg_generator_num_buffers(const srg_generator_t* g) { return int(G(g)->buffers.size()); }
+int64_t srg_generator_buffer_elems(const srg_generator_t* g) { return G(g)->buffer_elems; }
+int srg_generator_buffer_info(const srg_generator_t* g, int i, char* name, int name_cap, int64_t* offset, int64_t* numel) {
+  const GeneratorEngine* e = G(g);
+  if (i < 0 || i >= int(e->buffers.size())) { set_error("buffer index out of range"); return -3; }
+  const BufferInfo& b = e->buffers[size_t(i)];
+  copy_name(b.name, name, name_cap);
+  if (offset) *offset = b.offset;
+  if (numel) *numel = b.numel;
+  return 0;
+}
+size_t srg_generator_workspace_bytes(const srg_generator_t* g, int training) {
+  return training ? G(g)->workspace_bytes_train : G(g)->workspace_bytes_eval;
+}
+int srg_generator_bind(srg_generator_t* g, float* params, float* grads, float* bn_buffers, void* workspace,
+                       size_t workspace_bytes, int training) {
+  return generator_bind(G(g), params, grads, bn_buffers, workspace, workspace_bytes, training);
+}
+int srg_generator_pack(srg_generator_t* g, void* stream) { return generator_pack(G(g), S(stream)); }
+int srg_generator_forward(srg_generator_t* g, const float* lr_nchw, float* sr_nchw, int training, int update_running,
+                          void* stream) {
+  return generator_forward(G(g), lr_nchw, sr_nchw, training, update_running, S(stream));
+}
+int srg_generator_backward(srg_generator_t* g, const float* dsr_nchw, void* stream) {
+  return generator_backward(G(g), dsr_nchw, S(stream));
+}
+int srg_generator_num_tensors(const srg_generator_t* g) { return int(G(g)->tensors.size()); }
+int srg_generator_tensor_info(const srg_generator_t* g, int i, char* name, int name_cap, int64_t* byte_offset, int* dims4,
+                              int* dtype) {
+  const GeneratorEngine* e = G(g);
+  if (i < 0 || i >= int(e->tensors.size())) { set_error("tensor index out of range"); return -3; }
+  const TensorInfo& t = e->tensors[size_t(i)];
+  copy_name(t.name, name, name_cap);
+  if (byte_offset) *byte_offset = t.byte_offset;
+  if (dims4) for (int k = 0; k < 4; ++k) dims4[k] = t.dims[k];
+  if (dtype) *dtype = t.dtype;
+  return 0;
+}
+long long srg_generator_launch_count(const srg_generator_t* g) { return G(g)->launches; }
+
+int srg_generator_set_allreduce(srg_generator_t* g, srg_allreduce_f64_fn fn, void* ctx, int world) {
+  if (world < 1) { set_error("set_allreduce: world < 1"); return -4; }
+  GeneratorEngine* e = G(g);
+  e->allreduce = reinterpret_cast<AllreduceF64Fn>(fn);
+  e->allreduce_ctx = ctx;
+  e->world = world;
+  return 0;
+}
+
+int srg_nccl_unique_id(void* out128) {
+  int rc = nccl_load();
+  if (rc) return rc;
+  NcclId id;
+  rc = nccl_check(g_nccl.get_unique_id(&id), "ncclGetUniqueId");
+  if (rc) return rc;
+  memcpy(out128, &id, 128);
+  return 0;
+}
+int srg_nccl_init(const void* unique_id128, int world, int rank) {
+  int rc = nccl_load();
+  if (rc) return rc;
+  if (g_nccl.comm) { set_error("srg_nccl_init: already initialised"); return -43; }
+  NcclId id;
+  memcpy(&id, unique_id128, 128);
+  rc = nccl_check(g_nccl.comm_init_rank(&g_nccl.comm, world, id, rank), "ncclCommInitRank");
+  if (rc) return rc;
+  g_nccl.world = world;
+  return 0;
+}
+int srg_nccl_allreduce_f64(void* ctx, double* buf, int n, void* stream) {
+  (void)ctx;
+  if (!g_nccl.comm) { set_error("NCCL communicator not initialised"); return -44; }
+  return nccl_check(g_nccl.all_reduce(buf, buf, size_t(n), kNcclFloat64, kNcclSum, g_nccl.comm, S(stream)), "ncclAllReduce");
+}
+int srg_nccl_allreduce_f32(float* buf, int64_t n, void* stream) {
+  if (!g_nccl.comm) { set_error("NCCL communicator not initialised"); return -44; }
+  return nccl_check(g_nccl.all_reduce(buf, buf, size_t(n), kNcclFloat32, kNcclSum, g_nccl.comm, S(stream)), "ncclAllReduce");
+}
+int srg_generator_use_nccl(srg_generator_t* g) {
+  if (!g_nccl.comm) { set_error("NCCL communicator not initialised"); return -44; }
+  return srg_generator_set_allreduce(g, srg_nccl_allreduce_f64, nullptr, g_nccl.world);
+}
+void srg_nccl_shutdown(void) {
+  if (g_nccl.comm) g_nccl.comm_destroy(g_nccl.comm);
+  g_nccl.comm = nullptr;
+}
+
+size_t srg_recon_loss_scratch_bytes(void) { return size_t(loss_scratch_doubles()) * 8; }
+int srg_recon_loss_forward(const float* hr_nchw, const float* sr_nchw, int N, int C, int H, int W, void* scratch,
+                           size_t scratch_bytes, float* e_buf, float* g_buf, float* losses2, void* stream) {
+  if (scratch_bytes < srg_recon_loss_scratch_bytes()) { set_error("recon_loss: scratch too small"); return -5; }
+  if (!hr_nchw || !sr_nchw || !scratch || !e_buf || !g_buf || !losses2) { set_error("recon_loss: null pointer"); return -6; }
+  return launch_recon_loss_forward(hr_nchw, sr_nchw, N, C, H, W, reinterpret_cast<double*>(scratch), e_buf, g_buf, losses2,
+                                   S(stream));
+}
+int srg_recon_loss_backward(const float* hr_nchw, const float* sr_nchw, int N, int C, int H, int W, const void* scratch,
+                            const float* e_buf, const float* g_buf, const float* w_edge, const float* w_tv, float* grad_sr,
+                            float grad_scale, void* stream) {
+  if (!hr_nchw || !sr_nchw || !scratch || !e_buf || !g_buf || !grad_sr) { set_error("recon_loss_backward: null pointer"); return -6; }
+  return launch_recon_loss_backward(hr_nchw, sr_nchw, N, C, H, W, reinterpret_cast<const double*>(scratch), e_buf, g_buf,
+                                    w_edge, w_tv, grad_sr, grad_scale, S(stream));
+}
+int srg_tanh_mean(const float* a, const float* b, int64_t n, float sign, void* scratch, size_t scratch_bytes, float* out1,
+                  float* da, float* db, float grad_scale, void* stream) {
+  if (scratch_bytes < srg_recon_loss_scratch_bytes()) { set_error("tanh_mean: scratch too small"); return -5; }
+  return launch_tanh_mean(a, b, n, sign, reinterpret_cast<double*>(scratch), out1, da, db, grad_scale, S(stream));
+}
+int srg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, void* stream) {
+  if (step < 1) { set_error("adam: step must be >= 1"); return -7; }
+  return launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,666 @@
+// Memory-bound kernels of the SR-GAN hot path: BatchNorm statistics / apply / backward, LeakyReLU backward,
+// 9x9 unfold, weight packing, Adam, ReconstructionLoss and the relativistic tanh loss.
+// All loads/stores on activations are 128-bit (8 bf16 channels); reductions are warp-shuffle + fixed-order
+// partial sums (run-to-run deterministic, no float atomics).
+#include "elementwise.cuh"
+
+#include <cuda_bf16.h>
+
+#include "conv_gemm.cuh"
+
+namespace srg {
+
+#define SRG_LAUNCH_CHECK(name)                                                    \
+  do {                                                                            \
+    cudaError_t e_ = cudaGetLastError();                                          \
+    if (e_ != cudaSuccess) {                                                      \
+      set_error("%s launch: %s", name, cudaGetErrorString(e_));                   \
+      return int(e_);                                                             \
+    }                                                                             \
+  } while (0)
+
+__device__ __forceinline__ float blo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bhi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t bpack(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  f[0] = blo(r.x); f[1] = bhi(r.x); f[2] = blo(r.y); f[3] = bhi(r.y);
+  f[4] = blo(r.z); f[5] = bhi(r.z); f[6] = blo(r.w); f[7] = bhi(r.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = bpack(f[0], f[1]); o.y = bpack(f[2], f[3]); o.z = bpack(f[4], f[5]); o.w = bpack(f[6], f[7]);
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel reductions: thread = (pixel lane, channel group of 8)
+// ------------------------------------------------------------------------------------------------
+int reduce_blocks(int64_t pixels) {
+  int64_t b = (pixels + 32 * 8 - 1) / (32 * 8);
+  if (b < 1) b = 1;
+  if (b > kRedBlocksMax) b = kRedBlocksMax;
+  return int(b);
+}
+
+template <bool TWO>
+__global__ void __launch_bounds__(256) chan_reduce_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                          int64_t pixels, float* __restrict__ partials) {
+  __shared__ float red[32][129];
+  const int cg = threadIdx.x & 7;
+  const int lane_p = threadIdx.x >> 3;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+  for (int64_t p = int64_t(blockIdx.x) * 32 + lane_p; p < pixels; p += int64_t(gridDim.x) * 32) {
+    float fa[8], fb[8];
+    unpack8(a[p * 8 + cg], fa);
+    if (TWO) unpack8(b[p * 8 + cg], fb);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s1[e] += fa[e];
+      s2[e] += TWO ? fa[e] * fb[e] : fa[e] * fa[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[lane_p][cg * 8 + e] = s1[e];
+    red[lane_p][64 + cg * 8 + e] = s2[e];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) acc += red[l][threadIdx.x];
+    partials[size_t(blockIdx.x) * 128 + threadIdx.x] = acc;
+  }
+}
+
+int launch_chan_reduce(const void* a, const void* b, int64_t pixels, float* partials, cudaStream_t st) {
+  const int blocks = reduce_blocks(pixels);
+  if (b)
+    chan_reduce_kernel<true><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+                                                    pixels, partials);
+  else
+    chan_reduce_kernel<false><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(a), nullptr, pixels, partials);
+  SRG_LAUNCH_CHECK("chan_reduce");
+  return 0;
+}
+
+__global__ void partials_to_sums_kernel(const float* __restrict__ partials, int blocks, double* __restrict__ sums) {
+  // 128 columns x 8 row-lanes; fixed order => deterministic
+  __shared__ double red[8][128];
+  const int col = threadIdx.x & 127, rl = threadIdx.x >> 7;
+  double acc = 0.0;
+  for (int b = rl; b < blocks; b += 8) acc += double(partials[size_t(b) * 128 + col]);
+  red[rl][col] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][col];
+    sums[col] = t;
+  }
+}
+int launch_partials_to_sums(const float* partials, int blocks, double* sums, cudaStream_t st) {
+  partials_to_sums_kernel<<<1, 1024, 0, st>>>(partials, blocks, sums);
+  SRG_LAUNCH_CHECK("partials_to_sums");
+  return 0;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                                   float* running_var, float* scale, float* shift, float* save_mean, float* save_inv) {
+  const int c = threadIdx.x;
+  if (c >= 64) return;
+  const double mean = sums[c] / count;
+  double var = sums[64 + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float inv = float(1.0 / sqrt(var + double(eps)));
+  const float sc = gamma[c] * inv;
+  scale[c] = sc;
+  shift[c] = beta[c] - float(mean) * sc;
+  save_mean[c] = float(mean);
+  save_inv[c] = inv;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * float(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * float(unbiased);
+  }
+}
+int launch_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps,
+                       float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                       float* save_mean, float* save_inv, cudaStream_t st) {
+  bn_finalize_kernel<<<1, 64, 0, st>>>(sums, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift,
+                                       save_mean, save_inv);
+  SRG_LAUNCH_CHECK("bn_finalize");
+  return 0;
+}
+
+__global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                                      float* scale, float* shift) {
+  const int c = threadIdx.x;
+  const float sc = gamma[c] * rsqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - rm[c] * sc;
+}
+int launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                          float eps, float* scale, float* shift, cudaStream_t st) {
+  bn_eval_coeffs_kernel<<<1, 64, 0, st>>>(gamma, beta, running_mean, running_var, eps, scale, shift);
+  SRG_LAUNCH_CHECK("bn_eval_coeffs");
+  return 0;
+}
+
+template <bool RELU, bool SKIP>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const uint4* __restrict__ skip,
+                                                       uint4* __restrict__ out, int64_t n_vec) {
+  const int cg = threadIdx.x & 7;  // blockDim is a multiple of 8 and the grid stride too
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = scale[cg * 8 + e];
+    sh[e] = shift[cg * 8 + e];
+  }
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += int64_t(gridDim.x) * blockDim.x) {
+    float f[8], k[8];
+    unpack8(y[i], f);
+    if (SKIP) unpack8(skip[i], k);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = fmaf(f[e], sc[e], sh[e]);
+      if (RELU) v = fmaxf(v, 0.f);
+      if (SKIP) v += k[e];
+      f[e] = v;
+    }
+    out[i] = pack8(f);
+  }
+}
+static int ew_blocks(int64_t n_vec) {
+  int64_t b = (n_vec + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return int(b);
+}
+int launch_bn_apply(const void* y, const float* scale, const float* shift, const void* skip, int relu, void* out,
+                    int64_t pixels, cudaStream_t st) {
+  const int64_t n_vec = pixels * 8;
+  const int blocks = ew_blocks(n_vec);
+  const uint4* yy = reinterpret_cast<const uint4*>(y);
+  const uint4* kk = reinterpret_cast<const uint4*>(skip);
+  uint4* oo = reinterpret_cast<uint4*>(out);
+  if (relu && skip) bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(yy, scale, shift, kk, oo, n_vec);
+  else if (relu) bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(yy, scale, shift, kk, oo, n_vec);
+  else if (skip) bn_apply_kernel<false, true><<<blocks, 256, 0, st>>>(yy, scale, shift, kk, oo, n_vec);
+  else bn_apply_kernel<false, false><<<blocks, 256, 0, st>>>(yy, scale, shift, kk, oo, n_vec);
+  SRG_LAUNCH_CHECK("bn_apply");
+  return 0;
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                       const float* __restrict__ save_mean, const float* __restrict__ save_inv,
+                                       float* dgamma, float* dbeta, float* coefA, float* coefB, float* coefC) {
+  const int c = threadIdx.x;
+  if (c >= 64) return;
+  const double sd = sums[c], sdy = sums[64 + c];
+  const double mean = save_mean[c], inv = save_inv[c];
+  const double dg = inv * (sdy - mean * sd);  // sum dout * xhat
+  const double db = sd;
+  if (dgamma) dgamma[c] = float(dg);
+  if (dbeta) dbeta[c] = float(db);
+  const double sc = double(gamma[c]) * inv;
+  // dy = sc * (dout - db/M - xhat * dg/M),  xhat = (y - mean) * inv
+  coefA[c] = float(sc);
+  coefB[c] = float(-sc * inv * dg / count);
+  coefC[c] = float(-sc * db / count + sc * inv * mean * dg / count);
+}
+int launch_bn_bwd_finalize(const double* sums, double count, const float* gamma, const float* save_mean,
+                           const float* save_inv, float* dgamma, float* dbeta, float* coefA, float* coefB,
+                           float* coefC, cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<1, 64, 0, st>>>(sums, count, gamma, save_mean, save_inv, dgamma, dbeta, coefA, coefB, coefC);
+  SRG_LAUNCH_CHECK("bn_bwd_finalize");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y,
+                                                           const float* __restrict__ cA, const float* __restrict__ cB,
+                                                           const float* __restrict__ cC, uint4* __restrict__ dy,
+                                                           int64_t n_vec) {
+  const int cg = threadIdx.x & 7;
+  float a[8], b[8], c[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a[e] = cA[cg * 8 + e];
+    b[e] = cB[cg * 8 + e];
+    c[e] = cC[cg * 8 + e];
+  }
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += int64_t(gridDim.x) * blockDim.x) {
+    float d[8], v[8];
+    unpack8(dout[i], d);
+    unpack8(y[i], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = fmaf(a[e], d[e], fmaf(b[e], v[e], c[e]));
+    dy[i] = pack8(d);
+  }
+}
+int launch_bn_bwd_apply(const void* dout, const void* y, const float* coefA, const float* coefB, const float* coefC,
+                        void* dy, int64_t pixels, cudaStream_t st) {
+  const int64_t n_vec = pixels * 8;
+  bn_bwd_apply_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(reinterpret_cast<const uint4*>(dout),
+                                                        reinterpret_cast<const uint4*>(y), coefA, coefB, coefC,
+                                                        reinterpret_cast<uint4*>(dy), n_vec);
+  SRG_LAUNCH_CHECK("bn_bwd_apply");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) lrelu_bwd_add2_kernel(const uint4* __restrict__ ga, const uint4* __restrict__ gb,
+                                                             const uint4* __restrict__ post, float slope,
+                                                             uint4* __restrict__ dpre, int64_t n_vec) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += int64_t(gridDim.x) * blockDim.x) {
+    float a[8], b[8], p[8];
+    unpack8(ga[i], a);
+    if (gb) unpack8(gb[i], b);
+    unpack8(post[i], p);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float g = gb ? a[e] + b[e] : a[e];
+      a[e] = p[e] > 0.f ? g : g * slope;
+    }
+    dpre[i] = pack8(a);
+  }
+}
+int launch_lrelu_bwd_add2(const void* ga, const void* gb, const void* post, float slope, void* dpre, int64_t pixels,
+                          cudaStream_t st) {
+  const int64_t n_vec = pixels * 8;
+  lrelu_bwd_add2_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(reinterpret_cast<const uint4*>(ga),
+                                                          reinterpret_cast<const uint4*>(gb),
+                                                          reinterpret_cast<const uint4*>(post), slope,
+                                                          reinterpret_cast<uint4*>(dpre), n_vec);
+  SRG_LAUNCH_CHECK("lrelu_bwd_add2");
+  return 0;
+}
+
+__global__ void sums_to_float_kernel(const double* sums, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = float(sums[i]);
+}
+int launch_sums_to_float(const double* sums, float* out, int n, cudaStream_t st) {
+  sums_to_float_kernel<<<(n + 127) / 128, 128, 0, st>>>(sums, out, n);
+  SRG_LAUNCH_CHECK("sums_to_float");
+  return 0;
+}
+
+// One block per image row of the pixel-shuffled gradient: 256 threads = 16 pixel lanes x (j, channel group).
+__global__ void __launch_bounds__(256) ps_row_sums_kernel(const uint4* __restrict__ g, int W2, float* __restrict__ scratch) {
+  __shared__ float red[16][129];
+  const int64_t row = blockIdx.x;
+  const int slot = threadIdx.x & 15;   // (j, cg): j = slot >> 3
+  const int lane_p = threadIdx.x >> 4; // pixel-pair lane
+  float s[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = 0.f;
+  const int n_slots = W2 * 8;          // uint4 per row; slot index within a pixel pair = (w&1)*8 + cg
+  for (int i = lane_p * 16 + slot; i < n_slots; i += 256) {
+    float f[8];
+    unpack8(g[row * n_slots + i], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] += f[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[lane_p][slot * 8 + e] = s[e];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float acc = 0.f;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) acc += red[l][threadIdx.x];
+    scratch[row * 128 + threadIdx.x] = acc;  // [j*64 + c]
+  }
+}
+// dbias[4c + 2i + j] = sum over rows with (row & 1) == i of scratch[row][j*64 + c]
+__global__ void ps_bias_finalize_kernel(const float* __restrict__ scratch, int64_t rows, float* __restrict__ dbias) {
+  const int t = threadIdx.x;  // 256 = i(2) x j(2) x c(64)
+  const int i = t >> 7, j = (t >> 6) & 1, c = t & 63;
+  double acc = 0.0;
+  for (int64_t r = i; r < rows; r += 2) acc += double(scratch[r * 128 + j * 64 + c]);
+  dbias[4 * c + 2 * i + j] = float(acc);
+}
+int launch_ps_bias_grad(const void* g, int N, int H2, int W2, float* scratch, float* dbias, cudaStream_t st) {
+  if ((H2 & 1) || (W2 & 1)) { set_error("ps_bias_grad: odd extent"); return -1; }
+  const int64_t rows = int64_t(N) * H2;
+  ps_row_sums_kernel<<<unsigned(rows), 256, 0, st>>>(reinterpret_cast<const uint4*>(g), W2, scratch);
+  SRG_LAUNCH_CHECK("ps_row_sums");
+  ps_bias_finalize_kernel<<<1, 256, 0, st>>>(scratch, rows, dbias);
+  SRG_LAUNCH_CHECK("ps_bias_finalize");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// unfold9: one thread per (pixel of the H+1 row grid, channel group of 8)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unfold9_kernel(const float* __restrict__ src, int N, int H, int W, float scale,
+                                                      uint4* __restrict__ dst) {
+  const int64_t total = int64_t(N) * (H + 1) * W * 8;
+  const int64_t plane = int64_t(H) * W;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int cg = int(i & 7);
+    const int64_t pix = i >> 3;
+    const int w = int(pix % W);
+    const int64_t t = pix / W;
+    const int hp = int(t % (H + 1));
+    const int n = int(t / (H + 1));
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = cg * 8 + e;
+      float v = 0.f;
+      if (ch < 54) {
+        const int dr = ch / 27, rem = ch - dr * 27, s = rem / 3, c = rem - s * 3;
+        const int hh = hp - 1 + dr, ww = w + s - 4;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(src + (int64_t(n) * 3 + c) * plane + int64_t(hh) * W + ww) * scale;
+      }
+      f[e] = v;
+    }
+    dst[i] = pack8(f);
+  }
+}
+int launch_unfold9(const float* src, int N, int H, int W, float scale, void* dst, cudaStream_t st) {
+  const int64_t total = int64_t(N) * (H + 1) * W * 8;
+  unfold9_kernel<<<ew_blocks(total), 256, 0, st>>>(src, N, H, W, scale, reinterpret_cast<uint4*>(dst));
+  SRG_LAUNCH_CHECK("unfold9");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_bf16_kernel(const float* __restrict__ src, const int* __restrict__ idx, __nv_bfloat16* __restrict__ dst,
+                                 int64_t n) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int j = idx[i];
+    dst[i] = __float2bfloat16_rn(j >= 0 ? src[j] : 0.f);
+  }
+}
+int launch_pack_bf16(const float* src, const int* idx, void* dst, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  pack_bf16_kernel<<<ew_blocks(n), 256, 0, st>>>(src, idx, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  SRG_LAUNCH_CHECK("pack_bf16");
+  return 0;
+}
+__global__ void gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int j = idx[i];
+    dst[i] = j >= 0 ? src[j] : 0.f;
+  }
+}
+int launch_gather_f32(const float* src, const int* idx, float* dst, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  gather_f32_kernel<<<ew_blocks(n), 256, 0, st>>>(src, idx, dst, n);
+  SRG_LAUNCH_CHECK("gather_f32");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float lr_over_bc1, float beta1,
+                                                   float beta2, float eps, float inv_sqrt_bc2, float grad_scale) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);          // torch: exp_avg.lerp_(grad, 1-beta1)
+    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;       // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;           // (sqrt(v)/sqrt(bc2)).add_(eps)
+    p[i] -= lr_over_bc1 * (mi / denom);                            // addcdiv_(m, denom, -lr/bc1)
+  }
+}
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                int step, float grad_scale, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const double bc1 = 1.0 - pow(double(beta1), double(step));
+  const double bc2 = 1.0 - pow(double(beta2), double(step));
+  adam_kernel<<<ew_blocks(n), 256, 0, st>>>(p, g, m, v, n, float(double(lr) / bc1), beta1, beta2, eps,
+                                            float(1.0 / sqrt(bc2)), grad_scale);
+  SRG_LAUNCH_CHECK("adam");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ReconstructionLoss
+// ------------------------------------------------------------------------------------------------
+constexpr int kLossBlocks = 1184;  // 8 x 148
+constexpr int kLossHdr = 16;
+int loss_scratch_doubles() { return kLossHdr + 3 * kLossBlocks + 64; }
+
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+  // warp shuffle, then 8 warp totals in shared memory (fixed order)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += sh[i];
+  return t;
+}
+
+__device__ __forceinline__ float at_or_zero(const float* __restrict__ pl, int h, int w, int H, int W) {
+  return (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(pl + int64_t(h) * W + w) : 0.f;
+}
+// E0 = max(|Px * x|, |Py * x|), Prewitt x5, zero padding (src/utils.py:180-186, 200-209)
+__device__ __forceinline__ float edge0(const float* __restrict__ pl, int h, int w, int H, int W) {
+  const float a = at_or_zero(pl, h - 1, w - 1, H, W), b = at_or_zero(pl, h - 1, w, H, W), c = at_or_zero(pl, h - 1, w + 1, H, W);
+  const float d = at_or_zero(pl, h, w - 1, H, W), f = at_or_zero(pl, h, w + 1, H, W);
+  const float g = at_or_zero(pl, h + 1, w - 1, H, W), i = at_or_zero(pl, h + 1, w, H, W), j = at_or_zero(pl, h + 1, w + 1, H, W);
+  const float gx = 5.f * ((c - a) + (f - d) + (j - g));
+  const float gy = 5.f * ((g - a) + (i - b) + (j - c));
+  return fmaxf(fabsf(gx), fabsf(gy));
+}
+// L * x with L = [[-1/8 x3],[-1/8, 1, -1/8],[-1/8 x3]] (src/utils.py:190-192)
+__device__ __forceinline__ float lap8(const float* __restrict__ pl, int h, int w, int H, int W) {
+  const float nb = at_or_zero(pl, h - 1, w - 1, H, W) + at_or_zero(pl, h - 1, w, H, W) + at_or_zero(pl, h - 1, w + 1, H, W) +
+                   at_or_zero(pl, h, w - 1, H, W) + at_or_zero(pl, h, w + 1, H, W) + at_or_zero(pl, h + 1, w - 1, H, W) +
+                   at_or_zero(pl, h + 1, w, H, W) + at_or_zero(pl, h + 1, w + 1, H, W);
+  return __ldg(pl + int64_t(h) * W + w) - 0.125f * nb;
+}
+
+__global__ void __launch_bounds__(256) loss_pass1_kernel(const float* __restrict__ hr, int64_t total, int H, int W,
+                                                         double* __restrict__ scratch) {
+  __shared__ double sh[8];
+  double s1 = 0.0, s2 = 0.0;
+  const int64_t plane = int64_t(H) * W;
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += int64_t(gridDim.x) * 256) {
+    const int64_t pl = i / plane;
+    const int64_t r = i - pl * plane;
+    const int h = int(r / W), w = int(r - int64_t(h) * W);
+    const float e0 = edge0(hr + pl * plane, h, w, H, W);
+    s1 += double(e0);
+    s2 += double(e0) * double(e0);
+  }
+  s1 = block_sum_256(s1, sh);
+  s2 = block_sum_256(s2, sh);
+  if (threadIdx.x == 0) {
+    scratch[kLossHdr + blockIdx.x] = s1;
+    scratch[kLossHdr + kLossBlocks + blockIdx.x] = s2;
+  }
+}
+// 256 threads; sums `cnt` arrays of kLossBlocks partials into hdr[dst0 ...]
+__device__ void sum_partials(double* scratch, int which, int blocks, double* out, double* sh) {
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < blocks; b += 256) acc += scratch[kLossHdr + which * kLossBlocks + b];
+  acc = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) *out = acc;
+}
+__global__ void loss_stats_kernel(double* scratch, int blocks, double n) {
+  __shared__ double sh[8];
+  sum_partials(scratch, 0, blocks, &scratch[0], sh);
+  sum_partials(scratch, 1, blocks, &scratch[1], sh);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double mean = scratch[0] / n;
+    double var = (scratch[1] - n * mean * mean) / (n - 1.0);  // torch.std: unbiased
+    if (var < 0.0) var = 0.0;
+    scratch[2] = mean;
+    scratch[3] = sqrt(var);
+  }
+}
+__global__ void __launch_bounds__(256) loss_pass2_kernel(const float* __restrict__ hr, const float* __restrict__ sr,
+                                                         int64_t total, int H, int W, double* __restrict__ scratch,
+                                                         float* __restrict__ e_buf, float* __restrict__ g_buf) {
+  __shared__ double sh[8];
+  const float mean = float(scratch[2]), stdv = float(scratch[3]);
+  double sE = 0.0, sL = 0.0, sT = 0.0;
+  const int64_t plane = int64_t(H) * W;
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += int64_t(gridDim.x) * 256) {
+    const int64_t pl = i / plane;
+    const int64_t r = i - pl * plane;
+    const int h = int(r / W), w = int(r - int64_t(h) * W);
+    const float e0 = edge0(hr + pl * plane, h, w, H, W);
+    float e = (e0 - mean) / stdv * 0.2f + 1.f;                 // normalize(...)*0.2 + 1  (:213, :194-198)
+    e = fminf(fmaxf(e, 0.f), 2.f);
+    const float d = lap8(sr + pl * plane, h, w, H, W);
+    const float om = 1.f - e;
+    e_buf[i] = e;
+    g_buf[i] = (d > 0.f ? om : (d < 0.f ? -om : 0.f));        // sign(D) * (1 - E)
+    sE += double(e);
+    sL += double(fabsf(hr[i] - sr[i]) * e);
+    sT += double(fabsf(d) * om);
+  }
+  sE = block_sum_256(sE, sh);
+  sL = block_sum_256(sL, sh);
+  sT = block_sum_256(sT, sh);
+  if (threadIdx.x == 0) {
+    scratch[kLossHdr + blockIdx.x] = sE;
+    scratch[kLossHdr + kLossBlocks + blockIdx.x] = sL;
+    scratch[kLossHdr + 2 * kLossBlocks + blockIdx.x] = sT;
+  }
+}
+__global__ void loss_final_kernel(double* scratch, int blocks, double n, float* losses) {
+  __shared__ double sh[8];
+  sum_partials(scratch, 0, blocks, &scratch[4], sh);
+  sum_partials(scratch, 1, blocks, &scratch[5], sh);
+  sum_partials(scratch, 2, blocks, &scratch[6], sh);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double edge = scratch[5] / scratch[4];
+    const double m = scratch[6] / n;
+    scratch[7] = m;
+    losses[0] = float(edge);
+    losses[1] = float(m > 0.0 ? m : 0.0);
+  }
+}
+__global__ void __launch_bounds__(256) loss_pass3_kernel(const float* __restrict__ hr, const float* __restrict__ sr,
+                                                         const float* __restrict__ e_buf, const float* __restrict__ g_buf,
+                                                         int64_t total, int H, int W, const double* __restrict__ scratch,
+                                                         const float* __restrict__ w_edge, const float* __restrict__ w_tv,
+                                                         float* __restrict__ grad, float grad_scale) {
+  // w_edge / w_tv: optional device scalars = d(objective)/d(edge_loss), d(objective)/d(tv_loss) (autograd inputs)
+  const float inv_sum_e = float(1.0 / scratch[4]) * (w_edge ? *w_edge : 1.f);
+  const float tv_k = scratch[7] > 0.0 ? float(1.0 / double(total)) * (w_tv ? *w_tv : 1.f) : 0.f;
+  const int64_t plane = int64_t(H) * W;
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += int64_t(gridDim.x) * 256) {
+    const int64_t pl = i / plane;
+    const int64_t r = i - pl * plane;
+    const int h = int(r / W), w = int(r - int64_t(h) * W);
+    const float diff = sr[i] - hr[i];
+    const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    float g = sg * e_buf[i] * inv_sum_e;
+    if (tv_k != 0.f) g += tv_k * lap8(g_buf + pl * plane, h, w, H, W);
+    grad[i] = g * grad_scale;
+  }
+}
+int launch_recon_loss_forward(const float* hr, const float* sr, int N, int C, int H, int W, double* scratch, float* e_buf,
+                              float* g_buf, float* losses, cudaStream_t st) {
+  const int64_t total = int64_t(N) * C * H * W;
+  if (total <= 1) { set_error("recon_loss: need more than one element"); return -1; }
+  const int blocks = int((total + 255) / 256 < kLossBlocks ? (total + 255) / 256 : kLossBlocks);
+  loss_pass1_kernel<<<blocks, 256, 0, st>>>(hr, total, H, W, scratch);
+  SRG_LAUNCH_CHECK("loss_pass1");
+  loss_stats_kernel<<<1, 256, 0, st>>>(scratch, blocks, double(total));
+  SRG_LAUNCH_CHECK("loss_stats");
+  loss_pass2_kernel<<<blocks, 256, 0, st>>>(hr, sr, total, H, W, scratch, e_buf, g_buf);
+  SRG_LAUNCH_CHECK("loss_pass2");
+  loss_final_kernel<<<1, 256, 0, st>>>(scratch, blocks, double(total), losses);
+  SRG_LAUNCH_CHECK("loss_final");
+  return 0;
+}
+int launch_recon_loss_backward(const float* hr, const float* sr, int N, int C, int H, int W, const double* scratch,
+                               const float* e_buf, const float* g_buf, const float* w_edge, const float* w_tv, float* grad,
+                               float grad_scale, cudaStream_t st) {
+  const int64_t total = int64_t(N) * C * H * W;
+  const int blocks = int((total + 255) / 256 < kLossBlocks ? (total + 255) / 256 : kLossBlocks);
+  loss_pass3_kernel<<<blocks, 256, 0, st>>>(hr, sr, e_buf, g_buf, total, H, W, scratch, w_edge, w_tv, grad, grad_scale);
+  SRG_LAUNCH_CHECK("loss_pass3");
+  return 0;
+}
+
+// per-channel sums of NCHW fp32: grid = (chunks, N*C)
+__global__ void __launch_bounds__(256) nchw_plane_sum_kernel(const float* __restrict__ x, int64_t plane, double* __restrict__ scratch) {
+  __shared__ double sh[8];
+  const float* pl = x + int64_t(blockIdx.y) * plane;
+  double acc = 0.0;
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < plane; i += int64_t(gridDim.x) * 256) acc += double(pl[i]);
+  acc = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) scratch[int64_t(blockIdx.y) * gridDim.x + blockIdx.x] = acc;
+}
+__global__ void nchw_chan_final_kernel(const double* __restrict__ scratch, int N, int C, int chunks, float* out, float scale) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  double acc = 0.0;
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < chunks; ++k) acc += scratch[(int64_t(n) * C + c) * chunks + k];
+  out[c] = float(acc) * scale;
+}
+int launch_nchw_chan_sum(const float* x, int N, int C, int64_t plane, double* scratch, float* out, float scale,
+                         cudaStream_t st) {
+  int chunks = int((plane + 256 * 16 - 1) / (256 * 16));
+  if (chunks > 64) chunks = 64;
+  if (chunks < 1) chunks = 1;
+  // scratch needs N*C*chunks doubles; callers size it with loss_scratch_doubles() >= 16 + 3*1184 (N*C*chunks <= that)
+  if (int64_t(N) * C * chunks > 3 * kLossBlocks) chunks = int(3 * kLossBlocks / (int64_t(N) * C)) > 0 ? int(3 * kLossBlocks / (int64_t(N) * C)) : 1;
+  if (int64_t(N) * C * chunks > 3 * kLossBlocks) { set_error("nchw_chan_sum: batch too large for scratch"); return -1; }
+  nchw_plane_sum_kernel<<<dim3(chunks, N * C), 256, 0, st>>>(x, plane, scratch + kLossHdr);
+  SRG_LAUNCH_CHECK("nchw_plane_sum");
+  nchw_chan_final_kernel<<<1, 32, 0, st>>>(scratch + kLossHdr, N, C, chunks, out, scale);
+  SRG_LAUNCH_CHECK("nchw_chan_final");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mean(tanh(sign * (a - b))) and its gradients
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tanh_mean_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                        float sign, double* __restrict__ scratch, float* da, float* db,
+                                                        float gk) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += int64_t(gridDim.x) * 256) {
+    const float t = tanhf(sign * (a[i] - b[i]));
+    acc += double(t);
+    const float g = sign * (1.f - t * t) * gk;
+    if (da) da[i] = g;
+    if (db) db[i] = -g;
+  }
+  acc = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) scratch[kLossHdr + blockIdx.x] = acc;
+}
+__global__ void tanh_mean_final_kernel(double* scratch, int blocks, double n, float* out) {
+  __shared__ double sh[8];
+  sum_partials(scratch, 0, blocks, &scratch[8], sh);
+  __syncthreads();
+  if (threadIdx.x == 0) out[0] = float(scratch[8] / n);
+}
+int launch_tanh_mean(const float* a, const float* b, int64_t n, float sign, double* scratch, float* out, float* da,
+                     float* db, float gscale, cudaStream_t st) {
+  if (n <= 0) { set_error("tanh_mean: empty input"); return -1; }
+  int blocks = int((n + 255) / 256 < kLossBlocks ? (n + 255) / 256 : kLossBlocks);
+  tanh_mean_kernel<<<blocks, 256, 0, st>>>(a, b, n, sign, scratch, da, db, gscale / float(n));
+  SRG_LAUNCH_CHECK("tanh_mean");
+  tanh_mean_final_kernel<<<1, 256, 0, st>>>(scratch, blocks, double(n), out);
+  SRG_LAUNCH_CHECK("tanh_mean_final");
+  return 0;
+}
+
+}  // namespace srg

@@ -1,0 +1,652 @@
+// SRResNet generator engine (reference: src/models.py:10-25, :44-87).  Host-side orchestration only: every FLOP is in
+// conv_gemm.cu / wgrad_gemm.cu (tcgen05) or elementwise.cu (HBM-bound passes).
+//
+// Data layout: activations NHWC bf16, 64 channels per pixel; images NCHW fp32; parameters in ONE flat fp32 buffer in
+// the reference's parameters() order (state_dict keys of SURVEY Appendix A), gradients in a flat buffer of the same
+// layout; packed bf16 GEMM operands are re-derived from the fp32 master after every optimizer step (generator_pack).
+#include "generator.cuh"
+
+#include <stdio.h>
+#include <string.h>
+
+#include "conv_gemm.cuh"
+#include "elementwise.cuh"
+
+namespace srg {
+
+namespace {
+
+constexpr float kBnEps = 1e-5f;
+constexpr float kBnMomentum = 0.1f;
+constexpr float kSlope = 0.2f;
+
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 1023) & ~size_t(1023);
+    return o;
+  }
+};
+
+// ------------------------------------------------------------------ workspace layout
+struct Layout {
+  size_t packed, bias, bncoef, bwdcoef, partials, sums, wg_partials, ps_scratch, loss_scratch;
+  size_t U1, out1, trunk;
+  std::vector<size_t> y1, z1, y2, out;   // per residual block (eval: aliases of 4 rotating buffers)
+  std::vector<size_t> up;                // per upsample stage
+  size_t g[4];                           // P-sized gradient buffers
+  std::vector<size_t> dup;               // gradient of each upsample stage output
+  size_t Ud;                             // unfolded d(SR)
+  size_t total;
+};
+
+size_t t64(int64_t pixels) { return size_t(pixels) * 128; }
+
+int64_t wgrad_max_floats(int n_up) {
+  // splits * n_blocks * n_pairs * 8192, with splits = SMs / n_blocks  => <= 148 * n_pairs * 8192
+  (void)n_up;
+  return int64_t(148) * 5 * 8192;
+}
+
+Layout make_layout(const GeneratorEngine& e, bool training) {
+  Layout L;
+  Carver c;
+  const int64_t P = int64_t(e.N) * e.H * e.W;
+  L.packed = c.take(size_t(e.packed_elems) * 2);
+  L.bias = c.take(size_t(e.bias_elems) * 4);
+  L.bncoef = c.take(size_t(2 * e.n_res) * 256 * 4);
+  L.bwdcoef = c.take(192 * 4);
+  L.partials = c.take(size_t(kRedBlocksMax) * 128 * 4);
+  L.sums = c.take(128 * 8);
+  L.U1 = c.take(size_t(e.N) * (e.H + 1) * e.W * 128);
+  L.out1 = c.take(t64(P));
+  L.y1.resize(e.n_res); L.z1.resize(e.n_res); L.y2.resize(e.n_res); L.out.resize(e.n_res);
+  if (training) {
+    for (int b = 0; b < e.n_res; ++b) {
+      L.y1[b] = c.take(t64(P)); L.z1[b] = c.take(t64(P)); L.y2[b] = c.take(t64(P)); L.out[b] = c.take(t64(P));
+    }
+  } else {
+    const size_t y1 = c.take(t64(P)), z1 = c.take(t64(P)), y2 = c.take(t64(P)), oa = c.take(t64(P)), ob = c.take(t64(P));
+    for (int b = 0; b < e.n_res; ++b) { L.y1[b] = y1; L.z1[b] = z1; L.y2[b] = y2; L.out[b] = (b & 1) ? ob : oa; }
+  }
+  L.trunk = c.take(t64(P));
+  L.up.resize(e.n_up);
+  for (int j = 0; j < e.n_up; ++j) L.up[j] = c.take(t64(P << (2 * (j + 1))));
+  L.wg_partials = L.ps_scratch = L.loss_scratch = L.Ud = 0;
+  for (int i = 0; i < 4; ++i) L.g[i] = 0;
+  L.dup.assign(e.n_up, 0);
+  if (training) {
+    L.wg_partials = c.take(size_t(wgrad_max_floats(e.n_up)) * 4);
+    L.ps_scratch = c.take(size_t(e.N) * (size_t(e.H) << e.n_up) * 128 * 4);
+    L.loss_scratch = c.take(size_t(loss_scratch_doubles()) * 8);
+    for (int i = 0; i < 4; ++i) L.g[i] = c.take(t64(P));
+    for (int j = 0; j < e.n_up; ++j) L.dup[j] = c.take(t64(P << (2 * (j + 1))));
+    const int64_t Hs = int64_t(e.H) << e.n_up, Ws = int64_t(e.W) << e.n_up;
+    L.Ud = c.take(size_t(e.N) * (Hs + 1) * Ws * 128);
+  }
+  L.total = c.off;
+  return L;
+}
+
+// ------------------------------------------------------------------ parameter bookkeeping
+int64_t add_param(GeneratorEngine& e, const std::string& name, std::initializer_list<int> shape) {
+  ParamInfo p;
+  p.name = name;
+  p.ndim = int(shape.size());
+  p.numel = 1;
+  int i = 0;
+  for (int s : shape) { p.shape[i++] = s; p.numel *= s; }
+  for (; i < 4; ++i) p.shape[i] = 1;
+  p.offset = e.param_elems;
+  e.param_elems += (p.numel + 3) & ~int64_t(3);   // keep every tensor 16-byte aligned
+  e.params.push_back(p);
+  return p.offset;
+}
+int64_t poff(const GeneratorEngine& e, const std::string& name) {
+  for (const auto& p : e.params)
+    if (p.name == name) return p.offset;
+  return -1;
+}
+int64_t boff(const GeneratorEngine& e, const std::string& name) {
+  for (const auto& b : e.buffers)
+    if (b.name == name) return b.offset;
+  return -1;
+}
+
+// packed-weight offsets (bf16 elements)
+struct PackOffsets {
+  int64_t conv1_f;
+  std::vector<int64_t> rb_f[2], rb_d[2];
+  int64_t conv2_f, conv2_d;
+  std::vector<int64_t> up_f, up_d;
+  int64_t conv3_f, conv3_d;
+  std::vector<int64_t> up_bias;  // fp32 elements in the packed-bias buffer
+};
+
+// W[co][ci][kh][kw] of an OIHW tensor at flat offset `base`
+inline int widx(int64_t base, int Cin, int K, int co, int ci, int kh, int kw) {
+  return int(base + ((int64_t(co) * Cin + ci) * K + kh) * K + kw);
+}
+
+void pack_c3x3_fwd(std::vector<int>& idx, int64_t base, int cout, bool pixel_shuffle) {
+  // [kb = s*3 + r][n][ci]   s = kw, r = kh
+  for (int s = 0; s < 3; ++s)
+    for (int r = 0; r < 3; ++r)
+      for (int n = 0; n < cout; ++n) {
+        const int co = pixel_shuffle ? 4 * (n % 64) + n / 64 : n;
+        for (int ci = 0; ci < 64; ++ci) idx.push_back(widx(base, 64, 3, co, ci, r, s));
+      }
+}
+void pack_c3x3_dgrad(std::vector<int>& idx, int64_t base, int cout, bool pixel_shuffle) {
+  // [(c*3 + s)*3 + r][n = ci][k]   co = pixel_shuffle ? 4k + c : k ; kh = 2-r, kw = 2-s
+  const int chunks = cout / 64;
+  for (int c = 0; c < chunks; ++c)
+    for (int s = 0; s < 3; ++s)
+      for (int r = 0; r < 3; ++r)
+        for (int ci = 0; ci < 64; ++ci)
+          for (int k = 0; k < 64; ++k) {
+            const int co = pixel_shuffle ? 4 * k + c : c * 64 + k;
+            idx.push_back(widx(base, 64, 3, co, ci, 2 - r, 2 - s));
+          }
+}
+void pack_conv1_fwd(std::vector<int>& idx, int64_t base) {
+  // [r][co][(dr, s, c)] = W1[co][c][2r+dr][s]
+  for (int r = 0; r < 5; ++r)
+    for (int co = 0; co < 64; ++co)
+      for (int ch = 0; ch < 64; ++ch) {
+        int v = -1;
+        if (ch < 54) {
+          const int dr = ch / 27, s = (ch % 27) / 3, c = ch % 3, kh = 2 * r + dr;
+          if (kh <= 8) v = widx(base, 3, 9, co, c, kh, s);
+        }
+        idx.push_back(v);
+      }
+}
+void pack_conv3_fwd(std::vector<int>& idx, int64_t base) {
+  // fold9: [r = kh][n = s*3 + co (32)][ci] = W3[co][ci][kh][s]
+  for (int r = 0; r < 9; ++r)
+    for (int n = 0; n < 32; ++n)
+      for (int ci = 0; ci < 64; ++ci) idx.push_back(n < 27 ? widx(base, 64, 9, n % 3, ci, r, n / 3) : -1);
+}
+void pack_conv3_dgrad(std::vector<int>& idx, int64_t base) {
+  // [r][ci][(dr, s, co)] = W3[co][ci][8-2r-dr][8-s]
+  for (int r = 0; r < 5; ++r)
+    for (int ci = 0; ci < 64; ++ci)
+      for (int ch = 0; ch < 64; ++ch) {
+        int v = -1;
+        if (ch < 54) {
+          const int dr = ch / 27, s = (ch % 27) / 3, co = ch % 3, kh = 8 - 2 * r - dr;
+          if (kh >= 0) v = widx(base, 64, 9, co, ci, kh, 8 - s);
+        }
+        idx.push_back(v);
+      }
+}
+
+// index of D_t[row][col] inside one split's partial block: ((nb*n_pairs + t/2)*128 + (t&1)*64 + row)*64 + col
+inline int pidx(int nb, int n_pairs, int t, int row, int col) { return ((nb * n_pairs + t / 2) * 128 + (t & 1) * 64 + row) * 64 + col; }
+
+int* upload(const std::vector<int>& v) {
+  int* d = nullptr;
+  if (cudaMalloc(&d, v.size() * sizeof(int)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+  return d;
+}
+
+// the engine object handed out by generator_create
+struct EngineImpl : GeneratorEngine {
+  PackOffsets po;
+  Layout L;
+};
+
+#define RC(x)                  \
+  do {                         \
+    int rc_ = (x);             \
+    if (rc_ != 0) return rc_;  \
+  } while (0)
+
+InView plain_view(const void* ptr, int H, int W, int C = 64) {
+  InView v;
+  v.ptr = ptr; v.stride_w = C; v.stride_h = int64_t(W) * C; v.stride_n = int64_t(H) * W * C; v.channels = C;
+  return v;
+}
+// view q = (i, j) of a pixel-shuffled tensor [N, 2H, 2W, 64] on the (H, W) grid
+InView ps_view(const void* base, int H, int W, int q) {
+  const int i = q >> 1, j = q & 1;
+  InView v;
+  v.ptr = reinterpret_cast<const uint16_t*>(base) + (size_t(i) * 2 * W + j) * 64;
+  v.stride_w = 128; v.stride_h = int64_t(4) * W * 64; v.stride_n = int64_t(4) * H * W * 64; v.channels = 64;
+  return v;
+}
+
+void set_taps_3x3(ConvGemmArgs& a) {
+  a.TH = 16; a.TW = 8;
+  a.n_strips = 3; a.n_taps = 3; a.strip_rows = 18; a.strip_dh = -1;
+  for (int s = 0; s < 3; ++s) a.strip_dw[s] = s - 1;
+  for (int r = 0; r < 3; ++r) a.tap_row[r] = r;
+}
+void set_taps_pairs(ConvGemmArgs& a) {
+  a.TH = 16; a.TW = 8;
+  a.n_strips = 1; a.n_taps = 5; a.strip_rows = 24; a.strip_dh = -3; a.strip_dw[0] = 0;
+  for (int r = 0; r < 5; ++r) a.tap_row[r] = 2 * r;
+}
+
+}  // namespace
+
+GeneratorEngine::~GeneratorEngine() {
+  cudaFree(d_pack_idx); cudaFree(d_bias_idx); cudaFree(d_wg_idx_c3x3); cudaFree(d_wg_idx_up);
+  cudaFree(d_wg_idx_conv1); cudaFree(d_wg_idx_conv3);
+}
+
+GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up) {
+  if (N < 1 || H < 1 || W < 1 || n_res < 0 || n_up < 0 || n_up > 4) { set_error("generator_create: bad geometry"); return nullptr; }
+  EngineImpl* e = new EngineImpl();
+  e->N = N; e->H = H; e->W = W; e->n_res = n_res; e->n_up = n_up;
+  // ---- parameters in the reference's registration order (src/models.py:53-78)
+  add_param(*e, "conv1.weight", {64, 3, 9, 9});
+  add_param(*e, "conv1.bias", {64});
+  char nm[96];
+  for (int b = 0; b < n_res; ++b) {
+    const char* sub[2][2] = {{"conv1", "bn1"}, {"conv2", "bn2"}};
+    // registration order inside ResidualBlock: conv1, bn1, conv2, bn2 (src/models.py:15-19)
+    for (int k = 0; k < 2; ++k) {
+      snprintf(nm, sizeof(nm), "residual_blocks.%d.%s.weight", b, sub[k][0]); add_param(*e, nm, {64, 64, 3, 3});
+      snprintf(nm, sizeof(nm), "residual_blocks.%d.%s.bias", b, sub[k][0]); add_param(*e, nm, {64});
+      snprintf(nm, sizeof(nm), "residual_blocks.%d.%s.weight", b, sub[k][1]); add_param(*e, nm, {64});
+      snprintf(nm, sizeof(nm), "residual_blocks.%d.%s.bias", b, sub[k][1]); add_param(*e, nm, {64});
+      for (const char* stat : {"running_mean", "running_var"}) {
+        BufferInfo bi;
+        snprintf(nm, sizeof(nm), "residual_blocks.%d.%s.%s", b, sub[k][1], stat);
+        bi.name = nm; bi.offset = e->buffer_elems; bi.numel = 64;
+        e->buffer_elems += 64;
+        e->buffers.push_back(bi);
+      }
+    }
+  }
+  add_param(*e, "conv2.weight", {64, 64, 3, 3});
+  add_param(*e, "conv2.bias", {64});
+  for (int j = 0; j < n_up; ++j) {
+    snprintf(nm, sizeof(nm), "upsample.%d.weight", 3 * j); add_param(*e, nm, {256, 64, 3, 3});
+    snprintf(nm, sizeof(nm), "upsample.%d.bias", 3 * j); add_param(*e, nm, {256});
+  }
+  add_param(*e, "conv3.weight", {3, 64, 9, 9});
+  add_param(*e, "conv3.bias", {3});
+
+  // ---- pack maps
+  std::vector<int> idx;
+  idx.reserve(size_t(e->param_elems) * 2 + 65536);
+  PackOffsets& po = e->po;
+  po.conv1_f = int64_t(idx.size()); pack_conv1_fwd(idx, poff(*e, "conv1.weight"));
+  for (int k = 0; k < 2; ++k) { po.rb_f[k].resize(n_res); po.rb_d[k].resize(n_res); }
+  for (int b = 0; b < n_res; ++b)
+    for (int k = 0; k < 2; ++k) {
+      snprintf(nm, sizeof(nm), "residual_blocks.%d.conv%d.weight", b, k + 1);
+      const int64_t base = poff(*e, nm);
+      po.rb_f[k][b] = int64_t(idx.size()); pack_c3x3_fwd(idx, base, 64, false);
+      po.rb_d[k][b] = int64_t(idx.size()); pack_c3x3_dgrad(idx, base, 64, false);
+    }
+  po.conv2_f = int64_t(idx.size()); pack_c3x3_fwd(idx, poff(*e, "conv2.weight"), 64, false);
+  po.conv2_d = int64_t(idx.size()); pack_c3x3_dgrad(idx, poff(*e, "conv2.weight"), 64, false);
+  po.up_f.resize(n_up); po.up_d.resize(n_up); po.up_bias.resize(n_up);
+  std::vector<int> bidx;
+  for (int j = 0; j < n_up; ++j) {
+    snprintf(nm, sizeof(nm), "upsample.%d.weight", 3 * j);
+    const int64_t base = poff(*e, nm);
+    po.up_f[j] = int64_t(idx.size()); pack_c3x3_fwd(idx, base, 256, true);
+    po.up_d[j] = int64_t(idx.size()); pack_c3x3_dgrad(idx, base, 256, true);
+    snprintf(nm, sizeof(nm), "upsample.%d.bias", 3 * j);
+    const int64_t bb = poff(*e, nm);
+    po.up_bias[j] = int64_t(bidx.size());
+    for (int n = 0; n < 256; ++n) bidx.push_back(int(bb + 4 * (n % 64) + n / 64));
+  }
+  po.conv3_f = int64_t(idx.size()); pack_conv3_fwd(idx, poff(*e, "conv3.weight"));
+  po.conv3_d = int64_t(idx.size()); pack_conv3_dgrad(idx, poff(*e, "conv3.weight"));
+  e->packed_elems = int64_t(idx.size());
+  if (bidx.empty()) bidx.push_back(-1);
+  e->bias_elems = int64_t(bidx.size());
+
+  // ---- wgrad scatter maps: out element -> index inside one split's partial block
+  std::vector<int> m33(64 * 64 * 9), mup(256 * 64 * 9), mc1(64 * 3 * 81), mc3(3 * 64 * 81);
+  for (int co = 0; co < 64; ++co)
+    for (int ci = 0; ci < 64; ++ci)
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) m33[((co * 64 + ci) * 3 + kh) * 3 + kw] = pidx(0, 5, kw * 3 + kh, ci, co);
+  for (int co = 0; co < 256; ++co)
+    for (int ci = 0; ci < 64; ++ci)
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) mup[((co * 64 + ci) * 3 + kh) * 3 + kw] = pidx(co % 4, 5, kw * 3 + kh, ci, co / 4);
+  for (int co = 0; co < 64; ++co)
+    for (int c = 0; c < 3; ++c)
+      for (int kh = 0; kh < 9; ++kh)
+        for (int kw = 0; kw < 9; ++kw)
+          mc1[((co * 3 + c) * 9 + kh) * 9 + kw] = pidx(0, 3, kh / 2, (kh % 2) * 27 + kw * 3 + c, co);
+  for (int co = 0; co < 3; ++co)
+    for (int ci = 0; ci < 64; ++ci)
+      for (int kh = 0; kh < 9; ++kh)
+        for (int kw = 0; kw < 9; ++kw) {
+          const int dr = kh % 2, r = (8 - kh - dr) / 2, s = 8 - kw;
+          mc3[((co * 64 + ci) * 9 + kh) * 9 + kw] = pidx(0, 3, r, dr * 27 + s * 3 + co, ci);
+        }
+  e->d_pack_idx = upload(idx);
+  e->d_bias_idx = upload(bidx);
+  e->d_wg_idx_c3x3 = upload(m33);
+  e->d_wg_idx_up = upload(mup);
+  e->d_wg_idx_conv1 = upload(mc1);
+  e->d_wg_idx_conv3 = upload(mc3);
+  if (!e->d_pack_idx || !e->d_bias_idx || !e->d_wg_idx_c3x3 || !e->d_wg_idx_up || !e->d_wg_idx_conv1 || !e->d_wg_idx_conv3) {
+    set_error("generator_create: device allocation of index maps failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete e;
+    return nullptr;
+  }
+  e->workspace_bytes_train = make_layout(*e, true).total;
+  e->workspace_bytes_eval = make_layout(*e, false).total;
+  return e;
+}
+
+int generator_bind(GeneratorEngine* g, float* master, float* grads, float* bn_buffers, void* ws, size_t ws_bytes,
+                   int training) {
+  EngineImpl* e = static_cast<EngineImpl*>(g);
+  const size_t need = training ? e->workspace_bytes_train : e->workspace_bytes_eval;
+  if (ws_bytes < need) { set_error("generator_bind: workspace too small (%zu < %zu)", ws_bytes, need); return -20; }
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) { set_error("generator_bind: workspace must be 1024-byte aligned"); return -21; }
+  if (master == nullptr || bn_buffers == nullptr || (training && grads == nullptr)) { set_error("generator_bind: null buffer"); return -22; }
+  e->master = master; e->grads = grads; e->bn_buffers = bn_buffers;
+  e->ws = reinterpret_cast<uint8_t*>(ws); e->ws_bytes = ws_bytes; e->ws_training = training != 0;
+  e->L = make_layout(*e, training != 0);
+  // named tensors for parity tests
+  e->tensors.clear();
+  auto reg = [&](const std::string& name, size_t off, int n, int h, int w, int c, int dtype) {
+    TensorInfo t; t.name = name; t.byte_offset = int64_t(off); t.dims[0] = n; t.dims[1] = h; t.dims[2] = w; t.dims[3] = c; t.dtype = dtype;
+    e->tensors.push_back(t);
+  };
+  const Layout& L = e->L;
+  reg("out1", L.out1, e->N, e->H, e->W, 64, 0);
+  char nm[64];
+  if (training)
+    for (int b = 0; b < e->n_res; ++b) {
+      snprintf(nm, sizeof(nm), "rb%d.y1", b); reg(nm, L.y1[b], e->N, e->H, e->W, 64, 0);
+      snprintf(nm, sizeof(nm), "rb%d.z1", b); reg(nm, L.z1[b], e->N, e->H, e->W, 64, 0);
+      snprintf(nm, sizeof(nm), "rb%d.y2", b); reg(nm, L.y2[b], e->N, e->H, e->W, 64, 0);
+      snprintf(nm, sizeof(nm), "rb%d.out", b); reg(nm, L.out[b], e->N, e->H, e->W, 64, 0);
+    }
+  reg("trunk", L.trunk, e->N, e->H, e->W, 64, 0);
+  for (int j = 0; j < e->n_up; ++j) {
+    snprintf(nm, sizeof(nm), "up%d", j); reg(nm, L.up[j], e->N, e->H << (j + 1), e->W << (j + 1), 64, 0);
+    if (training) { snprintf(nm, sizeof(nm), "d_up%d", j); reg(nm, L.dup[j], e->N, e->H << (j + 1), e->W << (j + 1), 64, 0); }
+  }
+  if (training) {
+    reg("d_trunk", L.g[3], e->N, e->H, e->W, 64, 0);
+  }
+  return 0;
+}
+
+int generator_pack(GeneratorEngine* g, cudaStream_t st) {
+  EngineImpl* e = static_cast<EngineImpl*>(g);
+  if (!e->ws) { set_error("generator_pack: not bound"); return -23; }
+  RC(launch_pack_bf16(e->master, e->d_pack_idx, e->ws + e->L.packed, e->packed_elems, st));
+  RC(launch_gather_f32(e->master, e->d_bias_idx, reinterpret_cast<float*>(e->ws + e->L.bias), e->bias_elems, st));
+  e->launches += 2;
+  return 0;
+}
+
+// ------------------------------------------------------------------ forward
+int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int training, int update_running, cudaStream_t st) {
+  EngineImpl* e = static_cast<EngineImpl*>(g);
+  if (!e->ws) { set_error("generator_forward: not bound"); return -23; }
+  if (training && !e->ws_training) { set_error("generator_forward: bound workspace is eval-sized"); return -24; }
+  const Layout& L = e->L;
+  const PackOffsets& po = e->po;
+  uint8_t* ws = e->ws;
+  const uint16_t* packed = reinterpret_cast<const uint16_t*>(ws + L.packed);
+  const float* pbias = reinterpret_cast<const float*>(ws + L.bias);
+  const int N = e->N, H = e->H, W = e->W;
+  const int64_t P = int64_t(N) * H * W;
+  char nm[96];
+
+  // conv1: 9x9, 3->64, LeakyReLU(0.2)  (src/models.py:56-57,81)
+  RC(launch_unfold9(lr, N, H, W, 1.f, ws + L.U1, st));
+  {
+    ConvGemmArgs a; memset(&a, 0, sizeof(a));
+    a.N = N; a.H = H; a.W = W; set_taps_pairs(a);
+    a.n_views = 1; a.views[0] = plain_view(ws + L.U1, H + 1, W); a.in_H = H + 1; a.in_W = W;
+    a.weights = packed + po.conv1_f; a.cout_total = 64; a.block_n = 64;
+    a.bias = e->master + poff(*e, "conv1.bias"); a.act = ACT_LRELU; a.slope = kSlope;
+    a.out = ws + L.out1; a.out_mode = OUT_NHWC;
+    RC(launch_conv_gemm(a, st));
+  }
+  e->launches += 2;
+
+  auto conv3x3 = [&](const void* in, int64_t w_off, const float* bias, const void* residual, void* out) -> int {
+    ConvGemmArgs a; memset(&a, 0, sizeof(a));
+    a.N = N; a.H = H; a.W = W; set_taps_3x3(a);
+    a.n_views = 1; a.views[0] = plain_view(in, H, W); a.in_H = H; a.in_W = W;
+    a.weights = packed + w_off; a.cout_total = 64; a.block_n = 64;
+    a.bias = bias; a.act = ACT_NONE; a.residual = residual; a.out = out; a.out_mode = OUT_NHWC;
+    e->launches += 1;
+    return launch_conv_gemm(a, st);
+  };
+  auto bn_coeffs = [&](int b, int k, const void* y) -> int {
+    // BatchNorm2d(64): batch statistics in training (biased var), running stats in eval (src/models.py:16,19)
+    float* coef = reinterpret_cast<float*>(ws + L.bncoef) + size_t(2 * b + k) * 256;
+    snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.weight", b, k + 1);
+    const float* gamma = e->master + poff(*e, nm);
+    snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.bias", b, k + 1);
+    const float* beta = e->master + poff(*e, nm);
+    snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.running_mean", b, k + 1);
+    float* rm = e->bn_buffers + boff(*e, nm);
+    float* rv = rm + 64;
+    if (!training) {
+      e->launches += 1;
+      return launch_bn_eval_coeffs(gamma, beta, rm, rv, kBnEps, coef, coef + 64, st);
+    }
+    float* partials = reinterpret_cast<float*>(ws + L.partials);
+    double* sums = reinterpret_cast<double*>(ws + L.sums);
+    RC(launch_chan_reduce(y, nullptr, P, partials, st));
+    RC(launch_partials_to_sums(partials, reduce_blocks(P), sums, st));
+    if (e->allreduce) RC(e->allreduce(e->allreduce_ctx, sums, 128, st));
+    e->launches += 3;
+    return launch_bn_finalize(sums, double(P) * e->world, gamma, beta, kBnEps, kBnMomentum, update_running ? rm : nullptr,
+                              update_running ? rv : nullptr, coef, coef + 64, coef + 128, coef + 192, st);
+  };
+
+  const void* x = ws + L.out1;
+  for (int b = 0; b < e->n_res; ++b) {
+    const float* coef1 = reinterpret_cast<const float*>(ws + L.bncoef) + size_t(2 * b) * 256;
+    const float* coef2 = coef1 + 256;
+    snprintf(nm, sizeof(nm), "residual_blocks.%d.conv1.bias", b);
+    RC(conv3x3(x, po.rb_f[0][b], e->master + poff(*e, nm), nullptr, ws + L.y1[b]));
+    RC(bn_coeffs(b, 0, ws + L.y1[b]));
+    RC(launch_bn_apply(ws + L.y1[b], coef1, coef1 + 64, nullptr, 1, ws + L.z1[b], P, st));
+    snprintf(nm, sizeof(nm), "residual_blocks.%d.conv2.bias", b);
+    RC(conv3x3(ws + L.z1[b], po.rb_f[1][b], e->master + poff(*e, nm), nullptr, ws + L.y2[b]));
+    RC(bn_coeffs(b, 1, ws + L.y2[b]));
+    RC(launch_bn_apply(ws + L.y2[b], coef2, coef2 + 64, x, 0, ws + L.out[b], P, st));
+    e->launches += 2;
+    x = ws + L.out[b];
+  }
+  // conv2 + global skip (src/models.py:83-84)
+  RC(conv3x3(x, po.conv2_f, e->master + poff(*e, "conv2.bias"), ws + L.out1, ws + L.trunk));
+  // upsample stages: conv 64->256, PixelShuffle(2), ReLU (src/models.py:69-75,85)
+  const void* in = ws + L.trunk;
+  for (int j = 0; j < e->n_up; ++j) {
+    const int Hj = H << j, Wj = W << j;
+    ConvGemmArgs a; memset(&a, 0, sizeof(a));
+    a.N = N; a.H = Hj; a.W = Wj; set_taps_3x3(a);
+    a.n_views = 1; a.views[0] = plain_view(in, Hj, Wj); a.in_H = Hj; a.in_W = Wj;
+    a.weights = packed + po.up_f[j]; a.cout_total = 256; a.block_n = 64;
+    a.bias = pbias + po.up_bias[j]; a.act = ACT_RELU; a.out = ws + L.up[j]; a.out_mode = OUT_PIXEL_SHUFFLE;
+    RC(launch_conv_gemm(a, st));
+    e->launches += 1;
+    in = ws + L.up[j];
+  }
+  // conv3: 9x9, 64->3, no activation (src/models.py:78,86); fp32 NCHW output
+  {
+    const int Hs = H << e->n_up, Ws = W << e->n_up;
+    ConvGemmArgs a; memset(&a, 0, sizeof(a));
+    a.N = N; a.H = Hs; a.W = Ws; a.TH = 4; a.TW = 32;
+    a.n_strips = 1; a.n_taps = 9; a.strip_rows = 12; a.strip_dh = -4; a.strip_dw[0] = 0;
+    for (int r = 0; r < 9; ++r) a.tap_row[r] = r;
+    a.n_views = 1; a.views[0] = plain_view(in, Hs, Ws); a.in_H = Hs; a.in_W = Ws;
+    a.weights = packed + po.conv3_f; a.cout_total = 32; a.block_n = 32;
+    a.bias = e->master + poff(*e, "conv3.bias"); a.act = ACT_NONE; a.out = sr; a.out_mode = OUT_FOLD9_NCHW;
+    RC(launch_conv_gemm(a, st));
+    e->launches += 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ backward
+int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
+  EngineImpl* e = static_cast<EngineImpl*>(g);
+  if (!e->ws || !e->ws_training) { set_error("generator_backward: needs a training-sized bound workspace"); return -25; }
+  const Layout& L = e->L;
+  const PackOffsets& po = e->po;
+  uint8_t* ws = e->ws;
+  const uint16_t* packed = reinterpret_cast<const uint16_t*>(ws + L.packed);
+  const int N = e->N, H = e->H, W = e->W, S = e->n_up;
+  const int64_t P = int64_t(N) * H * W;
+  const int Hs = H << S, Ws = W << S;
+  float* partials = reinterpret_cast<float*>(ws + L.partials);
+  double* sums = reinterpret_cast<double*>(ws + L.sums);
+  float* wgp = reinterpret_cast<float*>(ws + L.wg_partials);
+  char nm[96];
+
+  if (cudaMemsetAsync(e->grads, 0, size_t(e->param_elems) * 4, st) != cudaSuccess) { set_error("memset grads failed"); return -26; }
+
+  auto wgrad = [&](InView xv, int in_H, int in_W, bool pairs, int gh, int gw, const void* dy_base, int n_blocks,
+                   bool dy_ps, const int* idx, const std::string& wname) -> int {
+    WgradArgs a; memset(&a, 0, sizeof(a));
+    a.N = N; a.H = gh; a.W = gw; a.TH = 16; a.TW = 8;
+    a.x = xv; a.in_H = in_H; a.in_W = in_W;
+    a.n_blocks = n_blocks;
+    if (dy_ps) {
+      a.dy_views = 4;
+      for (int q = 0; q < 4; ++q) a.dy[q] = ps_view(dy_base, gh, gw, q);
+    } else {
+      a.dy_views = 1; a.dy[0] = plain_view(dy_base, gh, gw, 64 * n_blocks);
+    }
+    if (pairs) {
+      a.n_strips = 1; a.n_taps = 5; a.strip_rows = 24; a.strip_dh = -3; a.strip_dw[0] = 0;
+      for (int r = 0; r < 5; ++r) a.tap_row[r] = 2 * r;
+    } else {
+      a.n_strips = 3; a.n_taps = 3; a.strip_rows = 18; a.strip_dh = -1;
+      for (int s = 0; s < 3; ++s) a.strip_dw[s] = s - 1;
+      for (int r = 0; r < 3; ++r) a.tap_row[r] = r;
+    }
+    a.partials = wgp;
+    int splits = 0;
+    const int floats = wgrad_partials_floats(a, &splits);
+    if (int64_t(floats) > wgrad_max_floats(S)) { set_error("wgrad partials exceed workspace"); return -27; }
+    RC(launch_wgrad_gemm(a, st));
+    const int n_pairs = (a.n_strips * a.n_taps + 1) / 2;
+    const ParamInfo* pi = nullptr;
+    for (const auto& p : e->params) if (p.name == wname) pi = &p;
+    if (!pi) { set_error("wgrad: unknown parameter %s", wname.c_str()); return -28; }
+    e->launches += 2;
+    return launch_wgrad_reduce(wgp, idx, e->grads + pi->offset, int(pi->numel), splits, size_t(n_blocks) * n_pairs * 128 * 64, 0, st);
+  };
+  auto bias_grad = [&](const void* dy, int64_t pixels, const std::string& bname) -> int {
+    RC(launch_chan_reduce(dy, nullptr, pixels, partials, st));
+    RC(launch_partials_to_sums(partials, reduce_blocks(pixels), sums, st));
+    e->launches += 3;
+    return launch_sums_to_float(sums, e->grads + poff(*e, bname), 64, st);
+  };
+  // dgrad of a 3x3 conv whose output gradient has `chunks`*64 channels (4 pixel-shuffle views when chunks == 4)
+  auto dgrad3x3 = [&](const void* dy_base, int gh, int gw, bool dy_ps, int64_t w_off, const void* residual, const void* mask,
+                      void* out) -> int {
+    ConvGemmArgs a; memset(&a, 0, sizeof(a));
+    a.N = N; a.H = gh; a.W = gw; set_taps_3x3(a);
+    if (dy_ps) {
+      a.n_views = 4;
+      for (int q = 0; q < 4; ++q) a.views[q] = ps_view(dy_base, gh, gw, q);
+    } else {
+      a.n_views = 1; a.views[0] = plain_view(dy_base, gh, gw);
+    }
+    a.in_H = gh; a.in_W = gw;
+    a.weights = packed + w_off; a.cout_total = 64; a.block_n = 64;
+    a.bias = nullptr; a.act = ACT_NONE; a.residual = residual; a.mask_src = mask; a.out = out; a.out_mode = OUT_NHWC;
+    e->launches += 1;
+    return launch_conv_gemm(a, st);
+  };
+
+  // ---- conv3 (9x9, 64->3): unfold d(SR) once; it feeds the bias sum, wgrad and dgrad
+  RC(launch_unfold9(dsr, N, Hs, Ws, 1.f, ws + L.Ud, st));
+  RC(launch_nchw_chan_sum(dsr, N, 3, int64_t(Hs) * Ws, reinterpret_cast<double*>(ws + L.loss_scratch),
+                          e->grads + poff(*e, "conv3.bias"), 1.f, st));
+  e->launches += 3;
+  const void* conv3_in = S > 0 ? ws + L.up[S - 1] : ws + L.trunk;
+  {
+    InView uv = plain_view(ws + L.Ud, Hs + 1, Ws);
+    RC(wgrad(uv, Hs + 1, Ws, true, Hs, Ws, conv3_in, 1, false, e->d_wg_idx_conv3, "conv3.weight"));
+  }
+  void* d_trunk = ws + L.g[3];
+  {
+    ConvGemmArgs a; memset(&a, 0, sizeof(a));
+    a.N = N; a.H = Hs; a.W = Ws; set_taps_pairs(a);
+    a.n_views = 1; a.views[0] = plain_view(ws + L.Ud, Hs + 1, Ws); a.in_H = Hs + 1; a.in_W = Ws;
+    a.weights = packed + po.conv3_d; a.cout_total = 64; a.block_n = 64;
+    a.act = ACT_NONE; a.out_mode = OUT_NHWC;
+    a.mask_src = S > 0 ? conv3_in : nullptr;      // ReLU after the last PixelShuffle (src/models.py:73)
+    a.out = S > 0 ? ws + L.dup[S - 1] : d_trunk;
+    RC(launch_conv_gemm(a, st));
+    e->launches += 1;
+  }
+  // ---- upsample stages, last to first
+  for (int j = S - 1; j >= 0; --j) {
+    const int Hj = H << j, Wj = W << j;
+    const void* in_j = j > 0 ? ws + L.up[j - 1] : ws + L.trunk;
+    snprintf(nm, sizeof(nm), "upsample.%d.bias", 3 * j);
+    RC(launch_ps_bias_grad(ws + L.dup[j], N, Hj * 2, Wj * 2, reinterpret_cast<float*>(ws + L.ps_scratch),
+                           e->grads + poff(*e, nm), st));
+    e->launches += 2;
+    snprintf(nm, sizeof(nm), "upsample.%d.weight", 3 * j);
+    RC(wgrad(plain_view(in_j, Hj, Wj), Hj, Wj, false, Hj, Wj, ws + L.dup[j], 4, true, e->d_wg_idx_up, nm));
+    RC(dgrad3x3(ws + L.dup[j], Hj, Wj, true, po.up_d[j], nullptr, j > 0 ? in_j : nullptr, j > 0 ? ws + L.dup[j - 1] : d_trunk));
+  }
+  // ---- conv2 (trunk = conv2(x_last) + out1)
+  const void* x_last = e->n_res > 0 ? ws + L.out[e->n_res - 1] : ws + L.out1;
+  RC(bias_grad(d_trunk, P, "conv2.bias"));
+  RC(wgrad(plain_view(x_last, H, W), H, W, false, H, W, d_trunk, 1, false, e->d_wg_idx_c3x3, "conv2.weight"));
+  void* dout = ws + L.g[0];
+  void* dother = ws + L.g[1];
+  void* dmid = ws + L.g[2];
+  RC(dgrad3x3(d_trunk, H, W, false, po.conv2_d, nullptr, nullptr, dout));
+  // ---- residual blocks, last to first (src/models.py:21-25)
+  float* bwd = reinterpret_cast<float*>(ws + L.bwdcoef);
+  auto bn_backward = [&](int b, int k, const void* dz, const void* y, void* dy) -> int {
+    const float* coef = reinterpret_cast<const float*>(ws + L.bncoef) + size_t(2 * b + k) * 256;
+    snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.weight", b, k + 1);
+    const int64_t go = poff(*e, nm);
+    snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.bias", b, k + 1);
+    const int64_t bo = poff(*e, nm);
+    RC(launch_chan_reduce(dz, y, P, partials, st));
+    RC(launch_partials_to_sums(partials, reduce_blocks(P), sums, st));
+    if (e->allreduce) RC(e->allreduce(e->allreduce_ctx, sums, 128, st));
+    RC(launch_bn_bwd_finalize(sums, double(P) * e->world, e->master + go, coef + 128, coef + 192, e->grads + go, e->grads + bo,
+                              bwd, bwd + 64, bwd + 128, st));
+    e->launches += 4;
+    return launch_bn_bwd_apply(dz, y, bwd, bwd + 64, bwd + 128, dy, P, st);
+  };
+  for (int b = e->n_res - 1; b >= 0; --b) {
+    const void* x_in = b > 0 ? ws + L.out[b - 1] : ws + L.out1;
+    // out = bn2(y2) + x
+    RC(bn_backward(b, 1, dout, ws + L.y2[b], dmid));
+    snprintf(nm, sizeof(nm), "residual_blocks.%d.conv2.weight", b);
+    RC(wgrad(plain_view(ws + L.z1[b], H, W), H, W, false, H, W, dmid, 1, false, e->d_wg_idx_c3x3, nm));
+    RC(dgrad3x3(dmid, H, W, false, po.rb_d[1][b], nullptr, ws + L.z1[b], dother));   // ReLU backward via mask
+    // z1 = relu(bn1(y1))
+    RC(bn_backward(b, 0, dother, ws + L.y1[b], dmid));
+    snprintf(nm, sizeof(nm), "residual_blocks.%d.conv1.weight", b);
+    RC(wgrad(plain_view(x_in, H, W), H, W, false, H, W, dmid, 1, false, e->d_wg_idx_c3x3, nm));
+    RC(dgrad3x3(dmid, H, W, false, po.rb_d[0][b], dout, nullptr, dother));            // + skip gradient
+    void* t = dout; dout = dother; dother = t;
+  }
+  // ---- conv1: out1 = lrelu(conv1(x)); d(out1) = block-chain gradient + trunk skip gradient
+  RC(launch_lrelu_bwd_add2(dout, d_trunk, ws + L.out1, kSlope, dmid, P, st));
+  e->launches += 1;
+  RC(bias_grad(dmid, P, "conv1.bias"));
+  RC(wgrad(plain_view(ws + L.U1, H + 1, W), H + 1, W, true, H, W, dmid, 1, false, e->d_wg_idx_conv1, "conv1.weight"));
+  return 0;
+}
+
+}  // namespace srg

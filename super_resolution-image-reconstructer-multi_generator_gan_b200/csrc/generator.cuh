@@ -1,0 +1,74 @@
+// SRResNet generator engine: owns the launch sequence of one forward / backward pass over caller-provided
+// device memory (reference: src/models.py:10-25 ResidualBlock, :44-87 SRResNet).  Internal C++ interface; the
+// C ABI wrappers live in api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace srg {
+
+struct ParamInfo {
+  std::string name;      // state_dict key
+  int64_t offset;        // element offset into the flat fp32 parameter / gradient buffers
+  int64_t numel;
+  int ndim;
+  int shape[4];
+};
+struct BufferInfo {      // BatchNorm running statistics (flat fp32 buffer)
+  std::string name;
+  int64_t offset;
+  int64_t numel;
+};
+struct TensorInfo {      // named intermediate inside the workspace (for per-layer parity tests)
+  std::string name;
+  int64_t byte_offset;
+  int dims[4];           // NHWC
+  int dtype;             // 0 = bf16 NHWC, 1 = fp32 NCHW
+};
+
+// Collective hook for SyncBatchNorm: sum `n` doubles in place across ranks, stream ordered.
+typedef int (*AllreduceF64Fn)(void* ctx, double* buf, int n, cudaStream_t stream);
+
+struct GeneratorEngine {
+  int N, H, W, n_res, n_up;
+  std::vector<ParamInfo> params;
+  std::vector<BufferInfo> buffers;
+  std::vector<TensorInfo> tensors;
+  int64_t param_elems = 0, buffer_elems = 0;
+  int64_t packed_elems = 0, bias_elems = 0;
+  size_t workspace_bytes_train = 0, workspace_bytes_eval = 0;
+  // device-resident constant index maps (owned)
+  int* d_pack_idx = nullptr;
+  int* d_bias_idx = nullptr;
+  int* d_wg_idx_c3x3 = nullptr;   // 64->64 3x3
+  int* d_wg_idx_up = nullptr;     // 64->256 3x3 (pixel-shuffle order)
+  int* d_wg_idx_conv1 = nullptr;  // 9x9 3->64
+  int* d_wg_idx_conv3 = nullptr;  // 9x9 64->3
+  // bound memory
+  float* master = nullptr;
+  float* grads = nullptr;
+  float* bn_buffers = nullptr;
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  bool ws_training = false;
+  // SyncBN
+  AllreduceF64Fn allreduce = nullptr;
+  void* allreduce_ctx = nullptr;
+  int world = 1;
+  long long launches = 0;  // kernels launched so far (bench bookkeeping)
+
+  virtual ~GeneratorEngine();
+};
+
+GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up);
+int generator_bind(GeneratorEngine* g, float* master, float* grads, float* bn_buffers, void* ws, size_t ws_bytes,
+                   int training);
+int generator_pack(GeneratorEngine* g, cudaStream_t st);
+int generator_forward(GeneratorEngine* g, const float* lr_nchw, float* sr_nchw, int training, int update_running,
+                      cudaStream_t st);
+int generator_backward(GeneratorEngine* g, const float* dsr_nchw, cudaStream_t st);
+
+}  // namespace srg
