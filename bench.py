@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the SR-GAN train step (BASELINE.json metric: train LR-patches/sec; conv tensor-pipe roofline).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                 # this repo's CUDA path on cuda:0
+    torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU, batch-sharded (weak scaling)
+    python bench.py --impl reference --steps 3 --warmup 1           # the reference's CPU arithmetic (oracle port)
+
+Workload (N=1): BASELINE.json configs[1] -- K=3 generators (count inferred from src/main.py:28), each doing the
+reference's train_generator step (SRResNet fwd+bwd, ReconstructionLoss, Adam) on one batch of 16x3x96x96 synthetic LR
+patches (HR 16x3x384x384), bf16 operands / fp32 accumulate.  The reference Discriminator raises on 384x384 HR inputs
+(SURVEY Appendix E), so like the reference's HEAD the discriminator step is not part of this configuration.
+One step = all K generator updates on one batch; value = batch patches / step time, summed over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "srgan_train_lr_patches_per_sec"
+UNIT = "patches/s"
+FLOP_PER_LR_PIXEL_FWD_BWD = 13277952.0          # generator fwd+bwd, conv MACs x 2
+TRUNK_CONV_FLOP_PER_PIXEL = 2.0 * 64 * 64 * 9   # one 3x3 64->64 conv (fprop or dgrad) per LR pixel
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--generators", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16, help="LR patches per GPU per step")
+    ap.add_argument("--lr-size", type=int, default=96)
+    ap.add_argument("--ref-sample-batch", type=int, default=4, help="patches per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"cfg2: {a.generators} generators x train_generator (SRResNet fwd+bwd + ReconstructionLoss + Adam), "
+            f"{a.batch}x3x{a.lr_size}x{a.lr_size} LR -> x4 HR per GPU, pixel-loss mode (reference D invalid at this HR size)")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.f.close()
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+            sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = float(rows[0][1])
+                out["power_w_max"] = max(float(r[2]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for i, nme in enumerate(names):
+                if any(len(r) > 4 + i and r[4 + i].strip().lower() == "active" for r in rows):
+                    out["reasons"].append(nme)
+            out["samples"] = len(rows)
+        except Exception:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arithmetic of the reference (oracle port): used by --impl reference and by the cpu_baseline leg only
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(a, steps, warmup, budget_s=150.0):
+    import torch
+    from oracle import srgan_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample: calibrate on one patch, then take the largest sample batch (<= --ref-sample-batch) that keeps
+    # the whole run inside the time budget
+    torch.manual_seed(0)
+    sd0 = O.init_srresnet_state(0)
+    opt0 = O.AdamState([sd0[k] for k in O.trainable_keys(sd0)], lr=1e-4)
+    t0 = time.perf_counter()
+    O.train_generator_step(sd0, opt0, torch.rand(1, 3, a.lr_size, a.lr_size), torch.rand(1, 3, 4 * a.lr_size, 4 * a.lr_size))
+    t_one = (time.perf_counter() - t0) * a.generators
+    b = max(1, min(a.ref_sample_batch, int(budget_s / max((steps + warmup) * t_one, 1e-9))))
+    torch.manual_seed(0)
+    gens = [O.init_srresnet_state(s) for s in range(a.generators)]
+    opts = []
+    for sd in gens:
+        keys = O.trainable_keys(sd)
+        opts.append(O.AdamState([sd[k] for k in keys], lr=1e-4))
+    lr = torch.rand(b, 3, a.lr_size, a.lr_size)
+    hr = torch.rand(b, 3, 4 * a.lr_size, 4 * a.lr_size)
+
+    def step():
+        for sd, opt in zip(gens, opts):
+            O.train_generator_step(sd, opt, lr, hr)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    sample = (f"{a.generators} generators x oracle train_generator_step on {b}x3x{a.lr_size}x{a.lr_size} LR patches per step "
+              f"(bounded sample of the {a.batch}-patch batch), fp32, torch CPU kernels, {cores} threads")
+    return b / dt, dt, cores, sample
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, dt, cores, sample = cpu_reference_steps(a, a.steps, a.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "generators": a.generators, "sample_batch": a.ref_sample_batch,
+                   "note": "reference arithmetic restated on torch CPU kernels (oracle/srgan_oracle.py); the Python "
+                           "reference itself does not travel to the GPU box"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import srgan_b200 as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    K, B, HW = a.generators, a.batch, a.lr_size
+    gens, opts = [], []
+    for s in range(K):
+        torch.manual_seed(s)
+        g = S.SRResNet().to(dev)
+        g.flat_parameters()
+        gens.append(g)
+        opts.append(S.Adam(g.parameters(), lr=1e-4))
+    crit = S.ReconstructionLoss()
+    loss_ar = None
+    if world > 1:
+        S.parallel.data_parallel(gens, sync_batchnorm=True)
+        loss_ar = S.parallel.mean_over_ranks()
+    policy = S.MultiGeneratorPolicy(S.PolicyConfig(num_generators=K, force=S.PIXEL, seed=0))
+    trainer = S.MultiGeneratorGAN(gens, opts, crit, discriminator=None, d_optimizer=None, policy=policy,
+                                  loss_allreduce=loss_ar)
+
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    lr_host = torch.rand(B, 3, HW, HW, generator=gen).pin_memory()
+    hr_host = torch.rand(B, 3, 4 * HW, 4 * HW, generator=gen).pin_memory()
+    lr_dev, hr_dev = lr_host.to(dev), hr_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    def step_resident():
+        trainer.step(lr_dev, hr_dev)
+
+    lr_stage, hr_stage = torch.empty_like(lr_dev), torch.empty_like(hr_dev)
+    d2h_bytes = [0]
+
+    def step_e2e():
+        lr_stage.copy_(lr_host, non_blocking=True)
+        hr_stage.copy_(hr_host, non_blocking=True)
+        out = trainer.step(lr_stage, hr_stage)
+        host = out.cpu()                       # the step's result (losses) back on the host
+        d2h_bytes[0] = host.numel() * host.element_size()
+
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    L = S.lib()
+    launches0 = L.srg_total_launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step_resident, a.steps)
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = L.srg_total_launches() - launches0
+    ms_per_step = total_ms / a.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # dominant kernel (3x3 64->64 conv fprop/dgrad, tcgen05): CUDA events around each launch, same stream
+    for g in gens:
+        g.profile_enable(True)
+    prof_steps = min(a.steps, 5)
+    timed(step_resident, prof_steps)
+    k_ms, k_n = 0.0, 0
+    for g in gens:
+        ms, n = g.profile_read()
+        k_ms += ms
+        k_n += n
+        g.profile_enable(False)
+    pk, pk_src = peaks()
+    flop_per_launch = TRUNK_CONV_FLOP_PER_PIXEL * B * HW * HW
+    avg_ms = k_ms / max(k_n, 1)
+    achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12 if k_n else 0.0
+    peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "conv_gemm_kernel<64,3> (3x3 64->64 fprop/dgrad implicit GEMM)",
+                "launches_timed": k_n, "avg_launch_us": avg_ms * 1e3, "kernel_share_of_step": (k_ms / prof_steps) / ms_per_step,
+                "flop_per_launch": flop_per_launch, "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "timed_over": f"{prof_steps} extra steps right after the timed region (per-launch CUDA events on the launch stream)"}
+    step_flop = FLOP_PER_LR_PIXEL_FWD_BWD * B * HW * HW * K
+    whole_step_tflops = step_flop / (ms_per_step * 1e-3) / 1e12
+
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(2):
+            step_e2e()
+        e2e_ms = timed(step_e2e, a.steps) / a.steps
+        e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(lr_host.numel() * 4 + hr_host.numel() * 4), "d2h_bytes_per_step": int(d2h_bytes[0]),
+               "ms_per_step": e2e_ms, "api": "MultiGeneratorGAN.step(lr, hr) after pinned-host -> device copies, losses read back"}
+    last = trainer.step(lr_dev, hr_dev).cpu().tolist()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, dt, cores, sample = cpu_reference_steps(a, 2, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "s_per_step": dt}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(a), "generators": K, "batch_per_gpu": B, "global_batch": B * world,
+                       "lr_hw": [HW, HW], "upscale": 4, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (~2.5 GB of activations per generator) exceeds the 126 MB L2; no flush needed",
+                       "generator_passes_per_sec": value * K, "whole_step_algorithmic_tflops": whole_step_tflops,
+                       "whole_step_frac_of_bf16_peak": whole_step_tflops / world / peak, "last_losses": last},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples", "power_w_max")},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        S.parallel.shutdown_nccl()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,8 @@ size_t srg_generator_workspace_bytes(const srg_generator_t* g, int training);
 int srg_generator_bind(srg_generator_t* g, float* params, float* grads, float* bn_buffers, void* workspace,
                        size_t workspace_bytes, int training);
 /* fp32 master weights -> packed bf16 GEMM operands; call after every optimizer step / load_state_dict */
+/* re-points the flat gradient buffer srg_generator_backward writes (same layout as `params`) */
+int srg_generator_set_grads(srg_generator_t* g, float* grads);
 int srg_generator_pack(srg_generator_t* g, void* stream);
 /* replaces SRResNet.forward (src/models.py:80-87); training != 0 uses batch statistics (and keeps the
  * activations backward needs), update_running != 0 updates running_mean/var (momentum 0.1, unbiased var). */
@@ -68,7 +70,16 @@ int srg_generator_backward(srg_generator_t* g, const float* dsr_nchw, void* stre
 int srg_generator_num_tensors(const srg_generator_t* g);
 int srg_generator_tensor_info(const srg_generator_t* g, int i, char* name, int name_cap, int64_t* byte_offset,
                               int* dims4, int* dtype);
-long long srg_generator_launch_count(const srg_generator_t* g); /* kernels enqueued so far */
+/* parity-test aid: call before srg_generator_bind; every inter-layer gradient then gets its own named tensor
+ * ("rb<i>.d_y2", "rb<i>.d_pre1", "rb<i>.d_y1", "rb<i>.d_in", "d_last", "d_pre_conv1") instead of rotating buffers. */
+int srg_generator_set_keep_grads(srg_generator_t* g, int keep);
+long long srg_generator_launch_count(const srg_generator_t* g); /* kernels enqueued so far by this engine */
+long long srg_total_launches(void);                             /* kernels enqueued so far by the whole library */
+/* CUDA-event timing of the dominant kernel class (the 3x3 64->64 forward / data-gradient conv_gemm launches, 66 per
+ * generator fwd+bwd): enable, run steps, then read the summed device time (ms) and launch count since the last read
+ * (read synchronises on the recorded events and resets the counters). */
+int srg_generator_profile_enable(srg_generator_t* g, int on);
+int srg_generator_profile_read(srg_generator_t* g, double* ms_sum, long long* count);
 
 /* SyncBatchNorm hook: called between the local per-channel sums and the BatchNorm finalize in forward and
  * backward with a device buffer of `n` doubles to be summed in place across `world` ranks on `stream`. */

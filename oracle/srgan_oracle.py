@@ -236,7 +236,7 @@ def generator_loss_and_grads(g_sd: Dict[str, Tensor], lr_imgs: Tensor, hr_imgs: 
     for k in g_sd:  # running stats were updated on the working copy's shared buffers
         if not k.endswith(PARAM_SUFFIXES):
             g_sd[k] = work[k]
-    return (float(loss), float(com), float(tv), float(g_d)), dict(zip(keys, grads)), sr.detach()
+    return (float(loss.detach()), float(com.detach()), float(tv.detach()), float(g_d.detach())), dict(zip(keys, grads)), sr.detach()
 
 
 def train_generator_step(g_sd, opt: AdamState, lr_imgs, hr_imgs, d_sd=None, gan_mode=False):
@@ -257,7 +257,7 @@ def discriminator_loss_and_grads(d_sd, g_sd, hr_imgs, lr_imgs):
     loss = torch.tanh(fake - real).mean()
     keys = trainable_keys(work)
     grads = torch.autograd.grad(loss, [work[k] for k in keys])
-    return float(loss), dict(zip(keys, grads))
+    return float(loss.detach()), dict(zip(keys, grads))
 
 
 def train_discriminator_step(d_sd, opt: AdamState, g_sd, hr_imgs, lr_imgs):

@@ -1,0 +1,27 @@
+"""B200-native (sm_100a) implementation of the SR-GAN hot path of
+angelowxx/Super_resolution-Image-Reconstructer-Multi_Generator_GAN behind the reference's own PyTorch surface.
+
+    from srgan_b200 import SRResNet, Discriminator, ReconstructionLoss, train_generator, train_discriminator
+
+All arithmetic runs in hand-written CUDA inside ``libsrgan_b200.so`` (C ABI: include/srgan_b200.h); importing this
+package without that library raises as soon as a kernel is needed -- there is no CPU or PyTorch fallback.
+"""
+from . import _lib
+from ._lib import build, lib
+from .models import BatchNormParams, ConvParams, ResidualBlock, SRResNet
+from .loss import ReconstructionLoss, tanh_mean
+from .optim import Adam
+from .policy import (GAN, PIXEL, MultiGeneratorPolicy, PolicyConfig, decide, gan_probability, interpolate_models,
+                     shuffle_lists_in_same_order)
+from .train import (MultiGeneratorGAN, train_discriminator, train_discriminator_async, train_generator,
+                    train_generator_async, train_one_epoch)
+from . import parallel
+
+try:  # the discriminator engine is built in the same library
+    from .discriminator import Discriminator
+except ImportError:  # pragma: no cover
+    Discriminator = None
+
+__all__ = ["SRResNet", "ResidualBlock", "Discriminator", "ReconstructionLoss", "tanh_mean", "Adam", "train_generator",
+           "train_discriminator", "train_one_epoch", "MultiGeneratorGAN", "MultiGeneratorPolicy", "PolicyConfig",
+           "build", "lib", "parallel"]

@@ -80,6 +80,7 @@ EXPORTS = {
     "srg_generator_buffer_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int64)]),
     "srg_generator_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "srg_generator_bind": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+    "srg_generator_set_grads": (c_int, [c_void_p, c_void_p]),
     "srg_generator_pack": (c_int, [c_void_p, c_void_p]),
     "srg_generator_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "srg_generator_backward": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -87,6 +88,10 @@ EXPORTS = {
     "srg_generator_tensor_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int),
                                           POINTER(c_int)]),
     "srg_generator_launch_count": (c_longlong, [c_void_p]),
+    "srg_generator_set_keep_grads": (c_int, [c_void_p, c_int]),
+    "srg_total_launches": (c_longlong, []),
+    "srg_generator_profile_enable": (c_int, [c_void_p, c_int]),
+    "srg_generator_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
     "srg_generator_set_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "srg_nccl_unique_id": (c_int, [c_void_p]),
     "srg_nccl_init": (c_int, [c_void_p, c_int, c_int]),

@@ -112,6 +112,11 @@ int srg_generator_bind(srg_generator_t* g, float* params, float* grads, float* b
                        size_t workspace_bytes, int training) {
   return generator_bind(G(g), params, grads, bn_buffers, workspace, workspace_bytes, training);
 }
+int srg_generator_set_grads(srg_generator_t* g, float* grads) {
+  if (grads == nullptr) { set_error("srg_generator_set_grads: null buffer"); return -22; }
+  G(g)->grads = grads;
+  return 0;
+}
 int srg_generator_pack(srg_generator_t* g, void* stream) { return generator_pack(G(g), S(stream)); }
 int srg_generator_forward(srg_generator_t* g, const float* lr_nchw, float* sr_nchw, int training, int update_running,
                           void* stream) {
@@ -133,6 +138,12 @@ int srg_generator_tensor_info(const srg_generator_t* g, int i, char* name, int n
   return 0;
 }
 long long srg_generator_launch_count(const srg_generator_t* g) { return G(g)->launches; }
+long long srg_total_launches(void) { return total_launches(); }
+int srg_generator_set_keep_grads(srg_generator_t* g, int keep) { return generator_set_keep_grads(G(g), keep); }
+int srg_generator_profile_enable(srg_generator_t* g, int on) { return generator_profile_enable(G(g), on); }
+int srg_generator_profile_read(srg_generator_t* g, double* ms_sum, long long* count) {
+  return generator_profile_read(G(g), ms_sum, count);
+}
 
 int srg_generator_set_allreduce(srg_generator_t* g, srg_allreduce_f64_fn fn, void* ctx, int world) {
   if (world < 1) { set_error("set_allreduce: world < 1"); return -4; }

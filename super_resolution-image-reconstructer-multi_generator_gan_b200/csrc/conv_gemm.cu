@@ -27,6 +27,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launch_total = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launch_total, (long long)n, __ATOMIC_RELAXED); }
+long long total_launches() { return __atomic_load_n(&g_launch_total, __ATOMIC_RELAXED); }
+
 // ------------------------------------------------------- device parameters
 struct ConvKParams {
   CUtensorMap in_map[kMaxInMaps];
@@ -415,6 +419,7 @@ static int launch_instance(const ConvKParams& p, dim3 grid, size_t smem_bytes, c
   conv_gemm_kernel<BLOCK_N, NT><<<grid, kThreads, smem_bytes, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv_gemm launch: %s", cudaGetErrorString(e)); return int(e); }
+  count_launch();
   return 0;
 }
 

@@ -83,6 +83,10 @@ int launch_wgrad_gemm(const WgradArgs& a, cudaStream_t stream);
 int launch_wgrad_reduce(const float* partials, const int* idx, float* out, int n_out, int splits, size_t split_stride,
                         int accumulate_into, cudaStream_t stream);
 
+// total kernels launched by this library in this process (bench bookkeeping: "gpu_launches")
+void count_launch(int n = 1);
+long long total_launches();
+
 const char* last_error();
 void set_error(const char* fmt, ...);
 

@@ -17,6 +17,7 @@ namespace srg {
       set_error("%s launch: %s", name, cudaGetErrorString(e_));                   \
       return int(e_);                                                             \
     }                                                                             \
+    count_launch();                                                               \
   } while (0)
 
 __device__ __forceinline__ float blo(uint32_t v) { return __uint_as_float(v << 16); }

@@ -38,6 +38,9 @@ struct Layout {
   size_t g[4];                           // P-sized gradient buffers
   std::vector<size_t> dup;               // gradient of each upsample stage output
   size_t Ud;                             // unfolded d(SR)
+  // debug (keep_grads): every inter-layer gradient in its own buffer instead of the 3 rotating ones
+  std::vector<size_t> kd_y2, kd_p1, kd_y1, kd_in;
+  size_t kd_last, kd_c1;
   size_t total;
 };
 
@@ -84,6 +87,15 @@ Layout make_layout(const GeneratorEngine& e, bool training) {
     for (int j = 0; j < e.n_up; ++j) L.dup[j] = c.take(t64(P << (2 * (j + 1))));
     const int64_t Hs = int64_t(e.H) << e.n_up, Ws = int64_t(e.W) << e.n_up;
     L.Ud = c.take(size_t(e.N) * (Hs + 1) * Ws * 128);
+    L.kd_last = L.kd_c1 = 0;
+    if (e.keep_grads) {
+      L.kd_y2.resize(e.n_res); L.kd_p1.resize(e.n_res); L.kd_y1.resize(e.n_res); L.kd_in.resize(e.n_res);
+      for (int b = 0; b < e.n_res; ++b) {
+        L.kd_y2[b] = c.take(t64(P)); L.kd_p1[b] = c.take(t64(P)); L.kd_y1[b] = c.take(t64(P)); L.kd_in[b] = c.take(t64(P));
+      }
+      L.kd_last = c.take(t64(P));
+      L.kd_c1 = c.take(t64(P));
+    }
   }
   L.total = c.off;
   return L;
@@ -197,6 +209,8 @@ int* upload(const std::vector<int>& v) {
 struct EngineImpl : GeneratorEngine {
   PackOffsets po;
   Layout L;
+  // host copies of the constant index maps; uploaded at the first bind (create() needs no device)
+  std::vector<int> h_pack_idx, h_bias_idx, h_wg_c3x3, h_wg_up, h_wg_conv1, h_wg_conv3;
 };
 
 #define RC(x)                  \
@@ -233,7 +247,53 @@ void set_taps_pairs(ConvGemmArgs& a) {
 
 }  // namespace
 
+namespace {
+struct ProfScope {
+  GeneratorEngine* e; cudaStream_t st; bool on;
+  ProfScope(GeneratorEngine* e_, cudaStream_t st_) : e(e_), st(st_), on(e_->prof_on) {
+    if (!on) return;
+    if (e->prof_used + 2 > e->prof_events.size()) {
+      if (e->prof_events.size() >= 8192) { on = false; return; }
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
+      e->prof_events.push_back(a); e->prof_events.push_back(b);
+    }
+    cudaEventRecord(e->prof_events[e->prof_used], st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(e->prof_events[e->prof_used + 1], st);
+    e->prof_used += 2;
+  }
+};
+}  // namespace
+
+int generator_set_keep_grads(GeneratorEngine* g, int keep) {
+  EngineImpl* e = static_cast<EngineImpl*>(g);
+  if (e->ws != nullptr) { set_error("set_keep_grads: call before bind"); return -30; }
+  e->keep_grads = keep != 0;
+  e->workspace_bytes_train = make_layout(*e, true).total;
+  return 0;
+}
+int generator_profile_enable(GeneratorEngine* g, int on) { g->prof_on = on != 0; return 0; }
+int generator_profile_read(GeneratorEngine* g, double* ms_sum, long long* count) {
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < g->prof_used; i += 2) {
+    cudaError_t e = cudaEventSynchronize(g->prof_events[i + 1]);
+    if (e != cudaSuccess) { set_error("profile_read: %s", cudaGetErrorString(e)); return int(e); }
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, g->prof_events[i], g->prof_events[i + 1]);
+    if (e != cudaSuccess) { set_error("profile_read: %s", cudaGetErrorString(e)); return int(e); }
+    total += double(ms);
+  }
+  if (ms_sum) *ms_sum = total;
+  if (count) *count = (long long)(g->prof_used / 2);
+  g->prof_used = 0;
+  return 0;
+}
+
 GeneratorEngine::~GeneratorEngine() {
+  for (cudaEvent_t ev : prof_events) cudaEventDestroy(ev);
   cudaFree(d_pack_idx); cudaFree(d_bias_idx); cudaFree(d_wg_idx_c3x3); cudaFree(d_wg_idx_up);
   cudaFree(d_wg_idx_conv1); cudaFree(d_wg_idx_conv3);
 }
@@ -327,17 +387,8 @@ GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up) {
           const int dr = kh % 2, r = (8 - kh - dr) / 2, s = 8 - kw;
           mc3[((co * 64 + ci) * 9 + kh) * 9 + kw] = pidx(0, 3, r, dr * 27 + s * 3 + co, ci);
         }
-  e->d_pack_idx = upload(idx);
-  e->d_bias_idx = upload(bidx);
-  e->d_wg_idx_c3x3 = upload(m33);
-  e->d_wg_idx_up = upload(mup);
-  e->d_wg_idx_conv1 = upload(mc1);
-  e->d_wg_idx_conv3 = upload(mc3);
-  if (!e->d_pack_idx || !e->d_bias_idx || !e->d_wg_idx_c3x3 || !e->d_wg_idx_up || !e->d_wg_idx_conv1 || !e->d_wg_idx_conv3) {
-    set_error("generator_create: device allocation of index maps failed: %s", cudaGetErrorString(cudaGetLastError()));
-    delete e;
-    return nullptr;
-  }
+  e->h_pack_idx.swap(idx); e->h_bias_idx.swap(bidx);
+  e->h_wg_c3x3.swap(m33); e->h_wg_up.swap(mup); e->h_wg_conv1.swap(mc1); e->h_wg_conv3.swap(mc3);
   e->workspace_bytes_train = make_layout(*e, true).total;
   e->workspace_bytes_eval = make_layout(*e, false).total;
   return e;
@@ -350,6 +401,18 @@ int generator_bind(GeneratorEngine* g, float* master, float* grads, float* bn_bu
   if (ws_bytes < need) { set_error("generator_bind: workspace too small (%zu < %zu)", ws_bytes, need); return -20; }
   if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) { set_error("generator_bind: workspace must be 1024-byte aligned"); return -21; }
   if (master == nullptr || bn_buffers == nullptr || (training && grads == nullptr)) { set_error("generator_bind: null buffer"); return -22; }
+  if (e->d_pack_idx == nullptr) {
+    e->d_pack_idx = upload(e->h_pack_idx);
+    e->d_bias_idx = upload(e->h_bias_idx);
+    e->d_wg_idx_c3x3 = upload(e->h_wg_c3x3);
+    e->d_wg_idx_up = upload(e->h_wg_up);
+    e->d_wg_idx_conv1 = upload(e->h_wg_conv1);
+    e->d_wg_idx_conv3 = upload(e->h_wg_conv3);
+    if (!e->d_pack_idx || !e->d_bias_idx || !e->d_wg_idx_c3x3 || !e->d_wg_idx_up || !e->d_wg_idx_conv1 || !e->d_wg_idx_conv3) {
+      set_error("generator_bind: device allocation of index maps failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return -29;
+    }
+  }
   e->master = master; e->grads = grads; e->bn_buffers = bn_buffers;
   e->ws = reinterpret_cast<uint8_t*>(ws); e->ws_bytes = ws_bytes; e->ws_training = training != 0;
   e->L = make_layout(*e, training != 0);
@@ -376,6 +439,16 @@ int generator_bind(GeneratorEngine* g, float* master, float* grads, float* bn_bu
   }
   if (training) {
     reg("d_trunk", L.g[3], e->N, e->H, e->W, 64, 0);
+    if (e->keep_grads) {
+      for (int b = 0; b < e->n_res; ++b) {
+        snprintf(nm, sizeof(nm), "rb%d.d_y2", b); reg(nm, L.kd_y2[b], e->N, e->H, e->W, 64, 0);
+        snprintf(nm, sizeof(nm), "rb%d.d_pre1", b); reg(nm, L.kd_p1[b], e->N, e->H, e->W, 64, 0);
+        snprintf(nm, sizeof(nm), "rb%d.d_y1", b); reg(nm, L.kd_y1[b], e->N, e->H, e->W, 64, 0);
+        snprintf(nm, sizeof(nm), "rb%d.d_in", b); reg(nm, L.kd_in[b], e->N, e->H, e->W, 64, 0);
+      }
+      reg("d_last", L.kd_last, e->N, e->H, e->W, 64, 0);
+      reg("d_pre_conv1", L.kd_c1, e->N, e->H, e->W, 64, 0);
+    }
   }
   return 0;
 }
@@ -423,6 +496,7 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
     a.weights = packed + w_off; a.cout_total = 64; a.block_n = 64;
     a.bias = bias; a.act = ACT_NONE; a.residual = residual; a.out = out; a.out_mode = OUT_NHWC;
     e->launches += 1;
+    ProfScope ps(e, st);
     return launch_conv_gemm(a, st);
   };
   auto bn_coeffs = [&](int b, int k, const void* y) -> int {
@@ -566,6 +640,8 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     a.weights = packed + w_off; a.cout_total = 64; a.block_n = 64;
     a.bias = nullptr; a.act = ACT_NONE; a.residual = residual; a.mask_src = mask; a.out = out; a.out_mode = OUT_NHWC;
     e->launches += 1;
+    if (dy_ps) return launch_conv_gemm(a, st);
+    ProfScope ps(e, st);
     return launch_conv_gemm(a, st);
   };
 
@@ -607,7 +683,8 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
   const void* x_last = e->n_res > 0 ? ws + L.out[e->n_res - 1] : ws + L.out1;
   RC(bias_grad(d_trunk, P, "conv2.bias"));
   RC(wgrad(plain_view(x_last, H, W), H, W, false, H, W, d_trunk, 1, false, e->d_wg_idx_c3x3, "conv2.weight"));
-  void* dout = ws + L.g[0];
+  const bool keep = e->keep_grads;
+  void* dout = keep ? ws + L.kd_last : ws + L.g[0];
   void* dother = ws + L.g[1];
   void* dmid = ws + L.g[2];
   RC(dgrad3x3(d_trunk, H, W, false, po.conv2_d, nullptr, nullptr, dout));
@@ -629,19 +706,24 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
   };
   for (int b = e->n_res - 1; b >= 0; --b) {
     const void* x_in = b > 0 ? ws + L.out[b - 1] : ws + L.out1;
+    void* d_y2 = keep ? ws + L.kd_y2[b] : dmid;
+    void* d_p1 = keep ? ws + L.kd_p1[b] : dother;
+    void* d_y1 = keep ? ws + L.kd_y1[b] : dmid;
+    void* d_in = keep ? ws + L.kd_in[b] : dother;
     // out = bn2(y2) + x
-    RC(bn_backward(b, 1, dout, ws + L.y2[b], dmid));
+    RC(bn_backward(b, 1, dout, ws + L.y2[b], d_y2));
     snprintf(nm, sizeof(nm), "residual_blocks.%d.conv2.weight", b);
-    RC(wgrad(plain_view(ws + L.z1[b], H, W), H, W, false, H, W, dmid, 1, false, e->d_wg_idx_c3x3, nm));
-    RC(dgrad3x3(dmid, H, W, false, po.rb_d[1][b], nullptr, ws + L.z1[b], dother));   // ReLU backward via mask
+    RC(wgrad(plain_view(ws + L.z1[b], H, W), H, W, false, H, W, d_y2, 1, false, e->d_wg_idx_c3x3, nm));
+    RC(dgrad3x3(d_y2, H, W, false, po.rb_d[1][b], nullptr, ws + L.z1[b], d_p1));      // ReLU backward via mask
     // z1 = relu(bn1(y1))
-    RC(bn_backward(b, 0, dother, ws + L.y1[b], dmid));
+    RC(bn_backward(b, 0, d_p1, ws + L.y1[b], d_y1));
     snprintf(nm, sizeof(nm), "residual_blocks.%d.conv1.weight", b);
-    RC(wgrad(plain_view(x_in, H, W), H, W, false, H, W, dmid, 1, false, e->d_wg_idx_c3x3, nm));
-    RC(dgrad3x3(dmid, H, W, false, po.rb_d[0][b], dout, nullptr, dother));            // + skip gradient
-    void* t = dout; dout = dother; dother = t;
+    RC(wgrad(plain_view(x_in, H, W), H, W, false, H, W, d_y1, 1, false, e->d_wg_idx_c3x3, nm));
+    RC(dgrad3x3(d_y1, H, W, false, po.rb_d[0][b], dout, nullptr, d_in));              // + skip gradient
+    if (keep) { dout = d_in; } else { void* t = dout; dout = dother; dother = t; }
   }
   // ---- conv1: out1 = lrelu(conv1(x)); d(out1) = block-chain gradient + trunk skip gradient
+  if (keep) dmid = ws + L.kd_c1;
   RC(launch_lrelu_bwd_add2(dout, d_trunk, ws + L.out1, kSlope, dmid, P, st));
   e->launches += 1;
   RC(bias_grad(dmid, P, "conv1.bias"));

@@ -59,6 +59,11 @@ struct GeneratorEngine {
   void* allreduce_ctx = nullptr;
   int world = 1;
   long long launches = 0;  // kernels launched so far (bench bookkeeping)
+  // optional CUDA-event timing of the dominant kernel class (3x3 64->64 fprop/dgrad conv_gemm launches)
+  bool keep_grads = false; // debug: keep every inter-layer gradient in its own named buffer (parity tests)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
+  size_t prof_used = 0;
 
   virtual ~GeneratorEngine();
 };
@@ -70,5 +75,10 @@ int generator_pack(GeneratorEngine* g, cudaStream_t st);
 int generator_forward(GeneratorEngine* g, const float* lr_nchw, float* sr_nchw, int training, int update_running,
                       cudaStream_t st);
 int generator_backward(GeneratorEngine* g, const float* dsr_nchw, cudaStream_t st);
+// dominant-kernel timing: enable/disable; read() synchronises on the recorded events, returns the summed duration
+// (ms) and launch count since the last read and resets.
+int generator_set_keep_grads(GeneratorEngine* g, int keep);
+int generator_profile_enable(GeneratorEngine* g, int on);
+int generator_profile_read(GeneratorEngine* g, double* ms_sum, long long* count);
 
 }  // namespace srg

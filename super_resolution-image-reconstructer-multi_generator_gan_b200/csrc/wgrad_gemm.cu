@@ -243,6 +243,7 @@ int launch_wgrad_gemm(const WgradArgs& a, cudaStream_t stream) {
   wgrad_gemm_kernel<<<p.n_blocks * p.splits, kWgThreads, smem_bytes, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("wgrad launch: %s", cudaGetErrorString(e)); return int(e); }
+  count_launch();
   return 0;
 }
 
@@ -253,6 +254,7 @@ int launch_wgrad_reduce(const float* partials, const int* idx, float* out, int n
                                                               accumulate_into);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("wgrad_reduce launch: %s", cudaGetErrorString(e)); return int(e); }
+  count_launch();
   return 0;
 }
 

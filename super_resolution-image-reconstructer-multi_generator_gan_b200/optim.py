@@ -1,0 +1,85 @@
+"""Adam over the flat parameter buffers of libsrgan_b200 modules.
+
+Replaces ``torch.optim.Adam(model.parameters(), lr=...)`` as used at src/train.py:61-62 (default betas (0.9, 0.999),
+eps 1e-8, no weight decay, no amsgrad) with ONE fused kernel launch per model (``srg_adam_step``) instead of torch's
+foreach op chain.  It is a ``torch.optim.Optimizer`` so LR schedulers (``LinearLR``, src/train.py:70-71) and
+``zero_grad()`` work unchanged.  Parameters that are not views of a flat libsrgan_b200 buffer are rejected.
+"""
+from __future__ import annotations
+
+from ctypes import c_void_p
+from typing import Dict, List
+
+import torch
+
+from . import _lib
+from ._lib import check, stream_ptr
+
+
+class Adam(torch.optim.Optimizer):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
+            raise ValueError("invalid Adam hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._flat_state: Dict[int, dict] = {}   # id(owner module) -> {"m", "v", "step"}
+        self.grad_scale = 1.0                     # multiplies gradients first (e.g. 1/world for a summed all-reduce)
+
+    def _owners(self, group) -> List:
+        owners, seen = [], set()
+        for p in group["params"]:
+            ref = getattr(p, "_srg_owner", None)
+            owner = ref() if ref is not None else None
+            if owner is None:
+                raise RuntimeError("optim.Adam only updates parameters of libsrgan_b200 modules (SRResNet / "
+                                   "Discriminator) after they have been moved to their CUDA device")
+            if id(owner) not in seen:
+                seen.add(id(owner))
+                owners.append(owner)
+        return owners
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        L = _lib.lib()
+        for group in self.param_groups:
+            # modules flatten lazily on first CUDA use; make sure that happened
+            for p in group["params"]:
+                if getattr(p, "_srg_owner", None) is None:
+                    raise RuntimeError("optim.Adam: run the model once (or call .flat_parameters()) before step()")
+            for owner in self._owners(group):
+                flat = owner.flat_parameters()
+                gflat = owner.flat_grads()
+                if gflat is None:
+                    continue                      # no backward since the last flatten: nothing to do
+                st = self._flat_state.get(id(owner))
+                if st is None or st["m"].data_ptr() == 0 or st["m"].numel() != flat.numel() or st["m"].device != flat.device:
+                    st = {"m": torch.zeros_like(flat), "v": torch.zeros_like(flat), "step": 0 if st is None else st["step"]}
+                    self._flat_state[id(owner)] = st
+                # every live .grad must be a view of the flat gradient buffer (it is, unless the user replaced it)
+                base = gflat.data_ptr()
+                ok = True
+                for p, (_, off, n, _) in zip(owner._rt["plist"], owner._ptable):
+                    if p.grad is None or p.grad.data_ptr() != base + 4 * off:
+                        ok = False
+                        break
+                if not ok:
+                    # gather user-modified / accumulated gradients back into flat layout with one copy per tensor
+                    g2 = torch.zeros_like(flat)
+                    for p, (_, off, n, shape) in zip(owner._rt["plist"], owner._ptable):
+                        if p.grad is not None:
+                            g2[off:off + n].view(shape).copy_(p.grad)
+                    gflat = g2
+                st["step"] += 1
+                b1, b2 = group["betas"]
+                check(L.srg_adam_step(c_void_p(flat.data_ptr()), c_void_p(gflat.data_ptr()), c_void_p(st["m"].data_ptr()),
+                                      c_void_p(st["v"].data_ptr()), flat.numel(), float(group["lr"]), float(b1), float(b2),
+                                      float(group["eps"]), int(st["step"]), float(self.grad_scale), stream_ptr()),
+                      "srg_adam_step")
+        return loss
+
+    def flat_state(self, owner) -> dict:
+        """{"m": exp_avg, "v": exp_avg_sq, "step": int} in the owner's flat layout (checkpointing / tests)."""
+        return self._flat_state.get(id(owner))

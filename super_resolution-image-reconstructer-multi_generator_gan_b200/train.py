@@ -1,0 +1,158 @@
+"""Train-step functions with the reference's signatures (src/train.py:175-203, :206-230, :142-172) driving the
+libsrgan_b200 modules, plus the multi-generator step the README describes (policy.py).
+
+Differences from the reference that do not change results: anomaly mode is opt-in
+(``detect_anomaly``; it costs 11 % of the CPU step upstream), ``torch.cuda.empty_cache()`` is not called every step, and
+the four ``.item()`` syncs are one device->host copy.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .loss import tanh_mean
+from .policy import GAN, PIXEL, MultiGeneratorPolicy, PolicyConfig, interpolate_models
+
+
+def train_generator(generator, discriminator, lr_imgs, hr_imgs, vgg_extractor, g_criterion, g_optimizer,
+                    gan_mode: bool = False, detect_anomaly: bool = False) -> Tuple[float, float, float, float]:
+    """One generator update (src/train.py:175-203).  Returns (g_loss, com_loss, tv_loss, g_d_loss) as floats.
+
+    ``gan_mode=False`` is HEAD's objective ``com_loss + tv_loss`` (src/train.py:191-192); ``gan_mode=True`` restores
+    the commented-out adversarial term ``mean(tanh(D(hr) - D(sr)))`` (src/train.py:184-190).  ``vgg_extractor`` is
+    accepted and ignored, as upstream."""
+    losses = train_generator_async(generator, discriminator, lr_imgs, hr_imgs, vgg_extractor, g_criterion, g_optimizer,
+                                   gan_mode, detect_anomaly)
+    g, c, t, d = losses.tolist()           # the step's single device->host sync
+    return g, c, t, d
+
+
+def train_generator_async(generator, discriminator, lr_imgs, hr_imgs, vgg_extractor, g_criterion, g_optimizer,
+                          gan_mode: bool = False, detect_anomaly: bool = False) -> torch.Tensor:
+    """Same step, but returns the 4 losses as a device tensor [g_loss, com_loss, tv_loss, g_d_loss] without
+    synchronising (lets the host run ahead; used by the multi-generator loop and bench.py)."""
+    if detect_anomaly:
+        torch.autograd.set_detect_anomaly(True)          # src/train.py:177
+    generator.train()
+    if discriminator is not None:
+        discriminator.eval()                              # src/train.py:180 (no-op for InstanceNorm)
+    sr_images = generator(lr_imgs)
+    com_loss, tv_loss = g_criterion(hr_imgs, sr_images)
+    if gan_mode:
+        fake_preds = discriminator(sr_images)
+        with torch.no_grad():
+            real_preds = discriminator(hr_imgs)
+        g_d_loss = tanh_mean(real_preds, fake_preds)      # mean(tanh(real - fake)), src/train.py:190
+        g_loss = com_loss + tv_loss + g_d_loss
+    else:
+        g_d_loss = torch.zeros((), dtype=torch.float32, device=com_loss.device)   # torch.tensor(0), src/train.py:191
+        g_loss = com_loss + tv_loss
+    g_optimizer.zero_grad()
+    g_loss.backward()
+    g_optimizer.step()
+    return torch.stack([g_loss.detach(), com_loss.detach(), tv_loss.detach(), g_d_loss.detach().float()])
+
+
+def train_discriminator(discriminator, generator, hr_imgs, lr_imgs, d_optimizer, detect_anomaly: bool = False) -> float:
+    """One discriminator update (src/train.py:206-230): ``d_loss = mean(tanh(D(G(lr)) - D(hr)))`` with G in eval mode.
+    The reference keeps the autograd graph into G and throws those gradients away; here G's output is
+    detached, which yields identical discriminator gradients."""
+    return float(train_discriminator_async(discriminator, generator, hr_imgs, lr_imgs, d_optimizer, detect_anomaly))
+
+
+def train_discriminator_async(discriminator, generator, hr_imgs, lr_imgs, d_optimizer,
+                              detect_anomaly: bool = False) -> torch.Tensor:
+    if detect_anomaly:
+        torch.autograd.set_detect_anomaly(True)
+    discriminator.train()
+    generator.eval()
+    with torch.no_grad():
+        sr_imgs = generator(lr_imgs)
+    real_preds = discriminator(hr_imgs)
+    fake_preds = discriminator(sr_imgs)
+    d_loss = tanh_mean(fake_preds, real_preds)            # mean(tanh(fake - real)), src/train.py:218
+    d_optimizer.zero_grad()
+    d_loss.backward()
+    d_optimizer.step()
+    return d_loss.detach()
+
+
+def train_one_epoch(generator, train_loader, g_optimizer, vgg_extractor, g_criterion, device, epoch, num_epochs,
+                    discriminator, d_optimizer, prefix, verbose: bool = True) -> float:
+    """Batch loop of src/train.py:142-172 (D update commented out upstream, kept off here)."""
+    sums = torch.zeros(4, dtype=torch.float64)
+    n = 0
+    for hr_imgs, lr_imgs in train_loader:
+        hr_imgs = hr_imgs.to(device, non_blocking=True)
+        lr_imgs = lr_imgs.to(device, non_blocking=True)
+        vals = train_generator(generator, discriminator, lr_imgs, hr_imgs, vgg_extractor, g_criterion, g_optimizer)
+        sums += torch.tensor(vals, dtype=torch.float64)
+        n += 1
+    n = max(n, 1)
+    avg = float(sums[0]) / n
+    if verbose:
+        print(f"Epoch [{epoch + 1}/{num_epochs}] {prefix} Loss: {avg:.6f}")
+        print(f"com_loss: {float(sums[1]) / n}, tv_loss: {float(sums[2]) / n}, g_d_loss: {float(sums[3]) / n}")
+    return avg
+
+
+class MultiGeneratorGAN:
+    """The README's multi-generator loop (readme.md:2-10): K generators + one discriminator, loss-ranked order,
+    per-generator PIXEL/GAN decision (policy.py), per-epoch re-sort.
+
+    One ``step(lr, hr)`` = [optional discriminator update against the leader's output] + K generator updates in rank
+    order.  Decisions for batch t use the running contrast losses through batch t-1, so the host never waits for
+    the batch it has just enqueued (losses are read back one batch late, in one copy)."""
+
+    def __init__(self, generators: Sequence, g_optimizers: Sequence, g_criterion, discriminator=None, d_optimizer=None,
+                 policy: Optional[MultiGeneratorPolicy] = None, loss_allreduce=None):
+        self.generators = list(generators)
+        self.g_optimizers = list(g_optimizers)
+        self.criterion = g_criterion
+        self.discriminator = discriminator
+        self.d_optimizer = d_optimizer
+        self.policy = policy or MultiGeneratorPolicy(PolicyConfig(num_generators=len(self.generators)))
+        if self.policy.cfg.num_generators != len(self.generators):
+            raise ValueError("policy.num_generators != len(generators)")
+        self.loss_allreduce = loss_allreduce      # callable(tensor) -> None: mean over ranks, in place (parallel.py)
+        self._pending: List[Tuple[List[int], torch.Tensor]] = []
+        self.last_plan: List[tuple] = []
+
+    def _drain(self, keep: int) -> None:
+        while len(self._pending) > keep:
+            gids, dev_losses = self._pending.pop(0)
+            host = dev_losses.tolist()
+            for gid, row in zip(gids, host):
+                self.policy.observe(gid, row[1])
+
+    def step(self, lr_imgs: torch.Tensor, hr_imgs: torch.Tensor) -> torch.Tensor:
+        """Returns a device tensor [K, 4] of (g_loss, com_loss, tv_loss, g_d_loss) rows in training order."""
+        self._drain(keep=1)
+        plan = self.policy.plan_batch()
+        self.last_plan = plan
+        any_gan = any(mode == GAN for _, mode in plan)
+        if any_gan and self.discriminator is None:
+            raise RuntimeError("the policy chose GAN mode but no discriminator was given")
+        if any_gan and self.d_optimizer is not None:
+            leader = self.generators[plan[0][0]]
+            train_discriminator_async(self.discriminator, leader, hr_imgs, lr_imgs, self.d_optimizer)
+        rows = []
+        for gid, mode in plan:
+            rows.append(train_generator_async(self.generators[gid], self.discriminator, lr_imgs, hr_imgs, None,
+                                              self.criterion, self.g_optimizers[gid], gan_mode=(mode == GAN)))
+        out = torch.stack(rows)
+        if self.loss_allreduce is not None:
+            self.loss_allreduce(out)
+        self._pending.append(([gid for gid, _ in plan], out))
+        return out
+
+    def end_epoch(self) -> List[int]:
+        self._drain(keep=0)
+        order = self.policy.end_epoch()
+        a = self.policy.cfg.lead_alpha
+        if a > 0.0:
+            best = self.generators[order[0]]
+            for gid in order[1:]:
+                interpolate_models(self.generators[gid], best, a)
+        return order

@@ -1,0 +1,323 @@
+"""GPU parity tests of the CUDA generator (through the nn.Module surface -> C ABI) against the CPU oracle and the
+golden fixtures recorded from the unmodified reference.
+
+Tolerances (BASELINE.json north_star): per-layer max relative error <= 1e-2 (bf16 operands / storage vs the fp32
+reference arithmetic, each layer fed the SAME input), output PSNR within 0.05 dB.  "Relative" is relative to the
+largest magnitude of the reference tensor (bf16 keeps ~3 significant digits per element).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL_LAYER = 1e-2       # per-layer, same inputs
+TOL_WGRAD = 5e-3       # fp32 outputs computed from identical bf16 inputs
+
+
+def maxrel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+def nchw(t):  # engine NHWC bf16 -> NCHW fp32 on the CPU
+    return t.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+@pytest.fixture(scope="module")
+def S():
+    import srgan_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return srgan_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import srgan_oracle
+    return srgan_oracle
+
+
+@pytest.fixture(scope="module")
+def run(S, O):
+    """One train-mode forward + backward of the default SRResNet at the golden geometry, all intermediates kept."""
+    torch.manual_seed(1)
+    g = S.SRResNet()
+    sd = {k: v.clone() for k, v in g.state_dict().items()}
+    lr = torch.rand(2, 3, 16, 24)
+    hr = torch.rand(2, 3, 64, 96)
+    g = g.cuda()
+    g.debug_keep_grads = True
+    g.eval()
+    with torch.no_grad():
+        y_eval = g(lr.cuda()).cpu()
+    g.train()
+    sr = g(lr.cuda())
+    crit = S.ReconstructionLoss()
+    com, tv = crit(hr.cuda(), sr)
+    (com + tv).backward()
+    torch.cuda.synchronize()
+    eng = g.last_engine()
+    T = {name: nchw(eng.named_tensor(name)) for name in eng.tensor_table()}
+    # the exact upstream gradient the engine's backward consumed (loss kernel output, checked separately)
+    srd = sr.detach().clone().requires_grad_(True)
+    c2, t2 = crit(hr.cuda(), srd)
+    (c2 + t2).backward()
+    grads = {k: p.grad.detach().cpu().clone() for k, p in g.named_parameters()}
+    return dict(g=g, sd=sd, lr=lr, hr=hr, y_eval=y_eval, sr=sr.detach().cpu(), com=float(com), tv=float(tv), T=T,
+                dsr=srd.grad.detach().cpu(), grads=grads, state=g.state_dict())
+
+
+# ------------------------------------------------------------------------------------------------ end to end
+def test_eval_forward_matches_reference_golden(run, O, golden_dir):
+    z = np.load(os.path.join(golden_dir, "generator_tiny.npz"))
+    ref = torch.from_numpy(z["y_eval"])
+    assert maxrel(run["y_eval"], ref) < 2e-2           # 37 stacked bf16 layers end to end
+    hr = run["hr"]
+    assert abs(O.psnr(run["y_eval"], hr) - O.psnr(ref, hr)) < 0.05      # north_star: output PSNR within 0.05 dB
+    assert O.psnr(run["y_eval"], ref) > 60.0
+
+
+def test_train_forward_and_losses_match_reference_golden(run, O, golden_dir):
+    z = np.load(os.path.join(golden_dir, "generator_tiny.npz"))
+    ref = torch.from_numpy(z["y_train"])
+    assert maxrel(run["sr"], ref) < 4e-2
+    assert abs(O.psnr(run["sr"], run["hr"]) - O.psnr(ref, run["hr"])) < 0.05
+    assert abs(run["com"] - float(z["com"])) < 2e-3 * float(z["com"])
+    assert abs(run["tv"] - float(z["tv"])) < 2e-2 * float(z["tv"])
+    # BatchNorm running statistics after one training forward (momentum 0.1, unbiased variance)
+    st = run["state"]
+    np.testing.assert_allclose(st["residual_blocks.0.bn1.running_mean"].cpu().numpy(), z["bn_rm"], atol=3e-3 * np.abs(z["bn_rm"]).max() + 1e-5)
+    np.testing.assert_allclose(st["residual_blocks.0.bn1.running_var"].cpu().numpy(), z["bn_rv"], rtol=2e-3)
+    assert int(st["residual_blocks.0.bn1.num_batches_tracked"]) == 1
+    assert int(st["residual_blocks.15.bn2.num_batches_tracked"]) == 1
+
+
+def test_state_dict_keys_and_init_match_reference(run, golden_dir):
+    with open(os.path.join(golden_dir, "golden.json")) as f:
+        ck = json.load(f)["generator_tiny"]["init_checksum"]
+    sd = run["sd"]
+    assert [k for k in sd if sd[k].dtype.is_floating_point] == list(ck.keys())
+    for k, (s, a) in ck.items():
+        assert abs(float(sd[k].double().sum()) - s) <= 1e-9 * max(1.0, abs(a)), k
+
+
+# ------------------------------------------------------------------------------------------------ per layer, forward
+def _bn_train(y, gamma, beta):
+    return F.batch_norm(y, None, None, gamma, beta, training=True, momentum=0.1, eps=1e-5)
+
+
+def test_forward_layers_isolated(run):
+    sd, T, lr = run["sd"], run["T"], run["lr"]
+    ref = F.leaky_relu(F.conv2d(lr, sd["conv1.weight"], sd["conv1.bias"], padding=4), 0.2)
+    assert maxrel(T["out1"], ref) < TOL_LAYER
+    x = T["out1"]
+    for b in range(16):
+        p = f"residual_blocks.{b}"
+        assert maxrel(T[f"rb{b}.y1"], F.conv2d(x, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)) < TOL_LAYER, p
+        z1 = F.relu(_bn_train(T[f"rb{b}.y1"], sd[p + ".bn1.weight"], sd[p + ".bn1.bias"]))
+        assert maxrel(T[f"rb{b}.z1"], z1) < TOL_LAYER, p
+        assert maxrel(T[f"rb{b}.y2"], F.conv2d(T[f"rb{b}.z1"], sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1)) < TOL_LAYER, p
+        out = _bn_train(T[f"rb{b}.y2"], sd[p + ".bn2.weight"], sd[p + ".bn2.bias"]) + x
+        assert maxrel(T[f"rb{b}.out"], out) < TOL_LAYER, p
+        x = T[f"rb{b}.out"]
+    trunk = F.conv2d(x, sd["conv2.weight"], sd["conv2.bias"], padding=1) + T["out1"]
+    assert maxrel(T["trunk"], trunk) < TOL_LAYER
+    x = T["trunk"]
+    for j in range(2):
+        up = F.relu(F.pixel_shuffle(F.conv2d(x, sd[f"upsample.{3 * j}.weight"], sd[f"upsample.{3 * j}.bias"], padding=1), 2))
+        assert maxrel(T[f"up{j}"], up) < TOL_LAYER, j
+        x = T[f"up{j}"]
+    sr = F.conv2d(x, sd["conv3.weight"], sd["conv3.bias"], padding=4)
+    assert maxrel(run["sr"], sr) < TOL_LAYER
+
+
+# ------------------------------------------------------------------------------------------------ per layer, backward
+def _conv_bwd(x, w, b, pad, dy):
+    x = x.clone().requires_grad_(True)
+    w = w.clone().requires_grad_(True)
+    b = b.clone().requires_grad_(True)
+    y = F.conv2d(x, w, b, padding=pad)
+    return torch.autograd.grad(y, [x, w, b], grad_outputs=dy)
+
+
+def _bn_bwd(y, gamma, beta, dz):
+    y = y.clone().requires_grad_(True)
+    gamma = gamma.clone().requires_grad_(True)
+    beta = beta.clone().requires_grad_(True)
+    return torch.autograd.grad(_bn_train(y, gamma, beta), [y, gamma, beta], grad_outputs=dz)
+
+
+def test_backward_layers_isolated(run):
+    sd, T, G, lr = run["sd"], run["T"], run["grads"], run["lr"]
+    dsr = run["dsr"]
+    # conv3 (9x9, 64->3): the engine rounds d(SR) to bf16 for the tensor-core operands
+    dx, dw, db = _conv_bwd(T["up1"], sd["conv3.weight"], sd["conv3.bias"], 4, dsr)
+    assert maxrel(G["conv3.weight"], dw) < TOL_WGRAD
+    assert maxrel(G["conv3.bias"], db) < 1e-4
+    assert maxrel(T["d_up1"], dx * (T["up1"] > 0)) < TOL_LAYER
+    # upsample stages (conv 64->256, PixelShuffle, ReLU), last to first
+    for j in (1, 0):
+        x_in = T["up0"] if j == 1 else T["trunk"]
+        dy = F.pixel_unshuffle(T[f"d_up{j}"], 2)
+        dx, dw, db = _conv_bwd(x_in, sd[f"upsample.{3 * j}.weight"], sd[f"upsample.{3 * j}.bias"], 1, dy)
+        assert maxrel(G[f"upsample.{3 * j}.weight"], dw) < TOL_WGRAD, j
+        assert maxrel(G[f"upsample.{3 * j}.bias"], db) < TOL_WGRAD, j
+        if j == 1:
+            assert maxrel(T["d_up0"], dx * (T["up0"] > 0)) < TOL_LAYER
+        else:
+            assert maxrel(T["d_trunk"], dx) < TOL_LAYER
+    # conv2 + global skip
+    dx, dw, db = _conv_bwd(T["rb15.out"], sd["conv2.weight"], sd["conv2.bias"], 1, T["d_trunk"])
+    assert maxrel(G["conv2.weight"], dw) < TOL_WGRAD
+    assert maxrel(G["conv2.bias"], db) < TOL_WGRAD
+    assert maxrel(T["d_last"], dx) < TOL_LAYER
+    dout = T["d_last"]
+    for b in range(15, -1, -1):
+        p = f"residual_blocks.{b}"
+        x_in = T[f"rb{b - 1}.out"] if b > 0 else T["out1"]
+        dy2, dg, dbeta = _bn_bwd(T[f"rb{b}.y2"], sd[p + ".bn2.weight"], sd[p + ".bn2.bias"], dout)
+        assert maxrel(T[f"rb{b}.d_y2"], dy2) < TOL_LAYER, p
+        assert maxrel(G[p + ".bn2.weight"], dg) < TOL_WGRAD and maxrel(G[p + ".bn2.bias"], dbeta) < TOL_WGRAD, p
+        dx, dw, db = _conv_bwd(T[f"rb{b}.z1"], sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], 1, T[f"rb{b}.d_y2"])
+        assert maxrel(G[p + ".conv2.weight"], dw) < TOL_WGRAD, p
+        # a bias in front of a training-mode BatchNorm has a mathematically zero gradient: the engine writes 0
+        assert float(G[p + ".conv2.bias"].abs().max()) == 0.0 and float(db.abs().max()) < 1e-3 * float(dw.abs().max())
+        assert maxrel(T[f"rb{b}.d_pre1"], dx * (T[f"rb{b}.z1"] > 0)) < TOL_LAYER, p
+        dy1, dg, dbeta = _bn_bwd(T[f"rb{b}.y1"], sd[p + ".bn1.weight"], sd[p + ".bn1.bias"], T[f"rb{b}.d_pre1"])
+        assert maxrel(T[f"rb{b}.d_y1"], dy1) < TOL_LAYER, p
+        assert maxrel(G[p + ".bn1.weight"], dg) < TOL_WGRAD and maxrel(G[p + ".bn1.bias"], dbeta) < TOL_WGRAD, p
+        dx, dw, db = _conv_bwd(x_in, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], 1, T[f"rb{b}.d_y1"])
+        assert maxrel(G[p + ".conv1.weight"], dw) < TOL_WGRAD, p
+        assert float(G[p + ".conv1.bias"].abs().max()) == 0.0
+        assert maxrel(T[f"rb{b}.d_in"], dx + dout) < TOL_LAYER, p
+        dout = T[f"rb{b}.d_in"]
+    # conv1 (9x9, 3->64) + LeakyReLU(0.2): both the block chain and the global skip feed out1
+    dpre = (dout + T["d_trunk"]) * torch.where(T["out1"] > 0, 1.0, 0.2)
+    assert maxrel(T["d_pre_conv1"], dpre) < TOL_LAYER
+    _, dw, db = _conv_bwd(lr, sd["conv1.weight"], sd["conv1.bias"], 4, T["d_pre_conv1"])
+    assert maxrel(G["conv1.weight"], dw) < TOL_WGRAD
+    assert maxrel(G["conv1.bias"], db) < TOL_WGRAD
+
+
+def test_gradients_end_to_end_direction(run, golden_dir):
+    """End to end against the reference's own gradients (golden fixtures).  Deep-layer gradients of a bf16 forward
+    differ from fp32 ones by a few percent because ReLU masks are taken on slightly different activations (the fp32
+    oracle with bf16 *storage* shows the same spread, see oracle/bf16_storage_model.py); the per-layer tests above
+    carry the 1e-2 bound, this one checks direction and scale."""
+    z = np.load(os.path.join(golden_dir, "generator_tiny.npz"))
+    for k in z.files:
+        if not k.startswith("grad/"):
+            continue
+        ref = torch.from_numpy(z[k]).double().flatten()
+        got = run["grads"][k[5:]].double().flatten()
+        cos = float(torch.dot(ref, got) / (ref.norm() * got.norm()))
+        ratio = float(got.norm() / ref.norm())
+        assert cos > 0.95 and 0.9 < ratio < 1.1, (k, cos, ratio)
+    for k in ("conv3.weight", "conv3.bias", "upsample.3.weight", "upsample.3.bias"):
+        assert maxrel(run["grads"][k], torch.from_numpy(z["grad/" + k])) < 2e-2, k
+
+
+# ------------------------------------------------------------------------------------------------ loss, Adam, shapes
+def test_reconstruction_loss_matches_reference_golden(S, golden_dir):
+    z = np.load(os.path.join(golden_dir, "recon_loss.npz"))
+    hr = torch.from_numpy(z["hr"]).cuda()
+    sr = torch.from_numpy(z["sr"]).cuda().requires_grad_(True)
+    e, t = S.ReconstructionLoss()(hr, sr)
+    (e + t).backward()
+    assert abs(float(e) - float(z["edge"])) < 1e-6 and abs(float(t) - float(z["tv"])) < 1e-7
+    assert maxrel(sr.grad, torch.from_numpy(z["grad"])) < 1e-5      # fp32 arithmetic; tolerance stated in the test
+
+
+def test_reconstruction_loss_weighted_backward(S, O):
+    torch.manual_seed(7)
+    hr = torch.rand(3, 3, 33, 41)
+    sr0 = hr + 0.05 * torch.randn_like(hr)
+    sr = sr0.clone().cuda().requires_grad_(True)
+    e, t = S.ReconstructionLoss()(hr.cuda(), sr)
+    (2.0 * e + 0.5 * t).backward()
+    src = sr0.clone().requires_grad_(True)
+    e_r, t_r = O.reconstruction_loss(hr, src)
+    (2.0 * e_r + 0.5 * t_r).backward()
+    assert abs(float(e) - float(e_r)) < 1e-6 and abs(float(t) - float(t_r)) < 1e-7
+    assert maxrel(sr.grad, src.grad) < 1e-5
+
+
+def test_adam_matches_oracle_three_steps(S, O):
+    torch.manual_seed(3)
+    g = S.SRResNet(num_residuals=1, upscale_factor=2).cuda()
+    flat = g.flat_parameters()
+    opt = S.Adam(g.parameters(), lr=1e-3)
+    p_ref = flat.detach().cpu().clone()
+    ref = O.AdamState([p_ref], lr=1e-3)
+    lr = torch.rand(1, 3, 8, 8).cuda()
+    for step in range(3):
+        out = g(lr)
+        opt.zero_grad()
+        (out * out).mean().backward()
+        gflat = g.flat_grads().detach().cpu().clone()
+        opt.step()
+        ref.step([gflat])
+        torch.cuda.synchronize()
+        assert maxrel(g.flat_parameters(), p_ref) < 1e-6, step
+    st = opt.flat_state(g)
+    assert st["step"] == 3 and maxrel(st["m"], ref.m[0]) < 1e-5
+
+
+def test_ragged_and_odd_geometries(S, O):
+    """Edge cases: extents that are not multiples of the 16x8 pixel tile, batch 1, and the reference's
+    upscale_factor quirk (int(f // 2) stages: 1 -> x1, 2 and 3 -> x2, 8 -> x16)."""
+    for (n, h, w, res, f) in [(1, 5, 7, 1, 2), (3, 17, 9, 2, 4), (1, 8, 8, 0, 1), (1, 4, 4, 1, 8), (2, 33, 20, 1, 3)]:
+        torch.manual_seed(11)
+        g = S.SRResNet(num_residuals=res, upscale_factor=f)
+        sd = {k: v.clone() for k, v in g.state_dict().items()}
+        x = torch.rand(n, 3, h, w)
+        g = g.cuda().eval()
+        with torch.no_grad():
+            y = g(x.cuda()).cpu()
+            y_ref = O.srresnet_forward(sd, x, training=False)
+        assert y.shape == y_ref.shape, (n, h, w, res, f)
+        assert maxrel(y, y_ref) < 1e-2, (n, h, w, res, f, maxrel(y, y_ref))
+        g.train()
+        y = g(x.cuda())
+        y.backward(torch.ones_like(y) * 1e-3)
+        work = O._with_grad({k: v.clone() for k, v in sd.items()})
+        yr = O.srresnet_forward(work, x, training=True)
+        assert maxrel(y.detach(), yr.detach()) < 2e-2
+        gr = torch.autograd.grad(yr, work["conv3.weight"], grad_outputs=torch.ones_like(yr) * 1e-3)[0]
+        assert maxrel(g.conv3.weight.grad, gr) < 2e-2, (n, h, w, res, f)
+
+
+def test_errors_are_python_exceptions(S):
+    g = S.SRResNet(num_residuals=1).cuda()
+    with pytest.raises(RuntimeError):
+        g(torch.rand(1, 4, 8, 8).cuda())          # wrong channel count
+    with pytest.raises(RuntimeError):
+        g(torch.rand(1, 3, 8, 8))                 # CPU tensor: no CPU path
+    with pytest.raises(NotImplementedError):
+        S.SRResNet(num_features=32)
+
+
+def test_train_generator_step_matches_oracle_sequence(S, O, golden_dir):
+    """Two consecutive train_generator steps (forward, loss, backward, Adam) against the oracle's steps."""
+    torch.manual_seed(1)
+    g = S.SRResNet()
+    sd = {k: v.clone() for k, v in g.state_dict().items()}
+    lr = torch.rand(2, 3, 16, 24)
+    hr = torch.rand(2, 3, 64, 96)
+    g = g.cuda()
+    crit = S.ReconstructionLoss()
+    opt = S.Adam(g.parameters(), lr=1e-4)
+    keys = O.trainable_keys(sd)
+    ref_opt = O.AdamState([sd[k] for k in keys], lr=1e-4)
+    for step in range(2):
+        ours = S.train_generator(g, None, lr.cuda(), hr.cuda(), None, crit, opt)
+        ref = O.train_generator_step(sd, ref_opt, lr, hr)
+        assert abs(ours[0] - ref[0]) < 5e-3 * abs(ref[0]), (step, ours, ref)
+        assert abs(ours[1] - ref[1]) < 5e-3 * abs(ref[1]), (step, ours, ref)
+        assert abs(ours[2] - ref[2]) < 5e-2 * abs(ref[2]), (step, ours, ref)
+        assert ours[3] == 0.0

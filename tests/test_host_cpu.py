@@ -1,0 +1,88 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/srgan_b200.h declares (no compute calls),
+the engine's parameter table equals the reference's state_dict layout, and the nn.Module surface keeps the reference's
+constructor / init / key conventions."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import srgan_b200 as S
+from oracle import srgan_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "srgan_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(srg_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"srg_allreduce_f64_fn"}
+    assert len(declared) >= 30
+    S.build()
+    lib = ctypes.CDLL(S._lib.SO_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    # the ctypes table binds exactly the declared set
+    assert set(S._lib.EXPORTS) == declared, set(S._lib.EXPORTS) ^ declared
+    assert S.lib().srg_abi_version() == 1
+
+
+def test_engine_parameter_table_matches_reference_state_dict():
+    torch.manual_seed(0)
+    g = S.SRResNet()
+    eng = S.models._GeneratorEngine(2, 16, 24, 16, 2, True, torch.device("cpu"))   # create() needs no device
+    table = eng.param_table()
+    named = list(g.named_parameters())
+    assert [t[0] for t in table] == [k for k, _ in named]
+    assert [t[3] for t in table] == [tuple(p.shape) for _, p in named]
+    assert sum(t[2] for t in table) == 1549315
+    offs = [t[1] for t in table]
+    assert offs == sorted(offs) and all(o % 4 == 0 for o in offs)     # 16-byte aligned slots
+    bufs = eng.buffer_table()
+    assert len(bufs) == 64 and sum(b[2] for b in bufs) == 4096
+    assert bufs[0][0] == "residual_blocks.0.bn1.running_mean" and bufs[1][0] == "residual_blocks.0.bn1.running_var"
+    assert eng.param_elems >= 1549315
+
+
+def test_module_init_and_keys_equal_oracle_restated_reference():
+    for seed, kw in [(1, {}), (5, dict(num_residuals=2, upscale_factor=2))]:
+        torch.manual_seed(seed)
+        g = S.SRResNet(**kw)
+        sd = g.state_dict()
+        ref = O.init_srresnet_state(seed, **kw)
+        assert list(sd.keys()) == list(ref.keys())
+        for k in sd:
+            assert torch.equal(sd[k].float(), ref[k].float()), k
+
+
+def test_upscale_factor_quirk_and_unsupported_widths():
+    assert S.SRResNet(upscale_factor=2).num_upsample_stages == 1
+    assert S.SRResNet(upscale_factor=3).num_upsample_stages == 1
+    assert S.SRResNet(upscale_factor=4).num_upsample_stages == 2
+    assert S.SRResNet(upscale_factor=8, num_residuals=1).num_upsample_stages == 4
+    with pytest.raises(NotImplementedError):
+        S.SRResNet(in_channels=1)
+
+
+def test_no_cpu_fallback():
+    g = S.SRResNet(num_residuals=1)
+    with pytest.raises(RuntimeError):
+        g(torch.rand(1, 3, 8, 8))
+    with pytest.raises(RuntimeError):
+        g.conv1(torch.rand(1, 3, 8, 8))            # holders never compute
+    with pytest.raises(RuntimeError):
+        S.ReconstructionLoss()(torch.rand(1, 3, 8, 8), torch.rand(1, 3, 8, 8))
+
+
+def test_state_dict_roundtrip_with_ddp_prefix():
+    """Checkpoints written by the reference carry DDP's "module." prefix (src/train.py:123-125); evaluation strips it
+    (src/evaluation.py:26-29).  Same convention works here."""
+    torch.manual_seed(2)
+    a = S.SRResNet(num_residuals=2)
+    ck = {"module." + k: v.clone() for k, v in a.state_dict().items()}
+    b = S.SRResNet(num_residuals=2)
+    b.load_state_dict({k.replace("module.", "", 1): v for k, v in ck.items()})
+    for (k1, v1), (k2, v2) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
