@@ -68,7 +68,7 @@ def run(S, O):
     c2, t2 = crit(hr.cuda(), srd)
     (c2 + t2).backward()
     grads = {k: p.grad.detach().cpu().clone() for k, p in g.named_parameters()}
-    return dict(g=g, sd=sd, lr=lr, hr=hr, y_eval=y_eval, sr=sr.detach().cpu(), com=float(com), tv=float(tv), T=T,
+    return dict(g=g, sd=sd, lr=lr, hr=hr, y_eval=y_eval, sr=sr.detach().cpu(), com=float(com.detach()), tv=float(tv.detach()), T=T,
                 dsr=srd.grad.detach().cpu(), grads=grads, state=g.state_dict())
 
 
@@ -186,7 +186,7 @@ def test_backward_layers_isolated(run):
         dx, dw, db = _conv_bwd(T[f"rb{b}.z1"], sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], 1, T[f"rb{b}.d_y2"])
         assert maxrel(G[p + ".conv2.weight"], dw) < TOL_WGRAD, p
         # a bias in front of a training-mode BatchNorm has a mathematically zero gradient: the engine writes 0
-        assert float(G[p + ".conv2.bias"].abs().max()) == 0.0 and float(db.abs().max()) < 1e-3 * float(dw.abs().max())
+        assert float(G[p + ".conv2.bias"].abs().max()) == 0.0 and float(db.abs().max()) < 1e-2 * float(dw.abs().max())
         assert maxrel(T[f"rb{b}.d_pre1"], dx * (T[f"rb{b}.z1"] > 0)) < TOL_LAYER, p
         dy1, dg, dbeta = _bn_bwd(T[f"rb{b}.y1"], sd[p + ".bn1.weight"], sd[p + ".bn1.bias"], T[f"rb{b}.d_pre1"])
         assert maxrel(T[f"rb{b}.d_y1"], dy1) < TOL_LAYER, p
