@@ -95,6 +95,38 @@ int srg_generator_use_nccl(srg_generator_t* g);
 void srg_nccl_shutdown(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Discriminator engine (src/models.py:90-120): conv 8x8 s2 p2 (3->64), then 3 x conv 4x4 s2 p1 (64->128->256->512),
+ * each followed by MaxPool2d(3,2), InstanceNorm2d (no affine, biased variance, eps 1e-5) and LeakyReLU(0.2); the last
+ * stage ends in Sigmoid.  N x 3 x H x W fp32 in -> N x 512 x h x w fp32 out.  create() fails with the same conditions
+ * that make the reference raise (a stage's conv output smaller than the 3x3 pooling window, or a final map of one
+ * element: every HR axis >= 428 and one >= 684).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct srg_discriminator srg_discriminator_t;
+int srg_discriminator_create(srg_discriminator_t** out, int N, int H, int W);
+void srg_discriminator_destroy(srg_discriminator_t* d);
+int srg_discriminator_output_hw(const srg_discriminator_t* d, int* h, int* w);
+int srg_discriminator_num_params(const srg_discriminator_t* d);
+int64_t srg_discriminator_param_elems(const srg_discriminator_t* d);
+int srg_discriminator_param_info(const srg_discriminator_t* d, int i, char* name, int name_cap, int64_t* offset,
+                                 int64_t* numel, int* ndim, int* shape4);
+size_t srg_discriminator_workspace_bytes(const srg_discriminator_t* d, int training);
+int srg_discriminator_bind(srg_discriminator_t* d, float* params, float* grads, void* workspace, size_t workspace_bytes,
+                           int training);
+int srg_discriminator_set_grads(srg_discriminator_t* d, float* grads);
+int srg_discriminator_pack(srg_discriminator_t* d, void* stream);
+/* replaces Discriminator.forward (src/models.py:117-119) */
+int srg_discriminator_forward(srg_discriminator_t* d, const float* x_nchw, float* out_nchw, void* stream);
+/* replaces autograd through the discriminator (src/train.py:195 in GAN mode, :222): dout = d(loss)/d(out).
+ * param_grads != 0: every parameter gradient is written to the bound flat `grads`; dx_nchw (may be NULL) receives
+ * d(loss)/d(input image), the path the generator's adversarial term back-propagates through. */
+int srg_discriminator_backward(srg_discriminator_t* d, const float* dout_nchw, int param_grads, float* dx_nchw,
+                               void* stream);
+/* named intermediates (parity tests): dtype 0 = bf16, 1 = fp32; dims = N,H,W,C (channel-last) */
+int srg_discriminator_num_tensors(const srg_discriminator_t* d);
+int srg_discriminator_tensor_info(const srg_discriminator_t* d, int i, char* name, int name_cap, int64_t* byte_offset,
+                                  int* dims4, int* dtype);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Losses and optimiser
  * ------------------------------------------------------------------------------------------------------------- */
 /* replaces ReconstructionLoss.forward (src/utils.py:173-241; called at src/train.py:189):

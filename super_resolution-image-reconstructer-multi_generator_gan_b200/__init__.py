@@ -8,7 +8,7 @@ package without that library raises as soon as a kernel is needed -- there is no
 """
 from . import _lib
 from ._lib import build, lib
-from .models import BatchNormParams, ConvParams, ResidualBlock, SRResNet
+from .models import BatchNormParams, ConvParams, Discriminator, ResidualBlock, SRResNet
 from .loss import ReconstructionLoss, tanh_mean
 from .optim import Adam
 from .policy import (GAN, PIXEL, MultiGeneratorPolicy, PolicyConfig, decide, gan_probability, interpolate_models,
@@ -16,11 +16,6 @@ from .policy import (GAN, PIXEL, MultiGeneratorPolicy, PolicyConfig, decide, gan
 from .train import (MultiGeneratorGAN, train_discriminator, train_discriminator_async, train_generator,
                     train_generator_async, train_one_epoch)
 from . import parallel
-
-try:  # the discriminator engine is built in the same library
-    from .discriminator import Discriminator
-except ImportError:  # pragma: no cover
-    Discriminator = None
 
 __all__ = ["SRResNet", "ResidualBlock", "Discriminator", "ReconstructionLoss", "tanh_mean", "Adam", "train_generator",
            "train_discriminator", "train_one_epoch", "MultiGeneratorGAN", "MultiGeneratorPolicy", "PolicyConfig",

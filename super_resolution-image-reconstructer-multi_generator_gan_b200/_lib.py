@@ -99,6 +99,22 @@ EXPORTS = {
     "srg_nccl_allreduce_f32": (c_int, [c_void_p, c_int64, c_void_p]),
     "srg_generator_use_nccl": (c_int, [c_void_p]),
     "srg_nccl_shutdown": (None, []),
+    "srg_discriminator_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
+    "srg_discriminator_destroy": (None, [c_void_p]),
+    "srg_discriminator_output_hw": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "srg_discriminator_num_params": (c_int, [c_void_p]),
+    "srg_discriminator_param_elems": (c_int64, [c_void_p]),
+    "srg_discriminator_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int64),
+                                             POINTER(c_int), POINTER(c_int)]),
+    "srg_discriminator_workspace_bytes": (c_size_t, [c_void_p, c_int]),
+    "srg_discriminator_bind": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+    "srg_discriminator_set_grads": (c_int, [c_void_p, c_void_p]),
+    "srg_discriminator_pack": (c_int, [c_void_p, c_void_p]),
+    "srg_discriminator_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "srg_discriminator_backward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "srg_discriminator_num_tensors": (c_int, [c_void_p]),
+    "srg_discriminator_tensor_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int),
+                                              POINTER(c_int)]),
     "srg_recon_loss_scratch_bytes": (c_size_t, []),
     "srg_recon_loss_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),

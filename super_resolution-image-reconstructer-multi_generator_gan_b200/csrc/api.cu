@@ -7,6 +7,7 @@
 
 #include "conv_gemm.cuh"
 #include "elementwise.cuh"
+#include "discriminator.cuh"
 #include "generator.cuh"
 
 using namespace srg;
@@ -190,6 +191,69 @@ int srg_generator_use_nccl(srg_generator_t* g) {
 void srg_nccl_shutdown(void) {
   if (g_nccl.comm) g_nccl.comm_destroy(g_nccl.comm);
   g_nccl.comm = nullptr;
+}
+
+// ---- discriminator ------------------------------------------------------------------------------------------------
+static inline DiscriminatorEngine* D(srg_discriminator_t* d) { return reinterpret_cast<DiscriminatorEngine*>(d); }
+static inline const DiscriminatorEngine* DC(const srg_discriminator_t* d) { return reinterpret_cast<const DiscriminatorEngine*>(d); }
+int srg_discriminator_create(srg_discriminator_t** out, int N, int H, int W) {
+  if (out == nullptr) { set_error("srg_discriminator_create: null out"); return -1; }
+  DiscriminatorEngine* d = discriminator_create(N, H, W);
+  if (d == nullptr) return -2;
+  *out = reinterpret_cast<srg_discriminator_t*>(d);
+  return 0;
+}
+void srg_discriminator_destroy(srg_discriminator_t* d) { delete D(d); }
+int srg_discriminator_output_hw(const srg_discriminator_t* d, int* h, int* w) {
+  if (h) *h = DC(d)->st[3].Hp;
+  if (w) *w = DC(d)->st[3].Wp;
+  return 0;
+}
+int srg_discriminator_num_params(const srg_discriminator_t* d) { return int(DC(d)->params.size()); }
+int64_t srg_discriminator_param_elems(const srg_discriminator_t* d) { return DC(d)->param_elems; }
+int srg_discriminator_param_info(const srg_discriminator_t* d, int i, char* name, int name_cap, int64_t* offset,
+                                 int64_t* numel, int* ndim, int* shape4) {
+  const DiscriminatorEngine* e = DC(d);
+  if (i < 0 || i >= int(e->params.size())) { set_error("param index out of range"); return -3; }
+  const ParamInfo& p = e->params[size_t(i)];
+  copy_name(p.name, name, name_cap);
+  if (offset) *offset = p.offset;
+  if (numel) *numel = p.numel;
+  if (ndim) *ndim = p.ndim;
+  if (shape4) for (int k = 0; k < 4; ++k) shape4[k] = p.shape[k];
+  return 0;
+}
+size_t srg_discriminator_workspace_bytes(const srg_discriminator_t* d, int training) {
+  return training ? DC(d)->workspace_bytes_train : DC(d)->workspace_bytes_eval;
+}
+int srg_discriminator_bind(srg_discriminator_t* d, float* params, float* grads, void* workspace, size_t workspace_bytes,
+                           int training) {
+  return discriminator_bind(D(d), params, grads, workspace, workspace_bytes, training);
+}
+int srg_discriminator_set_grads(srg_discriminator_t* d, float* grads) {
+  if (grads == nullptr) { set_error("srg_discriminator_set_grads: null buffer"); return -22; }
+  D(d)->grads = grads;
+  return 0;
+}
+int srg_discriminator_pack(srg_discriminator_t* d, void* stream) { return discriminator_pack(D(d), S(stream)); }
+int srg_discriminator_forward(srg_discriminator_t* d, const float* x_nchw, float* out_nchw, void* stream) {
+  return discriminator_forward(D(d), x_nchw, out_nchw, 1, S(stream));
+}
+int srg_discriminator_backward(srg_discriminator_t* d, const float* dout_nchw, int param_grads, float* dx_nchw,
+                               void* stream) {
+  return discriminator_backward(D(d), dout_nchw, param_grads, dx_nchw, S(stream));
+}
+int srg_discriminator_num_tensors(const srg_discriminator_t* d) { return int(DC(d)->tensors.size()); }
+int srg_discriminator_tensor_info(const srg_discriminator_t* d, int i, char* name, int name_cap, int64_t* byte_offset,
+                                  int* dims4, int* dtype) {
+  const DiscriminatorEngine* e = DC(d);
+  if (i < 0 || i >= int(e->tensors.size())) { set_error("tensor index out of range"); return -3; }
+  const TensorInfo& t = e->tensors[size_t(i)];
+  copy_name(t.name, name, name_cap);
+  if (byte_offset) *byte_offset = t.byte_offset;
+  if (dims4) for (int k = 0; k < 4; ++k) dims4[k] = t.dims[k];
+  if (dtype) *dtype = t.dtype;
+  return 0;
 }
 
 size_t srg_recon_loss_scratch_bytes(void) { return size_t(loss_scratch_doubles()) * 8; }

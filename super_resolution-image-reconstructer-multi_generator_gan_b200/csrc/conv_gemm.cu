@@ -297,6 +297,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = apply_act<ACT_LRELU>(f[j], p.slope);
         }
+        if (p.out_mode == OUT_NHWC_F32) {
+          // fp32 output: every thread owns 32 consecutive channels of one pixel (128 contiguous bytes)
+          const int th = m / p.TW;
+          const int h = h0 + th, w = w0 + (m - th * p.TW);
+          if (h < p.H && w < p.W) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                                  ((size_t(n) * p.H + h) * p.W + w) * p.cout_total + nblk * BLOCK_N + hf * 32);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) o[g] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+          continue;
+        }
         const uint32_t row_off = uint32_t(m) * 128u;
         const uint32_t sw = uint32_t(m & 7);
         if (p.aux_mode) {
@@ -502,7 +516,10 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     int rc = encode_map_bf16(&p.w_map, a.weights, 2, dims, strides, box);
     if (rc) return rc;
   }
-  if (!fold) {
+  if (a.out_mode == OUT_NHWC_F32) {
+    for (int q = 0; q < 4; ++q) p.out_map[q] = p.in_map[0];
+    p.aux_map = p.in_map[0];
+  } else if (!fold) {
     uint32_t box[4] = {64, uint32_t(a.TW), uint32_t(a.TH), 1};
     if (a.out_mode == OUT_PIXEL_SHUFFLE) {
       // view q=(i,j) of the HR tensor [N,2H,2W,64]: pixel (2h+i, 2w+j)

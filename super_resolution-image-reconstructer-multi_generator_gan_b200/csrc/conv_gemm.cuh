@@ -17,6 +17,7 @@ enum ConvOutMode : int {
   OUT_NHWC = 0,          // bf16 [N,H,W,cout_total]
   OUT_PIXEL_SHUFFLE = 1, // bf16 [N,2H,2W,64]; GEMM n-block q=(i,j) -> pixel (2h+i, 2w+j)
   OUT_FOLD9_NCHW = 2,    // fp32 [N,3,H,W]; GEMM n = s*3+co partial sums, shift-accumulated over s (9x9, Cout=3)
+  OUT_NHWC_F32 = 3,      // fp32 [N,H,W,cout_total] (direct 128-bit stores; discriminator conv outputs)
 };
 
 // One view of the (NHWC bf16) input that a K-chunk is loaded from. A plain tensor uses one view;

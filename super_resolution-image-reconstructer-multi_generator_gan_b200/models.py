@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from ._flat import _FlatModule
 from ._lib import check, stream_ptr
 
 
@@ -202,7 +203,7 @@ class _GeneratorFn(torch.autograd.Function):
         dsr = dsr.contiguous()
         if dsr.dtype != torch.float32:
             dsr = dsr.float()
-        flat_g = module._grad_buffer_for_backward()
+        flat_g = module._grad_buffer_for_backward(eng)
         check(L.srg_generator_set_grads(eng.handle, c_void_p(flat_g.data_ptr())))
         check(L.srg_generator_backward(eng.handle, c_void_p(dsr.data_ptr()), stream_ptr()), "srg_generator_backward")
         eng.busy = False
@@ -211,7 +212,7 @@ class _GeneratorFn(torch.autograd.Function):
         return (None, None, None) + grads
 
 
-class SRResNet(nn.Module):
+class SRResNet(_FlatModule):
     """Drop-in for the reference's SRResNet (src/models.py:44-87).
 
     conv 9x9 (3->64) + LeakyReLU(0.2) -> ``num_residuals`` x [conv3x3, BN, ReLU, conv3x3, BN, +skip] -> conv3x3 ->
@@ -239,136 +240,15 @@ class SRResNet(nn.Module):
         self.conv3 = ConvParams(num_features, in_channels, 9, padding=4)
         self._reset_runtime()
 
-    # ---- runtime state (never pickled / deep-copied) -----------------------------------------------------------
-    def _reset_runtime(self):
-        object.__setattr__(self, "_rt", {"flat": None, "flat_buf": None, "nbt": None, "engines": {}, "grad_flat": None,
-                                          "grad_hook": None, "sync_bn": False, "last_engine": None})
-
-    def __getstate__(self):
-        st = self.__dict__.copy()
-        st.pop("_rt", None)
-        return st
-
-    def __setstate__(self, st):
-        self.__dict__.update(st)
-        self._reset_runtime()
-
-    def __deepcopy__(self, memo):
-        import copy
-        cls = self.__class__
-        new = cls.__new__(cls)
-        memo[id(self)] = new
-        for k, v in self.__dict__.items():
-            if k == "_rt":
-                continue
-            object.__setattr__(new, k, copy.deepcopy(v, memo))
-        new._reset_runtime()
-        return new
-
-    def _apply(self, fn, recurse=True):
-        out = super()._apply(fn, recurse)
-        self._rt["flat"] = None           # parameters were re-materialised: re-flatten lazily
-        return out
-
-    # ---- flat parameter storage ----------------------------------------------------------------------------------
     def _probe_engine(self, device) -> _GeneratorEngine:
         rt = self._rt
         if rt.get("probe") is None:
             rt["probe"] = _GeneratorEngine(1, 8, 8, self.num_residuals, self.num_upsample_stages, False, device)
         return rt["probe"]
 
-    def _flatten(self, device: torch.device):
-        rt = self._rt
-        if rt["flat"] is not None and rt["flat"].device == device:
-            base = rt["flat"].data_ptr()
-            ok = True
-            for p, (name, off, n, shape) in zip(rt["plist"], self._ptable):
-                if p.data_ptr() != base + 4 * off:
-                    ok = False
-                    break
-            if ok:
-                return
-        named = dict(self.named_parameters())
-        named_buf = dict(self.named_buffers())
+    def _tables(self, device):
         probe = self._probe_engine(device)
-        ptable = probe.param_table()
-        btable = probe.buffer_table()
-        if [t[0] for t in ptable] != list(named.keys()):
-            raise RuntimeError("engine parameter table does not match the module's parameters() order")
-        with torch.no_grad():
-            flat = torch.zeros(probe.param_elems, dtype=torch.float32, device=device)
-            for name, off, n, shape in ptable:
-                p = named[name]
-                if tuple(p.shape) != shape:
-                    raise RuntimeError(f"parameter {name} has shape {tuple(p.shape)}, engine expects {shape}")
-                view = flat[off:off + n].view(shape)
-                view.copy_(p.data)
-                p.data = view
-            fbuf = torch.zeros(max(probe.buffer_elems, 1), dtype=torch.float32, device=device)
-            for name, off, n in btable:
-                view = fbuf[off:off + n]
-                view.copy_(named_buf[name])
-                self._set_buffer(name, view)
-            nbt_names = [k for k in named_buf if k.endswith("num_batches_tracked")]
-            nbt = torch.zeros(max(len(nbt_names), 1), dtype=torch.long, device=device)
-            for i, name in enumerate(nbt_names):
-                nbt[i] = named_buf[name].to(device)
-                self._set_buffer(name, nbt[i])
-        rt["flat"], rt["flat_buf"], rt["nbt"] = flat, fbuf, nbt
-        rt["grad_flat"] = None
-        rt["grad_store"] = None
-        rt["plist"] = [named[t[0]] for t in ptable]
-        self._ptable = ptable
-        for p in rt["plist"]:
-            p._srg_owner = weakref.ref(self)
-        for engs in rt["engines"].values():
-            for e in engs:
-                e.bound_key = None
-
-    def _set_buffer(self, dotted: str, tensor: torch.Tensor):
-        mod = self
-        parts = dotted.split(".")
-        for part in parts[:-1]:
-            mod = getattr(mod, part)
-        mod._buffers[parts[-1]] = tensor
-
-    def flat_parameters(self) -> torch.Tensor:
-        """The flat fp32 buffer every parameter is a view of (engine layout)."""
-        dev = next(self.parameters()).device
-        self._flatten(dev)
-        return self._rt["flat"]
-
-    def flat_grads(self) -> Optional[torch.Tensor]:
-        """Flat gradient buffer written by the last backward (same layout as flat_parameters), or None."""
-        return self._rt["grad_flat"]
-
-    def _grad_buffer_for_backward(self) -> torch.Tensor:
-        rt = self._rt
-        flat = rt["flat"]
-        g = rt.get("grad_store")
-        if g is None or g.device != flat.device or g.numel() != flat.numel():
-            g = torch.empty_like(flat)
-            rt["grad_store"] = g
-        else:
-            # gradient accumulation (a second backward before zero_grad): never alias live .grad views
-            base, end = g.data_ptr(), g.data_ptr() + 4 * g.numel()
-            for p in rt["plist"]:
-                if p.grad is not None and base <= p.grad.data_ptr() < end:
-                    g = torch.empty_like(flat)
-                    break
-        return g
-
-    def _after_backward(self, flat_g: torch.Tensor):
-        rt = self._rt
-        rt["grad_flat"] = flat_g
-        hook = rt["grad_hook"]
-        if hook is not None:
-            hook(self, flat_g)
-
-    def set_grad_hook(self, hook):
-        """hook(module, flat_grads) runs right after the engine's backward enqueued its kernels (data-parallel
-        gradient all-reduce is installed here, see parallel.py)."""
-        self._rt["grad_hook"] = hook
+        return probe.param_table(), probe.buffer_table(), probe.param_elems, probe.buffer_elems
 
     # ---- engines ---------------------------------------------------------------------------------------------------
     def _engine(self, N: int, H: int, W: int, training: bool, device, need_grad: bool) -> _GeneratorEngine:
@@ -439,9 +319,9 @@ class SRResNet(nn.Module):
         rt = self._rt
         need_grad = self.training and torch.is_grad_enabled()
         eng = self._engine(N, H, W, self.training, x.device, need_grad)
-        if self.training and rt.get("grad_store") is None:
-            rt["grad_store"] = torch.empty_like(rt["flat"])
-        eng.bind(rt["flat"], rt["grad_store"] if self.training else None, rt["flat_buf"])
+        if self.training and getattr(eng, "grad_flat", None) is None:
+            eng.grad_flat = torch.empty_like(rt["flat"])
+        eng.bind(rt["flat"], eng.grad_flat if self.training else None, rt["flat_buf"])
         L = _lib.lib()
         check(L.srg_generator_pack(eng.handle, stream_ptr()), "srg_generator_pack")
         rt["last_engine"] = eng
@@ -458,3 +338,210 @@ class SRResNet(nn.Module):
                                       1 if self.training else 0, 1 if self.training else 0, stream_ptr()),
               "srg_generator_forward")
         return sr
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Discriminator
+# ----------------------------------------------------------------------------------------------------------------
+class _DiscriminatorEngine:
+    """One srg_discriminator_t bound to a workspace: fixed (N, H, W) geometry, one in-flight forward at a time."""
+
+    def __init__(self, N: int, H: int, W: int, training: bool, device):
+        L = _lib.lib()
+        self.handle = c_void_p()
+        rc = L.srg_discriminator_create(byref(self.handle), N, H, W)
+        if rc != 0:
+            msg = L.srg_last_error()
+            # same failure mode as the reference (a RuntimeError out of MaxPool2d / InstanceNorm2d, SURVEY Appendix E)
+            raise RuntimeError(msg.decode() if msg else f"srg_discriminator_create failed ({rc})")
+        self.N, self.H, self.W, self.training, self.device = N, H, W, training, device
+        self.busy = False
+        self.ws = None
+        self.bound_key = None
+        self.param_elems = int(L.srg_discriminator_param_elems(self.handle))
+        oh, ow = c_int(), c_int()
+        L.srg_discriminator_output_hw(self.handle, byref(oh), byref(ow))
+        self.out_hw = (oh.value, ow.value)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().srg_discriminator_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def param_table(self):
+        L = _lib.lib()
+        out = []
+        name = create_string_buffer(128)
+        off, numel, ndim = c_int64(), c_int64(), c_int()
+        shape = (c_int * 4)()
+        for i in range(L.srg_discriminator_num_params(self.handle)):
+            check(L.srg_discriminator_param_info(self.handle, i, name, 128, byref(off), byref(numel), byref(ndim), shape))
+            out.append((name.value.decode(), off.value, numel.value, tuple(shape[k] for k in range(ndim.value))))
+        return out
+
+    def tensor_table(self):
+        L = _lib.lib()
+        out = {}
+        name = create_string_buffer(128)
+        off, dt = c_int64(), c_int()
+        dims = (c_int * 4)()
+        for i in range(L.srg_discriminator_num_tensors(self.handle)):
+            check(L.srg_discriminator_tensor_info(self.handle, i, name, 128, byref(off), dims, byref(dt)))
+            out[name.value.decode()] = (off.value, tuple(dims[k] for k in range(4)), dt.value)
+        return out
+
+    def bind(self, flat_params: torch.Tensor, flat_grads: Optional[torch.Tensor]):
+        L = _lib.lib()
+        key = flat_params.data_ptr()
+        if self.ws is None:
+            nbytes = int(L.srg_discriminator_workspace_bytes(self.handle, 1 if self.training else 0))
+            self.ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+        if key != self.bound_key:
+            base = self.ws.data_ptr()
+            aligned = (base + 1023) & ~1023
+            check(L.srg_discriminator_bind(self.handle, c_void_p(flat_params.data_ptr()),
+                                           c_void_p(flat_grads.data_ptr()) if flat_grads is not None else None,
+                                           c_void_p(aligned), self.ws.numel() - (aligned - base), 1 if self.training else 0),
+                  "srg_discriminator_bind")
+            self.ws_base = aligned
+            self.bound_key = key
+
+    def named_tensor(self, name: str) -> torch.Tensor:
+        off, dims, dt = self.tensor_table()[name]
+        n = dims[0] * dims[1] * dims[2] * dims[3]
+        start = (self.ws_base - self.ws.data_ptr()) + off
+        if dt == 0:
+            return self.ws[start:start + 2 * n].view(torch.bfloat16).view(*dims)
+        return self.ws[start:start + 4 * n].view(torch.float32).view(*dims)
+
+
+class _DiscriminatorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, eng, x, *params):
+        L = _lib.lib()
+        out = torch.empty(eng.N, 512, eng.out_hw[0], eng.out_hw[1], dtype=torch.float32, device=x.device)
+        check(L.srg_discriminator_forward(eng.handle, c_void_p(x.data_ptr()), c_void_p(out.data_ptr()), stream_ptr()),
+              "srg_discriminator_forward")
+        ctx.module_ref = weakref.ref(module)
+        ctx.eng = eng
+        ctx.n_params = len(params)
+        ctx.x_shape = tuple(x.shape)
+        ctx.param_grads = module._rt.get("param_grads", True)
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        module = ctx.module_ref()
+        eng = ctx.eng
+        if dout is None or module is None:
+            eng.busy = False
+            return (None,) * (3 + ctx.n_params)
+        L = _lib.lib()
+        dout = dout.contiguous()
+        if dout.dtype != torch.float32:
+            dout = dout.float()
+        want_dx = ctx.needs_input_grad[2]
+        want_pg = ctx.param_grads and any(ctx.needs_input_grad[3:])
+        dx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dout.device) if want_dx else None
+        flat_g = None
+        if want_pg:
+            flat_g = module._grad_buffer_for_backward(eng)
+            check(L.srg_discriminator_set_grads(eng.handle, c_void_p(flat_g.data_ptr())))
+        check(L.srg_discriminator_backward(eng.handle, c_void_p(dout.data_ptr()), 1 if want_pg else 0,
+                                           c_void_p(dx.data_ptr()) if dx is not None else None, stream_ptr()),
+              "srg_discriminator_backward")
+        eng.busy = False
+        if want_pg:
+            module._after_backward(flat_g)
+            grads = tuple(flat_g[off:off + n].view(shape) for (_, off, n, shape) in module._ptable)
+        else:
+            grads = (None,) * ctx.n_params
+        return (None, None, dx) + grads
+
+
+class Discriminator(_FlatModule):
+    """Drop-in for the reference's Discriminator (src/models.py:90-120): ``self.model`` is an nn.Sequential whose
+    indices 0, 4, 8, 12 hold the conv parameters (state_dict keys ``model.0.weight`` ...).  Input N x 3 x H x W fp32
+    CUDA -> N x 512 x h x w sigmoid map.  Raises RuntimeError for inputs the reference network cannot process (every
+    axis must be >= 428 and one >= 684)."""
+
+    def __init__(self, input_channels: int = 3, num_filters: int = 64):
+        super().__init__()
+        if input_channels != 3 or num_filters != 64:
+            raise NotImplementedError("libsrgan_b200 implements the reference configuration input_channels=3, num_filters=64")
+        nf = num_filters
+        layers: List[nn.Module] = []
+        specs = [(input_channels, nf, 8, 2), (nf, nf * 2, 4, 1), (nf * 2, nf * 4, 4, 1), (nf * 4, nf * 8, 4, 1)]
+        for i, (cin, cout, k, pad) in enumerate(specs):
+            layers += [ConvParams(cin, cout, k, stride=2, padding=pad), _Stateless("MaxPool2d(kernel_size=3, stride=2)"),
+                       _Stateless(f"InstanceNorm2d({cout})")]
+            layers.append(_Stateless("LeakyReLU(0.2)") if i < 3 else _Stateless("Sigmoid()"))
+        self.model = nn.Sequential(*layers)
+        self._reset_runtime()
+
+    def _tables(self, device):
+        rt = self._rt
+        if rt.get("probe") is None:
+            rt["probe"] = _DiscriminatorEngine(1, 428, 684, False, device)
+        probe = rt["probe"]
+        return probe.param_table(), [], probe.param_elems, 0
+
+    def _engine(self, N, H, W, training, device):
+        pool = self._rt["engines"].setdefault((N, H, W, training), [])
+        for e in pool:
+            if not e.busy:
+                return e
+        eng = _DiscriminatorEngine(N, H, W, training, device)
+        pool.append(eng)
+        return eng
+
+    def last_engine(self):
+        return self._rt["last_engine"]
+
+    class _InputGradOnly:
+        def __init__(self, module):
+            self.m = module
+
+        def __enter__(self):
+            self.prev = self.m._rt.get("param_grads", True)
+            self.m._rt["param_grads"] = False
+
+        def __exit__(self, *a):
+            self.m._rt["param_grads"] = self.prev
+
+    def input_grad_only(self):
+        """Context manager: forwards recorded inside back-propagate to the INPUT only (the generator's adversarial
+        term, src/train.py:184-190, needs d(D(sr))/d(sr); the reference also fills D's .grad there and then discards
+        it with the next d_optimizer.zero_grad())."""
+        return Discriminator._InputGradOnly(self)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("Discriminator (libsrgan_b200) runs on a CUDA device only; there is no CPU path")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError(f"expected an N x 3 x H x W input, got {tuple(x.shape)}")
+        xc = x.contiguous()
+        if xc.dtype != torch.float32:
+            xc = xc.float()
+        N, _, H, W = xc.shape
+        self._flatten(xc.device)
+        rt = self._rt
+        need_grad = torch.is_grad_enabled() and (xc.requires_grad or any(p.requires_grad for p in rt["plist"]))
+        eng = self._engine(N, H, W, need_grad, xc.device)
+        if need_grad and getattr(eng, "grad_flat", None) is None:
+            eng.grad_flat = torch.empty_like(rt["flat"])
+        eng.bind(rt["flat"], eng.grad_flat if need_grad else None)
+        L = _lib.lib()
+        check(L.srg_discriminator_pack(eng.handle, stream_ptr()), "srg_discriminator_pack")
+        rt["last_engine"] = eng
+        if need_grad:
+            eng.busy = True
+            return _DiscriminatorFn.apply(self, eng, xc, *rt["plist"])
+        out = torch.empty(N, 512, eng.out_hw[0], eng.out_hw[1], dtype=torch.float32, device=xc.device)
+        check(L.srg_discriminator_forward(eng.handle, c_void_p(xc.data_ptr()), c_void_p(out.data_ptr()), stream_ptr()),
+              "srg_discriminator_forward")
+        return out

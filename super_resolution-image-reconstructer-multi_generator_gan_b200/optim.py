@@ -51,27 +51,20 @@ class Adam(torch.optim.Optimizer):
                     raise RuntimeError("optim.Adam: run the model once (or call .flat_parameters()) before step()")
             for owner in self._owners(group):
                 flat = owner.flat_parameters()
-                gflat = owner.flat_grads()
-                if gflat is None:
-                    continue                      # no backward since the last flatten: nothing to do
+                plist, ptable = owner._rt["plist"], owner._ptable
+                if all(p.grad is None for p in plist):
+                    continue                      # no backward since zero_grad(): nothing to do
                 st = self._flat_state.get(id(owner))
-                if st is None or st["m"].data_ptr() == 0 or st["m"].numel() != flat.numel() or st["m"].device != flat.device:
+                if st is None or st["m"].numel() != flat.numel() or st["m"].device != flat.device:
                     st = {"m": torch.zeros_like(flat), "v": torch.zeros_like(flat), "step": 0 if st is None else st["step"]}
                     self._flat_state[id(owner)] = st
-                # every live .grad must be a view of the flat gradient buffer (it is, unless the user replaced it)
-                base = gflat.data_ptr()
-                ok = True
-                for p, (_, off, n, _) in zip(owner._rt["plist"], owner._ptable):
-                    if p.grad is None or p.grad.data_ptr() != base + 4 * off:
-                        ok = False
-                        break
-                if not ok:
-                    # gather user-modified / accumulated gradients back into flat layout with one copy per tensor
-                    g2 = torch.zeros_like(flat)
-                    for p, (_, off, n, shape) in zip(owner._rt["plist"], owner._ptable):
+                gflat = owner.flat_grads()
+                if gflat is None:
+                    # user-replaced gradients: gather them back into flat layout (one copy per tensor)
+                    gflat = torch.zeros_like(flat)
+                    for p, (_, off, n, shape) in zip(plist, ptable):
                         if p.grad is not None:
-                            g2[off:off + n].view(shape).copy_(p.grad)
-                    gflat = g2
+                            gflat[off:off + n].view(shape).copy_(p.grad)
                 st["step"] += 1
                 b1, b2 = group["betas"]
                 check(L.srg_adam_step(c_void_p(flat.data_ptr()), c_void_p(gflat.data_ptr()), c_void_p(st["m"].data_ptr()),

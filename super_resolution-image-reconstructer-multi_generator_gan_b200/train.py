@@ -40,7 +40,8 @@ def train_generator_async(generator, discriminator, lr_imgs, hr_imgs, vgg_extrac
     sr_images = generator(lr_imgs)
     com_loss, tv_loss = g_criterion(hr_imgs, sr_images)
     if gan_mode:
-        fake_preds = discriminator(sr_images)
+        with discriminator.input_grad_only():             # d(D(sr))/d(sr) only; D's own .grad is never used here
+            fake_preds = discriminator(sr_images)
         with torch.no_grad():
             real_preds = discriminator(hr_imgs)
         g_d_loss = tanh_mean(real_preds, fake_preds)      # mean(tanh(real - fake)), src/train.py:190
@@ -69,8 +70,11 @@ def train_discriminator_async(discriminator, generator, hr_imgs, lr_imgs, d_opti
     generator.eval()
     with torch.no_grad():
         sr_imgs = generator(lr_imgs)
-    real_preds = discriminator(hr_imgs)
-    fake_preds = discriminator(sr_imgs)
+    # D(hr) and D(sr) as ONE pass over the concatenated batch: every op of the discriminator is per-sample
+    # (InstanceNorm, no BatchNorm), so the two halves equal the reference's two separate calls (src/train.py:215-216)
+    n = hr_imgs.shape[0]
+    preds = discriminator(torch.cat([hr_imgs.float(), sr_imgs], dim=0))
+    real_preds, fake_preds = preds[:n], preds[n:]
     d_loss = tanh_mean(fake_preds, real_preds)            # mean(tanh(fake - real)), src/train.py:218
     d_optimizer.zero_grad()
     d_loss.backward()

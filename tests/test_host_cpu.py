@@ -86,3 +86,24 @@ def test_state_dict_roundtrip_with_ddp_prefix():
     b.load_state_dict({k.replace("module.", "", 1): v for k, v in ck.items()})
     for (k1, v1), (k2, v2) in zip(a.state_dict().items(), b.state_dict().items()):
         assert k1 == k2 and torch.equal(v1, v2)
+
+
+def test_discriminator_engine_tables_and_size_rule():
+    torch.manual_seed(3)
+    d = S.Discriminator()
+    ref = O.init_discriminator_state(3)
+    assert list(d.state_dict().keys()) == list(ref.keys())
+    for k in ref:
+        assert torch.equal(d.state_dict()[k], ref[k]), k
+    eng = S.models._DiscriminatorEngine(2, 512, 1024, True, torch.device("cpu"))     # create() needs no device
+    assert eng.out_hw == O.discriminator_output_hw(512, 1024) == (1, 3)
+    table = eng.param_table()
+    assert [t[0] for t in table] == [k for k, _ in d.named_parameters()]
+    assert sum(t[2] for t in table) == 2765760
+    for hw in ((684, 684), (428, 684), (940, 940), (512, 1024)):
+        assert S.models._DiscriminatorEngine(1, hw[0], hw[1], False, torch.device("cpu")).out_hw == O.discriminator_output_hw(*hw)
+    for bad in ((384, 384), (512, 512), (256, 256), (427, 1024)):
+        with pytest.raises(RuntimeError):
+            S.models._DiscriminatorEngine(1, bad[0], bad[1], False, torch.device("cpu"))
+        with pytest.raises(RuntimeError):
+            O.discriminator_output_hw(*bad)
