@@ -39,15 +39,28 @@ def parse():
     ap.add_argument("--generators", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16, help="LR patches per GPU per step")
     ap.add_argument("--lr-size", type=int, default=96)
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "gan-native"],
+                    help="cfg2: BASELINE configs[1] (default).  gan-native: D update + all generators in GAN mode at the "
+                         "reference's native geometry (LR 128x256, batch 12), where its Discriminator is valid")
     ap.add_argument("--ref-sample-batch", type=int, default=4, help="patches per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
+def geometry(a):
+    if a.workload == "gan-native":
+        return 12, 128, 256                  # batch 12 (src/train.py:94), LR 128x256 (src/transformers.py:74)
+    return a.batch, a.lr_size, a.lr_size
+
+
 def workload_name(a):
+    b, h, w = geometry(a)
+    if a.workload == "gan-native":
+        return (f"gan-native: train_discriminator + {a.generators} generators x train_generator in GAN mode "
+                f"(SRResNet fwd+bwd, ReconstructionLoss + tanh adversarial term through D, Adam), {b}x3x{h}x{w} LR -> x4 HR per GPU")
     return (f"cfg2: {a.generators} generators x train_generator (SRResNet fwd+bwd + ReconstructionLoss + Adam), "
-            f"{a.batch}x3x{a.lr_size}x{a.lr_size} LR -> x4 HR per GPU, pixel-loss mode (reference D invalid at this HR size)")
+            f"{b}x3x{h}x{w} LR -> x4 HR per GPU, pixel-loss mode (reference D invalid at this HR size)")
 
 
 def peaks():
@@ -179,7 +192,8 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    K, B, HW = a.generators, a.batch, a.lr_size
+    K = a.generators
+    B, LH, LW = geometry(a)
     gens, opts = [], []
     for s in range(K):
         torch.manual_seed(s)
@@ -188,17 +202,23 @@ def run_ours(a):
         gens.append(g)
         opts.append(S.Adam(g.parameters(), lr=1e-4))
     crit = S.ReconstructionLoss()
+    disc, d_opt = None, None
+    if a.workload == "gan-native":
+        torch.manual_seed(100)
+        disc = S.Discriminator().to(dev)
+        disc.flat_parameters()
+        d_opt = S.Adam(disc.parameters(), lr=5e-5)
     loss_ar = None
     if world > 1:
-        S.parallel.data_parallel(gens, sync_batchnorm=True)
+        S.parallel.data_parallel(gens + ([disc] if disc is not None else []), sync_batchnorm=True)
         loss_ar = S.parallel.mean_over_ranks()
-    policy = S.MultiGeneratorPolicy(S.PolicyConfig(num_generators=K, force=S.PIXEL, seed=0))
-    trainer = S.MultiGeneratorGAN(gens, opts, crit, discriminator=None, d_optimizer=None, policy=policy,
+    policy = S.MultiGeneratorPolicy(S.PolicyConfig(num_generators=K, force=S.GAN if disc is not None else S.PIXEL, seed=0))
+    trainer = S.MultiGeneratorGAN(gens, opts, crit, discriminator=disc, d_optimizer=d_opt, policy=policy,
                                   loss_allreduce=loss_ar)
 
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    lr_host = torch.rand(B, 3, HW, HW, generator=gen).pin_memory()
-    hr_host = torch.rand(B, 3, 4 * HW, 4 * HW, generator=gen).pin_memory()
+    lr_host = torch.rand(B, 3, LH, LW, generator=gen).pin_memory()
+    hr_host = torch.rand(B, 3, 4 * LH, 4 * LW, generator=gen).pin_memory()
     lr_dev, hr_dev = lr_host.to(dev), hr_host.to(dev)
 
     def barrier():
@@ -258,7 +278,7 @@ def run_ours(a):
         k_n += n
         g.profile_enable(False)
     pk, pk_src = peaks()
-    flop_per_launch = TRUNK_CONV_FLOP_PER_PIXEL * B * HW * HW
+    flop_per_launch = TRUNK_CONV_FLOP_PER_PIXEL * B * LH * LW
     avg_ms = k_ms / max(k_n, 1)
     achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12 if k_n else 0.0
     peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
@@ -267,7 +287,7 @@ def run_ours(a):
                 "launches_timed": k_n, "avg_launch_us": avg_ms * 1e3, "kernel_share_of_step": (k_ms / prof_steps) / ms_per_step,
                 "flop_per_launch": flop_per_launch, "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "timed_over": f"{prof_steps} extra steps right after the timed region (per-launch CUDA events on the launch stream)"}
-    step_flop = FLOP_PER_LR_PIXEL_FWD_BWD * B * HW * HW * K
+    step_flop = FLOP_PER_LR_PIXEL_FWD_BWD * B * LH * LW * K      # generator convs only (D adds ~4 % at gan-native)
     whole_step_tflops = step_flop / (ms_per_step * 1e-3) / 1e12
 
     e2e = None
@@ -281,7 +301,7 @@ def run_ours(a):
     last = trainer.step(lr_dev, hr_dev).cpu().tolist()
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.workload == "cfg2":
         v, dt, cores, sample = cpu_reference_steps(a, 2, 1)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "s_per_step": dt}
 
@@ -291,7 +311,7 @@ def run_ours(a):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(a), "generators": K, "batch_per_gpu": B, "global_batch": B * world,
-                       "lr_hw": [HW, HW], "upscale": 4, "parallelism": f"dp{world}",
+                       "lr_hw": [LH, LW], "upscale": 4, "parallelism": f"dp{world}",
                        "l2": "per-step working set (~2.5 GB of activations per generator) exceeds the 126 MB L2; no flush needed",
                        "generator_passes_per_sec": value * K, "whole_step_algorithmic_tflops": whole_step_tflops,
                        "whole_step_frac_of_bf16_peak": whole_step_tflops / world / peak, "last_losses": last},
