@@ -150,6 +150,12 @@ int srg_tanh_mean(const float* a, const float* b, int64_t n, float sign, void* s
 int srg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* same update, CUDA-graph capturable: the learning rate and the number of steps taken so far live in device memory
+ * (`*step_dev` is read as t-1 and incremented on the stream), so a captured step replays correctly under an LR
+ * scheduler. */
+int srg_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr_dev,
+                      float beta1, float beta2, float eps, int* step_dev, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

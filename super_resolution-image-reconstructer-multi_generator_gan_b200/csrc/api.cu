@@ -282,4 +282,10 @@ int srg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
   return launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, S(stream));
 }
 
+int srg_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr_dev,
+                      float beta1, float beta2, float eps, int* step_dev, float grad_scale, void* stream) {
+  if (lr_dev == nullptr || step_dev == nullptr) { set_error("adam_dev: null device scalar"); return -7; }
+  return launch_adam_dev(params, grads, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev, grad_scale, S(stream));
+}
+
 }  // extern "C"

@@ -88,6 +88,10 @@ int launch_wgrad_reduce(const float* partials, const int* idx, float* out, int n
 void count_launch(int n = 1);
 long long total_launches();
 
+// partial-side reduction: inv[j] = output element (or -1) for partial element j of one split; n_part % 4 == 0
+int launch_wgrad_reduce_inv(const float* partials, const int* inv, float* out, int n_part, int splits, size_t split_stride,
+                            cudaStream_t stream);
+
 const char* last_error();
 void set_error(const char* fmt, ...);
 

@@ -79,6 +79,103 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const uint4* __restric
   }
 }
 
+// ---- fused reduction + finalize: the last block to finish (atomic ticket) sums the block partials in a fixed order
+// and runs the per-channel finalize in the same launch (3 launches -> 1 when no cross-GPU all-reduce sits in between).
+__device__ __forceinline__ void finalize_channels(const ReduceFinalize& f, int c, double s1, double s2) {
+  if (f.mode == RF_BN_FWD) {
+    const double mean = s1 / f.count;
+    double var = s2 / f.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float inv = float(1.0 / sqrt(var + double(f.eps)));
+    const float sc = f.gamma[c] * inv;
+    f.out0[c] = sc;                                 // scale
+    f.out1[c] = f.beta[c] - float(mean) * sc;       // shift
+    f.out2[c] = float(mean);                        // save_mean
+    f.out3[c] = inv;                                // save_inv
+    if (f.running_mean != nullptr) {
+      const double unbiased = f.count > 1.0 ? var * (f.count / (f.count - 1.0)) : var;
+      f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * float(mean);
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * float(unbiased);
+    }
+  } else if (f.mode == RF_BN_BWD) {
+    const double mean = f.save_mean[c], inv = f.save_inv[c];
+    const double dg = inv * (s2 - mean * s1);
+    const double db = s1;
+    if (f.dgamma) f.dgamma[c] = float(dg);
+    if (f.dbeta) f.dbeta[c] = float(db);
+    const double sc = double(f.gamma[c]) * inv;
+    f.out0[c] = float(sc);
+    f.out1[c] = float(-sc * inv * dg / f.count);
+    f.out2[c] = float(-sc * db / f.count + sc * inv * mean * dg / f.count);
+  } else {
+    f.out0[c] = float(s1);                          // RF_SUM: bias gradient
+  }
+}
+
+template <bool TWO>
+__global__ void __launch_bounds__(256) chan_reduce_final_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                                int64_t pixels, float* __restrict__ partials,
+                                                                unsigned int* __restrict__ ticket, const ReduceFinalize f) {
+  __shared__ float red[32][129];
+  __shared__ double dred[2][128];
+  __shared__ bool is_last;
+  const int cg = threadIdx.x & 7;
+  const int lane_p = threadIdx.x >> 3;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+  for (int64_t p = int64_t(blockIdx.x) * 32 + lane_p; p < pixels; p += int64_t(gridDim.x) * 32) {
+    float fa[8], fb[8];
+    unpack8(a[p * 8 + cg], fa);
+    if (TWO) unpack8(b[p * 8 + cg], fb);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s1[e] += fa[e];
+      s2[e] += TWO ? fa[e] * fb[e] : fa[e] * fa[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[lane_p][cg * 8 + e] = s1[e];
+    red[lane_p][64 + cg * 8 + e] = s2[e];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) acc += red[l][threadIdx.x];
+    partials[size_t(blockIdx.x) * 128 + threadIdx.x] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
+  double acc = 0.0;
+  for (int blk = half; blk < int(gridDim.x); blk += 2) acc += double(__ldcg(partials + size_t(blk) * 128 + col));
+  dred[half][col] = acc;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    finalize_channels(f, c, dred[0][c] + dred[1][c], dred[0][64 + c] + dred[1][64 + c]);
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+int launch_chan_reduce_final(const void* a, const void* b, int64_t pixels, float* partials, unsigned int* ticket,
+                             const ReduceFinalize& f, cudaStream_t st) {
+  const int blocks = reduce_blocks(pixels);
+  if (b)
+    chan_reduce_final_kernel<true><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+                                                          pixels, partials, ticket, f);
+  else
+    chan_reduce_final_kernel<false><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(a), nullptr, pixels, partials, ticket, f);
+  SRG_LAUNCH_CHECK("chan_reduce_final");
+  return 0;
+}
+
 int launch_chan_reduce(const void* a, const void* b, int64_t pixels, float* partials, cudaStream_t st) {
   const int blocks = reduce_blocks(pixels);
   if (b)
@@ -319,20 +416,27 @@ __global__ void __launch_bounds__(256) ps_row_sums_kernel(const uint4* __restric
     scratch[row * 128 + threadIdx.x] = acc;  // [j*64 + c]
   }
 }
-// dbias[4c + 2i + j] = sum over rows with (row & 1) == i of scratch[row][j*64 + c]
-__global__ void ps_bias_finalize_kernel(const float* __restrict__ scratch, int64_t rows, float* __restrict__ dbias) {
-  const int t = threadIdx.x;  // 256 = i(2) x j(2) x c(64)
-  const int i = t >> 7, j = (t >> 6) & 1, c = t & 63;
+// dbias[4c + 2i + j] = sum over rows with (row & 1) == i of scratch[row][j*64 + c]; one block per output, fixed-order tree
+__global__ void __launch_bounds__(256) ps_bias_finalize_kernel(const float* __restrict__ scratch, int64_t rows, float* __restrict__ dbias) {
+  __shared__ double sh[256];
+  const int o = blockIdx.x;  // 256 = i(2) x j(2) x c(64)
+  const int i = o >> 7, j = (o >> 6) & 1, c = o & 63;
   double acc = 0.0;
-  for (int64_t r = i; r < rows; r += 2) acc += double(scratch[r * 128 + j * 64 + c]);
-  dbias[4 * c + 2 * i + j] = float(acc);
+  for (int64_t r = i + 2 * int64_t(threadIdx.x); r < rows; r += 512) acc += double(scratch[r * 128 + j * 64 + c]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dbias[4 * c + 2 * i + j] = float(sh[0]);
 }
 int launch_ps_bias_grad(const void* g, int N, int H2, int W2, float* scratch, float* dbias, cudaStream_t st) {
   if ((H2 & 1) || (W2 & 1)) { set_error("ps_bias_grad: odd extent"); return -1; }
   const int64_t rows = int64_t(N) * H2;
   ps_row_sums_kernel<<<unsigned(rows), 256, 0, st>>>(reinterpret_cast<const uint4*>(g), W2, scratch);
   SRG_LAUNCH_CHECK("ps_row_sums");
-  ps_bias_finalize_kernel<<<1, 256, 0, st>>>(scratch, rows, dbias);
+  ps_bias_finalize_kernel<<<256, 256, 0, st>>>(scratch, rows, dbias);
   SRG_LAUNCH_CHECK("ps_bias_finalize");
   return 0;
 }
@@ -342,32 +446,43 @@ int launch_ps_bias_grad(const void* g, int N, int H2, int W2, float* scratch, fl
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) unfold9_kernel(const float* __restrict__ src, int N, int H, int W, float scale,
                                                       uint4* __restrict__ dst) {
-  const int64_t total = int64_t(N) * (H + 1) * W * 8;
+  // one thread per (n, h', w): gathers the 2 x 9 x 3 neighbourhood once and writes the pixel's 128-byte row
+  const int64_t total = int64_t(N) * (H + 1) * W;
   const int64_t plane = int64_t(H) * W;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int cg = int(i & 7);
-    const int64_t pix = i >> 3;
+  for (int64_t pix = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; pix < total; pix += int64_t(gridDim.x) * blockDim.x) {
     const int w = int(pix % W);
     const int64_t t = pix / W;
     const int hp = int(t % (H + 1));
     const int n = int(t / (H + 1));
-    float f[8];
+    float f[64];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int ch = cg * 8 + e;
-      float v = 0.f;
-      if (ch < 54) {
-        const int dr = ch / 27, rem = ch - dr * 27, s = rem / 3, c = rem - s * 3;
-        const int hh = hp - 1 + dr, ww = w + s - 4;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(src + (int64_t(n) * 3 + c) * plane + int64_t(hh) * W + ww) * scale;
+    for (int ch = 54; ch < 64; ++ch) f[ch] = 0.f;
+#pragma unroll
+    for (int dr = 0; dr < 2; ++dr) {
+      const int hh = hp - 1 + dr;
+      const bool row_ok = hh >= 0 && hh < H;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* row = src + (int64_t(n) * 3 + c) * plane + int64_t(row_ok ? hh : 0) * W;
+#pragma unroll
+        for (int sft = 0; sft < 9; ++sft) {
+          const int ww = w + sft - 4;
+          f[dr * 27 + sft * 3 + c] = (row_ok && ww >= 0 && ww < W) ? __ldg(row + ww) * scale : 0.f;
+        }
       }
-      f[e] = v;
     }
-    dst[i] = pack8(f);
+    uint4* o = dst + pix * 8;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      uint4 v;
+      v.x = bpack(f[8 * g + 0], f[8 * g + 1]); v.y = bpack(f[8 * g + 2], f[8 * g + 3]);
+      v.z = bpack(f[8 * g + 4], f[8 * g + 5]); v.w = bpack(f[8 * g + 6], f[8 * g + 7]);
+      o[g] = v;
+    }
   }
 }
 int launch_unfold9(const float* src, int N, int H, int W, float scale, void* dst, cudaStream_t st) {
-  const int64_t total = int64_t(N) * (H + 1) * W * 8;
+  const int64_t total = int64_t(N) * (H + 1) * W;
   unfold9_kernel<<<ew_blocks(total), 256, 0, st>>>(src, N, H, W, scale, reinterpret_cast<uint4*>(dst));
   SRG_LAUNCH_CHECK("unfold9");
   return 0;
@@ -426,6 +541,38 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float l
   return 0;
 }
 
+// Graph-capturable variant: learning rate and step count live in device memory, so a captured launch stays valid while
+// the host scheduler changes the LR and the step advances (bias corrections are computed on the device).
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, int64_t n, const float* __restrict__ lr_dev,
+                                                       float beta1, float beta2, float eps, const int* __restrict__ step_dev,
+                                                       float grad_scale) {
+  const int t = *step_dev + 1;
+  const double bc1 = 1.0 - pow(double(beta1), double(t));
+  const double bc2 = 1.0 - pow(double(beta2), double(t));
+  const float lr_over_bc1 = float(double(*lr_dev) / bc1);
+  const float inv_sqrt_bc2 = float(1.0 / sqrt(bc2));
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
+    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] -= lr_over_bc1 * (mi / denom);
+  }
+}
+__global__ void step_inc_kernel(int* step_dev) { *step_dev += 1; }
+int launch_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
+                    float eps, int* step_dev, float grad_scale, cudaStream_t st) {
+  if (n <= 0) return 0;
+  adam_dev_kernel<<<ew_blocks(n), 256, 0, st>>>(p, g, m, v, n, lr_dev, beta1, beta2, eps, step_dev, grad_scale);
+  SRG_LAUNCH_CHECK("adam_dev");
+  step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
+  SRG_LAUNCH_CHECK("adam_step_inc");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // ReconstructionLoss
 // ------------------------------------------------------------------------------------------------
@@ -447,41 +594,69 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
   return t;
 }
 
-__device__ __forceinline__ float at_or_zero(const float* __restrict__ pl, int h, int w, int H, int W) {
-  return (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(pl + int64_t(h) * W + w) : 0.f;
+// Row-wise helpers: r0/r1/r2 = rows h-1, h, h+1 of one image plane (nullptr when outside), zero padding.
+struct Rows3 {
+  const float* r0;
+  const float* r1;
+  const float* r2;
+};
+__device__ __forceinline__ Rows3 rows3(const float* __restrict__ plane_base, int h, int H, int W) {
+  Rows3 r;
+  r.r1 = plane_base + int64_t(h) * W;
+  r.r0 = h > 0 ? r.r1 - W : nullptr;
+  r.r2 = h + 1 < H ? r.r1 + W : nullptr;
+  return r;
+}
+__device__ __forceinline__ float ldz(const float* __restrict__ row, int w, int W) {
+  return (row != nullptr && w >= 0 && w < W) ? __ldg(row + w) : 0.f;
 }
 // E0 = max(|Px * x|, |Py * x|), Prewitt x5, zero padding (src/utils.py:180-186, 200-209)
-__device__ __forceinline__ float edge0(const float* __restrict__ pl, int h, int w, int H, int W) {
-  const float a = at_or_zero(pl, h - 1, w - 1, H, W), b = at_or_zero(pl, h - 1, w, H, W), c = at_or_zero(pl, h - 1, w + 1, H, W);
-  const float d = at_or_zero(pl, h, w - 1, H, W), f = at_or_zero(pl, h, w + 1, H, W);
-  const float g = at_or_zero(pl, h + 1, w - 1, H, W), i = at_or_zero(pl, h + 1, w, H, W), j = at_or_zero(pl, h + 1, w + 1, H, W);
+__device__ __forceinline__ float edge0(const Rows3& r, int w, int W) {
+  const float a = ldz(r.r0, w - 1, W), b = ldz(r.r0, w, W), c = ldz(r.r0, w + 1, W);
+  const float d = ldz(r.r1, w - 1, W), f = ldz(r.r1, w + 1, W);
+  const float g = ldz(r.r2, w - 1, W), i = ldz(r.r2, w, W), j = ldz(r.r2, w + 1, W);
   const float gx = 5.f * ((c - a) + (f - d) + (j - g));
   const float gy = 5.f * ((g - a) + (i - b) + (j - c));
   return fmaxf(fabsf(gx), fabsf(gy));
 }
 // L * x with L = [[-1/8 x3],[-1/8, 1, -1/8],[-1/8 x3]] (src/utils.py:190-192)
-__device__ __forceinline__ float lap8(const float* __restrict__ pl, int h, int w, int H, int W) {
-  const float nb = at_or_zero(pl, h - 1, w - 1, H, W) + at_or_zero(pl, h - 1, w, H, W) + at_or_zero(pl, h - 1, w + 1, H, W) +
-                   at_or_zero(pl, h, w - 1, H, W) + at_or_zero(pl, h, w + 1, H, W) + at_or_zero(pl, h + 1, w - 1, H, W) +
-                   at_or_zero(pl, h + 1, w, H, W) + at_or_zero(pl, h + 1, w + 1, H, W);
-  return __ldg(pl + int64_t(h) * W + w) - 0.125f * nb;
+__device__ __forceinline__ float lap8(const Rows3& r, int w, int W) {
+  const float nb = ldz(r.r0, w - 1, W) + ldz(r.r0, w, W) + ldz(r.r0, w + 1, W) + ldz(r.r1, w - 1, W) + ldz(r.r1, w + 1, W) +
+                   ldz(r.r2, w - 1, W) + ldz(r.r2, w, W) + ldz(r.r2, w + 1, W);
+  return __ldg(r.r1 + w) - 0.125f * nb;
+}
+constexpr int kLossThreads = 128;
+__device__ __forceinline__ double block_sum_any(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < nw; ++i) t += sh[i];
+  return t;
 }
 
-__global__ void __launch_bounds__(256) loss_pass1_kernel(const float* __restrict__ hr, int64_t total, int H, int W,
-                                                         double* __restrict__ scratch) {
+// All three passes walk image rows: block -> rows (grid stride), thread -> columns; no per-element divisions.
+__global__ void __launch_bounds__(kLossThreads) loss_pass1_kernel(const float* __restrict__ hr, int rows_total, int H, int W,
+                                                                  double* __restrict__ scratch) {
   __shared__ double sh[8];
   double s1 = 0.0, s2 = 0.0;
-  const int64_t plane = int64_t(H) * W;
-  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += int64_t(gridDim.x) * 256) {
-    const int64_t pl = i / plane;
-    const int64_t r = i - pl * plane;
-    const int h = int(r / W), w = int(r - int64_t(h) * W);
-    const float e0 = edge0(hr + pl * plane, h, w, H, W);
-    s1 += double(e0);
-    s2 += double(e0) * double(e0);
+  for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
+    const int pl = row / H, h = row - pl * H;
+    const Rows3 r = rows3(hr + int64_t(pl) * H * W, h, H, W);
+    float a1 = 0.f, a2 = 0.f;
+    for (int w = threadIdx.x; w < W; w += kLossThreads) {
+      const float e0 = edge0(r, w, W);
+      a1 += e0;
+      a2 += e0 * e0;
+    }
+    s1 += double(a1);
+    s2 += double(a2);
   }
-  s1 = block_sum_256(s1, sh);
-  s2 = block_sum_256(s2, sh);
+  s1 = block_sum_any(s1, sh);
+  s2 = block_sum_any(s2, sh);
   if (threadIdx.x == 0) {
     scratch[kLossHdr + blockIdx.x] = s1;
     scratch[kLossHdr + kLossBlocks + blockIdx.x] = s2;
@@ -507,31 +682,38 @@ __global__ void loss_stats_kernel(double* scratch, int blocks, double n) {
     scratch[3] = sqrt(var);
   }
 }
-__global__ void __launch_bounds__(256) loss_pass2_kernel(const float* __restrict__ hr, const float* __restrict__ sr,
-                                                         int64_t total, int H, int W, double* __restrict__ scratch,
-                                                         float* __restrict__ e_buf, float* __restrict__ g_buf) {
+__global__ void __launch_bounds__(kLossThreads) loss_pass2_kernel(const float* __restrict__ hr, const float* __restrict__ sr,
+                                                                  int rows_total, int H, int W, double* __restrict__ scratch,
+                                                                  float* __restrict__ e_buf, float* __restrict__ g_buf) {
   __shared__ double sh[8];
   const float mean = float(scratch[2]), stdv = float(scratch[3]);
   double sE = 0.0, sL = 0.0, sT = 0.0;
-  const int64_t plane = int64_t(H) * W;
-  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += int64_t(gridDim.x) * 256) {
-    const int64_t pl = i / plane;
-    const int64_t r = i - pl * plane;
-    const int h = int(r / W), w = int(r - int64_t(h) * W);
-    const float e0 = edge0(hr + pl * plane, h, w, H, W);
-    float e = (e0 - mean) / stdv * 0.2f + 1.f;                 // normalize(...)*0.2 + 1  (:213, :194-198)
-    e = fminf(fmaxf(e, 0.f), 2.f);
-    const float d = lap8(sr + pl * plane, h, w, H, W);
-    const float om = 1.f - e;
-    e_buf[i] = e;
-    g_buf[i] = (d > 0.f ? om : (d < 0.f ? -om : 0.f));        // sign(D) * (1 - E)
-    sE += double(e);
-    sL += double(fabsf(hr[i] - sr[i]) * e);
-    sT += double(fabsf(d) * om);
+  for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
+    const int pl = row / H, h = row - pl * H;
+    const int64_t pbase = int64_t(pl) * H * W;
+    const Rows3 rh = rows3(hr + pbase, h, H, W);
+    const Rows3 rs = rows3(sr + pbase, h, H, W);
+    const int64_t o = pbase + int64_t(h) * W;
+    float aE = 0.f, aL = 0.f, aT = 0.f;
+    for (int w = threadIdx.x; w < W; w += kLossThreads) {
+      const float e0 = edge0(rh, w, W);
+      float e = (e0 - mean) / stdv * 0.2f + 1.f;                 // normalize(...)*0.2 + 1  (:213, :194-198)
+      e = fminf(fmaxf(e, 0.f), 2.f);
+      const float d = lap8(rs, w, W);
+      const float om = 1.f - e;
+      e_buf[o + w] = e;
+      g_buf[o + w] = (d > 0.f ? om : (d < 0.f ? -om : 0.f));    // sign(D) * (1 - E)
+      aE += e;
+      aL += fabsf(__ldg(rh.r1 + w) - __ldg(rs.r1 + w)) * e;
+      aT += fabsf(d) * om;
+    }
+    sE += double(aE);
+    sL += double(aL);
+    sT += double(aT);
   }
-  sE = block_sum_256(sE, sh);
-  sL = block_sum_256(sL, sh);
-  sT = block_sum_256(sT, sh);
+  sE = block_sum_any(sE, sh);
+  sL = block_sum_any(sL, sh);
+  sT = block_sum_any(sT, sh);
   if (threadIdx.x == 0) {
     scratch[kLossHdr + blockIdx.x] = sE;
     scratch[kLossHdr + kLossBlocks + blockIdx.x] = sL;
@@ -552,36 +734,42 @@ __global__ void loss_final_kernel(double* scratch, int blocks, double n, float* 
     losses[1] = float(m > 0.0 ? m : 0.0);
   }
 }
-__global__ void __launch_bounds__(256) loss_pass3_kernel(const float* __restrict__ hr, const float* __restrict__ sr,
-                                                         const float* __restrict__ e_buf, const float* __restrict__ g_buf,
-                                                         int64_t total, int H, int W, const double* __restrict__ scratch,
-                                                         const float* __restrict__ w_edge, const float* __restrict__ w_tv,
-                                                         float* __restrict__ grad, float grad_scale) {
+__global__ void __launch_bounds__(kLossThreads) loss_pass3_kernel(const float* __restrict__ hr, const float* __restrict__ sr,
+                                                                  const float* __restrict__ e_buf, const float* __restrict__ g_buf,
+                                                                  int rows_total, int64_t total, int H, int W,
+                                                                  const double* __restrict__ scratch,
+                                                                  const float* __restrict__ w_edge, const float* __restrict__ w_tv,
+                                                                  float* __restrict__ grad, float grad_scale) {
   // w_edge / w_tv: optional device scalars = d(objective)/d(edge_loss), d(objective)/d(tv_loss) (autograd inputs)
   const float inv_sum_e = float(1.0 / scratch[4]) * (w_edge ? *w_edge : 1.f);
   const float tv_k = scratch[7] > 0.0 ? float(1.0 / double(total)) * (w_tv ? *w_tv : 1.f) : 0.f;
-  const int64_t plane = int64_t(H) * W;
-  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += int64_t(gridDim.x) * 256) {
-    const int64_t pl = i / plane;
-    const int64_t r = i - pl * plane;
-    const int h = int(r / W), w = int(r - int64_t(h) * W);
-    const float diff = sr[i] - hr[i];
-    const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-    float g = sg * e_buf[i] * inv_sum_e;
-    if (tv_k != 0.f) g += tv_k * lap8(g_buf + pl * plane, h, w, H, W);
-    grad[i] = g * grad_scale;
+  for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
+    const int pl = row / H, h = row - pl * H;
+    const int64_t pbase = int64_t(pl) * H * W;
+    const Rows3 rg = rows3(g_buf + pbase, h, H, W);
+    const int64_t o = pbase + int64_t(h) * W;
+    for (int w = threadIdx.x; w < W; w += kLossThreads) {
+      const float diff = sr[o + w] - hr[o + w];
+      const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+      float g = sg * e_buf[o + w] * inv_sum_e;
+      if (tv_k != 0.f) g += tv_k * lap8(rg, w, W);
+      grad[o + w] = g * grad_scale;
+    }
   }
 }
 int launch_recon_loss_forward(const float* hr, const float* sr, int N, int C, int H, int W, double* scratch, float* e_buf,
                               float* g_buf, float* losses, cudaStream_t st) {
   const int64_t total = int64_t(N) * C * H * W;
   if (total <= 1) { set_error("recon_loss: need more than one element"); return -1; }
-  const int blocks = int((total + 255) / 256 < kLossBlocks ? (total + 255) / 256 : kLossBlocks);
-  loss_pass1_kernel<<<blocks, 256, 0, st>>>(hr, total, H, W, scratch);
+  const int64_t rows64 = int64_t(N) * C * H;
+  if (rows64 > 0x7fffffff) { set_error("recon_loss: too many rows"); return -1; }
+  const int rows = int(rows64);
+  const int blocks = rows < kLossBlocks ? rows : kLossBlocks;
+  loss_pass1_kernel<<<blocks, kLossThreads, 0, st>>>(hr, rows, H, W, scratch);
   SRG_LAUNCH_CHECK("loss_pass1");
   loss_stats_kernel<<<1, 256, 0, st>>>(scratch, blocks, double(total));
   SRG_LAUNCH_CHECK("loss_stats");
-  loss_pass2_kernel<<<blocks, 256, 0, st>>>(hr, sr, total, H, W, scratch, e_buf, g_buf);
+  loss_pass2_kernel<<<blocks, kLossThreads, 0, st>>>(hr, sr, rows, H, W, scratch, e_buf, g_buf);
   SRG_LAUNCH_CHECK("loss_pass2");
   loss_final_kernel<<<1, 256, 0, st>>>(scratch, blocks, double(total), losses);
   SRG_LAUNCH_CHECK("loss_final");
@@ -591,8 +779,10 @@ int launch_recon_loss_backward(const float* hr, const float* sr, int N, int C, i
                                const float* e_buf, const float* g_buf, const float* w_edge, const float* w_tv, float* grad,
                                float grad_scale, cudaStream_t st) {
   const int64_t total = int64_t(N) * C * H * W;
-  const int blocks = int((total + 255) / 256 < kLossBlocks ? (total + 255) / 256 : kLossBlocks);
-  loss_pass3_kernel<<<blocks, 256, 0, st>>>(hr, sr, e_buf, g_buf, total, H, W, scratch, w_edge, w_tv, grad, grad_scale);
+  const int rows = int(int64_t(N) * C * H);
+  const int blocks = rows < kLossBlocks ? rows : kLossBlocks;
+  loss_pass3_kernel<<<blocks, kLossThreads, 0, st>>>(hr, sr, e_buf, g_buf, rows, total, H, W, scratch, w_edge, w_tv, grad,
+                                                    grad_scale);
   SRG_LAUNCH_CHECK("loss_pass3");
   return 0;
 }

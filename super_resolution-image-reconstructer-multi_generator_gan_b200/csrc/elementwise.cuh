@@ -12,6 +12,28 @@ constexpr int kRedBlocksMax = 592;  // 4 x 148 SMs
 // partials: float [blocks][128]  ([0,64) = sum a ; [64,128) = sum a*a (b == null) or sum a*b)
 int reduce_blocks(int64_t pixels);
 int launch_chan_reduce(const void* a, const void* b, int64_t pixels, float* partials, cudaStream_t st);
+// Fused variant: reduction + fixed-order partial sum + per-channel finalize in ONE launch (last block done).
+enum ReduceFinalizeMode : int { RF_BN_FWD = 0, RF_BN_BWD = 1, RF_SUM = 2 };
+struct ReduceFinalize {
+  int mode;
+  double count;                 // elements per channel
+  float eps, momentum;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;          // RF_BN_FWD: optional
+  float* running_var;
+  const float* save_mean;       // RF_BN_BWD inputs
+  const float* save_inv;
+  float* dgamma;                // RF_BN_BWD outputs (optional)
+  float* dbeta;
+  float* out0;                  // FWD: scale | BWD: coefA | SUM: sums (float[64])
+  float* out1;                  // FWD: shift | BWD: coefB
+  float* out2;                  // FWD: save_mean | BWD: coefC
+  float* out3;                  // FWD: save_inv
+};
+// `ticket` is a device counter that must be 0 before the first launch (the kernel resets it).
+int launch_chan_reduce_final(const void* a, const void* b, int64_t pixels, float* partials, unsigned int* ticket,
+                             const ReduceFinalize& f, cudaStream_t st);
 // sums[128] (double) = fixed-order sum of the block partials
 int launch_partials_to_sums(const float* partials, int blocks, double* sums, cudaStream_t st);
 
@@ -55,6 +77,10 @@ int launch_gather_f32(const float* src, const int* idx, float* dst, int64_t n, c
 // torch.optim.Adam (no weight decay, no amsgrad) over flat fp32 buffers; step = 1-based step count.
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                 int step, float grad_scale, cudaStream_t st);
+
+// same update with the learning rate and the (0-based, pre-increment) step count in DEVICE memory: CUDA-graph capturable
+int launch_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
+                    float eps, int* step_dev, float grad_scale, cudaStream_t st);
 
 // ---- ReconstructionLoss (reference src/utils.py:173-241) ------------------------------------------
 // hr, sr: fp32 [N][3][H][W].  scratch doubles: >= loss_scratch_doubles().  e_buf, g_buf: fp32, same size as hr.

@@ -31,7 +31,7 @@ struct Carver {
 
 // ------------------------------------------------------------------ workspace layout
 struct Layout {
-  size_t packed, bias, bncoef, bwdcoef, partials, sums, wg_partials, ps_scratch, loss_scratch;
+  size_t packed, bias, bncoef, bwdcoef, partials, sums, ticket, wg_partials, ps_scratch, loss_scratch;
   size_t U1, out1, trunk;
   std::vector<size_t> y1, z1, y2, out;   // per residual block (eval: aliases of 4 rotating buffers)
   std::vector<size_t> up;                // per upsample stage
@@ -62,6 +62,7 @@ Layout make_layout(const GeneratorEngine& e, bool training) {
   L.bwdcoef = c.take(192 * 4);
   L.partials = c.take(size_t(kRedBlocksMax) * 128 * 4);
   L.sums = c.take(128 * 8);
+  L.ticket = c.take(256);
   L.U1 = c.take(size_t(e.N) * (e.H + 1) * e.W * 128);
   L.out1 = c.take(t64(P));
   L.y1.resize(e.n_res); L.z1.resize(e.n_res); L.y2.resize(e.n_res); L.out.resize(e.n_res);
@@ -387,6 +388,16 @@ GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up) {
           const int dr = kh % 2, r = (8 - kh - dr) / 2, s = 8 - kw;
           mc3[((co * 64 + ci) * 9 + kh) * 9 + kw] = pidx(0, 3, r, dr * 27 + s * 3 + co, ci);
         }
+  auto invert = [](const std::vector<int>& fwd, size_t n_part) {
+    std::vector<int> inv(n_part, -1);
+    for (size_t i = 0; i < fwd.size(); ++i)
+      if (fwd[i] >= 0) inv[size_t(fwd[i])] = int(i);
+    return inv;
+  };
+  m33 = invert(m33, size_t(1) * 5 * 8192);
+  mup = invert(mup, size_t(4) * 5 * 8192);
+  mc1 = invert(mc1, size_t(1) * 3 * 8192);
+  mc3 = invert(mc3, size_t(1) * 3 * 8192);
   e->h_pack_idx.swap(idx); e->h_bias_idx.swap(bidx);
   e->h_wg_c3x3.swap(m33); e->h_wg_up.swap(mup); e->h_wg_conv1.swap(mc1); e->h_wg_conv3.swap(mc3);
   e->workspace_bytes_train = make_layout(*e, true).total;
@@ -416,6 +427,7 @@ int generator_bind(GeneratorEngine* g, float* master, float* grads, float* bn_bu
   e->master = master; e->grads = grads; e->bn_buffers = bn_buffers;
   e->ws = reinterpret_cast<uint8_t*>(ws); e->ws_bytes = ws_bytes; e->ws_training = training != 0;
   e->L = make_layout(*e, training != 0);
+  if (cudaMemset(e->ws + e->L.ticket, 0, 256) != cudaSuccess) { set_error("generator_bind: memset failed"); return -29; }
   // named tensors for parity tests
   e->tensors.clear();
   auto reg = [&](const std::string& name, size_t off, int n, int h, int w, int c, int dtype) {
@@ -515,9 +527,18 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
     }
     float* partials = reinterpret_cast<float*>(ws + L.partials);
     double* sums = reinterpret_cast<double*>(ws + L.sums);
+    if (!e->allreduce) {
+      // single GPU: statistics + finalize in one launch
+      ReduceFinalize f; memset(&f, 0, sizeof(f));
+      f.mode = RF_BN_FWD; f.count = double(P); f.eps = kBnEps; f.momentum = kBnMomentum; f.gamma = gamma; f.beta = beta;
+      f.running_mean = update_running ? rm : nullptr; f.running_var = update_running ? rv : nullptr;
+      f.out0 = coef; f.out1 = coef + 64; f.out2 = coef + 128; f.out3 = coef + 192;
+      e->launches += 1;
+      return launch_chan_reduce_final(y, nullptr, P, partials, reinterpret_cast<unsigned int*>(ws + L.ticket), f, st);
+    }
     RC(launch_chan_reduce(y, nullptr, P, partials, st));
     RC(launch_partials_to_sums(partials, reduce_blocks(P), sums, st));
-    if (e->allreduce) RC(e->allreduce(e->allreduce_ctx, sums, 128, st));
+    RC(e->allreduce(e->allreduce_ctx, sums, 128, st));
     e->launches += 3;
     return launch_bn_finalize(sums, double(P) * e->world, gamma, beta, kBnEps, kBnMomentum, update_running ? rm : nullptr,
                               update_running ? rv : nullptr, coef, coef + 64, coef + 128, coef + 192, st);
@@ -617,13 +638,14 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     for (const auto& p : e->params) if (p.name == wname) pi = &p;
     if (!pi) { set_error("wgrad: unknown parameter %s", wname.c_str()); return -28; }
     e->launches += 2;
-    return launch_wgrad_reduce(wgp, idx, e->grads + pi->offset, int(pi->numel), splits, size_t(n_blocks) * n_pairs * 128 * 64, 0, st);
+    const size_t per_split = size_t(n_blocks) * n_pairs * 128 * 64;
+    return launch_wgrad_reduce_inv(wgp, idx, e->grads + pi->offset, int(per_split), splits, per_split, st);
   };
   auto bias_grad = [&](const void* dy, int64_t pixels, const std::string& bname) -> int {
-    RC(launch_chan_reduce(dy, nullptr, pixels, partials, st));
-    RC(launch_partials_to_sums(partials, reduce_blocks(pixels), sums, st));
-    e->launches += 3;
-    return launch_sums_to_float(sums, e->grads + poff(*e, bname), 64, st);
+    ReduceFinalize f; memset(&f, 0, sizeof(f));
+    f.mode = RF_SUM; f.count = double(pixels); f.out0 = e->grads + poff(*e, bname);
+    e->launches += 1;
+    return launch_chan_reduce_final(dy, nullptr, pixels, partials, reinterpret_cast<unsigned int*>(ws + L.ticket), f, st);
   };
   // dgrad of a 3x3 conv whose output gradient has `chunks`*64 channels (4 pixel-shuffle views when chunks == 4)
   auto dgrad3x3 = [&](const void* dy_base, int gh, int gw, bool dy_ps, int64_t w_off, const void* residual, const void* mask,
@@ -696,12 +718,20 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     const int64_t go = poff(*e, nm);
     snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.bias", b, k + 1);
     const int64_t bo = poff(*e, nm);
-    RC(launch_chan_reduce(dz, y, P, partials, st));
-    RC(launch_partials_to_sums(partials, reduce_blocks(P), sums, st));
-    if (e->allreduce) RC(e->allreduce(e->allreduce_ctx, sums, 128, st));
-    RC(launch_bn_bwd_finalize(sums, double(P) * e->world, e->master + go, coef + 128, coef + 192, e->grads + go, e->grads + bo,
-                              bwd, bwd + 64, bwd + 128, st));
-    e->launches += 4;
+    if (!e->allreduce) {
+      ReduceFinalize f; memset(&f, 0, sizeof(f));
+      f.mode = RF_BN_BWD; f.count = double(P); f.gamma = e->master + go; f.save_mean = coef + 128; f.save_inv = coef + 192;
+      f.dgamma = e->grads + go; f.dbeta = e->grads + bo; f.out0 = bwd; f.out1 = bwd + 64; f.out2 = bwd + 128;
+      RC(launch_chan_reduce_final(dz, y, P, partials, reinterpret_cast<unsigned int*>(ws + L.ticket), f, st));
+      e->launches += 2;
+    } else {
+      RC(launch_chan_reduce(dz, y, P, partials, st));
+      RC(launch_partials_to_sums(partials, reduce_blocks(P), sums, st));
+      RC(e->allreduce(e->allreduce_ctx, sums, 128, st));
+      RC(launch_bn_bwd_finalize(sums, double(P) * e->world, e->master + go, coef + 128, coef + 192, e->grads + go, e->grads + bo,
+                                bwd, bwd + 64, bwd + 128, st));
+      e->launches += 4;
+    }
     return launch_bn_bwd_apply(dz, y, bwd, bwd + 64, bwd + 128, dy, P, st);
   };
   for (int b = e->n_res - 1; b >= 0; --b) {

@@ -171,6 +171,49 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, const in
   out[e] = accumulate_into ? out[e] + acc : acc;
 }
 
+// Same reduction driven from the PARTIAL side: thread = 4 consecutive partial elements (coalesced 16-byte loads), 8 warps
+// of a block split the `splits` dimension, fixed-order combine, scatter through the inverse map (inv[j] = output element
+// or -1).  Output elements no partial maps to are left untouched (the caller zero-fills the gradient buffer).
+__global__ void __launch_bounds__(256) wgrad_reduce_inv_kernel(const float4* __restrict__ partials, const int* __restrict__ inv,
+                                                               float* __restrict__ out, int n_part4, int splits,
+                                                               size_t split_stride4) {
+  __shared__ float4 sh[8][32];
+  const int lane = threadIdx.x & 31, sg = threadIdx.x >> 5;
+  const int j4 = blockIdx.x * 32 + lane;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j4 < n_part4) {
+    const float4* p = partials + j4;
+#pragma unroll 4
+    for (int s = sg; s < splits; s += 8) {
+      const float4 v = __ldcs(p + size_t(s) * split_stride4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  sh[sg][lane] = acc;
+  __syncthreads();
+  if (sg == 0 && j4 < n_part4) {
+    float4 t = sh[0][lane];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) { t.x += sh[g][lane].x; t.y += sh[g][lane].y; t.z += sh[g][lane].z; t.w += sh[g][lane].w; }
+    const int4 o = *reinterpret_cast<const int4*>(inv + 4 * j4);
+    if (o.x >= 0) out[o.x] = t.x;
+    if (o.y >= 0) out[o.y] = t.y;
+    if (o.z >= 0) out[o.z] = t.z;
+    if (o.w >= 0) out[o.w] = t.w;
+  }
+}
+int launch_wgrad_reduce_inv(const float* partials, const int* inv, float* out, int n_part, int splits, size_t split_stride,
+                            cudaStream_t stream) {
+  if (n_part <= 0 || (n_part & 3) || (split_stride & 3)) { set_error("wgrad_reduce_inv: sizes must be multiples of 4"); return -1; }
+  const int n4 = n_part / 4;
+  wgrad_reduce_inv_kernel<<<(n4 + 31) / 32, 256, 0, stream>>>(reinterpret_cast<const float4*>(partials), inv, out, n4, splits,
+                                                              split_stride / 4);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("wgrad_reduce_inv launch: %s", cudaGetErrorString(e)); return int(e); }
+  count_launch();
+  return 0;
+}
+
 int wgrad_partials_floats(const WgradArgs& a, int* splits_out) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -17,10 +17,13 @@ from ._lib import check, stream_ptr
 
 
 class Adam(torch.optim.Optimizer):
-    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, capturable: bool = False):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        # capturable: step count and learning rate are device scalars, so step() can be recorded into a CUDA graph
+        # (train.GraphedGeneratorStep); call sync_lr() after a scheduler changed param_groups[...]["lr"]
+        self.capturable = capturable
         self._flat_state: Dict[int, dict] = {}   # id(owner module) -> {"m", "v", "step"}
         self.grad_scale = 1.0                     # multiplies gradients first (e.g. 1/world for a summed all-reduce)
 
@@ -65,13 +68,33 @@ class Adam(torch.optim.Optimizer):
                     for p, (_, off, n, shape) in zip(plist, ptable):
                         if p.grad is not None:
                             gflat[off:off + n].view(shape).copy_(p.grad)
-                st["step"] += 1
                 b1, b2 = group["betas"]
+                if self.capturable:
+                    if "step_dev" not in st:
+                        st["step_dev"] = torch.full((1,), int(st["step"]), dtype=torch.int32, device=flat.device)
+                        st["lr_dev"] = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=flat.device)
+                        st["lr_host"] = float(group["lr"])
+                    check(L.srg_adam_step_dev(c_void_p(flat.data_ptr()), c_void_p(gflat.data_ptr()),
+                                              c_void_p(st["m"].data_ptr()), c_void_p(st["v"].data_ptr()), flat.numel(),
+                                              c_void_p(st["lr_dev"].data_ptr()), float(b1), float(b2), float(group["eps"]),
+                                              c_void_p(st["step_dev"].data_ptr()), float(self.grad_scale), stream_ptr()),
+                          "srg_adam_step_dev")
+                    continue
+                st["step"] += 1
                 check(L.srg_adam_step(c_void_p(flat.data_ptr()), c_void_p(gflat.data_ptr()), c_void_p(st["m"].data_ptr()),
                                       c_void_p(st["v"].data_ptr()), flat.numel(), float(group["lr"]), float(b1), float(b2),
                                       float(group["eps"]), int(st["step"]), float(self.grad_scale), stream_ptr()),
                       "srg_adam_step")
         return loss
+
+    def sync_lr(self) -> None:
+        """capturable mode: push param_groups' learning rates to their device scalars (outside graph capture)."""
+        for group in self.param_groups:
+            for owner in self._owners(group):
+                st = self._flat_state.get(id(owner))
+                if st is not None and "lr_dev" in st and st["lr_host"] != float(group["lr"]):
+                    st["lr_dev"].fill_(float(group["lr"]))
+                    st["lr_host"] = float(group["lr"])
 
     def flat_state(self, owner) -> dict:
         """{"m": exp_avg, "v": exp_avg_sq, "step": int} in the owner's flat layout (checkpointing / tests)."""

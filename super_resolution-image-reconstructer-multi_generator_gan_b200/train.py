@@ -101,6 +101,64 @@ def train_one_epoch(generator, train_loader, g_optimizer, vgg_extractor, g_crite
     return avg
 
 
+class GraphedGeneratorStep:
+    """One ``train_generator`` step (forward, loss, backward, Adam) captured into a CUDA graph and replayed.
+
+    The ~430 kernel launches of a generator step take longer to enqueue from Python than to execute on a B200; a graph
+    replay is one launch.  Everything the step touches is static device memory (flat parameters / gradients / moments,
+    engine workspaces, the Adam step count and learning rate as device scalars), so the replay is bit-identical to the
+    eager step.  Warm-up steps needed before capture run on a side stream and are rolled back (parameters, BatchNorm
+    buffers, optimiser state), so constructing this object does not train the model."""
+
+    def __init__(self, generator, discriminator, g_criterion, g_optimizer, lr_example: torch.Tensor,
+                 hr_example: torch.Tensor, gan_mode: bool = False, warmup: int = 2):
+        if not getattr(g_optimizer, "capturable", False):
+            raise ValueError("GraphedGeneratorStep needs optim.Adam(..., capturable=True)")
+        self.generator, self.optimizer = generator, g_optimizer
+        self.lr = lr_example.detach().clone()
+        self.hr = hr_example.detach().clone()
+        args = (generator, discriminator, self.lr, self.hr, None, g_criterion, g_optimizer, gan_mode)
+        flat = generator.flat_parameters()
+        rt = generator._rt
+        snap = [t.clone() for t in (flat, rt["flat_buf"], rt["nbt"])]
+        st0 = g_optimizer.flat_state(generator)
+        opt_snap = [st0[k].clone() for k in ("m", "v", "step_dev")] if st0 is not None and "step_dev" in st0 else None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                train_generator_async(*args)
+        torch.cuda.current_stream().wait_stream(side)
+        st = g_optimizer.flat_state(generator)
+        with torch.no_grad():
+            for dst, src in zip((flat, rt["flat_buf"], rt["nbt"]), snap):
+                dst.copy_(src)
+            if opt_snap is None:
+                st["m"].zero_(); st["v"].zero_(); st["step_dev"].zero_()
+            else:
+                for k, src in zip(("m", "v", "step_dev"), opt_snap):
+                    st[k].copy_(src)
+        g_optimizer.zero_grad()
+        torch.cuda.synchronize()
+        from . import _lib
+        n0 = _lib.lib().srg_total_launches()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses = train_generator_async(*args)
+        self.launches_per_replay = int(_lib.lib().srg_total_launches() - n0)
+
+    def __call__(self, lr_imgs: torch.Tensor, hr_imgs: torch.Tensor) -> torch.Tensor:
+        """Copies the batch into the graph's static inputs, replays, returns the static [4] loss tensor (valid until
+        the next call)."""
+        if lr_imgs.data_ptr() != self.lr.data_ptr():
+            self.lr.copy_(lr_imgs, non_blocking=True)
+        if hr_imgs.data_ptr() != self.hr.data_ptr():
+            self.hr.copy_(hr_imgs, non_blocking=True)
+        self.optimizer.sync_lr()
+        self.graph.replay()
+        return self.losses
+
+
 class MultiGeneratorGAN:
     """The README's multi-generator loop (readme.md:2-10): K generators + one discriminator, loss-ranked order,
     per-generator PIXEL/GAN decision (policy.py), per-epoch re-sort.
@@ -110,7 +168,7 @@ class MultiGeneratorGAN:
     the batch it has just enqueued (losses are read back one batch late, in one copy)."""
 
     def __init__(self, generators: Sequence, g_optimizers: Sequence, g_criterion, discriminator=None, d_optimizer=None,
-                 policy: Optional[MultiGeneratorPolicy] = None, loss_allreduce=None):
+                 policy: Optional[MultiGeneratorPolicy] = None, loss_allreduce=None, use_cuda_graphs: bool = False):
         self.generators = list(generators)
         self.g_optimizers = list(g_optimizers)
         self.criterion = g_criterion
@@ -122,6 +180,9 @@ class MultiGeneratorGAN:
         self.loss_allreduce = loss_allreduce      # callable(tensor) -> None: mean over ranks, in place (parallel.py)
         self._pending: List[Tuple[List[int], torch.Tensor]] = []
         self.last_plan: List[tuple] = []
+        # pixel-mode generator steps replay a captured CUDA graph per generator (built lazily on the first batch)
+        self.use_cuda_graphs = use_cuda_graphs
+        self._graphs: Dict[int, GraphedGeneratorStep] = {}
 
     def _drain(self, keep: int) -> None:
         while len(self._pending) > keep:
@@ -129,6 +190,12 @@ class MultiGeneratorGAN:
             host = dev_losses.tolist()
             for gid, row in zip(gids, host):
                 self.policy.observe(gid, row[1])
+
+    def launches_per_step(self) -> Optional[int]:
+        """Kernel launches replayed per step when every generator runs from its captured graph."""
+        if not self._graphs:
+            return None
+        return sum(g.launches_per_replay for g in self._graphs.values())
 
     def step(self, lr_imgs: torch.Tensor, hr_imgs: torch.Tensor) -> torch.Tensor:
         """Returns a device tensor [K, 4] of (g_loss, com_loss, tv_loss, g_d_loss) rows in training order."""
@@ -143,8 +210,16 @@ class MultiGeneratorGAN:
             train_discriminator_async(self.discriminator, leader, hr_imgs, lr_imgs, self.d_optimizer)
         rows = []
         for gid, mode in plan:
-            rows.append(train_generator_async(self.generators[gid], self.discriminator, lr_imgs, hr_imgs, None,
-                                              self.criterion, self.g_optimizers[gid], gan_mode=(mode == GAN)))
+            if self.use_cuda_graphs and mode == PIXEL:
+                gs = self._graphs.get(gid)
+                if gs is None or gs.lr.shape != lr_imgs.shape:
+                    gs = GraphedGeneratorStep(self.generators[gid], self.discriminator, self.criterion,
+                                              self.g_optimizers[gid], lr_imgs, hr_imgs)
+                    self._graphs[gid] = gs
+                rows.append(gs(lr_imgs, hr_imgs).clone())
+            else:
+                rows.append(train_generator_async(self.generators[gid], self.discriminator, lr_imgs, hr_imgs, None,
+                                                  self.criterion, self.g_optimizers[gid], gan_mode=(mode == GAN)))
         out = torch.stack(rows)
         if self.loss_allreduce is not None:
             self.loss_allreduce(out)

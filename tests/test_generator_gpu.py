@@ -321,3 +321,30 @@ def test_train_generator_step_matches_oracle_sequence(S, O, golden_dir):
         assert abs(ours[1] - ref[1]) < 5e-3 * abs(ref[1]), (step, ours, ref)
         assert abs(ours[2] - ref[2]) < 5e-2 * abs(ref[2]), (step, ours, ref)
         assert ours[3] == 0.0
+
+
+def test_cuda_graph_step_is_identical_to_eager(S):
+    """GraphedGeneratorStep replays must equal eagerly enqueued train_generator steps bit for bit, and building the
+    graph (warm-up + capture) must not change the model."""
+    def make():
+        torch.manual_seed(21)
+        g = S.SRResNet(num_residuals=2).cuda()
+        return g, S.Adam(g.parameters(), lr=1e-3, capturable=True)
+    crit = S.ReconstructionLoss()
+    torch.manual_seed(22)
+    lr, hr = torch.rand(2, 3, 24, 16).cuda(), torch.rand(2, 3, 96, 64).cuda()
+    lr2, hr2 = torch.rand(2, 3, 24, 16).cuda(), torch.rand(2, 3, 96, 64).cuda()
+    g_e, o_e = make()
+    eager = [S.train_generator_async(g_e, None, a, b, None, crit, o_e).clone() for a, b in ((lr, hr), (lr2, hr2), (lr, hr))]
+    g_g, o_g = make()
+    before = g_g.flat_parameters().clone()
+    step = S.GraphedGeneratorStep(g_g, None, crit, o_g, lr, hr)
+    assert torch.equal(g_g.flat_parameters(), before)
+    graphed = [step(a, b).clone() for a, b in ((lr, hr), (lr2, hr2), (lr, hr))]
+    torch.cuda.synchronize()
+    for e, q in zip(eager, graphed):
+        assert torch.equal(e, q), (e, q)
+    assert torch.equal(g_e.flat_parameters(), g_g.flat_parameters())
+    assert torch.equal(g_e.state_dict()["residual_blocks.1.bn2.running_var"], g_g.state_dict()["residual_blocks.1.bn2.running_var"])
+    assert int(g_g.state_dict()["residual_blocks.0.bn1.num_batches_tracked"]) == 3
+    assert step.launches_per_replay > 50
