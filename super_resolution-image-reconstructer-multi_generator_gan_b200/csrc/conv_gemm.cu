@@ -54,6 +54,7 @@ struct ConvKParams {
   int aux_mode;  // 0 none, 1 add (residual), 2 mask (zero where aux <= 0)
   void* out;     // fold9 only (fp32 NCHW)
   int out_mode;
+  float* stats;  // per-CTA channel sums / sums of squares (BatchNorm statistics fused into the epilogue)
   long long* prof;  // optional per-CTA role timers (debug)
 };
 
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* auxfull = bars + 21;                          // [2]
   uint64_t* auxempty = bars + 23;                         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  float* s_stats = reinterpret_cast<float*>(tail2 + 512);  // [8][128] floats (p.stats only)
 
   const int nblk = blockIdx.x % p.n_blocks;
   const int tile0 = blockIdx.x / p.n_blocks;
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int etid = threadIdx.x - 64;
     int acc = 0, ob = 0, ab = 0;
     uint32_t acc_phase = 0, aux_phase = 0;
+    float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;   // BatchNorm statistics of this thread's channel pair
     for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
@@ -358,12 +361,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           tma_store_4d(&p.out_map[ps ? nblk : 0], out_stage + ob * kTileOutBytes, ps ? 0 : nblk * BLOCK_N, w0, h0, n);
           tma_store_commit();
         }
+        if (p.stats != nullptr) {
+          // column sums of the staged bf16 tile (exactly the values BatchNorm will normalise): thread = channel pair
+          // c2 x 16-row part; rows outside the image (ragged tiles) are skipped
+          const int c2 = etid & 31, part = etid >> 5;
+          const uint8_t* sp = out_stage + ob * kTileOutBytes;
+#pragma unroll 4
+          for (int r = 0; r < 16; ++r) {
+            const int mm = part * 16 + r;
+            const int th = mm / p.TW;
+            if (h0 + th < p.H && w0 + (mm - th * p.TW) < p.W) {
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(sp + mm * 128 + ((((c2 >> 2)) ^ (mm & 7)) << 4) + (c2 & 3) * 4);
+              const float a0 = bf16_lo(v), a1 = bf16_hi(v);
+              st_s0 += a0; st_s1 += a1;
+              st_q0 = fmaf(a0, a0, st_q0); st_q1 = fmaf(a1, a1, st_q1);
+            }
+          }
+        }
         ob ^= 1;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (!kFold && etid == 0) tma_store_wait_all<0>();
+    if (!kFold && p.stats != nullptr) {
+      const int c2 = etid & 31, part = etid >> 5;
+      s_stats[part * 128 + 2 * c2] = st_s0;
+      s_stats[part * 128 + 2 * c2 + 1] = st_s1;
+      s_stats[part * 128 + 64 + 2 * c2] = st_q0;
+      s_stats[part * 128 + 64 + 2 * c2 + 1] = st_q1;
+      named_bar_sync(3, kEpiThreads);
+      if (etid < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += s_stats[g * 128 + etid];
+        p.stats[size_t(blockIdx.x) * 128 + etid] = t;
+      }
+    }
   }
 
   if (p.prof != nullptr && lane == 0 && (warp <= 2)) {
@@ -437,6 +471,17 @@ static int launch_instance(const ConvKParams& p, dim3 grid, size_t smem_bytes, c
   return 0;
 }
 
+int conv_gemm_grid(const ConvGemmArgs& a) {
+  const bool fold = a.out_mode == OUT_FOLD9_NCHW;
+  const int step_w = fold ? a.TW - 8 : a.TW;
+  const int tiles = a.N * ((a.H + a.TH - 1) / a.TH) * ((a.W + step_w - 1) / step_w);
+  const int n_blocks = a.cout_total / a.block_n;
+  int per = num_sms() / n_blocks;
+  if (per < 1) per = 1;
+  if (per > tiles) per = tiles;
+  return per * n_blocks;
+}
+
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   if (a.TH * a.TW != 128 || a.TW % 8 != 0) { set_error("conv_gemm: tile must be 128 pixels with TW%%8==0"); return -1; }
   if (a.block_n != 64 && a.block_n != 32) { set_error("conv_gemm: block_n must be 32 or 64"); return -2; }
@@ -489,7 +534,11 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   p.strip_bytes = uint32_t(a.strip_rows) * a.TW * 128u;
   const uint32_t w_all = uint32_t(kb_total) * btile;
   p.aux_mode = a.residual ? 1 : (a.mask_src ? 2 : 0);
-  const uint32_t fixed_bytes = (fold ? 128 * kFoldPad * 4 : 2 * kTileOutBytes) + (has_aux ? 2 * kTileOutBytes : 0) + 256 + 256;
+  if (a.stats != nullptr && (a.out_mode != OUT_NHWC || a.cout_total != 64)) {
+    set_error("conv_gemm: fused statistics need OUT_NHWC with 64 output channels"); return -16;
+  }
+  const uint32_t fixed_bytes = (fold ? 128 * kFoldPad * 4 : 2 * kTileOutBytes) + (has_aux ? 2 * kTileOutBytes : 0) + 256 + 256 +
+                               (a.stats != nullptr ? 8 * 128 * 4 : 0);
   const uint32_t budget = 227 * 1024 - 1024 - fixed_bytes;
   p.resident = (w_all + 3 * p.strip_bytes <= budget) ? 1 : 0;
   p.w_resident_bytes = p.resident ? w_all : 0;
@@ -550,6 +599,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   }
   p.bias = a.bias; p.act = a.act; p.slope = a.slope;
   p.out = a.out; p.out_mode = a.out_mode;
+  p.stats = a.stats;
   p.prof = reinterpret_cast<long long*>(a.prof);
 
   const dim3 grid(p.ctas_per_block * p.n_blocks);

@@ -56,12 +56,16 @@ struct ConvGemmArgs {
   const void* mask_src;      // bf16, same layout as out: out = (mask_src > 0) ? out : 0  (ReLU backward)
   void* out;
   int out_mode;
+  float* stats;              // optional (OUT_NHWC, cout 64): per-CTA column sums of the STORED bf16 tile values,
+                             // float [conv_gemm_grid(a)][128] = {sum over valid pixels [64], sum of squares [64]}
   void* prof;                // optional debug timers: int64 [grid][3][6]
   // fold9: tile columns overlap; valid output columns per tile = TW-8
 };
 
 // Returns 0 on success, cudaError_t (>0) or a negative argument-check code otherwise.
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream);
+// number of CTAs launch_conv_gemm uses for `a` (= rows written to a.stats)
+int conv_gemm_grid(const ConvGemmArgs& a);
 
 // Weight gradient: D_t[ci][co] = sum_p x[p + shift_t][ci] * dy[p][co] for every tap t = s*n_taps + r
 // (strip-major), taps paired (2i, 2i+1) into 128-row accumulators.  Partials layout:

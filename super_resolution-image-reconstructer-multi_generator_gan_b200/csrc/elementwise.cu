@@ -5,6 +5,7 @@
 #include "elementwise.cuh"
 
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "conv_gemm.cuh"
 
@@ -162,6 +163,46 @@ __global__ void __launch_bounds__(256) chan_reduce_final_kernel(const uint4* __r
     finalize_channels(f, c, dred[0][c] + dred[1][c], dred[0][64 + c] + dred[1][64 + c]);
   }
   if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// partials [rows][128] -> fixed-order column sums (8 row lanes x 128 columns, 4 independent accumulators per thread) ->
+// per-channel finalize, one 1024-thread block.
+__global__ void __launch_bounds__(1024) partials_finalize_kernel(const float* __restrict__ partials, int rows,
+                                                                 const ReduceFinalize f, double* __restrict__ sums_out) {
+  __shared__ double red[8][128];
+  const int col = threadIdx.x & 127, rl = threadIdx.x >> 7;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int b = rl;
+  for (; b + 24 < rows; b += 32) {
+    a0 += double(partials[size_t(b) * 128 + col]);
+    a1 += double(partials[size_t(b + 8) * 128 + col]);
+    a2 += double(partials[size_t(b + 16) * 128 + col]);
+    a3 += double(partials[size_t(b + 24) * 128 + col]);
+  }
+  for (; b < rows; b += 8) a0 += double(partials[size_t(b) * 128 + col]);
+  red[rl][col] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (rl == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][col];
+    red[0][col] = t;
+    if (sums_out != nullptr) sums_out[col] = t;
+  }
+  __syncthreads();
+  if (sums_out == nullptr && threadIdx.x < 64) finalize_channels(f, threadIdx.x, red[0][threadIdx.x], red[0][64 + threadIdx.x]);
+}
+int launch_partials_finalize(const float* partials, int rows, const ReduceFinalize& f, cudaStream_t st) {
+  partials_finalize_kernel<<<1, 1024, 0, st>>>(partials, rows, f, nullptr);
+  SRG_LAUNCH_CHECK("partials_finalize");
+  return 0;
+}
+int launch_partials_sums(const float* partials, int rows, double* sums, cudaStream_t st) {
+  ReduceFinalize f;
+  memset(&f, 0, sizeof(f));
+  partials_finalize_kernel<<<1, 1024, 0, st>>>(partials, rows, f, sums);
+  SRG_LAUNCH_CHECK("partials_sums");
+  return 0;
 }
 
 int launch_chan_reduce_final(const void* a, const void* b, int64_t pixels, float* partials, unsigned int* ticket,

@@ -6,7 +6,7 @@
 
 namespace srg {
 
-constexpr int kRedBlocksMax = 592;  // 4 x 148 SMs
+constexpr int kRedBlocksMax = 296;  // 2 x 148 SMs
 
 // ---- per-channel reductions over [P pixels][64 ch] bf16 ------------------------------------------
 // partials: float [blocks][128]  ([0,64) = sum a ; [64,128) = sum a*a (b == null) or sum a*b)
@@ -31,6 +31,11 @@ struct ReduceFinalize {
   float* out2;                  // FWD: save_mean | BWD: coefC
   float* out3;                  // FWD: save_inv
 };
+// Two-launch form used on the hot path: any producer of [rows][128] fp32 partials (launch_chan_reduce, or the conv
+// epilogue's fused statistics) followed by ONE 1024-thread block that sums them in a fixed order and finalizes.
+int launch_partials_finalize(const float* partials, int rows, const ReduceFinalize& f, cudaStream_t st);
+// SyncBatchNorm path: only the fixed-order column sums (double[128]); the all-reduce and finalize follow.
+int launch_partials_sums(const float* partials, int rows, double* sums, cudaStream_t st);
 // `ticket` is a device counter that must be 0 before the first launch (the kernel resets it).
 int launch_chan_reduce_final(const void* a, const void* b, int64_t pixels, float* partials, unsigned int* ticket,
                              const ReduceFinalize& f, cudaStream_t st);

@@ -501,12 +501,14 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
   }
   e->launches += 2;
 
-  auto conv3x3 = [&](const void* in, int64_t w_off, const float* bias, const void* residual, void* out) -> int {
+  int stats_rows = 0;
+  auto conv3x3 = [&](const void* in, int64_t w_off, const float* bias, const void* residual, void* out, bool stats) -> int {
     ConvGemmArgs a; memset(&a, 0, sizeof(a));
     a.N = N; a.H = H; a.W = W; set_taps_3x3(a);
     a.n_views = 1; a.views[0] = plain_view(in, H, W); a.in_H = H; a.in_W = W;
     a.weights = packed + w_off; a.cout_total = 64; a.block_n = 64;
     a.bias = bias; a.act = ACT_NONE; a.residual = residual; a.out = out; a.out_mode = OUT_NHWC;
+    if (stats) { a.stats = reinterpret_cast<float*>(ws + L.partials); stats_rows = conv_gemm_grid(a); }
     e->launches += 1;
     ProfScope ps(e, st);
     return launch_conv_gemm(a, st);
@@ -527,19 +529,19 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
     }
     float* partials = reinterpret_cast<float*>(ws + L.partials);
     double* sums = reinterpret_cast<double*>(ws + L.sums);
+    // batch statistics were accumulated by the producing conv's epilogue: [stats_rows][128] per-CTA partial sums
+    (void)y;
     if (!e->allreduce) {
-      // single GPU: statistics + finalize in one launch
       ReduceFinalize f; memset(&f, 0, sizeof(f));
       f.mode = RF_BN_FWD; f.count = double(P); f.eps = kBnEps; f.momentum = kBnMomentum; f.gamma = gamma; f.beta = beta;
       f.running_mean = update_running ? rm : nullptr; f.running_var = update_running ? rv : nullptr;
       f.out0 = coef; f.out1 = coef + 64; f.out2 = coef + 128; f.out3 = coef + 192;
       e->launches += 1;
-      return launch_chan_reduce_final(y, nullptr, P, partials, reinterpret_cast<unsigned int*>(ws + L.ticket), f, st);
+      return launch_partials_finalize(partials, stats_rows, f, st);
     }
-    RC(launch_chan_reduce(y, nullptr, P, partials, st));
-    RC(launch_partials_to_sums(partials, reduce_blocks(P), sums, st));
+    RC(launch_partials_sums(partials, stats_rows, sums, st));
     RC(e->allreduce(e->allreduce_ctx, sums, 128, st));
-    e->launches += 3;
+    e->launches += 2;
     return launch_bn_finalize(sums, double(P) * e->world, gamma, beta, kBnEps, kBnMomentum, update_running ? rm : nullptr,
                               update_running ? rv : nullptr, coef, coef + 64, coef + 128, coef + 192, st);
   };
@@ -549,18 +551,18 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
     const float* coef1 = reinterpret_cast<const float*>(ws + L.bncoef) + size_t(2 * b) * 256;
     const float* coef2 = coef1 + 256;
     snprintf(nm, sizeof(nm), "residual_blocks.%d.conv1.bias", b);
-    RC(conv3x3(x, po.rb_f[0][b], e->master + poff(*e, nm), nullptr, ws + L.y1[b]));
+    RC(conv3x3(x, po.rb_f[0][b], e->master + poff(*e, nm), nullptr, ws + L.y1[b], training != 0));
     RC(bn_coeffs(b, 0, ws + L.y1[b]));
     RC(launch_bn_apply(ws + L.y1[b], coef1, coef1 + 64, nullptr, 1, ws + L.z1[b], P, st));
     snprintf(nm, sizeof(nm), "residual_blocks.%d.conv2.bias", b);
-    RC(conv3x3(ws + L.z1[b], po.rb_f[1][b], e->master + poff(*e, nm), nullptr, ws + L.y2[b]));
+    RC(conv3x3(ws + L.z1[b], po.rb_f[1][b], e->master + poff(*e, nm), nullptr, ws + L.y2[b], training != 0));
     RC(bn_coeffs(b, 1, ws + L.y2[b]));
     RC(launch_bn_apply(ws + L.y2[b], coef2, coef2 + 64, x, 0, ws + L.out[b], P, st));
     e->launches += 2;
     x = ws + L.out[b];
   }
   // conv2 + global skip (src/models.py:83-84)
-  RC(conv3x3(x, po.conv2_f, e->master + poff(*e, "conv2.bias"), ws + L.out1, ws + L.trunk));
+  RC(conv3x3(x, po.conv2_f, e->master + poff(*e, "conv2.bias"), ws + L.out1, ws + L.trunk, false));
   // upsample stages: conv 64->256, PixelShuffle(2), ReLU (src/models.py:69-75,85)
   const void* in = ws + L.trunk;
   for (int j = 0; j < e->n_up; ++j) {
@@ -644,8 +646,9 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
   auto bias_grad = [&](const void* dy, int64_t pixels, const std::string& bname) -> int {
     ReduceFinalize f; memset(&f, 0, sizeof(f));
     f.mode = RF_SUM; f.count = double(pixels); f.out0 = e->grads + poff(*e, bname);
-    e->launches += 1;
-    return launch_chan_reduce_final(dy, nullptr, pixels, partials, reinterpret_cast<unsigned int*>(ws + L.ticket), f, st);
+    RC(launch_chan_reduce(dy, nullptr, pixels, partials, st));
+    e->launches += 2;
+    return launch_partials_finalize(partials, reduce_blocks(pixels), f, st);
   };
   // dgrad of a 3x3 conv whose output gradient has `chunks`*64 channels (4 pixel-shuffle views when chunks == 4)
   auto dgrad3x3 = [&](const void* dy_base, int gh, int gw, bool dy_ps, int64_t w_off, const void* residual, const void* mask,
@@ -718,15 +721,15 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     const int64_t go = poff(*e, nm);
     snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.bias", b, k + 1);
     const int64_t bo = poff(*e, nm);
+    RC(launch_chan_reduce(dz, y, P, partials, st));
     if (!e->allreduce) {
       ReduceFinalize f; memset(&f, 0, sizeof(f));
       f.mode = RF_BN_BWD; f.count = double(P); f.gamma = e->master + go; f.save_mean = coef + 128; f.save_inv = coef + 192;
       f.dgamma = e->grads + go; f.dbeta = e->grads + bo; f.out0 = bwd; f.out1 = bwd + 64; f.out2 = bwd + 128;
-      RC(launch_chan_reduce_final(dz, y, P, partials, reinterpret_cast<unsigned int*>(ws + L.ticket), f, st));
-      e->launches += 2;
+      RC(launch_partials_finalize(partials, reduce_blocks(P), f, st));
+      e->launches += 3;
     } else {
-      RC(launch_chan_reduce(dz, y, P, partials, st));
-      RC(launch_partials_to_sums(partials, reduce_blocks(P), sums, st));
+      RC(launch_partials_sums(partials, reduce_blocks(P), sums, st));
       RC(e->allreduce(e->allreduce_ctx, sums, 128, st));
       RC(launch_bn_bwd_finalize(sums, double(P) * e->world, e->master + go, coef + 128, coef + 192, e->grads + go, e->grads + bo,
                                 bwd, bwd + 64, bwd + 128, st));
