@@ -9,6 +9,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
 // Persistent CTAs; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "conv_gemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <stdarg.h>
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   constexpr bool kFold = (BLOCK_N == 32);
+  pdl_trigger();   // let the next kernel's CTAs take this SM as soon as this CTA leaves it
 
   uint8_t* w_smem = smem;                                 // resident weights (may be empty)
   uint8_t* stages = smem + p.w_resident_bytes;            // n_stages * stage_bytes
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int kb = 0; kb < kb_total; ++kb)
           tma_load_2d(w_smem + size_t(kb) * kBTile, &p.w_map, wfull, 0, kb * p.cout_total + nblk * BLOCK_N);
       }
+      pdl_wait();      // the activations (and aux tensor) come from the previous kernel; the weights above do not
       int stage = 0, ab = 0;
       uint32_t phase = 0, aux_phase = 0;
       for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
@@ -464,8 +467,8 @@ static int launch_instance(const ConvKParams& p, dim3 grid, size_t smem_bytes, c
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     attr_set = true;
   }
-  conv_gemm_kernel<BLOCK_N, NT><<<grid, kThreads, smem_bytes, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(conv_gemm_kernel<BLOCK_N, NT>, grid, dim3(kThreads), smem_bytes, stream, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv_gemm launch: %s", cudaGetErrorString(e)); return int(e); }
   count_launch();
   return 0;

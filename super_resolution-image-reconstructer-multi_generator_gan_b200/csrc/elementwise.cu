@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "conv_gemm.cuh"
+#include "launch.cuh"
 
 namespace srg {
 
@@ -51,6 +52,8 @@ template <bool TWO>
 __global__ void __launch_bounds__(256) chan_reduce_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
                                                           int64_t pixels, float* __restrict__ partials) {
   __shared__ float red[32][129];
+  pdl_trigger();
+  pdl_wait();
   const int cg = threadIdx.x & 7;
   const int lane_p = threadIdx.x >> 3;
   float s1[8], s2[8];
@@ -170,6 +173,8 @@ __global__ void __launch_bounds__(256) chan_reduce_final_kernel(const uint4* __r
 __global__ void __launch_bounds__(1024) partials_finalize_kernel(const float* __restrict__ partials, int rows,
                                                                  const ReduceFinalize f, double* __restrict__ sums_out) {
   __shared__ double red[8][128];
+  pdl_trigger();
+  pdl_wait();
   const int col = threadIdx.x & 127, rl = threadIdx.x >> 7;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int b = rl;
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(1024) partials_finalize_kernel(const float* __
   if (sums_out == nullptr && threadIdx.x < 64) finalize_channels(f, threadIdx.x, red[0][threadIdx.x], red[0][64 + threadIdx.x]);
 }
 int launch_partials_finalize(const float* partials, int rows, const ReduceFinalize& f, cudaStream_t st) {
-  partials_finalize_kernel<<<1, 1024, 0, st>>>(partials, rows, f, nullptr);
+  launch_pdl(partials_finalize_kernel, dim3(1), dim3(1024), 0, st, partials, rows, f, static_cast<double*>(nullptr));
   SRG_LAUNCH_CHECK("partials_finalize");
   return 0;
 }
@@ -220,10 +225,11 @@ int launch_chan_reduce_final(const void* a, const void* b, int64_t pixels, float
 int launch_chan_reduce(const void* a, const void* b, int64_t pixels, float* partials, cudaStream_t st) {
   const int blocks = reduce_blocks(pixels);
   if (b)
-    chan_reduce_kernel<true><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
-                                                    pixels, partials);
+    launch_pdl(chan_reduce_kernel<true>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint4*>(a),
+               reinterpret_cast<const uint4*>(b), pixels, partials);
   else
-    chan_reduce_kernel<false><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(a), nullptr, pixels, partials);
+    launch_pdl(chan_reduce_kernel<false>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint4*>(a),
+               static_cast<const uint4*>(nullptr), pixels, partials);
   SRG_LAUNCH_CHECK("chan_reduce");
   return 0;
 }
@@ -296,6 +302,8 @@ template <bool RELU, bool SKIP>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, const uint4* __restrict__ skip,
                                                        uint4* __restrict__ out, int64_t n_vec) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = threadIdx.x & 7;  // blockDim is a multiple of 8 and the grid stride too
   float sc[8], sh[8];
 #pragma unroll
@@ -330,10 +338,10 @@ int launch_bn_apply(const void* y, const float* scale, const float* shift, const
   const uint4* yy = reinterpret_cast<const uint4*>(y);
   const uint4* kk = reinterpret_cast<const uint4*>(skip);
   uint4* oo = reinterpret_cast<uint4*>(out);
-  if (relu && skip) bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(yy, scale, shift, kk, oo, n_vec);
-  else if (relu) bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(yy, scale, shift, kk, oo, n_vec);
-  else if (skip) bn_apply_kernel<false, true><<<blocks, 256, 0, st>>>(yy, scale, shift, kk, oo, n_vec);
-  else bn_apply_kernel<false, false><<<blocks, 256, 0, st>>>(yy, scale, shift, kk, oo, n_vec);
+  if (relu && skip) launch_pdl(bn_apply_kernel<true, true>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec);
+  else if (relu) launch_pdl(bn_apply_kernel<true, false>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec);
+  else if (skip) launch_pdl(bn_apply_kernel<false, true>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec);
+  else launch_pdl(bn_apply_kernel<false, false>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec);
   SRG_LAUNCH_CHECK("bn_apply");
   return 0;
 }
@@ -367,6 +375,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
                                                            const float* __restrict__ cA, const float* __restrict__ cB,
                                                            const float* __restrict__ cC, uint4* __restrict__ dy,
                                                            int64_t n_vec) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = threadIdx.x & 7;
   float a[8], b[8], c[8];
 #pragma unroll
@@ -387,9 +397,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
 int launch_bn_bwd_apply(const void* dout, const void* y, const float* coefA, const float* coefB, const float* coefC,
                         void* dy, int64_t pixels, cudaStream_t st) {
   const int64_t n_vec = pixels * 8;
-  bn_bwd_apply_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(reinterpret_cast<const uint4*>(dout),
-                                                        reinterpret_cast<const uint4*>(y), coefA, coefB, coefC,
-                                                        reinterpret_cast<uint4*>(dy), n_vec);
+  launch_pdl(bn_bwd_apply_kernel, dim3(ew_blocks(n_vec)), dim3(256), 0, st, reinterpret_cast<const uint4*>(dout),
+             reinterpret_cast<const uint4*>(y), coefA, coefB, coefC, reinterpret_cast<uint4*>(dy), n_vec);
   SRG_LAUNCH_CHECK("bn_bwd_apply");
   return 0;
 }

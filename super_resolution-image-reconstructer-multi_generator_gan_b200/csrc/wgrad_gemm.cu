@@ -9,6 +9,7 @@
 // its pixel tiles (split-K over CTAs) and writes one fp32 partial block at the end; wgrad_reduce_kernel sums the
 // partials in a fixed order (deterministic) and scatters them into the OIHW gradient through an index map.
 #include "conv_gemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <string.h>
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
 
   uint8_t* stages = smem;  // n_stages * stage_bytes; stage = [dy tile 16 KB][strip 0][strip 1]...
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + size_t(p.n_stages) * p.stage_bytes);
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
 
   if (warp == 0) {
     if (elect_one()) {
+      pdl_wait();      // x and dy come from the previous kernels
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = split; tile < p.tiles_total; tile += p.splits) {
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
     // epilogue: once per CTA
     const int q = warp & 3;
     const int m = q * 32 + lane;
+    pdl_wait();        // the split-K partial buffer is still being read by the previous layer's reduce kernel
     mbar_wait(done, 0);
     tc_fence_after();
     const bool any = split < p.tiles_total;
@@ -178,6 +182,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_inv_kernel(const float4* __r
                                                                float* __restrict__ out, int n_part4, int splits,
                                                                size_t split_stride4) {
   __shared__ float4 sh[8][32];
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, sg = threadIdx.x >> 5;
   const int j4 = blockIdx.x * 32 + lane;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -206,9 +212,9 @@ int launch_wgrad_reduce_inv(const float* partials, const int* inv, float* out, i
                             cudaStream_t stream) {
   if (n_part <= 0 || (n_part & 3) || (split_stride & 3)) { set_error("wgrad_reduce_inv: sizes must be multiples of 4"); return -1; }
   const int n4 = n_part / 4;
-  wgrad_reduce_inv_kernel<<<(n4 + 31) / 32, 256, 0, stream>>>(reinterpret_cast<const float4*>(partials), inv, out, n4, splits,
-                                                              split_stride / 4);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(wgrad_reduce_inv_kernel, dim3((n4 + 31) / 32), dim3(256), 0, stream,
+                             reinterpret_cast<const float4*>(partials), inv, out, n4, splits, split_stride / 4);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("wgrad_reduce_inv launch: %s", cudaGetErrorString(e)); return int(e); }
   count_launch();
   return 0;
@@ -283,8 +289,8 @@ int launch_wgrad_gemm(const WgradArgs& a, cudaStream_t stream) {
     attr = true;
   }
   const size_t smem_bytes = 1024 + size_t(stages) * p.stage_bytes + 256;
-  wgrad_gemm_kernel<<<p.n_blocks * p.splits, kWgThreads, smem_bytes, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(wgrad_gemm_kernel, dim3(p.n_blocks * p.splits), dim3(kWgThreads), smem_bytes, stream, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("wgrad launch: %s", cudaGetErrorString(e)); return int(e); }
   count_launch();
   return 0;
