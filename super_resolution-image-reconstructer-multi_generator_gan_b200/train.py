@@ -159,6 +159,79 @@ class GraphedGeneratorStep:
         return self.losses
 
 
+class GraphedMultiGeneratorStep:
+    """K independent pixel-mode generator steps captured as PARALLEL branches of one CUDA graph (one capture stream
+    forks into K side streams and joins them again).
+
+    The generators share nothing but the input batch, so their kernel chains may interleave: while one generator's
+    persistent tensor-core kernel owns the SMs' shared memory, the HBM-bound passes (BatchNorm apply / backward,
+    reductions, loss, Adam) of another generator run in the leftover thread slots instead of idling the tensor cores.
+    Results are identical to running the K steps one after the other."""
+
+    def __init__(self, generators, g_criterion, g_optimizers, lr_example: torch.Tensor, hr_example: torch.Tensor,
+                 warmup: int = 2):
+        from . import _lib
+        self.generators, self.optimizers = list(generators), list(g_optimizers)
+        for o in self.optimizers:
+            if not getattr(o, "capturable", False):
+                raise ValueError("GraphedMultiGeneratorStep needs optim.Adam(..., capturable=True)")
+        self.lr = lr_example.detach().clone()
+        self.hr = hr_example.detach().clone()
+        K = len(self.generators)
+        snaps = []
+        for g, o in zip(self.generators, self.optimizers):
+            flat = g.flat_parameters()
+            rt = g._rt
+            st0 = o.flat_state(g)
+            snaps.append(([t.clone() for t in (flat, rt["flat_buf"], rt["nbt"])],
+                          [st0[k].clone() for k in ("m", "v", "step_dev")] if st0 is not None and "step_dev" in st0 else None))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                for g, o in zip(self.generators, self.optimizers):
+                    train_generator_async(g, None, self.lr, self.hr, None, g_criterion, o)
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.no_grad():
+            for g, o, (snap, osnap) in zip(self.generators, self.optimizers, snaps):
+                rt = g._rt
+                for dst, src in zip((rt["flat"], rt["flat_buf"], rt["nbt"]), snap):
+                    dst.copy_(src)
+                st = o.flat_state(g)
+                if osnap is None:
+                    st["m"].zero_(); st["v"].zero_(); st["step_dev"].zero_()
+                else:
+                    for k, src in zip(("m", "v", "step_dev"), osnap):
+                        st[k].copy_(src)
+                o.zero_grad()
+        torch.cuda.synchronize()
+        n0 = _lib.lib().srg_total_launches()
+        self.streams = [torch.cuda.Stream() for _ in range(K)]
+        self.graph = torch.cuda.CUDAGraph()
+        rows = [None] * K
+        with torch.cuda.graph(self.graph):
+            main = torch.cuda.current_stream()
+            for i, (g, o) in enumerate(zip(self.generators, self.optimizers)):
+                self.streams[i].wait_stream(main)
+                with torch.cuda.stream(self.streams[i]):
+                    rows[i] = train_generator_async(g, None, self.lr, self.hr, None, g_criterion, o)
+            for s_ in self.streams:
+                main.wait_stream(s_)
+            self.losses = torch.stack(rows)
+        self.launches_per_replay = int(_lib.lib().srg_total_launches() - n0)
+
+    def __call__(self, lr_imgs: torch.Tensor, hr_imgs: torch.Tensor) -> torch.Tensor:
+        """Replays all K steps; returns the static [K, 4] loss tensor in generator-id order."""
+        if lr_imgs.data_ptr() != self.lr.data_ptr():
+            self.lr.copy_(lr_imgs, non_blocking=True)
+        if hr_imgs.data_ptr() != self.hr.data_ptr():
+            self.hr.copy_(hr_imgs, non_blocking=True)
+        for o in self.optimizers:
+            o.sync_lr()
+        self.graph.replay()
+        return self.losses
+
+
 class MultiGeneratorGAN:
     """The README's multi-generator loop (readme.md:2-10): K generators + one discriminator, loss-ranked order,
     per-generator PIXEL/GAN decision (policy.py), per-epoch re-sort.
@@ -183,6 +256,7 @@ class MultiGeneratorGAN:
         # pixel-mode generator steps replay a captured CUDA graph per generator (built lazily on the first batch)
         self.use_cuda_graphs = use_cuda_graphs
         self._graphs: Dict[int, GraphedGeneratorStep] = {}
+        self._multi: Optional[GraphedMultiGeneratorStep] = None     # all-PIXEL batches: K parallel branches, one graph
 
     def _drain(self, keep: int) -> None:
         while len(self._pending) > keep:
@@ -193,6 +267,8 @@ class MultiGeneratorGAN:
 
     def launches_per_step(self) -> Optional[int]:
         """Kernel launches replayed per step when every generator runs from its captured graph."""
+        if self._multi is not None:
+            return self._multi.launches_per_replay
         if not self._graphs:
             return None
         return sum(g.launches_per_replay for g in self._graphs.values())
@@ -208,6 +284,14 @@ class MultiGeneratorGAN:
         if any_gan and self.d_optimizer is not None:
             leader = self.generators[plan[0][0]]
             train_discriminator_async(self.discriminator, leader, hr_imgs, lr_imgs, self.d_optimizer)
+        if self.use_cuda_graphs and not any_gan and self.loss_allreduce is None:
+            if self._multi is None or self._multi.lr.shape != lr_imgs.shape:
+                self._multi = GraphedMultiGeneratorStep(self.generators, self.criterion, self.g_optimizers, lr_imgs, hr_imgs)
+            by_id = self._multi(lr_imgs, hr_imgs)
+            gids = [gid for gid, _ in plan]
+            out = by_id[gids].clone() if gids != list(range(len(gids))) else by_id.clone()
+            self._pending.append((gids, out))
+            return out
         rows = []
         for gid, mode in plan:
             if self.use_cuda_graphs and mode == PIXEL:

@@ -348,3 +348,31 @@ def test_cuda_graph_step_is_identical_to_eager(S):
     assert torch.equal(g_e.state_dict()["residual_blocks.1.bn2.running_var"], g_g.state_dict()["residual_blocks.1.bn2.running_var"])
     assert int(g_g.state_dict()["residual_blocks.0.bn1.num_batches_tracked"]) == 3
     assert step.launches_per_replay > 50
+
+
+def test_parallel_branch_graph_of_three_generators_matches_sequential(S):
+    """MultiGeneratorGAN with CUDA graphs runs the K pixel-mode steps as parallel branches of one graph; losses and
+    weights must equal the sequential eager loop exactly."""
+    crit = S.ReconstructionLoss()
+    torch.manual_seed(31)
+    lr, hr = torch.rand(2, 3, 16, 24).cuda(), torch.rand(2, 3, 64, 96).cuda()
+
+    def make(graphs):
+        gens, opts = [], []
+        for s_ in range(3):
+            torch.manual_seed(40 + s_)
+            g = S.SRResNet(num_residuals=1).cuda()
+            gens.append(g)
+            opts.append(S.Adam(g.parameters(), lr=1e-3, capturable=True))
+        pol = S.MultiGeneratorPolicy(S.PolicyConfig(num_generators=3, force=S.PIXEL))
+        return gens, S.MultiGeneratorGAN(gens, opts, crit, policy=pol, use_cuda_graphs=graphs)
+    g_a, t_a = make(False)
+    g_b, t_b = make(True)
+    for _ in range(3):
+        la = t_a.step(lr, hr).clone()
+        lb = t_b.step(lr, hr).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(la, lb), (la, lb)
+    for a, b in zip(g_a, g_b):
+        assert torch.equal(a.flat_parameters(), b.flat_parameters())
+    assert t_b.end_epoch() == t_a.end_epoch()
