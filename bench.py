@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--ref-sample-batch", type=int, default=4, help="patches per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--syncbn", default="peer", choices=["peer", "nccl"], help="SyncBatchNorm transport for N > 1: fused "
+                    "NVLink peer-memory exchange kernel (default) or ncclAllReduce between reduce and finalize kernels")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from the host instead of replaying "
                     "one captured CUDA graph per generator step")
     return ap.parse_args()
@@ -75,7 +77,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -89,7 +91,7 @@ class ClockSampler:
             os.close(fd)
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -212,10 +214,10 @@ def run_ours(a):
         d_opt = S.Adam(disc.parameters(), lr=5e-5)
     loss_ar = None
     if world > 1:
-        S.parallel.data_parallel(gens + ([disc] if disc is not None else []), sync_batchnorm=True)
+        S.parallel.data_parallel(gens + ([disc] if disc is not None else []), sync_batchnorm=True, sync_bn_transport=a.syncbn)
         loss_ar = S.parallel.mean_over_ranks()
     policy = S.MultiGeneratorPolicy(S.PolicyConfig(num_generators=K, force=S.GAN if disc is not None else S.PIXEL, seed=0))
-    use_graphs = (not a.no_graphs) and world == 1 and disc is None
+    use_graphs = (not a.no_graphs) and disc is None
     trainer = S.MultiGeneratorGAN(gens, opts, crit, discriminator=disc, d_optimizer=d_opt, policy=policy,
                                   loss_allreduce=loss_ar, use_cuda_graphs=use_graphs)
 
@@ -318,7 +320,8 @@ def run_ours(a):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(a), "generators": K, "batch_per_gpu": B, "global_batch": B * world,
-                       "lr_hw": [LH, LW], "upscale": 4, "cuda_graphs": bool(use_graphs), "parallelism": f"dp{world}",
+                       "lr_hw": [LH, LW], "upscale": 4, "cuda_graphs": bool(use_graphs), "parallelism": f"dp{world}", "syncbn": (a.syncbn if world > 1 else None),
+                       "peer_sync_timeouts": (S.parallel.peer_sync_errors() if world > 1 else 0),
                        "l2": "per-step working set (~2.5 GB of activations per generator) exceeds the 126 MB L2; no flush needed",
                        "generator_passes_per_sec": value * K, "whole_step_algorithmic_tflops": whole_step_tflops,
                        "whole_step_frac_of_bf16_peak": whole_step_tflops / world / peak, "last_losses": last},
@@ -327,8 +330,13 @@ def run_ours(a):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        S.parallel.shutdown_nccl()
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL collectives are still alive: synchronise, then leave without tearing the
+        # communicators down (process exit releases them; destroying them first can block)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -86,13 +86,27 @@ int srg_generator_profile_read(srg_generator_t* g, double* ms_sum, long long* co
 typedef int (*srg_allreduce_f64_fn)(void* ctx, double* buf, int n, void* stream);
 int srg_generator_set_allreduce(srg_generator_t* g, srg_allreduce_f64_fn fn, void* ctx, int world);
 
-/* NCCL-backed implementation of the hook (libnccl is resolved with dlopen at first use). */
+/* NCCL-backed implementation of the hook (libnccl is resolved with dlopen at first use).  Communicators are
+ * explicit handles: one per model lets the models' steps run concurrently on separate streams / graph branches
+ * without sharing a communicator.  srg_nccl_allreduce_f64 has the hook's signature (ctx = communicator). */
 int srg_nccl_unique_id(void* out128); /* host buffer, 128 bytes */
-int srg_nccl_init(const void* unique_id128, int world, int rank);
-int srg_nccl_allreduce_f64(void* ctx, double* buf, int n, void* stream);
-int srg_nccl_allreduce_f32(float* buf, int64_t n, void* stream);
-int srg_generator_use_nccl(srg_generator_t* g);
-void srg_nccl_shutdown(void);
+int srg_nccl_comm_create(const void* unique_id128, int world, int rank, void** comm_out);
+void srg_nccl_comm_destroy(void* comm);
+int srg_nccl_allreduce_f64(void* comm, double* buf, int n, void* stream);
+int srg_nccl_allreduce_f32(void* comm, float* buf, int64_t n, void* stream); /* flat gradient all-reduce (sum) */
+int srg_generator_use_nccl(srg_generator_t* g, void* comm, int world);
+
+/* SyncBatchNorm over NVLink peer memory (preferred to the NCCL hook): the statistics reduction, the exchange with all
+ * ranks (P2P stores into every peer's buffer + release flags through NVSwitch) and the BatchNorm finalize are ONE
+ * kernel per BatchNorm layer and direction, CUDA-graph capturable.  Set-up: every rank creates its object, the 64-byte
+ * IPC handles are all-gathered by the host (any transport), connect() maps the peers' buffers. */
+typedef struct srg_peer_sync srg_peer_sync_t;
+int srg_peer_sync_create(srg_peer_sync_t** out, int world, int rank);
+int srg_peer_sync_handle(srg_peer_sync_t* ps, void* out64);
+int srg_peer_sync_connect(srg_peer_sync_t* ps, const void* handles_world_x_64);
+void srg_peer_sync_destroy(srg_peer_sync_t* ps);
+int srg_peer_sync_error(srg_peer_sync_t* ps); /* 1 if a wait on a peer ever timed out (synchronises the device) */
+int srg_generator_use_peer_sync(srg_generator_t* g, srg_peer_sync_t* ps);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Discriminator engine (src/models.py:90-120): conv 8x8 s2 p2 (3->64), then 3 x conv 4x4 s2 p1 (64->128->256->512),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "libsrgan_b200.so")
-SOURCES = ["conv_gemm.cu", "wgrad_gemm.cu", "elementwise.cu", "generator.cu", "discriminator.cu", "api.cu"]
+SOURCES = ["conv_gemm.cu", "wgrad_gemm.cu", "elementwise.cu", "peer_sync.cu", "generator.cu", "discriminator.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
@@ -94,11 +94,17 @@ EXPORTS = {
     "srg_generator_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
     "srg_generator_set_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "srg_nccl_unique_id": (c_int, [c_void_p]),
-    "srg_nccl_init": (c_int, [c_void_p, c_int, c_int]),
+    "srg_nccl_comm_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "srg_nccl_comm_destroy": (None, [c_void_p]),
     "srg_nccl_allreduce_f64": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
-    "srg_nccl_allreduce_f32": (c_int, [c_void_p, c_int64, c_void_p]),
-    "srg_generator_use_nccl": (c_int, [c_void_p]),
-    "srg_nccl_shutdown": (None, []),
+    "srg_nccl_allreduce_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "srg_generator_use_nccl": (c_int, [c_void_p, c_void_p, c_int]),
+    "srg_peer_sync_create": (c_int, [POINTER(c_void_p), c_int, c_int]),
+    "srg_peer_sync_handle": (c_int, [c_void_p, c_void_p]),
+    "srg_peer_sync_connect": (c_int, [c_void_p, c_void_p]),
+    "srg_peer_sync_destroy": (None, [c_void_p]),
+    "srg_peer_sync_error": (c_int, [c_void_p]),
+    "srg_generator_use_peer_sync": (c_int, [c_void_p, c_void_p]),
     "srg_discriminator_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
     "srg_discriminator_destroy": (None, [c_void_p]),
     "srg_discriminator_output_hw": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),

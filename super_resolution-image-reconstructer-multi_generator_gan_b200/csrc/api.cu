@@ -9,6 +9,7 @@
 #include "elementwise.cuh"
 #include "discriminator.cuh"
 #include "generator.cuh"
+#include "peer_sync.cuh"
 
 using namespace srg;
 
@@ -36,8 +37,6 @@ struct NcclApi {
   AllReduceFn all_reduce = nullptr;
   CommDestroyFn comm_destroy = nullptr;
   GetErrorStringFn error_string = nullptr;
-  NcclComm comm = nullptr;
-  int world = 1;
 } g_nccl;
 constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
 
@@ -164,33 +163,57 @@ int srg_nccl_unique_id(void* out128) {
   memcpy(out128, &id, 128);
   return 0;
 }
-int srg_nccl_init(const void* unique_id128, int world, int rank) {
+int srg_nccl_comm_create(const void* unique_id128, int world, int rank, void** comm_out) {
   int rc = nccl_load();
   if (rc) return rc;
-  if (g_nccl.comm) { set_error("srg_nccl_init: already initialised"); return -43; }
+  if (comm_out == nullptr || unique_id128 == nullptr || world < 1 || rank < 0 || rank >= world) {
+    set_error("srg_nccl_comm_create: bad arguments");
+    return -43;
+  }
   NcclId id;
   memcpy(&id, unique_id128, 128);
-  rc = nccl_check(g_nccl.comm_init_rank(&g_nccl.comm, world, id, rank), "ncclCommInitRank");
+  NcclComm comm = nullptr;
+  rc = nccl_check(g_nccl.comm_init_rank(&comm, world, id, rank), "ncclCommInitRank");
   if (rc) return rc;
-  g_nccl.world = world;
+  *comm_out = comm;
   return 0;
 }
-int srg_nccl_allreduce_f64(void* ctx, double* buf, int n, void* stream) {
-  (void)ctx;
-  if (!g_nccl.comm) { set_error("NCCL communicator not initialised"); return -44; }
-  return nccl_check(g_nccl.all_reduce(buf, buf, size_t(n), kNcclFloat64, kNcclSum, g_nccl.comm, S(stream)), "ncclAllReduce");
+void srg_nccl_comm_destroy(void* comm) {
+  if (comm != nullptr && g_nccl.comm_destroy) g_nccl.comm_destroy(comm);
 }
-int srg_nccl_allreduce_f32(float* buf, int64_t n, void* stream) {
-  if (!g_nccl.comm) { set_error("NCCL communicator not initialised"); return -44; }
-  return nccl_check(g_nccl.all_reduce(buf, buf, size_t(n), kNcclFloat32, kNcclSum, g_nccl.comm, S(stream)), "ncclAllReduce");
+int srg_nccl_allreduce_f64(void* comm, double* buf, int n, void* stream) {
+  if (comm == nullptr) { set_error("NCCL communicator is null"); return -44; }
+  return nccl_check(g_nccl.all_reduce(buf, buf, size_t(n), kNcclFloat64, kNcclSum, comm, S(stream)), "ncclAllReduce");
 }
-int srg_generator_use_nccl(srg_generator_t* g) {
-  if (!g_nccl.comm) { set_error("NCCL communicator not initialised"); return -44; }
-  return srg_generator_set_allreduce(g, srg_nccl_allreduce_f64, nullptr, g_nccl.world);
+int srg_nccl_allreduce_f32(void* comm, float* buf, int64_t n, void* stream) {
+  if (comm == nullptr) { set_error("NCCL communicator is null"); return -44; }
+  return nccl_check(g_nccl.all_reduce(buf, buf, size_t(n), kNcclFloat32, kNcclSum, comm, S(stream)), "ncclAllReduce");
 }
-void srg_nccl_shutdown(void) {
-  if (g_nccl.comm) g_nccl.comm_destroy(g_nccl.comm);
-  g_nccl.comm = nullptr;
+int srg_generator_use_nccl(srg_generator_t* g, void* comm, int world) {
+  if (comm == nullptr) { set_error("NCCL communicator is null"); return -44; }
+  return srg_generator_set_allreduce(g, srg_nccl_allreduce_f64, comm, world);
+}
+
+// ---- NVLink peer-memory SyncBatchNorm exchange ----------------------------------------------------------------------
+int srg_peer_sync_create(srg_peer_sync_t** out, int world, int rank) {
+  if (out == nullptr) { set_error("srg_peer_sync_create: null out"); return -1; }
+  PeerSync* ps = peer_sync_create(world, rank);
+  if (ps == nullptr) return -2;
+  *out = reinterpret_cast<srg_peer_sync_t*>(ps);
+  return 0;
+}
+int srg_peer_sync_handle(srg_peer_sync_t* ps, void* out64) { return peer_sync_handle(reinterpret_cast<PeerSync*>(ps), out64); }
+int srg_peer_sync_connect(srg_peer_sync_t* ps, const void* handles) {
+  return peer_sync_connect(reinterpret_cast<PeerSync*>(ps), handles);
+}
+void srg_peer_sync_destroy(srg_peer_sync_t* ps) { peer_sync_destroy(reinterpret_cast<PeerSync*>(ps)); }
+int srg_peer_sync_error(srg_peer_sync_t* ps) { return peer_sync_error(reinterpret_cast<PeerSync*>(ps)); }
+int srg_generator_use_peer_sync(srg_generator_t* g, srg_peer_sync_t* ps) {
+  if (ps == nullptr) { set_error("srg_generator_use_peer_sync: null"); return -45; }
+  GeneratorEngine* e = G(g);
+  e->peer = reinterpret_cast<PeerSync*>(ps);
+  e->world = peer_sync_world(e->peer);
+  return 0;
 }
 
 // ---- discriminator ------------------------------------------------------------------------------------------------

@@ -348,15 +348,18 @@ int launch_bn_apply(const void* y, const float* scale, const float* shift, const
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
                                        const float* __restrict__ save_mean, const float* __restrict__ save_inv,
-                                       float* dgamma, float* dbeta, float* coefA, float* coefB, float* coefC) {
+                                       float* dgamma, float* dbeta, float* coefA, float* coefB, float* coefC,
+                                       float param_grad_scale) {
   const int c = threadIdx.x;
   if (c >= 64) return;
   const double sd = sums[c], sdy = sums[64 + c];
   const double mean = save_mean[c], inv = save_inv[c];
   const double dg = inv * (sdy - mean * sd);  // sum dout * xhat
   const double db = sd;
-  if (dgamma) dgamma[c] = float(dg);
-  if (dbeta) dbeta[c] = float(db);
+  // under SyncBatchNorm the sums are global: every rank then holds d(sum of rank losses)/d(gamma); scaling by
+  // 1/world makes the rank-mean of the (identical) values the gradient of the MEAN loss, like DDP + SyncBatchNorm
+  if (dgamma) dgamma[c] = float(dg) * param_grad_scale;
+  if (dbeta) dbeta[c] = float(db) * param_grad_scale;
   const double sc = double(gamma[c]) * inv;
   // dy = sc * (dout - db/M - xhat * dg/M),  xhat = (y - mean) * inv
   coefA[c] = float(sc);
@@ -365,8 +368,9 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double c
 }
 int launch_bn_bwd_finalize(const double* sums, double count, const float* gamma, const float* save_mean,
                            const float* save_inv, float* dgamma, float* dbeta, float* coefA, float* coefB,
-                           float* coefC, cudaStream_t st) {
-  bn_bwd_finalize_kernel<<<1, 64, 0, st>>>(sums, count, gamma, save_mean, save_inv, dgamma, dbeta, coefA, coefB, coefC);
+                           float* coefC, float param_grad_scale, cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<1, 64, 0, st>>>(sums, count, gamma, save_mean, save_inv, dgamma, dbeta, coefA, coefB, coefC,
+                                           param_grad_scale);
   SRG_LAUNCH_CHECK("bn_bwd_finalize");
   return 0;
 }

@@ -57,7 +57,7 @@ int launch_bn_apply(const void* y, const float* scale, const float* shift, const
 // per-channel coefficients of  dy = A*dout + B*y + C.
 int launch_bn_bwd_finalize(const double* sums, double count, const float* gamma, const float* save_mean,
                            const float* save_inv, float* dgamma, float* dbeta, float* coefA, float* coefB,
-                           float* coefC, cudaStream_t st);
+                           float* coefC, float param_grad_scale, cudaStream_t st);
 int launch_bn_bwd_apply(const void* dout, const void* y, const float* coefA, const float* coefB, const float* coefC,
                         void* dy, int64_t pixels, cudaStream_t st);
 // d(pre-activation) of LeakyReLU from two incoming gradients: dpre = (ga + gb) * (post > 0 ? 1 : slope)

@@ -11,6 +11,7 @@
 
 #include "conv_gemm.cuh"
 #include "elementwise.cuh"
+#include "peer_sync.cuh"
 
 namespace srg {
 
@@ -531,12 +532,13 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
     double* sums = reinterpret_cast<double*>(ws + L.sums);
     // batch statistics were accumulated by the producing conv's epilogue: [stats_rows][128] per-CTA partial sums
     (void)y;
-    if (!e->allreduce) {
+    if (!e->allreduce || e->peer) {
       ReduceFinalize f; memset(&f, 0, sizeof(f));
-      f.mode = RF_BN_FWD; f.count = double(P); f.eps = kBnEps; f.momentum = kBnMomentum; f.gamma = gamma; f.beta = beta;
+      f.mode = RF_BN_FWD; f.count = double(P) * e->world; f.eps = kBnEps; f.momentum = kBnMomentum; f.gamma = gamma; f.beta = beta;
       f.running_mean = update_running ? rm : nullptr; f.running_var = update_running ? rv : nullptr;
       f.out0 = coef; f.out1 = coef + 64; f.out2 = coef + 128; f.out3 = coef + 192;
       e->launches += 1;
+      if (e->peer) return launch_peer_finalize(e->peer, partials, stats_rows, f, st);
       return launch_partials_finalize(partials, stats_rows, f, st);
     }
     RC(launch_partials_sums(partials, stats_rows, sums, st));
@@ -722,17 +724,18 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.bias", b, k + 1);
     const int64_t bo = poff(*e, nm);
     RC(launch_chan_reduce(dz, y, P, partials, st));
-    if (!e->allreduce) {
+    if (!e->allreduce || e->peer) {
       ReduceFinalize f; memset(&f, 0, sizeof(f));
-      f.mode = RF_BN_BWD; f.count = double(P); f.gamma = e->master + go; f.save_mean = coef + 128; f.save_inv = coef + 192;
+      f.mode = RF_BN_BWD; f.count = double(P) * e->world; f.gamma = e->master + go; f.save_mean = coef + 128; f.save_inv = coef + 192;
       f.dgamma = e->grads + go; f.dbeta = e->grads + bo; f.out0 = bwd; f.out1 = bwd + 64; f.out2 = bwd + 128;
-      RC(launch_partials_finalize(partials, reduce_blocks(P), f, st));
+      if (e->peer) RC(launch_peer_finalize(e->peer, partials, reduce_blocks(P), f, st));
+      else RC(launch_partials_finalize(partials, reduce_blocks(P), f, st));
       e->launches += 3;
     } else {
       RC(launch_partials_sums(partials, reduce_blocks(P), sums, st));
       RC(e->allreduce(e->allreduce_ctx, sums, 128, st));
       RC(launch_bn_bwd_finalize(sums, double(P) * e->world, e->master + go, coef + 128, coef + 192, e->grads + go, e->grads + bo,
-                                bwd, bwd + 64, bwd + 128, st));
+                                bwd, bwd + 64, bwd + 128, 1.f / float(e->world), st));
       e->launches += 4;
     }
     return launch_bn_bwd_apply(dz, y, bwd, bwd + 64, bwd + 128, dy, P, st);

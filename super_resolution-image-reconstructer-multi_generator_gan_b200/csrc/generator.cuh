@@ -57,6 +57,7 @@ struct GeneratorEngine {
   // SyncBN
   AllreduceF64Fn allreduce = nullptr;
   void* allreduce_ctx = nullptr;
+  struct PeerSync* peer = nullptr;   // NVLink peer-memory exchange fused with the finalize (preferred over `allreduce`)
   int world = 1;
   long long launches = 0;  // kernels launched so far (bench bookkeeping)
   // optional CUDA-event timing of the dominant kernel class (3x3 64->64 fprop/dgrad conv_gemm launches)

@@ -263,7 +263,7 @@ class SRResNet(_FlatModule):
         if eng is None:
             eng = _GeneratorEngine(N, H, W, self.num_residuals, self.num_upsample_stages, training, device)
             if rt["sync_bn"]:
-                check(_lib.lib().srg_generator_use_nccl(eng.handle), "srg_generator_use_nccl")
+                self._attach_sync_bn(eng)
             if getattr(self, "debug_keep_grads", False):
                 check(_lib.lib().srg_generator_set_keep_grads(eng.handle, 1))
             if rt.get("profile"):
@@ -271,13 +271,21 @@ class SRResNet(_FlatModule):
             pool.append(eng)
         return eng
 
-    def enable_sync_batchnorm(self):
-        """SyncBatchNorm over the communicator created by parallel.init_nccl(): per-channel sums are all-reduced
-        between the local reduction and the BatchNorm finalize, forward and backward."""
-        self._rt["sync_bn"] = True
+    def _attach_sync_bn(self, eng):
+        kind, obj, world = self._rt["sync_bn"]
+        if kind == "peer":
+            check(_lib.lib().srg_generator_use_peer_sync(eng.handle, obj), "srg_generator_use_peer_sync")
+        else:
+            check(_lib.lib().srg_generator_use_nccl(eng.handle, obj, world), "srg_generator_use_nccl")
+
+    def enable_sync_batchnorm(self, comm=None, world: int = 1, peer_sync=None):
+        """SyncBatchNorm: per-channel sums are reduced across ranks between the local reduction and the BatchNorm
+        finalize, forward and backward -- through ``peer_sync`` (parallel.create_peer_sync(): NVLink peer-memory
+        exchange fused with the finalize kernel) or an NCCL communicator (parallel.create_comm())."""
+        self._rt["sync_bn"] = ("peer", peer_sync, int(world)) if peer_sync is not None else ("nccl", comm, int(world))
         for pool in self._rt["engines"].values():
             for e in pool:
-                check(_lib.lib().srg_generator_use_nccl(e.handle), "srg_generator_use_nccl")
+                self._attach_sync_bn(e)
 
     def launch_count(self) -> int:
         L = _lib.lib()

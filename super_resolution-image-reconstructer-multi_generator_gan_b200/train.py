@@ -284,12 +284,14 @@ class MultiGeneratorGAN:
         if any_gan and self.d_optimizer is not None:
             leader = self.generators[plan[0][0]]
             train_discriminator_async(self.discriminator, leader, hr_imgs, lr_imgs, self.d_optimizer)
-        if self.use_cuda_graphs and not any_gan and self.loss_allreduce is None:
+        if self.use_cuda_graphs and not any_gan:
             if self._multi is None or self._multi.lr.shape != lr_imgs.shape:
                 self._multi = GraphedMultiGeneratorStep(self.generators, self.criterion, self.g_optimizers, lr_imgs, hr_imgs)
             by_id = self._multi(lr_imgs, hr_imgs)
             gids = [gid for gid, _ in plan]
             out = by_id[gids].clone() if gids != list(range(len(gids))) else by_id.clone()
+            if self.loss_allreduce is not None:
+                self.loss_allreduce(out)
             self._pending.append((gids, out))
             return out
         rows = []
