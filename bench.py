@@ -291,8 +291,14 @@ def run_ours(a):
     avg_ms = k_ms / max(k_n, 1)
     achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12 if k_n else 0.0
     peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_conv_gemm_traffic.json")) as f:
+            traffic = json.load(f)["dram_bytes_per_launch"]       # dram__bytes_read.sum + dram__bytes_write.sum (ncu)
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "conv_gemm_kernel<64,3> (3x3 64->64 fprop/dgrad implicit GEMM)",
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, cfg2 geometry)", "kernel": "conv_gemm_kernel<64,3> (3x3 64->64 fprop/dgrad implicit GEMM)",
                 "launches_timed": k_n, "avg_launch_us": avg_ms * 1e3, "kernel_share_of_step": (k_ms / prof_steps) / ms_per_step,
                 "flop_per_launch": flop_per_launch, "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "timed_over": f"{prof_steps} extra steps right after the timed region (per-launch CUDA events on the launch stream)"}

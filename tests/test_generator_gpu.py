@@ -376,3 +376,34 @@ def test_parallel_branch_graph_of_three_generators_matches_sequential(S):
     for a, b in zip(g_a, g_b):
         assert torch.equal(a.flat_parameters(), b.flat_parameters())
     assert t_b.end_epoch() == t_a.end_epoch()
+
+
+def test_peer_sync_kernel_world1_matches_local_finalize(S):
+    """The fused reduce + NVLink exchange + finalize kernel (csrc/peer_sync.cu) with a single rank (its own buffer is
+    the only peer) must reproduce the local finalize path bit for bit; the multi-rank behaviour is covered by
+    tools/check_multigpu.py (profiles/r01_multigpu_equivalence_*.log)."""
+    import ctypes
+    from ctypes import c_void_p
+    L = S.lib()
+    ps = c_void_p()
+    S._lib.check(L.srg_peer_sync_create(ctypes.byref(ps), 1, 0))
+    buf = ctypes.create_string_buffer(64)
+    S._lib.check(L.srg_peer_sync_handle(ps, buf))
+    S._lib.check(L.srg_peer_sync_connect(ps, buf.raw))
+    torch.manual_seed(51)
+    lr = torch.rand(2, 3, 20, 12).cuda()
+    dsr = torch.randn(2, 3, 80, 48).cuda() * 1e-3
+    outs = []
+    for use_peer in (False, True):
+        torch.manual_seed(52)
+        g = S.SRResNet(num_residuals=2).cuda()
+        if use_peer:
+            g.enable_sync_batchnorm(world=1, peer_sync=ps)
+        y = g(lr)
+        y.backward(dsr)
+        torch.cuda.synchronize()
+        outs.append((y.detach().clone(), g.flat_grads().clone(), g.state_dict()["residual_blocks.1.bn2.running_var"].clone()))
+    assert L.srg_peer_sync_error(ps) == 0
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    L.srg_peer_sync_destroy(ps)
