@@ -412,6 +412,323 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+
+// =====================================================================================================================
+// 3x3 convolution with the three row taps of every strip fused into one N = 192 MMA ("fuse_taps").
+//
+// Measured on B200 (tools/mma_probe.cu): an SS-mode M128 x K16 tcgen05.mma costs ~69 cycles for N = 64 and for N = 128
+// and 128 cycles for N = 256 -- a ~64-cycle floor per instruction -- so the N = 64 MMAs of the generic kernel run the
+// tensor pipe at 46 %.  Here ONE 16-row x 8-pixel input window per column shift is multiplied by the stacked weights of
+// its three row taps, B = [W_kh0 | W_kh1 | W_kh2] (192 rows): 12 MMAs of 96 cycles per tile instead of 36 of 69.
+// Accumulator column group kh holds E_kh[m] = W_kh . x[window pixel m]; the output is
+//     out[m] = E_0[m - 8] + E_1[m] + E_2[m + 8]        (8 = tile width: one image row up / down)
+// re-aligned in the epilogue with warp shuffles (+ a small shared-memory exchange at warp boundaries).  Window rows 0
+// and 15 have no complete sum, so tiles advance by 14 rows (87.5 % of the MMA rows are useful).
+// =====================================================================================================================
+constexpr uint32_t kFuseBTile = 192 * 128;            // bytes of one fused weight k-block (3 taps x 64 cout x 64 k)
+constexpr uint32_t kXchgBytes = 2 * 2 * 4 * 2 * 8 * 16 * 4;   // [buf 2][hf 2][q 4][kind 2][8 lanes][16 cols] floats
+
+__global__ void __launch_bounds__(kThreads, 1) conv3_fused_kernel(const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  pdl_trigger();
+
+  uint8_t* w_smem = smem;
+  uint8_t* stages = smem + p.w_resident_bytes;
+  uint8_t* out_stage = stages + size_t(p.n_stages) * p.stage_bytes;   // 2 x 16 KB
+  uint8_t* aux_stage = out_stage + 2 * kTileOutBytes;                  // 2 x 16 KB (aux_mode != 0)
+  uint8_t* tail = aux_stage + (p.aux_mode ? 2 * kTileOutBytes : 0);
+  float* xchg = reinterpret_cast<float*>(tail);                        // boundary-row exchange
+  uint8_t* tail2 = tail + kXchgBytes;
+  float* s_bias = reinterpret_cast<float*>(tail2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail2 + 256);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 8;
+  uint64_t* wfull = bars + 16;
+  uint64_t* tfull = bars + 17;
+  uint64_t* tempty = bars + 19;
+  uint64_t* auxfull = bars + 21;
+  uint64_t* auxempty = bars + 23;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  float* s_stats = reinterpret_cast<float*>(tail2 + 512);
+
+  const int nblk = blockIdx.x % p.n_blocks;
+  const int tile0 = blockIdx.x / p.n_blocks;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int kb_total = p.n_chunks * p.n_strips;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(wfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], kEpiThreads);
+      mbar_init(&auxfull[i], 1);
+      mbar_init(&auxempty[i], kEpiThreads);
+    }
+    fence_barrier_init();
+    for (int v = 0; v < kMaxInMaps; ++v) tma_prefetch_desc(&p.in_map[v]);
+    tma_prefetch_desc(&p.w_map);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (t < 64) s_bias[t] = p.bias != nullptr ? p.bias[nblk * 64 + t] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long prof_acc[4] = {0, 0, 0, 0};
+  const long long t_start = clock64();
+
+  if (warp == 0) {
+    // =============================================================== TMA producer
+    if (elect_one()) {
+      if (p.resident) {
+        mbar_expect_tx(wfull, uint32_t(kb_total) * kFuseBTile);
+        for (int kb = 0; kb < kb_total; ++kb)
+          tma_load_2d(w_smem + size_t(kb) * kFuseBTile, &p.w_map, wfull, 0, (kb * p.n_blocks + nblk) * 192);
+      }
+      pdl_wait();
+      int stage = 0, ab = 0;
+      uint32_t phase = 0, aux_phase = 0;
+      for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * 14 - 1;     // window row 0 (output rows h0+1 .. h0+14)
+        const int w0 = (rem % p.tiles_w) * p.TW;
+        if (p.aux_mode) {
+          mbar_wait(&auxempty[ab], aux_phase ^ 1);
+          mbar_expect_tx(&auxfull[ab], kTileOutBytes);
+          tma_load_4d(aux_stage + ab * kTileOutBytes, &p.aux_map, &auxfull[ab], nblk * 64, w0, h0, n);
+          ab ^= 1;
+          if (ab == 0) aux_phase ^= 1;
+        }
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const int view = c / p.chunks_per_view;
+          const int coff = (c - view * p.chunks_per_view) * 64;
+          for (int s = 0; s < p.n_strips; ++s) {
+            { long long t0_ = clock64(); mbar_wait(&empty[stage], phase ^ 1); prof_acc[0] += clock64() - t0_; }
+            uint8_t* dst = stages + size_t(stage) * p.stage_bytes;
+            mbar_expect_tx(&full[stage], p.resident ? p.strip_bytes : p.stage_bytes);
+            tma_load_4d(dst, &p.in_map[view], &full[stage], coff, w0 + p.strip_dw[s], h0, n);
+            if (!p.resident)
+              tma_load_2d(dst + p.strip_bytes, &p.w_map, &full[stage], 0, ((c * p.n_strips + s) * p.n_blocks + nblk) * 192);
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(128, 192, 0, 0);
+    const uint64_t desc_hi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+    const uint32_t stage0_lo = smem_u32(stages) >> 4;
+    const uint32_t stage_lo_stride = p.stage_bytes >> 4;
+    const uint32_t w_lo = smem_u32(w_smem) >> 4;
+    const uint32_t strip_lo = p.strip_bytes >> 4;
+    if (p.resident) mbar_wait(wfull, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
+      { long long t0_ = clock64(); mbar_wait(&tempty[acc], acc_phase ^ 1); prof_acc[1] += clock64() - t0_; }
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(acc * 192);
+      uint32_t accumulate = 0;
+      uint32_t kb = 0;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        for (int s = 0; s < p.n_strips; ++s) {
+          { long long t0_ = clock64(); mbar_wait(&full[stage], phase); prof_acc[2] += clock64() - t0_; }
+          tc_fence_after();
+          const uint32_t a_lo = stage0_lo + uint32_t(stage) * stage_lo_stride;
+          const uint32_t b_lo = p.resident ? w_lo + kb * (kFuseBTile >> 4) : a_lo + strip_lo;
+          if (elect_one()) {
+            const uint64_t adesc = desc_hi | uint64_t(a_lo);
+            const uint64_t bdesc = desc_hi | uint64_t(b_lo);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty[stage]);
+          }
+          __syncwarp();
+          accumulate = 1;
+          kb += 1;
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // =================================================================== epilogue
+    const int q = warp & 3;            // TMEM lane quadrant
+    const int m = q * 32 + lane;       // window pixel: row r = m / 8 (0..15), column m % 8
+    const int hf = (warp - 2) >> 2;    // 32-channel half
+    const int etid = threadIdx.x - 64;
+    int acc = 0, ob = 0, ab = 0, xb = 0;
+    uint32_t acc_phase = 0, aux_phase = 0;
+    float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;
+    for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * 14 - 1;
+      const int w0 = (rem % p.tiles_w) * p.TW;
+      { long long t0_ = clock64(); mbar_wait(&tfull[acc], acc_phase); prof_acc[3] += clock64() - t0_; }
+      tc_fence_after();
+      float f[32];
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 192 + hf * 32 + pass * 16);
+        uint32_t e0[16], e1[16], e2[16];
+        tmem_ld16(t_addr, e0);
+        tmem_ld16(t_addr + 64, e1);
+        tmem_ld16(t_addr + 128, e2);
+        tmem_ld_wait();
+        if (pass == 1) {
+          tc_fence_before();
+          mbar_arrive(&tempty[acc]);
+        }
+        // rows at warp boundaries: publish what the neighbouring quadrants need
+        float* xw = xchg + size_t(((xb * 2 + hf) * 4 + q) * 2) * 128;
+        if (lane >= 24) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xw[(lane - 24) * 16 + j] = __uint_as_float(e0[j]);          // kind 0: E_0 of my last row
+        }
+        if (lane < 8) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xw[128 + lane * 16 + j] = __uint_as_float(e2[j]);           // kind 1: E_2 of my first row
+        }
+        named_bar_sync(4, kEpiThreads);
+        const float* up_w = xchg + size_t(((xb * 2 + hf) * 4 + ((q + 3) & 3)) * 2) * 128;           // quadrant q-1, kind 0
+        const float* dn_w = xchg + size_t(((xb * 2 + hf) * 4 + ((q + 1) & 3)) * 2) * 128 + 128;     // quadrant q+1, kind 1
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[j]), 8);
+          float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[j]), 8);
+          if (lane < 8) up = up_w[lane * 16 + j];             // (window row 0 reads junk: never stored)
+          if (lane >= 24) dn = dn_w[(lane - 24) * 16 + j];    // (window row 15 likewise)
+          f[pass * 16 + j] = __uint_as_float(e1[j]) + up + dn;
+        }
+        xb ^= 1;
+      }
+      {
+        const float4* bp = reinterpret_cast<const float4*>(s_bias + hf * 32);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 b = bp[g];
+          f[4 * g + 0] += b.x; f[4 * g + 1] += b.y; f[4 * g + 2] += b.z; f[4 * g + 3] += b.w;
+        }
+      }
+      if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      } else if (p.act == ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
+      }
+      const uint32_t row_off = uint32_t(m) * 128u;
+      const uint32_t sw = uint32_t(m & 7);
+      if (p.aux_mode) {
+        mbar_wait(&auxfull[ab], aux_phase);
+        const uint8_t* ap = aux_stage + ab * kTileOutBytes + row_off;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 rr = *reinterpret_cast<const uint4*>(ap + (((uint32_t(hf * 4 + g)) ^ sw) << 4));
+          const uint32_t ws[4] = {rr.x, rr.y, rr.z, rr.w};
+          if (p.aux_mode == 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f[g * 8 + 2 * e] += bf16_lo(ws[e]);
+              f[g * 8 + 2 * e + 1] += bf16_hi(ws[e]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (!(bf16_lo(ws[e]) > 0.f)) f[g * 8 + 2 * e] = 0.f;
+              if (!(bf16_hi(ws[e]) > 0.f)) f[g * 8 + 2 * e + 1] = 0.f;
+            }
+          }
+        }
+        mbar_arrive(&auxempty[ab]);
+        ab ^= 1;
+        if (ab == 0) aux_phase ^= 1;
+      }
+      if (etid == 0) tma_store_wait_read<1>();
+      named_bar_sync(1, kEpiThreads);
+      uint8_t* op = out_stage + ob * kTileOutBytes + row_off;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]);
+        o.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
+        o.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]);
+        o.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
+        *reinterpret_cast<uint4*>(op + (((uint32_t(hf * 4 + g)) ^ sw) << 4)) = o;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, kEpiThreads);
+      if (etid == 0) {
+        // window rows 1..14 -> output rows h0+1 .. h0+14: staging bytes [1024, 15360)
+        const bool ps = p.out_mode == OUT_PIXEL_SHUFFLE;
+        tma_store_4d(&p.out_map[ps ? nblk : 0], out_stage + ob * kTileOutBytes + 1024, ps ? 0 : nblk * 64, w0, h0 + 1, n);
+        tma_store_commit();
+      }
+      if (p.stats != nullptr) {
+        const int c2 = etid & 31, part = etid >> 5;
+        const uint8_t* sp = out_stage + ob * kTileOutBytes;
+#pragma unroll 4
+        for (int rr = 0; rr < 16; ++rr) {
+          const int mm = part * 16 + rr;
+          const int wr = mm >> 3;
+          if (wr >= 1 && wr <= 14 && h0 + wr < p.H && w0 + (mm & 7) < p.W) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(sp + mm * 128 + ((((c2 >> 2)) ^ (mm & 7)) << 4) + (c2 & 3) * 4);
+            const float a0 = bf16_lo(v), a1 = bf16_hi(v);
+            st_s0 += a0; st_s1 += a1;
+            st_q0 = fmaf(a0, a0, st_q0); st_q1 = fmaf(a1, a1, st_q1);
+          }
+        }
+      }
+      ob ^= 1;
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (etid == 0) tma_store_wait_all<0>();
+    if (p.stats != nullptr) {
+      const int c2 = etid & 31, part = etid >> 5;
+      s_stats[part * 128 + 2 * c2] = st_s0;
+      s_stats[part * 128 + 2 * c2 + 1] = st_s1;
+      s_stats[part * 128 + 64 + 2 * c2] = st_q0;
+      s_stats[part * 128 + 64 + 2 * c2 + 1] = st_q1;
+      named_bar_sync(3, kEpiThreads);
+      if (etid < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += s_stats[g * 128 + etid];
+        p.stats[size_t(blockIdx.x) * 128 + etid] = t;
+      }
+    }
+  }
+  if (p.prof != nullptr && lane == 0 && (warp <= 2)) {
+    long long* d = p.prof + (size_t(blockIdx.x) * 3 + warp) * 6;
+    d[0] = prof_acc[0]; d[1] = prof_acc[1]; d[2] = prof_acc[2]; d[3] = prof_acc[3]; d[4] = clock64() - t_start; d[5] = t_start;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // ----------------------------------------------------------- host launcher
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -474,10 +791,119 @@ static int launch_instance(const ConvKParams& p, dim3 grid, size_t smem_bytes, c
   return 0;
 }
 
+static int launch_conv3_fused(const ConvGemmArgs& a, cudaStream_t stream) {
+  if (a.TH != 16 || a.TW != 8 || a.n_taps != 3 || a.block_n != 64 || a.n_strips < 1 || a.n_strips > kMaxStrips) {
+    set_error("conv3_fused: needs a 16x8 tile, 3 row taps and 64-channel n-blocks"); return -30;
+  }
+  if (a.out_mode != OUT_NHWC && a.out_mode != OUT_PIXEL_SHUFFLE) { set_error("conv3_fused: bf16 NHWC / pixel-shuffle output only"); return -31; }
+  if (a.residual != nullptr && a.mask_src != nullptr) { set_error("conv_gemm: residual and mask are exclusive"); return -11; }
+  const bool has_aux = a.residual != nullptr || a.mask_src != nullptr;
+  if (has_aux && a.out_mode != OUT_NHWC) { set_error("conv_gemm: residual/mask need OUT_NHWC"); return -12; }
+  if (a.out_mode == OUT_PIXEL_SHUFFLE && a.cout_total != 256) { set_error("conv_gemm: pixel shuffle needs cout 256"); return -13; }
+  if (a.stats != nullptr && (a.out_mode != OUT_NHWC || a.cout_total != 64)) { set_error("conv_gemm: fused statistics need 64 channels"); return -16; }
+  if (a.cout_total % 64 != 0 || a.n_views < 1 || a.n_views > kMaxInMaps) { set_error("conv3_fused: bad channel/view count"); return -3; }
+  ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a.N; p.H = a.H; p.W = a.W; p.TH = 16; p.TW = 8;
+  p.tile_step_w = 8; p.tile_w_org = 0;
+  p.tiles_h = (a.H + 13) / 14;
+  p.tiles_w = (a.W + 7) / 8;
+  p.tiles_total = a.N * p.tiles_h * p.tiles_w;
+  if (p.tiles_total == 0) return 0;
+  int total_ch = 0;
+  for (int v = 0; v < a.n_views; ++v) {
+    if (a.views[v].channels % 64 != 0 || a.views[v].channels != a.views[0].channels) { set_error("conv_gemm: view channels must be equal multiples of 64"); return -8; }
+    total_ch += a.views[v].channels;
+  }
+  p.n_chunks = total_ch / 64;
+  p.chunks_per_view = a.views[0].channels / 64;
+  p.n_strips = a.n_strips; p.strip_rows = 16; p.strip_dh = 0;
+  for (int s = 0; s < a.n_strips; ++s) p.strip_dw[s] = a.strip_dw[s];
+  p.cout_total = a.cout_total;
+  p.n_blocks = a.cout_total / 64;
+  const int sms = num_sms();
+  p.ctas_per_block = sms / p.n_blocks;
+  if (p.ctas_per_block < 1) p.ctas_per_block = 1;
+  if (p.ctas_per_block > p.tiles_total) p.ctas_per_block = p.tiles_total;
+  const int kb_total = p.n_chunks * a.n_strips;
+  p.strip_bytes = 16 * 8 * 128u;
+  const uint32_t w_all = uint32_t(kb_total) * kFuseBTile;
+  p.aux_mode = a.residual ? 1 : (a.mask_src ? 2 : 0);
+  const uint32_t fixed_bytes = 2 * kTileOutBytes + (has_aux ? 2 * kTileOutBytes : 0) + kXchgBytes + 512 + 8 * 128 * 4;
+  const uint32_t budget = 227 * 1024 - 1024 - fixed_bytes;
+  p.resident = (w_all + 3 * p.strip_bytes <= budget) ? 1 : 0;
+  p.w_resident_bytes = p.resident ? w_all : 0;
+  p.stage_bytes = p.strip_bytes + (p.resident ? 0 : kFuseBTile);
+  int stages = int((budget - p.w_resident_bytes) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) { set_error("conv3_fused: shared memory too small for 2 stages"); return -10; }
+  p.n_stages = stages;
+  const size_t smem_bytes = 1024 + p.w_resident_bytes + size_t(stages) * p.stage_bytes + fixed_bytes;
+  for (int v = 0; v < a.n_views; ++v) {
+    const InView& iv = a.views[v];
+    uint64_t dims[4] = {uint64_t(iv.channels), uint64_t(a.in_W), uint64_t(a.in_H), uint64_t(a.N)};
+    uint64_t strides[3] = {uint64_t(iv.stride_w) * 2, uint64_t(iv.stride_h) * 2, uint64_t(iv.stride_n) * 2};
+    uint32_t box[4] = {64, 8, 16, 1};
+    int rc = encode_map_bf16(&p.in_map[v], iv.ptr, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  for (int v = a.n_views; v < kMaxInMaps; ++v) p.in_map[v] = p.in_map[0];
+  {
+    uint64_t dims[2] = {64, uint64_t(kb_total) * p.n_blocks * 192};
+    uint64_t strides[1] = {128};
+    uint32_t box[2] = {64, 192};
+    int rc = encode_map_bf16(&p.w_map, a.weights, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    uint32_t box[4] = {64, 8, 14, 1};
+    if (a.out_mode == OUT_PIXEL_SHUFFLE) {
+      for (int q = 0; q < 4; ++q) {
+        const int i = q >> 1, j = q & 1;
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a.out) + (size_t(i) * 2 * a.W + j) * 64;
+        uint64_t dims[4] = {64, uint64_t(a.W), uint64_t(a.H), uint64_t(a.N)};
+        uint64_t strides[3] = {128 * 2, uint64_t(4) * a.W * 64 * 2, uint64_t(4) * a.H * a.W * 64 * 2};
+        int rc = encode_map_bf16(&p.out_map[q], base, 4, dims, strides, box);
+        if (rc) return rc;
+      }
+      p.aux_map = p.out_map[0];
+    } else {
+      uint64_t dims[4] = {uint64_t(a.cout_total), uint64_t(a.W), uint64_t(a.H), uint64_t(a.N)};
+      uint64_t strides[3] = {uint64_t(a.cout_total) * 2, uint64_t(a.W) * a.cout_total * 2, uint64_t(a.H) * a.W * a.cout_total * 2};
+      int rc = encode_map_bf16(&p.out_map[0], a.out, 4, dims, strides, box);
+      if (rc) return rc;
+      for (int q = 1; q < 4; ++q) p.out_map[q] = p.out_map[0];
+      if (has_aux) {
+        uint32_t abox[4] = {64, 8, 16, 1};
+        rc = encode_map_bf16(&p.aux_map, a.residual ? a.residual : a.mask_src, 4, dims, strides, abox);
+        if (rc) return rc;
+      } else {
+        p.aux_map = p.out_map[0];
+      }
+    }
+  }
+  p.bias = a.bias; p.act = a.act; p.slope = a.slope;
+  p.out = a.out; p.out_mode = a.out_mode;
+  p.stats = a.stats;
+  p.prof = reinterpret_cast<long long*>(a.prof);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    attr_set = true;
+  }
+  cudaError_t e = launch_pdl(conv3_fused_kernel, dim3(p.ctas_per_block * p.n_blocks), dim3(kThreads), smem_bytes, stream, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("conv3_fused launch: %s", cudaGetErrorString(e)); return int(e); }
+  count_launch();
+  return 0;
+}
+
 int conv_gemm_grid(const ConvGemmArgs& a) {
   const bool fold = a.out_mode == OUT_FOLD9_NCHW;
   const int step_w = fold ? a.TW - 8 : a.TW;
-  const int tiles = a.N * ((a.H + a.TH - 1) / a.TH) * ((a.W + step_w - 1) / step_w);
+  const int step_h = a.fuse_taps ? 14 : a.TH;
+  const int tiles = a.N * ((a.H + step_h - 1) / step_h) * ((a.W + step_w - 1) / step_w);
   const int n_blocks = a.cout_total / a.block_n;
   int per = num_sms() / n_blocks;
   if (per < 1) per = 1;
@@ -486,6 +912,7 @@ int conv_gemm_grid(const ConvGemmArgs& a) {
 }
 
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
+  if (a.fuse_taps) return launch_conv3_fused(a, stream);
   if (a.TH * a.TW != 128 || a.TW % 8 != 0) { set_error("conv_gemm: tile must be 128 pixels with TW%%8==0"); return -1; }
   if (a.block_n != 64 && a.block_n != 32) { set_error("conv_gemm: block_n must be 32 or 64"); return -2; }
   if (a.cout_total % a.block_n != 0) { set_error("conv_gemm: cout_total %% block_n != 0"); return -3; }

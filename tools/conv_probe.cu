@@ -50,6 +50,7 @@ struct Problem {
   int act;
   bool residual, mask;
   int out_mode;
+  bool fuse;                 // fused-tap 3x3 kernel (weights repacked [c][s][nb][r][64][64])
 };
 
 static int run(const Problem& pr, int timing_iters) {
@@ -94,7 +95,21 @@ static int run(const Problem& pr, int timing_iters) {
   CK(cudaMalloc(&dmsk, out_elems * 2));
   CK(cudaMalloc(&dbias, bias.size() * 4));
   CK(cudaMemcpy(dx, xphys.data(), xphys.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dw, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  if (pr.fuse) {
+    std::vector<uint16_t> wf(wp.size());
+    const int nbk = pr.cout_total / 64;
+    for (int c = 0; c < n_chunks; ++c)
+      for (int s = 0; s < pr.n_strips; ++s)
+        for (int nb = 0; nb < nbk; ++nb)
+          for (int r = 0; r < 3; ++r)
+            for (int nl = 0; nl < 64; ++nl)
+              for (int k = 0; k < 64; ++k)
+                wf[(((((size_t(c) * pr.n_strips + s) * nbk + nb) * 3 + r) * 64 + nl) * 64) + k] =
+                    wp[((size_t((c * pr.n_strips + s) * 3 + r) * pr.cout_total) + nb * 64 + nl) * 64 + k];
+    CK(cudaMemcpy(dw, wf.data(), wf.size() * 2, cudaMemcpyHostToDevice));
+  } else {
+    CK(cudaMemcpy(dw, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  }
   CK(cudaMemcpy(dres, res.data(), out_elems * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dmsk, msk.data(), out_elems * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dbias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
@@ -126,7 +141,7 @@ static int run(const Problem& pr, int timing_iters) {
   a.weights = dw; a.cout_total = pr.cout_total; a.block_n = pr.block_n;
   a.bias = pr.bias ? dbias : nullptr; a.act = pr.act; a.slope = 0.2f;
   a.residual = pr.residual ? dres : nullptr; a.mask_src = pr.mask ? dmsk : nullptr;
-  a.out = dout; a.out_mode = pr.out_mode;
+  a.out = dout; a.out_mode = pr.out_mode; a.fuse_taps = pr.fuse ? 1 : 0;
 
   int rc = launch_conv_gemm(a, 0);
   if (rc != 0) { printf("[%s] launch rc=%d err=%s\n", pr.name, rc, last_error()); return 1; }
@@ -403,7 +418,15 @@ int main(int argc, char** argv) {
     p.block_n = 32; p.out_mode = OUT_FOLD9_NCHW;
     fails += run(p, 0);
   }
+  {
+    Problem p = conv3x3("fused_small", 2, 32, 24, 64, false); p.fuse = true; fails += run(p, 0);
+    Problem q = conv3x3("fused_ragged_res", 3, 37, 20, 64, false); q.fuse = true; q.residual = true; q.act = ACT_LRELU; fails += run(q, 0);
+    Problem u = conv3x3("fused_relu_ps", 2, 30, 16, 256, true); u.fuse = true; u.act = ACT_RELU; fails += run(u, 0);
+    Problem v = conv3x3("fused_cin256_views_mask", 2, 32, 16, 64, false); v.fuse = true; v.n_views = 4; v.strided_views = true; v.mask = true; fails += run(v, 0);
+  }
   if (iters > 0) {
+    { Problem p = conv3x3("perf_fused_trunk_16x96x96", 16, 96, 96, 64, false); p.fuse = true; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_fused_up3_16x192x192", 16, 192, 192, 256, true); p.fuse = true; p.act = ACT_RELU; fails += run(p, iters); }
     fails += run(conv3x3("perf_trunk_16x96x96", 16, 96, 96, 64, false), iters);
     Problem p = conv3x3("perf_up3_16x192x192", 16, 192, 192, 256, true);
     p.act = ACT_RELU;

@@ -58,6 +58,6 @@ void run(int a_tiles) {
 }
 
 int main() {
-  run<64>(1); run<64>(6); run<128>(1); run<128>(6); run<256>(1); run<256>(6);
+  run<64>(1); run<128>(1); run<192>(1); run<192>(6); run<256>(1); run<96>(1); run<160>(1); run<224>(1);
   return 0;
 }
