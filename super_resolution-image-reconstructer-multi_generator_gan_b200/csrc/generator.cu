@@ -395,8 +395,18 @@ GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up) {
       if (fwd[i] >= 0) inv[size_t(fwd[i])] = int(i);
     return inv;
   };
-  m33 = invert(m33, size_t(1) * 5 * 8192);
-  mup = invert(mup, size_t(4) * 5 * 8192);
+  // 3x3 layers use the fused wgrad kernel: partial index ((nb*3 + kw)*64 + ci)*192 + (2-kh)*64 + co
+  for (int co = 0; co < 64; ++co)
+    for (int ci = 0; ci < 64; ++ci)
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) m33[((co * 64 + ci) * 3 + kh) * 3 + kw] = ((0 * 3 + kw) * 64 + ci) * 192 + (2 - kh) * 64 + co;
+  for (int co = 0; co < 256; ++co)
+    for (int ci = 0; ci < 64; ++ci)
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw)
+          mup[((co * 64 + ci) * 3 + kh) * 3 + kw] = (((co % 4) * 3 + kw) * 64 + ci) * 192 + (2 - kh) * 64 + co / 4;
+  m33 = invert(m33, size_t(1) * 3 * 64 * 192);
+  mup = invert(mup, size_t(4) * 3 * 64 * 192);
   mc1 = invert(mc1, size_t(1) * 3 * 8192);
   mc3 = invert(mc3, size_t(1) * 3 * 8192);
   e->h_pack_idx.swap(idx); e->h_bias_idx.swap(bidx);
@@ -634,14 +644,22 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     }
     a.partials = wgp;
     int splits = 0;
-    const int floats = wgrad_partials_floats(a, &splits);
-    if (int64_t(floats) > wgrad_max_floats(S)) { set_error("wgrad partials exceed workspace"); return -27; }
-    RC(launch_wgrad_gemm(a, st));
-    const int n_pairs = (a.n_strips * a.n_taps + 1) / 2;
     const ParamInfo* pi = nullptr;
     for (const auto& p : e->params) if (p.name == wname) pi = &p;
     if (!pi) { set_error("wgrad: unknown parameter %s", wname.c_str()); return -28; }
     e->launches += 2;
+    if (!pairs) {
+      // 3x3: taps fused along M (two column shifts) and N (three row shifts)
+      const int floats = wgrad3x3_partials_floats(a, &splits);
+      if (int64_t(floats) > wgrad_max_floats(S)) { set_error("wgrad partials exceed workspace"); return -27; }
+      RC(launch_wgrad3x3(a, st));
+      const size_t per_split = size_t(n_blocks) * 3 * 64 * 192;
+      return launch_wgrad_reduce_inv(wgp, idx, e->grads + pi->offset, int(per_split), splits, per_split, st);
+    }
+    const int floats = wgrad_partials_floats(a, &splits);
+    if (int64_t(floats) > wgrad_max_floats(S)) { set_error("wgrad partials exceed workspace"); return -27; }
+    RC(launch_wgrad_gemm(a, st));
+    const int n_pairs = (a.n_strips * a.n_taps + 1) / 2;
     const size_t per_split = size_t(n_blocks) * n_pairs * 128 * 64;
     return launch_wgrad_reduce_inv(wgp, idx, e->grads + pi->offset, int(per_split), splits, per_split, st);
   };

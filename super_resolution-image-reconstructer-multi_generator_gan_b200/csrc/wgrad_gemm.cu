@@ -220,6 +220,195 @@ int launch_wgrad_reduce_inv(const float* partials, const int* inv, float* out, i
   return 0;
 }
 
+int wgrad_partials_floats(const WgradArgs& a, int* splits_out);
+
+// =====================================================================================================================
+// 3x3 weight gradient with taps fused along BOTH GEMM dimensions (one MMA covers 6 of the 9 taps).
+//
+//   D_t[ci][co] = sum_{h', w} x[h'][w + kw - 1][ci] * dy[h' - kh + 1][w][co]            t = (kh, kw)
+//
+// The column shift kw selects one of three un-haloed 16-row x strips (A operand, MN-major); the row shift kh selects a
+// window of ONE vertically haloed 18-row dy strip (B operand, MN-major).  Because the leading-dimension byte offset of an
+// MN-major descriptor is free, M = 128 stacks two x strips (LBO = strip size) and N = 192 stacks the three dy windows
+// (LBO = one image row): chain 1 = [kw0; kw1] x [kh2 | kh1 | kh0], chain 2 = [kw1; kw2] x same (its first half repeats
+// kw1 and is dropped).  Per 16 pixels that is 2 MMAs of 96 cycles instead of 5 of 69 (tools/mma_probe.cu: an M128 x K16
+// MMA costs max(~64, N/2) cycles), and one dy tile + three x tiles per 128 pixels instead of one dy + three haloed x.
+// Partials: [split][n-block][kw 3][ci 64][(2 - kh) * 64 + co] fp32.
+// =====================================================================================================================
+constexpr uint32_t kW3DyBytes = 18 * 8 * 128;   // 18 KB haloed dy strip
+constexpr uint32_t kW3XBytes = 16 * 8 * 128;    // 16 KB x strip
+constexpr uint32_t kW3Stage = kW3DyBytes + 3 * kW3XBytes;
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_constant__ WgradKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  uint8_t* stages = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + size_t(p.n_stages) * kW3Stage);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 4;
+  uint64_t* done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const int nblk = blockIdx.x % p.n_blocks;
+  const int split = blockIdx.x / p.n_blocks;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.x_map);
+    tma_prefetch_desc(&p.dy_map[nblk]);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      pdl_wait();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = split; tile < p.tiles_total; tile += p.splits) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * 16;
+        const int w0 = (rem % p.tiles_w) * 8;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* dst = stages + size_t(stage) * kW3Stage;
+        mbar_expect_tx(&full[stage], kW3Stage);
+        tma_load_4d(dst, &p.dy_map[nblk], &full[stage], nblk * p.dy_c0_step, w0, h0 - 1, n);
+        for (int kw = 0; kw < 3; ++kw)
+          tma_load_4d(dst + kW3DyBytes + size_t(kw) * kW3XBytes, &p.x_map, &full[stage], 0, w0 + kw - 1, h0, n);
+        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 192, 1, 1);
+    const uint64_t hi_common = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+    const uint64_t a_hi = hi_common | (uint64_t((kW3XBytes >> 4) & 0x3FFF) << 16);   // M atoms: two x strips
+    const uint64_t b_hi = hi_common | (uint64_t((1024 >> 4) & 0x3FFF) << 16);        // N atoms: dy windows one row apart
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (int tile = split; tile < p.tiles_total; tile += p.splits) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t base = smem_u32(stages + size_t(stage) * kW3Stage);
+      if (elect_one()) {
+        const uint64_t bdesc = b_hi | uint64_t(base >> 4);
+        const uint64_t a1 = a_hi | uint64_t((base + kW3DyBytes) >> 4);               // [kw0; kw1]
+        const uint64_t a2 = a_hi | uint64_t((base + kW3DyBytes + kW3XBytes) >> 4);   // [kw1; kw2]
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // 16 pixels (2 image rows = 2048 bytes) per MMA
+          umma_bf16(tmem_base, a1 + uint64_t(128 * k), bdesc + uint64_t(128 * k), idesc, (k > 0) ? 1u : accumulate);
+          umma_bf16(tmem_base + 192, a2 + uint64_t(128 * k), bdesc + uint64_t(128 * k), idesc, (k > 0) ? 1u : accumulate);
+        }
+        umma_commit(&empty[stage]);
+      }
+      __syncwarp();
+      accumulate = 1;
+      if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
+  } else {
+    // epilogue, once per CTA: lanes 0-63 of chain 1 = kw0, lanes 64-127 of chain 1 = kw1, lanes 64-127 of chain 2 = kw2
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    pdl_wait();
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const bool any = split < p.tiles_total;
+    float* dst = p.partials + (size_t(split) * p.n_blocks + nblk) * (3 * 64 * 192);
+    for (int chain = 0; chain < 2; ++chain) {
+      if (chain == 1 && q < 2) continue;
+      const int kw = chain == 0 ? (m >> 6) : 2;
+      float* row = dst + (size_t(kw) * 64 + (m & 63)) * 192;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 192; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(chain * 192 + c0), v);
+        tmem_ld_wait();
+        float4* o = reinterpret_cast<float4*>(row + c0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 f;
+          f.x = any ? __uint_as_float(v[4 * g + 0]) : 0.f;
+          f.y = any ? __uint_as_float(v[4 * g + 1]) : 0.f;
+          f.z = any ? __uint_as_float(v[4 * g + 2]) : 0.f;
+          f.w = any ? __uint_as_float(v[4 * g + 3]) : 0.f;
+          o[g] = f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int wgrad3x3_partials_floats(const WgradArgs& a, int* splits_out) {
+  int splits = 0;
+  wgrad_partials_floats(a, &splits);      // same split policy: SMs / n_blocks, capped by the tile count
+  if (splits_out) *splits_out = splits;
+  return splits * a.n_blocks * 3 * 64 * 192;
+}
+
+int launch_wgrad3x3(const WgradArgs& a, cudaStream_t stream) {
+  if (a.TH != 16 || a.TW != 8) { set_error("wgrad3x3: tile must be 16x8"); return -1; }
+  if (a.n_blocks < 1 || a.n_blocks > 4) { set_error("wgrad3x3: n_blocks must be 1..4"); return -2; }
+  if (a.in_H != a.H || a.in_W != a.W) { set_error("wgrad3x3: stride-1 'same' convolution only"); return -3; }
+  WgradKParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a.N; p.H = a.H; p.W = a.W; p.TH = 16; p.TW = 8;
+  p.tiles_h = (a.H + 15) / 16;
+  p.tiles_w = (a.W + 7) / 8;
+  p.tiles_total = a.N * p.tiles_h * p.tiles_w;
+  if (p.tiles_total == 0) return 0;
+  p.n_blocks = a.n_blocks;
+  int splits = 0;
+  wgrad3x3_partials_floats(a, &splits);
+  p.splits = splits;
+  p.n_stages = 3;
+  p.partials = a.partials;
+  p.dy_c0_step = a.dy_views == 1 ? 64 : 0;
+  {
+    uint64_t dims[4] = {64, uint64_t(a.in_W), uint64_t(a.in_H), uint64_t(a.N)};
+    uint64_t strides[3] = {uint64_t(a.x.stride_w) * 2, uint64_t(a.x.stride_h) * 2, uint64_t(a.x.stride_n) * 2};
+    uint32_t box[4] = {64, 8, 16, 1};
+    int rc = encode_map_bf16(&p.x_map, a.x.ptr, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  for (int v = 0; v < 4; ++v) {
+    const InView& dv = a.dy[v < a.dy_views ? v : 0];
+    uint64_t dims[4] = {uint64_t(dv.channels), uint64_t(a.W), uint64_t(a.H), uint64_t(a.N)};
+    uint64_t strides[3] = {uint64_t(dv.stride_w) * 2, uint64_t(dv.stride_h) * 2, uint64_t(dv.stride_n) * 2};
+    uint32_t box[4] = {64, 8, 18, 1};
+    int rc = encode_map_bf16(&p.dy_map[v], dv.ptr, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    attr = true;
+  }
+  const size_t smem_bytes = 1024 + size_t(p.n_stages) * kW3Stage + 256;
+  cudaError_t e = launch_pdl(wgrad3_kernel, dim3(p.n_blocks * p.splits), dim3(kWgThreads), smem_bytes, stream, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("wgrad3x3 launch: %s", cudaGetErrorString(e)); return int(e); }
+  count_launch();
+  return 0;
+}
+
 int wgrad_partials_floats(const WgradArgs& a, int* splits_out) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
