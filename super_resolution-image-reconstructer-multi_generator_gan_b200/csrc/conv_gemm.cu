@@ -56,6 +56,7 @@ struct ConvKParams {
   void* out;     // fold9 only (fp32 NCHW)
   int out_mode;
   float* stats;  // per-CTA channel sums / sums of squares (BatchNorm statistics fused into the epilogue)
+  const uint32_t* stats_y;  // optional second factor (bf16 pairs) for the product sums
   long long* prof;  // optional per-CTA role timers (debug)
 };
 
@@ -244,11 +245,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     int acc = 0, ob = 0, ab = 0;
     uint32_t acc_phase = 0, aux_phase = 0;
     float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;   // BatchNorm statistics of this thread's channel pair
+    uint32_t yv_next[16];
+    auto load_stats_y = [&](int t, uint32_t (&dst)[16]) {
+      if (t >= p.tiles_total) return;
+      const int n_ = t / tiles_per_img;
+      const int rem_ = t - n_ * tiles_per_img;
+      const int h0_ = (rem_ / p.tiles_w) * p.TH;
+      const int w0_ = (rem_ % p.tiles_w) * p.tile_step_w + p.tile_w_org;
+      const int c2 = etid & 31, part = etid >> 5;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        const int mm = part * 16 + rr;
+        const int th = mm >> 3;                      // statistics are only offered for 8-pixel-wide tiles
+        const int hh = h0_ + th, ww = w0_ + (mm & 7);
+        dst[rr] = (hh < p.H && ww < p.W) ? __ldg(p.stats_y + ((size_t(n_) * p.H + hh) * p.W + ww) * 32 + c2) : 0u;
+      }
+    };
+    if (!kFold && p.stats_y != nullptr) load_stats_y(tile0, yv_next);
     for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
       const int h0 = (rem / p.tiles_w) * p.TH;
       const int w0 = (rem % p.tiles_w) * p.tile_step_w + p.tile_w_org;
+      uint32_t yv[16];
+      if (!kFold && p.stats_y != nullptr) {
+        // second factor of the product statistics, software-pipelined one tile ahead: this tile's values were loaded
+        // during the previous iteration, the next tile's loads are issued now and land while this tile is processed
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) yv[rr] = yv_next[rr];
+        load_stats_y(tile + p.ctas_per_block, yv_next);
+      }
       { long long t0_ = clock64(); mbar_wait(&tfull[acc], acc_phase); prof_acc[3] += clock64() - t0_; }
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N + hf * 32);
@@ -369,15 +395,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           // c2 x 16-row part; rows outside the image (ragged tiles) are skipped
           const int c2 = etid & 31, part = etid >> 5;
           const uint8_t* sp = out_stage + ob * kTileOutBytes;
-#pragma unroll 4
+#pragma unroll
           for (int r = 0; r < 16; ++r) {
             const int mm = part * 16 + r;
-            const int th = mm / p.TW;
-            if (h0 + th < p.H && w0 + (mm - th * p.TW) < p.W) {
+            const int th = mm >> 3;
+            if (h0 + th < p.H && w0 + (mm & 7) < p.W) {
               const uint32_t v = *reinterpret_cast<const uint32_t*>(sp + mm * 128 + ((((c2 >> 2)) ^ (mm & 7)) << 4) + (c2 & 3) * 4);
               const float a0 = bf16_lo(v), a1 = bf16_hi(v);
+              float b0 = a0, b1 = a1;
+              if (p.stats_y != nullptr) { b0 = bf16_lo(yv[r]); b1 = bf16_hi(yv[r]); }
               st_s0 += a0; st_s1 += a1;
-              st_q0 = fmaf(a0, a0, st_q0); st_q1 = fmaf(a1, a1, st_q1);
+              st_q0 = fmaf(a0, b0, st_q0); st_q1 = fmaf(a1, b1, st_q1);
             }
           }
         }
@@ -964,8 +992,8 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   p.strip_bytes = uint32_t(a.strip_rows) * a.TW * 128u;
   const uint32_t w_all = uint32_t(kb_total) * btile;
   p.aux_mode = a.residual ? 1 : (a.mask_src ? 2 : 0);
-  if (a.stats != nullptr && (a.out_mode != OUT_NHWC || a.cout_total != 64)) {
-    set_error("conv_gemm: fused statistics need OUT_NHWC with 64 output channels"); return -16;
+  if (a.stats != nullptr && (a.out_mode != OUT_NHWC || a.cout_total != 64 || a.TW != 8)) {
+    set_error("conv_gemm: fused statistics need OUT_NHWC with 64 output channels and 8-pixel-wide tiles"); return -16;
   }
   const uint32_t fixed_bytes = (fold ? 128 * kFoldPad * 4 : 2 * kTileOutBytes) + (has_aux ? 2 * kTileOutBytes : 0) + 256 + 256 +
                                (a.stats != nullptr ? 8 * 128 * 4 : 0);
@@ -1030,6 +1058,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   p.bias = a.bias; p.act = a.act; p.slope = a.slope;
   p.out = a.out; p.out_mode = a.out_mode;
   p.stats = a.stats;
+  p.stats_y = reinterpret_cast<const uint32_t*>(a.stats_y);
   p.prof = reinterpret_cast<long long*>(a.prof);
 
   const dim3 grid(p.ctas_per_block * p.n_blocks);

@@ -61,6 +61,8 @@ struct ConvGemmArgs {
                              // [chunk][strip][n-block][tap][64 cout][64 k]; tiles step 14 rows (16-row window).
   float* stats;              // optional (OUT_NHWC, cout 64): per-CTA column sums of the STORED bf16 tile values,
                              // float [conv_gemm_grid(a)][128] = {sum over valid pixels [64], sum of squares [64]}
+  const void* stats_y;       // optional with `stats`: bf16 tensor of the output's geometry; the second 64 columns then hold
+                             // sum(out * stats_y) instead of sum(out^2) (BatchNorm backward: sum dz, sum dz*y)
   void* prof;                // optional debug timers: int64 [grid][3][6]
   // fold9: tile columns overlap; valid output columns per tile = TW-8
 };

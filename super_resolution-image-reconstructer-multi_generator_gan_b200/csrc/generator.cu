@@ -671,8 +671,11 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     return launch_partials_finalize(partials, reduce_blocks(pixels), f, st);
   };
   // dgrad of a 3x3 conv whose output gradient has `chunks`*64 channels (4 pixel-shuffle views when chunks == 4)
+  int bwd_stats_rows = 0;
+  // stats_y != null: the epilogue also accumulates sum(out) and sum(out * stats_y) per channel (BatchNorm backward
+  // statistics of the NEXT step, which consumes `out` as dz and stats_y as the saved conv output)
   auto dgrad3x3 = [&](const void* dy_base, int gh, int gw, bool dy_ps, int64_t w_off, const void* residual, const void* mask,
-                      void* out) -> int {
+                      void* out, const void* stats_y) -> int {
     ConvGemmArgs a; memset(&a, 0, sizeof(a));
     a.N = N; a.H = gh; a.W = gw; set_taps_3x3(a);
     if (dy_ps) {
@@ -684,6 +687,9 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     a.in_H = gh; a.in_W = gw;
     a.weights = packed + w_off; a.cout_total = 64; a.block_n = 64;
     a.bias = nullptr; a.act = ACT_NONE; a.residual = residual; a.mask_src = mask; a.out = out; a.out_mode = OUT_NHWC;
+    // Measured (profiles/r01_notes.md): the extra epilogue work costs more than the separate 7 us reduction pass it
+    // replaces (13.1 vs 12.8 ms per 3-generator step), so the fusion is off unless e->fuse_bwd_stats is set.
+    if (stats_y != nullptr && e->fuse_bwd_stats) { a.stats = partials; a.stats_y = stats_y; bwd_stats_rows = conv_gemm_grid(a); }
     e->launches += 1;
     if (dy_ps) return launch_conv_gemm(a, st);
     ProfScope ps(e, st);
@@ -722,7 +728,7 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     e->launches += 2;
     snprintf(nm, sizeof(nm), "upsample.%d.weight", 3 * j);
     RC(wgrad(plain_view(in_j, Hj, Wj), Hj, Wj, false, Hj, Wj, ws + L.dup[j], 4, true, e->d_wg_idx_up, nm));
-    RC(dgrad3x3(ws + L.dup[j], Hj, Wj, true, po.up_d[j], nullptr, j > 0 ? in_j : nullptr, j > 0 ? ws + L.dup[j - 1] : d_trunk));
+    RC(dgrad3x3(ws + L.dup[j], Hj, Wj, true, po.up_d[j], nullptr, j > 0 ? in_j : nullptr, j > 0 ? ws + L.dup[j - 1] : d_trunk, nullptr));
   }
   // ---- conv2 (trunk = conv2(x_last) + out1)
   const void* x_last = e->n_res > 0 ? ws + L.out[e->n_res - 1] : ws + L.out1;
@@ -732,7 +738,7 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
   void* dout = keep ? ws + L.kd_last : ws + L.g[0];
   void* dother = ws + L.g[1];
   void* dmid = ws + L.g[2];
-  RC(dgrad3x3(d_trunk, H, W, false, po.conv2_d, nullptr, nullptr, dout));
+  RC(dgrad3x3(d_trunk, H, W, false, po.conv2_d, nullptr, nullptr, dout, e->n_res > 0 ? ws + L.y2[e->n_res - 1] : nullptr));
   // ---- residual blocks, last to first (src/models.py:21-25)
   float* bwd = reinterpret_cast<float*>(ws + L.bwdcoef);
   auto bn_backward = [&](int b, int k, const void* dz, const void* y, void* dy) -> int {
@@ -741,16 +747,22 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     const int64_t go = poff(*e, nm);
     snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.bias", b, k + 1);
     const int64_t bo = poff(*e, nm);
-    RC(launch_chan_reduce(dz, y, P, partials, st));
+    // sum dz and sum dz*y: either accumulated by the dgrad kernel that produced dz (fuse_bwd_stats) or by one pass here
+    int rows = bwd_stats_rows;
+    if (!e->fuse_bwd_stats) {
+      RC(launch_chan_reduce(dz, y, P, partials, st));
+      rows = reduce_blocks(P);
+      e->launches += 1;
+    }
     if (!e->allreduce || e->peer) {
       ReduceFinalize f; memset(&f, 0, sizeof(f));
       f.mode = RF_BN_BWD; f.count = double(P) * e->world; f.gamma = e->master + go; f.save_mean = coef + 128; f.save_inv = coef + 192;
       f.dgamma = e->grads + go; f.dbeta = e->grads + bo; f.out0 = bwd; f.out1 = bwd + 64; f.out2 = bwd + 128;
-      if (e->peer) RC(launch_peer_finalize(e->peer, partials, reduce_blocks(P), f, st));
-      else RC(launch_partials_finalize(partials, reduce_blocks(P), f, st));
-      e->launches += 3;
+      if (e->peer) RC(launch_peer_finalize(e->peer, partials, rows, f, st));
+      else RC(launch_partials_finalize(partials, rows, f, st));
+      e->launches += 2;
     } else {
-      RC(launch_partials_sums(partials, reduce_blocks(P), sums, st));
+      RC(launch_partials_sums(partials, rows, sums, st));
       RC(e->allreduce(e->allreduce_ctx, sums, 128, st));
       RC(launch_bn_bwd_finalize(sums, double(P) * e->world, e->master + go, coef + 128, coef + 192, e->grads + go, e->grads + bo,
                                 bwd, bwd + 64, bwd + 128, 1.f / float(e->world), st));
@@ -768,12 +780,12 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     RC(bn_backward(b, 1, dout, ws + L.y2[b], d_y2));
     snprintf(nm, sizeof(nm), "residual_blocks.%d.conv2.weight", b);
     RC(wgrad(plain_view(ws + L.z1[b], H, W), H, W, false, H, W, d_y2, 1, false, e->d_wg_idx_c3x3, nm));
-    RC(dgrad3x3(d_y2, H, W, false, po.rb_d[1][b], nullptr, ws + L.z1[b], d_p1));      // ReLU backward via mask
+    RC(dgrad3x3(d_y2, H, W, false, po.rb_d[1][b], nullptr, ws + L.z1[b], d_p1, ws + L.y1[b]));   // ReLU backward via mask
     // z1 = relu(bn1(y1))
     RC(bn_backward(b, 0, d_p1, ws + L.y1[b], d_y1));
     snprintf(nm, sizeof(nm), "residual_blocks.%d.conv1.weight", b);
     RC(wgrad(plain_view(x_in, H, W), H, W, false, H, W, d_y1, 1, false, e->d_wg_idx_c3x3, nm));
-    RC(dgrad3x3(d_y1, H, W, false, po.rb_d[0][b], dout, nullptr, d_in));              // + skip gradient
+    RC(dgrad3x3(d_y1, H, W, false, po.rb_d[0][b], dout, nullptr, d_in, b > 0 ? ws + L.y2[b - 1] : nullptr));   // + skip gradient
     if (keep) { dout = d_in; } else { void* t = dout; dout = dother; dother = t; }
   }
   // ---- conv1: out1 = lrelu(conv1(x)); d(out1) = block-chain gradient + trunk skip gradient
