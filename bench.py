@@ -243,13 +243,13 @@ def run_ours(a):
         torch.manual_seed(100)
         disc = S.Discriminator().to(dev)
         disc.flat_parameters()
-        d_opt = S.Adam(disc.parameters(), lr=5e-5)
+        d_opt = S.Adam(disc.parameters(), lr=5e-5, capturable=True)
     loss_ar = None
     if world > 1:
         S.parallel.data_parallel(gens + ([disc] if disc is not None else []), sync_batchnorm=True, sync_bn_transport=a.syncbn)
         loss_ar = S.parallel.mean_over_ranks()
     policy = S.MultiGeneratorPolicy(S.PolicyConfig(num_generators=K, force=S.GAN if disc is not None else S.PIXEL, seed=0))
-    use_graphs = (not a.no_graphs) and disc is None
+    use_graphs = (not a.no_graphs) and (disc is None or world == 1)
     trainer = S.MultiGeneratorGAN(gens, opts, crit, discriminator=disc, d_optimizer=d_opt, policy=policy,
                                   loss_allreduce=loss_ar, use_cuda_graphs=use_graphs)
 

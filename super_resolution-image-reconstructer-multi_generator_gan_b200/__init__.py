@@ -13,7 +13,7 @@ from .loss import ReconstructionLoss, tanh_mean
 from .optim import Adam
 from .policy import (GAN, PIXEL, MultiGeneratorPolicy, PolicyConfig, decide, gan_probability, interpolate_models,
                      shuffle_lists_in_same_order)
-from .train import (GraphedGeneratorStep, GraphedMultiGeneratorStep, MultiGeneratorGAN, train_discriminator, train_discriminator_async, train_generator,
+from .train import (GraphedDiscriminatorStep, GraphedGeneratorStep, GraphedMultiGeneratorStep, MultiGeneratorGAN, train_discriminator, train_discriminator_async, train_generator,
                     train_generator_async, train_one_epoch)
 from . import parallel
 

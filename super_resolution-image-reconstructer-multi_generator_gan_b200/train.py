@@ -159,6 +159,57 @@ class GraphedGeneratorStep:
         return self.losses
 
 
+class GraphedDiscriminatorStep:
+    """One ``train_discriminator`` step (generator eval forward, D forward over [hr; sr], tanh loss, D backward, Adam)
+    captured into a CUDA graph; same contract as GraphedGeneratorStep (warm-up is rolled back)."""
+
+    def __init__(self, discriminator, generator, d_optimizer, lr_example: torch.Tensor, hr_example: torch.Tensor,
+                 warmup: int = 2):
+        if not getattr(d_optimizer, "capturable", False):
+            raise ValueError("GraphedDiscriminatorStep needs optim.Adam(..., capturable=True)")
+        from . import _lib
+        self.optimizer = d_optimizer
+        self.lr = lr_example.detach().clone()
+        self.hr = hr_example.detach().clone()
+        args = (discriminator, generator, self.hr, self.lr, d_optimizer)
+        flat = discriminator.flat_parameters()
+        snap = flat.clone()
+        st0 = d_optimizer.flat_state(discriminator)
+        opt_snap = [st0[k].clone() for k in ("m", "v", "step_dev")] if st0 is not None and "step_dev" in st0 else None
+        was_training = generator.training
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                train_discriminator_async(*args)
+        torch.cuda.current_stream().wait_stream(side)
+        st = d_optimizer.flat_state(discriminator)
+        with torch.no_grad():
+            flat.copy_(snap)
+            if opt_snap is None:
+                st["m"].zero_(); st["v"].zero_(); st["step_dev"].zero_()
+            else:
+                for k, src in zip(("m", "v", "step_dev"), opt_snap):
+                    st[k].copy_(src)
+        d_optimizer.zero_grad()
+        torch.cuda.synchronize()
+        n0 = _lib.lib().srg_total_launches()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = train_discriminator_async(*args)
+        self.launches_per_replay = int(_lib.lib().srg_total_launches() - n0)
+        generator.train(was_training)
+
+    def __call__(self, lr_imgs: torch.Tensor, hr_imgs: torch.Tensor) -> torch.Tensor:
+        if lr_imgs.data_ptr() != self.lr.data_ptr():
+            self.lr.copy_(lr_imgs, non_blocking=True)
+        if hr_imgs.data_ptr() != self.hr.data_ptr():
+            self.hr.copy_(hr_imgs, non_blocking=True)
+        self.optimizer.sync_lr()
+        self.graph.replay()
+        return self.loss
+
+
 class GraphedMultiGeneratorStep:
     """K independent pixel-mode generator steps captured as PARALLEL branches of one CUDA graph (one capture stream
     forks into K side streams and joins them again).
@@ -257,6 +308,8 @@ class MultiGeneratorGAN:
         self.use_cuda_graphs = use_cuda_graphs
         self._graphs: Dict[int, GraphedGeneratorStep] = {}
         self._multi: Optional[GraphedMultiGeneratorStep] = None     # all-PIXEL batches: K parallel branches, one graph
+        self._d_graphs: Dict[int, "GraphedDiscriminatorStep"] = {}  # keyed by the leader generator's id
+        self._gan_graphs: Dict[int, GraphedGeneratorStep] = {}
 
     def _drain(self, keep: int) -> None:
         while len(self._pending) > keep:
@@ -269,9 +322,10 @@ class MultiGeneratorGAN:
         """Kernel launches replayed per step when every generator runs from its captured graph."""
         if self._multi is not None:
             return self._multi.launches_per_replay
-        if not self._graphs:
+        graphs = list(self._graphs.values()) + list(self._gan_graphs.values()) + list(self._d_graphs.values())
+        if not graphs:
             return None
-        return sum(g.launches_per_replay for g in self._graphs.values())
+        return sum(g.launches_per_replay for g in graphs)
 
     def step(self, lr_imgs: torch.Tensor, hr_imgs: torch.Tensor) -> torch.Tensor:
         """Returns a device tensor [K, 4] of (g_loss, com_loss, tv_loss, g_d_loss) rows in training order."""
@@ -282,8 +336,16 @@ class MultiGeneratorGAN:
         if any_gan and self.discriminator is None:
             raise RuntimeError("the policy chose GAN mode but no discriminator was given")
         if any_gan and self.d_optimizer is not None:
-            leader = self.generators[plan[0][0]]
-            train_discriminator_async(self.discriminator, leader, hr_imgs, lr_imgs, self.d_optimizer)
+            leader_id = plan[0][0]
+            leader = self.generators[leader_id]
+            if self.use_cuda_graphs and getattr(self.d_optimizer, "capturable", False) and self.loss_allreduce is None:
+                dg = self._d_graphs.get(leader_id)
+                if dg is None or dg.lr.shape != lr_imgs.shape:
+                    dg = GraphedDiscriminatorStep(self.discriminator, leader, self.d_optimizer, lr_imgs, hr_imgs)
+                    self._d_graphs[leader_id] = dg
+                dg(lr_imgs, hr_imgs)
+            else:
+                train_discriminator_async(self.discriminator, leader, hr_imgs, lr_imgs, self.d_optimizer)
         if self.use_cuda_graphs and not any_gan:
             if self._multi is None or self._multi.lr.shape != lr_imgs.shape:
                 self._multi = GraphedMultiGeneratorStep(self.generators, self.criterion, self.g_optimizers, lr_imgs, hr_imgs)
@@ -296,12 +358,13 @@ class MultiGeneratorGAN:
             return out
         rows = []
         for gid, mode in plan:
-            if self.use_cuda_graphs and mode == PIXEL:
-                gs = self._graphs.get(gid)
+            if self.use_cuda_graphs and (mode == PIXEL or self.loss_allreduce is None):
+                cache = self._graphs if mode == PIXEL else self._gan_graphs
+                gs = cache.get(gid)
                 if gs is None or gs.lr.shape != lr_imgs.shape:
                     gs = GraphedGeneratorStep(self.generators[gid], self.discriminator, self.criterion,
-                                              self.g_optimizers[gid], lr_imgs, hr_imgs)
-                    self._graphs[gid] = gs
+                                              self.g_optimizers[gid], lr_imgs, hr_imgs, gan_mode=(mode == GAN))
+                    cache[gid] = gs
                 rows.append(gs(lr_imgs, hr_imgs).clone())
             else:
                 rows.append(train_generator_async(self.generators[gid], self.discriminator, lr_imgs, hr_imgs, None,

@@ -193,3 +193,34 @@ def test_train_discriminator_and_gan_mode_steps(S, O):
     assert abs(losses[1] - ref[1]) < 5e-3 * abs(ref[1])       # com_loss
     assert abs(losses[3]) <= 1.0 and abs(losses[0] - (losses[1] + losses[2] + losses[3])) < 1e-5
     assert all(p.grad is None or torch.isfinite(p.grad).all() for p in g.parameters())
+
+
+def test_gan_mode_cuda_graphs_match_eager(S):
+    """D step + GAN-mode generator steps replayed from CUDA graphs equal the eagerly enqueued steps bit for bit."""
+    crit = S.ReconstructionLoss()
+    torch.manual_seed(61)
+    lr, hr = torch.rand(1, 3, 107, 171).cuda(), torch.rand(1, 3, 428, 684).cuda()
+
+    def make(graphs):
+        gens, opts = [], []
+        for s_ in range(2):
+            torch.manual_seed(70 + s_)
+            g = S.SRResNet(num_residuals=1).cuda()
+            gens.append(g)
+            opts.append(S.Adam(g.parameters(), lr=1e-3, capturable=True))
+        torch.manual_seed(80)
+        d = S.Discriminator().cuda()
+        d_opt = S.Adam(d.parameters(), lr=1e-4, capturable=True)
+        pol = S.MultiGeneratorPolicy(S.PolicyConfig(num_generators=2, force=S.GAN))
+        return gens, d, S.MultiGeneratorGAN(gens, opts, crit, discriminator=d, d_optimizer=d_opt, policy=pol,
+                                            use_cuda_graphs=graphs)
+    ga, da, ta = make(False)
+    gb, db, tb = make(True)
+    for _ in range(3):
+        la = ta.step(lr, hr).clone()
+        lb = tb.step(lr, hr).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(la, lb), (la, lb)
+    assert torch.equal(da.flat_parameters(), db.flat_parameters())
+    for a, b in zip(ga, gb):
+        assert torch.equal(a.flat_parameters(), b.flat_parameters())
