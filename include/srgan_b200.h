@@ -170,6 +170,14 @@ int srg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
 int srg_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr_dev,
                       float beta1, float beta2, float eps, int* step_dev, float grad_scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Evaluation path (src/evaluation.py:48-52)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* replaces ImageEnhancer.forward (src/models.py:36-41): out = clamp(x + factor * Laplacian3x3(x), 0, 1), NCHW fp32 */
+int srg_image_enhance(const float* x_nchw, int N, int C, int H, int W, float factor, float* out_nchw, void* stream);
+/* out1[0] (DEVICE double) = mean((a - b)^2); calculate_psnr (src/utils.py:141-144) = 10 * log10(1 / mse) */
+int srg_mse(const float* a, const float* b, int64_t n, void* scratch, size_t scratch_bytes, double* out1, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

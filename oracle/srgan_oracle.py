@@ -274,6 +274,11 @@ def psnr(a: Tensor, b: Tensor) -> float:
     return float("inf") if mse == 0 else 10.0 * math.log10(1.0 / mse)
 
 
+def image_enhancer(x: Tensor, factor: float = 1.0) -> Tensor:
+    """ImageEnhancer.forward (src/models.py:36-41): x + factor * depthwise Laplacian(x), clamped to [0, 1]."""
+    return torch.clamp(x + factor * _depthwise3(x, _LAP), 0.0, 1.0)
+
+
 # --------------------------------------------------------------------------------------------------
 # Seeded default initialisation with the reference's construction order (nn.Conv2d / nn.BatchNorm2d
 # defaults; order = src/models.py:53-78 and :91-114) so weights can be regenerated anywhere from a seed.

@@ -16,6 +16,8 @@ from .policy import (GAN, PIXEL, MultiGeneratorPolicy, PolicyConfig, decide, gan
 from .train import (GraphedDiscriminatorStep, GraphedGeneratorStep, GraphedMultiGeneratorStep, MultiGeneratorGAN, train_discriminator, train_discriminator_async, train_generator,
                     train_generator_async, train_one_epoch)
 from . import parallel
+from .evaluation import (ImageEnhancer, calculate_psnr, load_reference_checkpoint, resume_learning_rates,
+                         save_reference_checkpoint, strip_module_prefix)
 
 __all__ = ["SRResNet", "ResidualBlock", "Discriminator", "ReconstructionLoss", "tanh_mean", "Adam", "train_generator",
            "train_discriminator", "train_one_epoch", "MultiGeneratorGAN", "GraphedGeneratorStep", "MultiGeneratorPolicy", "PolicyConfig",

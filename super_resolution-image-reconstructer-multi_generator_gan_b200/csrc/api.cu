@@ -311,4 +311,14 @@ int srg_adam_step_dev(float* params, const float* grads, float* exp_avg, float* 
   return launch_adam_dev(params, grads, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev, grad_scale, S(stream));
 }
 
+int srg_image_enhance(const float* x_nchw, int N, int C, int H, int W, float factor, float* out_nchw, void* stream) {
+  if (!x_nchw || !out_nchw) { set_error("image_enhance: null pointer"); return -6; }
+  return launch_image_enhance(x_nchw, N, C, H, W, factor, out_nchw, S(stream));
+}
+int srg_mse(const float* a, const float* b, int64_t n, void* scratch, size_t scratch_bytes, double* out1, void* stream) {
+  if (scratch_bytes < srg_recon_loss_scratch_bytes()) { set_error("mse: scratch too small"); return -5; }
+  if (!a || !b || !out1) { set_error("mse: null pointer"); return -6; }
+  return launch_mse(a, b, n, reinterpret_cast<double*>(scratch), out1, S(stream));
+}
+
 }  // extern "C"

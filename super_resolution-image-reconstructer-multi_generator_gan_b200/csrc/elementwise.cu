@@ -841,6 +841,57 @@ int launch_recon_loss_backward(const float* hr, const float* sr, int N, int C, i
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// evaluation path: ImageEnhancer (src/models.py:28-41) and the PSNR numerator (src/utils.py:141-144)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads) enhance_kernel(const float* __restrict__ x, int rows_total, int H, int W,
+                                                               float factor, float* __restrict__ out) {
+  for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
+    const int pl = row / H, h = row - pl * H;
+    const int64_t pbase = int64_t(pl) * H * W;
+    const Rows3 r = rows3(x + pbase, h, H, W);
+    const int64_t o = pbase + int64_t(h) * W;
+    for (int w = threadIdx.x; w < W; w += kLossThreads) {
+      const float v = __ldg(r.r1 + w) + factor * lap8(r, w, W);     // x + factor * (L * x), zero padding
+      out[o + w] = fminf(fmaxf(v, 0.f), 1.f);                        // torch.clamp(x, 0, 1)
+    }
+  }
+}
+int launch_image_enhance(const float* x, int N, int C, int H, int W, float factor, float* out, cudaStream_t st) {
+  const int64_t rows64 = int64_t(N) * C * H;
+  if (rows64 <= 0 || rows64 > 0x7fffffff) { set_error("image_enhance: bad shape"); return -1; }
+  const int rows = int(rows64);
+  enhance_kernel<<<rows < 8 * 1184 ? rows : 8 * 1184, kLossThreads, 0, st>>>(x, rows, H, W, factor, out);
+  SRG_LAUNCH_CHECK("image_enhance");
+  return 0;
+}
+__global__ void __launch_bounds__(256) sqdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                     double* __restrict__ scratch) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += int64_t(gridDim.x) * 256) {
+    const float d = a[i] - b[i];
+    acc += double(d) * double(d);
+  }
+  acc = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) scratch[kLossHdr + blockIdx.x] = acc;
+}
+__global__ void sqdiff_final_kernel(double* scratch, int blocks, double n, double* out) {
+  __shared__ double sh[8];
+  sum_partials(scratch, 0, blocks, &scratch[9], sh);
+  __syncthreads();
+  if (threadIdx.x == 0) out[0] = scratch[9] / n;
+}
+int launch_mse(const float* a, const float* b, int64_t n, double* scratch, double* out, cudaStream_t st) {
+  if (n <= 0) { set_error("mse: empty input"); return -1; }
+  const int blocks = int((n + 255) / 256 < kLossBlocks ? (n + 255) / 256 : kLossBlocks);
+  sqdiff_kernel<<<blocks, 256, 0, st>>>(a, b, n, scratch);
+  SRG_LAUNCH_CHECK("sqdiff");
+  sqdiff_final_kernel<<<1, 256, 0, st>>>(scratch, blocks, double(n), out);
+  SRG_LAUNCH_CHECK("sqdiff_final");
+  return 0;
+}
+
 // per-channel sums of NCHW fp32: grid = (chunks, N*C)
 __global__ void __launch_bounds__(256) nchw_plane_sum_kernel(const float* __restrict__ x, int64_t plane, double* __restrict__ scratch) {
   __shared__ double sh[8];

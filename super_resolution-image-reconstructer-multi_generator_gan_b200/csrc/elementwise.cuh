@@ -101,6 +101,12 @@ int launch_recon_loss_backward(const float* hr, const float* sr, int N, int C, i
 int launch_nchw_chan_sum(const float* x, int N, int C, int64_t plane, double* scratch, float* out, float scale,
                          cudaStream_t st);
 
+// ---- evaluation path ------------------------------------------------------------------------------
+// ImageEnhancer.forward (src/models.py:36-41): out = clamp(x + factor * (L * x), 0, 1), L = Laplacian of the loss
+int launch_image_enhance(const float* x, int N, int C, int H, int W, float factor, float* out, cudaStream_t st);
+// out[0] (double, device) = mean((a - b)^2): the PSNR numerator of src/utils.py:141-144 (psnr = 10 log10(1 / mse))
+int launch_mse(const float* a, const float* b, int64_t n, double* scratch, double* out, cudaStream_t st);
+
 // relativistic tanh losses of the reference (src/train.py:190,218): out[0] = mean(tanh(sign*(a-b)));
 // grads (optional): da = sign*(1-tanh^2)/n * gscale, db = -da
 int launch_tanh_mean(const float* a, const float* b, int64_t n, float sign, double* scratch, float* out, float* da,

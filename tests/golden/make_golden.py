@@ -39,6 +39,15 @@ def checksum(sd):
             if v.dtype.is_floating_point}
 
 
+def make_enhancer_fixture(models):
+    """ImageEnhancer (src/models.py:28-41) on a fixed input; separate file so it can be regenerated on its own:
+    python tests/golden/make_golden.py enhancer"""
+    torch.manual_seed(6)
+    x = torch.rand(2, 3, 18, 26) * 1.4 - 0.2          # values outside [0, 1] exercise the clamp
+    np.savez_compressed(os.path.join(HERE, "enhancer.npz"), x=x.numpy(),
+                        y1=models.ImageEnhancer().forward(x).numpy(), y05=models.ImageEnhancer(factor=0.5).forward(x).numpy())
+
+
 def main():
     torch.set_num_threads(8)
     models, train, utils = import_reference()
@@ -137,10 +146,15 @@ def main():
     out["gan_mode"] = {"seed": 5, "com": com.item(), "tv": tv.item(), "g_d": g_d.item(),
                        "grad_norms": {k: float(p.grad.double().norm()) for k, p in g.named_parameters()}}
 
+    make_enhancer_fixture(models)
+
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("golden fixtures written to", HERE)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "enhancer":
+        make_enhancer_fixture(import_reference()[0])
+    else:
+        main()

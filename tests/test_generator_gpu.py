@@ -407,3 +407,14 @@ def test_peer_sync_kernel_world1_matches_local_finalize(S):
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
     L.srg_peer_sync_destroy(ps)
+
+
+def test_image_enhancer_and_psnr_match_reference(S, O, golden_dir):
+    z = np.load(os.path.join(golden_dir, "enhancer.npz"))
+    x = torch.from_numpy(z["x"]).cuda()
+    assert maxrel(S.ImageEnhancer().forward(x), torch.from_numpy(z["y1"])) < 1e-6
+    assert maxrel(S.ImageEnhancer(factor=0.5).forward(x), torch.from_numpy(z["y05"])) < 1e-6
+    torch.manual_seed(9)
+    a, b = torch.rand(1, 3, 40, 56), torch.rand(1, 3, 40, 56)
+    assert abs(S.calculate_psnr(a.cuda(), b.cuda()) - O.psnr(a, b)) < 1e-4
+    assert S.calculate_psnr(a.cuda(), a.cuda()) == float("inf")

@@ -107,3 +107,23 @@ def test_discriminator_engine_tables_and_size_rule():
             S.models._DiscriminatorEngine(1, bad[0], bad[1], False, torch.device("cpu"))
         with pytest.raises(RuntimeError):
             O.discriminator_output_hw(*bad)
+
+
+def test_reference_checkpoint_interop(tmp_path):
+    """f-1: files written like the reference's training run (DDP 'module.' prefix, src/train.py:123-125) load into the
+    modules, with or without the prefix (src/evaluation.py:24-31); the resume protocol divides both LRs by 5."""
+    torch.manual_seed(8)
+    g = S.SRResNet(num_residuals=2)
+    d = S.Discriminator()
+    gp, dp = str(tmp_path / "Training_generator_model_0.pth"), str(tmp_path / "Training_discriminator_model_0.pth")
+    S.save_reference_checkpoint(g, gp)
+    S.save_reference_checkpoint(d, dp, ddp_prefix=False)
+    assert all(k.startswith("module.") for k in torch.load(gp, weights_only=True))
+    g2, d2 = S.SRResNet(num_residuals=2), S.Discriminator()
+    S.load_reference_checkpoint(g2, gp)
+    S.load_reference_checkpoint(d2, dp)
+    for a, b in zip(g.state_dict().values(), g2.state_dict().values()):
+        assert torch.equal(a, b)
+    for a, b in zip(d.state_dict().values(), d2.state_dict().values()):
+        assert torch.equal(a, b)
+    assert S.resume_learning_rates(1e-4, 5e-5) == (2e-5, 1e-5)

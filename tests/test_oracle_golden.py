@@ -133,3 +133,10 @@ def test_discriminator_step_and_gan_mode(gj):
         # gradient through D at its smallest valid geometry (last InstanceNorm over 1x2 elements) is sensitive to fp32
         # summation order; pinned to 5e-3
         assert abs(float(grads[k].double().norm()) - n) <= 5e-3 * n + 2e-8, k
+
+
+def test_image_enhancer_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "enhancer.npz"))
+    x = torch.from_numpy(z["x"])
+    np.testing.assert_allclose(O.image_enhancer(x, 1.0).numpy(), z["y1"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(O.image_enhancer(x, 0.5).numpy(), z["y05"], rtol=0, atol=1e-6)
