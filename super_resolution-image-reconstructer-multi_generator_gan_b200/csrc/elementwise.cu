@@ -679,6 +679,30 @@ __device__ __forceinline__ float lap8(const Rows3& r, int w, int W) {
                    ldz(r.r2, w - 1, W) + ldz(r.r2, w, W) + ldz(r.r2, w + 1, W);
   return __ldg(r.r1 + w) - 0.125f * nb;
 }
+// 4 consecutive pixels of a row plus their left / right neighbours: v[0] = x[w-1], v[1..4] = x[w..w+3], v[5] = x[w+4]
+struct Row6 { float v[6]; };
+__device__ __forceinline__ Row6 load_row6(const float* __restrict__ row, int w, int W) {
+  Row6 r;
+  if (row == nullptr) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = 0.f;
+    return r;
+  }
+  const float4 c = __ldg(reinterpret_cast<const float4*>(row + w));     // w % 4 == 0, W % 4 == 0, row 16-byte aligned
+  r.v[1] = c.x; r.v[2] = c.y; r.v[3] = c.z; r.v[4] = c.w;
+  r.v[0] = w > 0 ? __ldg(row + w - 1) : 0.f;
+  r.v[5] = w + 4 < W ? __ldg(row + w + 4) : 0.f;
+  return r;
+}
+__device__ __forceinline__ float edge0_v(const Row6& a, const Row6& b, const Row6& c, int i) {   // pixel i (0..3) of the quad
+  const float gx = 5.f * ((a.v[i + 2] - a.v[i]) + (b.v[i + 2] - b.v[i]) + (c.v[i + 2] - c.v[i]));
+  const float gy = 5.f * ((c.v[i] - a.v[i]) + (c.v[i + 1] - a.v[i + 1]) + (c.v[i + 2] - a.v[i + 2]));
+  return fmaxf(fabsf(gx), fabsf(gy));
+}
+__device__ __forceinline__ float lap8_v(const Row6& a, const Row6& b, const Row6& c, int i) {
+  const float nb = a.v[i] + a.v[i + 1] + a.v[i + 2] + b.v[i] + b.v[i + 2] + c.v[i] + c.v[i + 1] + c.v[i + 2];
+  return b.v[i + 1] - 0.125f * nb;
+}
 constexpr int kLossThreads = 128;
 __device__ __forceinline__ double block_sum_any(double v, double* sh) {
 #pragma unroll
@@ -701,10 +725,22 @@ __global__ void __launch_bounds__(kLossThreads) loss_pass1_kernel(const float* _
     const int pl = row / H, h = row - pl * H;
     const Rows3 r = rows3(hr + int64_t(pl) * H * W, h, H, W);
     float a1 = 0.f, a2 = 0.f;
-    for (int w = threadIdx.x; w < W; w += kLossThreads) {
-      const float e0 = edge0(r, w, W);
-      a1 += e0;
-      a2 += e0 * e0;
+    if ((W & 3) == 0) {
+      for (int w = threadIdx.x * 4; w < W; w += kLossThreads * 4) {
+        const Row6 ra = load_row6(r.r0, w, W), rb = load_row6(r.r1, w, W), rc = load_row6(r.r2, w, W);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float e0 = edge0_v(ra, rb, rc, i);
+          a1 += e0;
+          a2 += e0 * e0;
+        }
+      }
+    } else {
+      for (int w = threadIdx.x; w < W; w += kLossThreads) {
+        const float e0 = edge0(r, w, W);
+        a1 += e0;
+        a2 += e0 * e0;
+      }
     }
     s1 += double(a1);
     s2 += double(a2);
@@ -749,6 +785,28 @@ __global__ void __launch_bounds__(kLossThreads) loss_pass2_kernel(const float* _
     const Rows3 rs = rows3(sr + pbase, h, H, W);
     const int64_t o = pbase + int64_t(h) * W;
     float aE = 0.f, aL = 0.f, aT = 0.f;
+    if ((W & 3) == 0) {
+      for (int w = threadIdx.x * 4; w < W; w += kLossThreads * 4) {
+        const Row6 ha = load_row6(rh.r0, w, W), hb = load_row6(rh.r1, w, W), hc = load_row6(rh.r2, w, W);
+        const Row6 sa = load_row6(rs.r0, w, W), sb = load_row6(rs.r1, w, W), sc = load_row6(rs.r2, w, W);
+        float ev[4], gv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float e0 = edge0_v(ha, hb, hc, i);
+          float e = (e0 - mean) / stdv * 0.2f + 1.f;
+          e = fminf(fmaxf(e, 0.f), 2.f);
+          const float d = lap8_v(sa, sb, sc, i);
+          const float om = 1.f - e;
+          ev[i] = e;
+          gv[i] = (d > 0.f ? om : (d < 0.f ? -om : 0.f));
+          aE += e;
+          aL += fabsf(hb.v[i + 1] - sb.v[i + 1]) * e;
+          aT += fabsf(d) * om;
+        }
+        *reinterpret_cast<float4*>(e_buf + o + w) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+        *reinterpret_cast<float4*>(g_buf + o + w) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+      }
+    } else
     for (int w = threadIdx.x; w < W; w += kLossThreads) {
       const float e0 = edge0(rh, w, W);
       float e = (e0 - mean) / stdv * 0.2f + 1.f;                 // normalize(...)*0.2 + 1  (:213, :194-198)
@@ -802,6 +860,26 @@ __global__ void __launch_bounds__(kLossThreads) loss_pass3_kernel(const float* _
     const int64_t pbase = int64_t(pl) * H * W;
     const Rows3 rg = rows3(g_buf + pbase, h, H, W);
     const int64_t o = pbase + int64_t(h) * W;
+    if ((W & 3) == 0) {
+      for (int w = threadIdx.x * 4; w < W; w += kLossThreads * 4) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(sr + o + w));
+        const float4 h4 = __ldg(reinterpret_cast<const float4*>(hr + o + w));
+        const float4 e4 = __ldg(reinterpret_cast<const float4*>(e_buf + o + w));
+        const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, hv[4] = {h4.x, h4.y, h4.z, h4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
+        float gout[4];
+        Row6 ga, gb, gc;
+        if (tv_k != 0.f) { ga = load_row6(rg.r0, w, W); gb = load_row6(rg.r1, w, W); gc = load_row6(rg.r2, w, W); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float diff = sv[i] - hv[i];
+          const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+          float g = sg * ev[i] * inv_sum_e;
+          if (tv_k != 0.f) g += tv_k * lap8_v(ga, gb, gc, i);
+          gout[i] = g * grad_scale;
+        }
+        *reinterpret_cast<float4*>(grad + o + w) = make_float4(gout[0], gout[1], gout[2], gout[3]);
+      }
+    } else
     for (int w = threadIdx.x; w < W; w += kLossThreads) {
       const float diff = sr[o + w] - hr[o + w];
       const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
@@ -901,13 +979,24 @@ __global__ void __launch_bounds__(256) nchw_plane_sum_kernel(const float* __rest
   acc = block_sum_256(acc, sh);
   if (threadIdx.x == 0) scratch[int64_t(blockIdx.y) * gridDim.x + blockIdx.x] = acc;
 }
-__global__ void nchw_chan_final_kernel(const double* __restrict__ scratch, int N, int C, int chunks, float* out, float scale) {
-  const int c = threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256) nchw_chan_final_kernel(const double* __restrict__ scratch, int N, int C, int chunks,
+                                                              float* out, float scale) {
+  // one block per channel; fixed-order tree over the N x chunks partial sums
+  __shared__ double sh[256];
+  const int c = blockIdx.x;
+  const int total = N * chunks;
   double acc = 0.0;
-  for (int n = 0; n < N; ++n)
-    for (int k = 0; k < chunks; ++k) acc += scratch[(int64_t(n) * C + c) * chunks + k];
-  out[c] = float(acc) * scale;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int n = i / chunks, k = i - n * chunks;
+    acc += scratch[(int64_t(n) * C + c) * chunks + k];
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[c] = float(sh[0]) * scale;
 }
 int launch_nchw_chan_sum(const float* x, int N, int C, int64_t plane, double* scratch, float* out, float scale,
                          cudaStream_t st) {
@@ -919,7 +1008,7 @@ int launch_nchw_chan_sum(const float* x, int N, int C, int64_t plane, double* sc
   if (int64_t(N) * C * chunks > 3 * kLossBlocks) { set_error("nchw_chan_sum: batch too large for scratch"); return -1; }
   nchw_plane_sum_kernel<<<dim3(chunks, N * C), 256, 0, st>>>(x, plane, scratch + kLossHdr);
   SRG_LAUNCH_CHECK("nchw_plane_sum");
-  nchw_chan_final_kernel<<<1, 32, 0, st>>>(scratch + kLossHdr, N, C, chunks, out, scale);
+  nchw_chan_final_kernel<<<C, 256, 0, st>>>(scratch + kLossHdr, N, C, chunks, out, scale);
   SRG_LAUNCH_CHECK("nchw_chan_final");
   return 0;
 }
