@@ -418,3 +418,58 @@ def test_image_enhancer_and_psnr_match_reference(S, O, golden_dir):
     a, b = torch.rand(1, 3, 40, 56), torch.rand(1, 3, 40, 56)
     assert abs(S.calculate_psnr(a.cuda(), b.cuda()) - O.psnr(a, b)) < 1e-4
     assert S.calculate_psnr(a.cuda(), a.cuda()) == float("inf")
+
+
+def test_cfg1_four_train_steps_follow_reference_anchors(S, golden_dir):
+    """BASELINE configs[0]: 4 consecutive train_generator steps at 8x3x64x64 against the loss trajectory recorded from
+    the UNMODIFIED reference (tests/golden/golden.json: cfg1_anchors).  bf16 operands: 1 % on the losses."""
+    with open(os.path.join(golden_dir, "golden.json")) as f:
+        a = json.load(f)["cfg1_anchors"]
+    torch.manual_seed(0)
+    g = S.SRResNet()
+    S.Discriminator()                      # the reference constructs D after G: it consumes RNG before the data
+    lr = torch.rand(8, 3, 64, 64)
+    hr = torch.rand(8, 3, 256, 256)
+    g = g.cuda()
+    g.eval()
+    with torch.no_grad():
+        y = g(lr.cuda())
+    assert abs(float(y.double().sum()) - a["eval_sum"]) < 5e-3 * abs(a["eval_sum"])
+    assert abs(float(y.double().abs().mean()) - a["eval_mean_abs"]) < 5e-3 * a["eval_mean_abs"]
+    crit = S.ReconstructionLoss()
+    opt = S.Adam(g.parameters(), lr=1e-4)
+    for ref in a["steps"]:
+        got = S.train_generator(g, None, lr.cuda(), hr.cuda(), None, crit, opt)
+        assert abs(got[0] - ref[0]) < 1e-2 * abs(ref[0]), (got, ref)     # g_loss
+        assert abs(got[1] - ref[1]) < 1e-2 * abs(ref[1]), (got, ref)     # com_loss
+        assert abs(got[2] - ref[2]) < 0.15 * abs(ref[2]) + 2e-5, (got, ref)   # tv_loss (1e-4 scale, noise-dominated)
+        assert got[3] == 0.0
+
+
+def test_full_size_properties_cfg2(S):
+    """Size-independent properties at the BASELINE configs[1] geometry (16x3x96x96), where the CPU oracle is too slow:
+    run-to-run determinism, eval-mode batch independence, linearity of the backward pass in the upstream gradient."""
+    torch.manual_seed(5)
+    g = S.SRResNet().cuda()
+    lr = torch.rand(16, 3, 96, 96).cuda()
+    g.eval()
+    with torch.no_grad():
+        y_all = g(lr)
+        y_one = g(lr[3:4].contiguous())
+    assert torch.equal(y_all[3:4], y_one)                      # eval mode: samples do not interact
+    assert torch.isfinite(y_all).all()
+    g.train()
+    torch.manual_seed(6)
+    dsr = torch.randn(16, 3, 384, 384).cuda() * 1e-4
+    state = {k: v.clone() for k, v in g.state_dict().items()}
+    grads = []
+    for scale in (1.0, 1.0, 2.0):
+        g.load_state_dict(state)                               # same running statistics every time
+        g.zero_grad()
+        y = g(lr)
+        y.backward(dsr * scale)
+        torch.cuda.synchronize()
+        grads.append(g.flat_grads().clone())
+    assert torch.equal(grads[0], grads[1])                     # deterministic (fixed-order reductions, no atomics)
+    rel = float((grads[2] - 2.0 * grads[0]).abs().max() / grads[0].abs().max())
+    assert rel < 2e-2, rel                                     # linear up to bf16 rounding of the scaled gradients
