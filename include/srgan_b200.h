@@ -159,6 +159,12 @@ int srg_recon_loss_backward(const float* hr_nchw, const float* sr_nchw, int N, i
  * out[0] = mean(tanh(sign * (a - b))); da / db (may be NULL) receive the gradients times grad_scale. */
 int srg_tanh_mean(const float* a, const float* b, int64_t n, float sign, void* scratch, size_t scratch_bytes,
                   float* out1, float* da, float* db, float grad_scale, void* stream);
+/* Plain mean losses the scope statement names next to the reference's own objective (the reference code has no L1 / MSE
+ * / BCE call on its hot path; oracle: torch.nn.functional.l1_loss / mse_loss / binary_cross_entropy):
+ * kind 0 = mean|a-b|, 1 = mean (a-b)^2, 2 = BCE with a = probabilities, b = targets (logs clamped at -100 like torch).
+ * grad_a (may be NULL) receives d out / d a times grad_scale. */
+int srg_point_loss(int kind, const float* a, const float* b, int64_t n, void* scratch, size_t scratch_bytes, float* out1,
+                   float* grad_a, float grad_scale, void* stream);
 /* replaces torch.optim.Adam.step with default betas/eps, no weight decay (src/train.py:61-62,196,223) on flat
  * buffers; `step` is the 1-based step count; gradients are multiplied by grad_scale first (1/world for DDP mean). */
 int srg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

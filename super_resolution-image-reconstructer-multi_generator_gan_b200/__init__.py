@@ -9,7 +9,7 @@ package without that library raises as soon as a kernel is needed -- there is no
 from . import _lib
 from ._lib import build, lib
 from .models import BatchNormParams, ConvParams, Discriminator, ResidualBlock, SRResNet
-from .loss import ReconstructionLoss, tanh_mean
+from .loss import ReconstructionLoss, bce_loss, l1_loss, mse_loss, tanh_mean
 from .optim import Adam
 from .policy import (GAN, PIXEL, MultiGeneratorPolicy, PolicyConfig, decide, gan_probability, interpolate_models,
                      shuffle_lists_in_same_order)

@@ -128,6 +128,7 @@ EXPORTS = {
                                         c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
     "srg_tanh_mean": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
                               c_float, c_void_p]),
+    "srg_point_loss": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p, c_void_p, c_float, c_void_p]),
     "srg_image_enhance": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "srg_mse": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "srg_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float,

@@ -311,6 +311,12 @@ int srg_adam_step_dev(float* params, const float* grads, float* exp_avg, float* 
   return launch_adam_dev(params, grads, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev, grad_scale, S(stream));
 }
 
+int srg_point_loss(int kind, const float* a, const float* b, int64_t n, void* scratch, size_t scratch_bytes, float* out1,
+                   float* grad_a, float grad_scale, void* stream) {
+  if (scratch_bytes < srg_recon_loss_scratch_bytes()) { set_error("point_loss: scratch too small"); return -5; }
+  if (!a || !b || !out1) { set_error("point_loss: null pointer"); return -6; }
+  return launch_point_loss(kind, a, b, n, reinterpret_cast<double*>(scratch), out1, grad_a, grad_scale, S(stream));
+}
 int srg_image_enhance(const float* x_nchw, int N, int C, int H, int W, float factor, float* out_nchw, void* stream) {
   if (!x_nchw || !out_nchw) { set_error("image_enhance: null pointer"); return -6; }
   return launch_image_enhance(x_nchw, N, C, H, W, factor, out_nchw, S(stream));

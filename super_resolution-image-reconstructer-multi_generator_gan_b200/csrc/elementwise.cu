@@ -970,6 +970,78 @@ int launch_mse(const float* a, const float* b, int64_t n, double* scratch, doubl
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// plain pixel losses named by the north_star (L1 / MSE) and the discriminator BCE: 128-bit vectorised
+// mean reductions with the gradient written in the same pass (oracle: torch.nn.functional)
+// ------------------------------------------------------------------------------------------------
+template <int KIND>  // 0: L1 mean |a-b|, 1: MSE mean (a-b)^2, 2: BCE mean -(t log p + (1-t) log(1-p)), a = p, b = t
+__device__ __forceinline__ void point_loss(float a, float b, float gk, float& val, float& ga) {
+  if (KIND == 0) {
+    const float d = a - b;
+    val = fabsf(d);
+    ga = (d > 0.f ? gk : (d < 0.f ? -gk : 0.f));
+  } else if (KIND == 1) {
+    const float d = a - b;
+    val = d * d;
+    ga = 2.f * d * gk;
+  } else {
+    const float lp = fmaxf(logf(a), -100.f), lq = fmaxf(logf(1.f - a), -100.f);     // torch clamps the logs at -100
+    val = -(b * lp + (1.f - b) * lq);
+    ga = (a - b) / fmaxf(a * (1.f - a), 1e-12f) * gk;                                 // torch: (p - t) / max(p(1-p), eps)
+  }
+}
+template <int KIND>
+__global__ void __launch_bounds__(256) point_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                         double* __restrict__ scratch, float* __restrict__ grad_a, float gk) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < n4; i += int64_t(gridDim.x) * 256) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+    float v0, v1, v2, v3;
+    float4 g;
+    point_loss<KIND>(x.x, y.x, gk, v0, g.x);
+    point_loss<KIND>(x.y, y.y, gk, v1, g.y);
+    point_loss<KIND>(x.z, y.z, gk, v2, g.z);
+    point_loss<KIND>(x.w, y.w, gk, v3, g.w);
+    acc += double((v0 + v1) + (v2 + v3));
+    if (grad_a) reinterpret_cast<float4*>(grad_a)[i] = g;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < int(n & 3)) {      // tail (n not a multiple of 4)
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    float v, g;
+    point_loss<KIND>(a[i], b[i], gk, v, g);
+    acc += double(v);
+    if (grad_a) grad_a[i] = g;
+  }
+  acc = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) scratch[kLossHdr + blockIdx.x] = acc;
+}
+__global__ void point_loss_final_kernel(double* scratch, int blocks, double n, float* out) {
+  __shared__ double sh[8];
+  sum_partials(scratch, 0, blocks, &scratch[10], sh);
+  __syncthreads();
+  if (threadIdx.x == 0) out[0] = float(scratch[10] / n);
+}
+int launch_point_loss(int kind, const float* a, const float* b, int64_t n, double* scratch, float* out, float* grad_a,
+                      float grad_scale, cudaStream_t st) {
+  if (n <= 0) { set_error("point_loss: empty input"); return -1; }
+  if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(grad_a)) & 15) != 0) {
+    set_error("point_loss: pointers must be 16-byte aligned"); return -2;
+  }
+  const int64_t n4 = (n + 3) / 4;
+  const int blocks = int((n4 + 255) / 256 < kLossBlocks ? (n4 + 255) / 256 : kLossBlocks);
+  const float gk = grad_scale / float(n);
+  if (kind == 0) point_loss_kernel<0><<<blocks, 256, 0, st>>>(a, b, n, scratch, grad_a, gk);
+  else if (kind == 1) point_loss_kernel<1><<<blocks, 256, 0, st>>>(a, b, n, scratch, grad_a, gk);
+  else if (kind == 2) point_loss_kernel<2><<<blocks, 256, 0, st>>>(a, b, n, scratch, grad_a, gk);
+  else { set_error("point_loss: kind must be 0 (L1), 1 (MSE) or 2 (BCE)"); return -3; }
+  SRG_LAUNCH_CHECK("point_loss");
+  point_loss_final_kernel<<<1, 256, 0, st>>>(scratch, blocks, double(n), out);
+  SRG_LAUNCH_CHECK("point_loss_final");
+  return 0;
+}
+
 // per-channel sums of NCHW fp32: grid = (chunks, N*C)
 __global__ void __launch_bounds__(256) nchw_plane_sum_kernel(const float* __restrict__ x, int64_t plane, double* __restrict__ scratch) {
   __shared__ double sh[8];

@@ -107,6 +107,11 @@ int launch_image_enhance(const float* x, int N, int C, int H, int W, float facto
 // out[0] (double, device) = mean((a - b)^2): the PSNR numerator of src/utils.py:141-144 (psnr = 10 log10(1 / mse))
 int launch_mse(const float* a, const float* b, int64_t n, double* scratch, double* out, cudaStream_t st);
 
+// plain mean losses (kind 0: L1, 1: MSE, 2: BCE with a = probabilities, b = targets); grad_a (optional) = d out / d a
+// times grad_scale.  Vectorised 128-bit loads/stores, fixed-order reduction.
+int launch_point_loss(int kind, const float* a, const float* b, int64_t n, double* scratch, float* out, float* grad_a,
+                      float grad_scale, cudaStream_t st);
+
 // relativistic tanh losses of the reference (src/train.py:190,218): out[0] = mean(tanh(sign*(a-b)));
 // grads (optional): da = sign*(1-tanh^2)/n * gscale, db = -da
 int launch_tanh_mean(const float* a, const float* b, int64_t n, float sign, double* scratch, float* out, float* da,

@@ -118,3 +118,47 @@ def tanh_mean(a: torch.Tensor, b: torch.Tensor, sign: float = 1.0) -> torch.Tens
     if a.shape != b.shape:
         raise RuntimeError("tanh_mean: shape mismatch")
     return _TanhMeanFn.apply(_as_f32_cuda(a, "tanh_mean"), _as_f32_cuda(b, "tanh_mean"), sign)
+
+
+class _PointLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, kind):
+        L = _lib.lib()
+        scratch = _scratch(a.device)
+        out = torch.empty(1, dtype=torch.float32, device=a.device)
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        check(L.srg_point_loss(int(kind), c_void_p(a.data_ptr()), c_void_p(b.data_ptr()), a.numel(),
+                               c_void_p(scratch.data_ptr()), scratch.numel(), c_void_p(out.data_ptr()),
+                               c_void_p(ga.data_ptr()) if ga is not None else None, 1.0, stream_ptr()), "srg_point_loss")
+        ctx.ga = ga
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        ga = ctx.ga
+        ctx.ga = None
+        if ga is not None:
+            ga.mul_(g)
+        return ga, None, None
+
+
+def _point(a, b, kind, what):
+    if a.shape != b.shape:
+        raise RuntimeError(f"{what}: shape mismatch")
+    return _PointLossFn.apply(_as_f32_cuda(a, what), _as_f32_cuda(b.detach(), what), kind)
+
+
+def l1_loss(input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """mean |input - target| (torch.nn.functional.l1_loss); gradient w.r.t. ``input``."""
+    return _point(input, target, 0, "l1_loss")
+
+
+def mse_loss(input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """mean (input - target)^2 (torch.nn.functional.mse_loss); gradient w.r.t. ``input``."""
+    return _point(input, target, 1, "mse_loss")
+
+
+def bce_loss(probabilities: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """binary cross entropy on probabilities, e.g. the discriminator's sigmoid map against 1 / 0 labels
+    (torch.nn.functional.binary_cross_entropy, logs clamped at -100); gradient w.r.t. ``probabilities``."""
+    return _point(probabilities, target, 2, "bce_loss")

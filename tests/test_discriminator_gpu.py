@@ -224,3 +224,20 @@ def test_gan_mode_cuda_graphs_match_eager(S):
     assert torch.equal(da.flat_parameters(), db.flat_parameters())
     for a, b in zip(ga, gb):
         assert torch.equal(a.flat_parameters(), b.flat_parameters())
+
+
+def test_l1_mse_bce_match_torch_functional(S):
+    """The plain pixel / BCE losses the scope statement names: values and gradients against torch.nn.functional (fp32,
+    tolerance 1e-6 relative)."""
+    torch.manual_seed(13)
+    for shape in [(2, 3, 33, 47), (1, 512, 1, 3), (5,)]:
+        a0, b0 = torch.rand(shape) * 0.98 + 0.01, torch.rand(shape)
+        for fn, ref in ((S.l1_loss, F.l1_loss), (S.mse_loss, F.mse_loss), (S.bce_loss, F.binary_cross_entropy)):
+            a = a0.clone().cuda().requires_grad_(True)
+            out = fn(a, b0.cuda())
+            (1.5 * out).backward()
+            ar = a0.clone().requires_grad_(True)
+            r = ref(ar, b0)
+            (1.5 * r).backward()
+            assert abs(float(out.detach()) - float(r.detach())) <= 2e-6 * max(1.0, abs(float(r.detach()))), (fn.__name__, shape)
+            assert maxrel(a.grad, ar.grad) < 1e-5, (fn.__name__, shape)
