@@ -14,7 +14,7 @@ from .optim import Adam
 from .policy import (GAN, PIXEL, MultiGeneratorPolicy, PolicyConfig, decide, gan_probability, interpolate_models,
                      shuffle_lists_in_same_order)
 from .train import (GraphedDiscriminatorStep, GraphedGeneratorStep, GraphedMultiGeneratorStep, MultiGeneratorGAN, train_discriminator, train_discriminator_async, train_generator,
-                    train_generator_async, train_one_epoch)
+                    train_generator_async, train_one_epoch, setup_training)
 from . import parallel
 from .evaluation import (ImageEnhancer, calculate_psnr, load_reference_checkpoint, resume_learning_rates,
                          save_reference_checkpoint, strip_module_prefix)

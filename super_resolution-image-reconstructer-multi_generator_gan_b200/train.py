@@ -101,6 +101,56 @@ def train_one_epoch(generator, train_loader, g_optimizer, vgg_extractor, g_crite
     return avg
 
 
+def setup_training(rank: int, world_size: int, num_epochs: int, continue_training: bool = False, prefix: str = "Training",
+                   results_dir: str = "results", num_generators: int = 1, init_process_group: bool = True,
+                   capturable: bool = True):
+    """The model / optimiser / scheduler set-up of the reference's ``train_example`` (src/train.py:27-71) without its
+    dataset plumbing: NCCL process group on 127.0.0.1:12355 (:29-31), device = rank (:34-35), SRResNet + Discriminator
+    (:45-47; data parallel through parallel.data_parallel instead of two DDP wraps), Adam with lr 1e-4 / 5e-5 (:40-41,
+    61-62), ``continue_training`` resume protocol (:51-59: load rank 0's ``{prefix}_*_model_0.pth``, both LRs / 5,
+    prefix "Post-Training"), LinearLR 1 -> 0.01 over ``num_epochs`` for both optimisers (:70-71).  With
+    ``num_generators`` > 1 it returns the README's generator list (one optimiser / scheduler each).
+
+    Returns a dict: generators, g_optimizers, g_schedulers, discriminator, d_optimizer, d_scheduler, g_criterion,
+    device, prefix."""
+    import os
+    import torch.distributed as dist
+    from . import parallel
+    from .evaluation import load_reference_checkpoint, resume_learning_rates
+    from .loss import ReconstructionLoss
+    from .models import Discriminator, SRResNet
+    from .optim import Adam
+    if init_process_group and world_size > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "12355")
+        dist.init_process_group("nccl", rank=rank, world_size=world_size)
+    torch.cuda.set_device(rank)
+    device = torch.device(f"cuda:{rank}")
+    os.makedirs(results_dir, exist_ok=True)
+    lr_generator = 1e-4
+    lr_discriminator = lr_generator / 2
+    g_criterion = ReconstructionLoss()
+    generators = [SRResNet().to(device) for _ in range(num_generators)]
+    discriminator = Discriminator().to(device)
+    if continue_training:
+        for i, g in enumerate(generators):
+            load_reference_checkpoint(g, os.path.join(results_dir, f"{prefix}_generator_model_{0 if num_generators == 1 else i}.pth"))
+        load_reference_checkpoint(discriminator, os.path.join(results_dir, f"{prefix}_discriminator_model_0.pth"))
+        lr_generator, lr_discriminator = resume_learning_rates(lr_generator, lr_discriminator)
+        prefix = "Post-Training"
+    for m in generators + [discriminator]:
+        m.flat_parameters()
+    if world_size > 1:
+        parallel.data_parallel(generators + [discriminator])
+    g_optimizers = [Adam(g.parameters(), lr=lr_generator, capturable=capturable) for g in generators]
+    d_optimizer = Adam(discriminator.parameters(), lr=lr_discriminator, capturable=capturable)
+    linear = torch.optim.lr_scheduler.LinearLR
+    g_schedulers = [linear(optimizer=o, start_factor=1, end_factor=0.01, total_iters=num_epochs) for o in g_optimizers]
+    d_scheduler = linear(optimizer=d_optimizer, start_factor=1, end_factor=0.01, total_iters=num_epochs)
+    return dict(generators=generators, g_optimizers=g_optimizers, g_schedulers=g_schedulers, discriminator=discriminator,
+                d_optimizer=d_optimizer, d_scheduler=d_scheduler, g_criterion=g_criterion, device=device, prefix=prefix)
+
+
 class GraphedGeneratorStep:
     """One ``train_generator`` step (forward, loss, backward, Adam) captured into a CUDA graph and replayed.
 

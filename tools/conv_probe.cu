@@ -50,6 +50,7 @@ struct Problem {
   int act;
   bool residual, mask;
   int out_mode;
+  bool stats;                // exercise the fused BatchNorm-statistics epilogue (timing only)
   bool fuse;                 // fused-tap 3x3 kernel (weights repacked [c][s][nb][r][64][64])
 };
 
@@ -142,6 +143,8 @@ static int run(const Problem& pr, int timing_iters) {
   a.bias = pr.bias ? dbias : nullptr; a.act = pr.act; a.slope = 0.2f;
   a.residual = pr.residual ? dres : nullptr; a.mask_src = pr.mask ? dmsk : nullptr;
   a.out = dout; a.out_mode = pr.out_mode; a.fuse_taps = pr.fuse ? 1 : 0;
+  float* dstats = nullptr;
+  if (pr.stats) { CK(cudaMalloc(&dstats, 148 * 128 * 4)); a.stats = dstats; }
 
   int rc = launch_conv_gemm(a, 0);
   if (rc != 0) { printf("[%s] launch rc=%d err=%s\n", pr.name, rc, last_error()); return 1; }
@@ -428,6 +431,9 @@ int main(int argc, char** argv) {
     { Problem p = conv3x3("perf_fused_trunk_16x96x96", 16, 96, 96, 64, false); p.fuse = true; fails += run(p, iters); }
     { Problem p = conv3x3("perf_fused_up3_16x192x192", 16, 192, 192, 256, true); p.fuse = true; p.act = ACT_RELU; fails += run(p, iters); }
     fails += run(conv3x3("perf_trunk_16x96x96", 16, 96, 96, 64, false), iters);
+    { Problem p = conv3x3("perf_trunk_stats", 16, 96, 96, 64, false); p.stats = true; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_trunk_mask", 16, 96, 96, 64, false); p.mask = true; p.bias = false; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_trunk_residual", 16, 96, 96, 64, false); p.residual = true; p.bias = false; fails += run(p, iters); }
     Problem p = conv3x3("perf_up3_16x192x192", 16, 192, 192, 256, true);
     p.act = ACT_RELU;
     fails += run(p, iters);
