@@ -90,7 +90,7 @@ struct WgradArgs {
 };
 int wgrad_partials_floats(const WgradArgs& a, int* splits_out);
 int launch_wgrad_gemm(const WgradArgs& a, cudaStream_t stream);
-// 3x3 stride-1 specialisation (taps fused along M and N): partials [splits][n_blocks][kw 3][ci 64][(2-kh)*64 + co]
+// 3x3 stride-1 specialisation (taps fused along M and N): partials [splits][n_blocks][kw 3][(2-kh)*64 + co][ci 64]
 int wgrad3x3_partials_floats(const WgradArgs& a, int* splits_out);
 int launch_wgrad3x3(const WgradArgs& a, cudaStream_t stream);
 int launch_wgrad_reduce(const float* partials, const int* idx, float* out, int n_out, int splits, size_t split_stride,

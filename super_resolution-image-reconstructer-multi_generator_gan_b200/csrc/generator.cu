@@ -395,16 +395,16 @@ GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up) {
       if (fwd[i] >= 0) inv[size_t(fwd[i])] = int(i);
     return inv;
   };
-  // 3x3 layers use the fused wgrad kernel: partial index ((nb*3 + kw)*64 + ci)*192 + (2-kh)*64 + co
+  // 3x3 layers use the fused wgrad kernel: partial index ((nb*3 + kw)*192 + (2-kh)*64 + co)*64 + ci
   for (int co = 0; co < 64; ++co)
     for (int ci = 0; ci < 64; ++ci)
       for (int kh = 0; kh < 3; ++kh)
-        for (int kw = 0; kw < 3; ++kw) m33[((co * 64 + ci) * 3 + kh) * 3 + kw] = ((0 * 3 + kw) * 64 + ci) * 192 + (2 - kh) * 64 + co;
+        for (int kw = 0; kw < 3; ++kw) m33[((co * 64 + ci) * 3 + kh) * 3 + kw] = ((0 * 3 + kw) * 192 + (2 - kh) * 64 + co) * 64 + ci;
   for (int co = 0; co < 256; ++co)
     for (int ci = 0; ci < 64; ++ci)
       for (int kh = 0; kh < 3; ++kh)
         for (int kw = 0; kw < 3; ++kw)
-          mup[((co * 64 + ci) * 3 + kh) * 3 + kw] = (((co % 4) * 3 + kw) * 64 + ci) * 192 + (2 - kh) * 64 + co / 4;
+          mup[((co * 64 + ci) * 3 + kh) * 3 + kw] = (((co % 4) * 3 + kw) * 192 + (2 - kh) * 64 + co / 4) * 64 + ci;
   m33 = invert(m33, size_t(1) * 3 * 64 * 192);
   mup = invert(mup, size_t(4) * 3 * 64 * 192);
   mc1 = invert(mc1, size_t(1) * 3 * 8192);

@@ -233,7 +233,7 @@ int wgrad_partials_floats(const WgradArgs& a, int* splits_out);
 // (LBO = one image row): chain 1 = [kw0; kw1] x [kh2 | kh1 | kh0], chain 2 = [kw1; kw2] x same (its first half repeats
 // kw1 and is dropped).  Per 16 pixels that is 2 MMAs of 96 cycles instead of 5 of 69 (tools/mma_probe.cu: an M128 x K16
 // MMA costs max(~64, N/2) cycles), and one dy tile + three x tiles per 128 pixels instead of one dy + three haloed x.
-// Partials: [split][n-block][kw 3][ci 64][(2 - kh) * 64 + co] fp32.
+// Partials: [split][n-block][kw 3][(2 - kh) * 64 + co][ci 64] fp32 (ci fastest: the lanes of a warp store contiguously).
 // =====================================================================================================================
 constexpr uint32_t kW3DyBytes = 18 * 8 * 128;   // 18 KB haloed dy strip
 constexpr uint32_t kW3XBytes = 16 * 8 * 128;    // 16 KB x strip
@@ -326,27 +326,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_cons
     pdl_wait();
     mbar_wait(done, 0);
     tc_fence_after();
-    const bool any = split < p.tiles_total;
     float* dst = p.partials + (size_t(split) * p.n_blocks + nblk) * (3 * 64 * 192);
     for (int chain = 0; chain < 2; ++chain) {
       if (chain == 1 && q < 2) continue;
       const int kw = chain == 0 ? (m >> 6) : 2;
-      float* row = dst + (size_t(kw) * 64 + (m & 63)) * 192;
+      float* col0 = dst + size_t(kw) * 192 * 64 + (m & 63);
 #pragma unroll 1
       for (int c0 = 0; c0 < 192; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(chain * 192 + c0), v);
         tmem_ld_wait();
-        float4* o = reinterpret_cast<float4*>(row + c0);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float4 f;
-          f.x = any ? __uint_as_float(v[4 * g + 0]) : 0.f;
-          f.y = any ? __uint_as_float(v[4 * g + 1]) : 0.f;
-          f.z = any ? __uint_as_float(v[4 * g + 2]) : 0.f;
-          f.w = any ? __uint_as_float(v[4 * g + 3]) : 0.f;
-          o[g] = f;
-        }
+        for (int j = 0; j < 32; ++j) col0[size_t(c0 + j) * 64] = __uint_as_float(v[j]);
       }
     }
   }

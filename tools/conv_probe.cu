@@ -273,7 +273,7 @@ static Problem conv3x3(const char* name, int N, int H, int W, int cout, bool ps)
 
 // ------------------------------------------------------------------ wgrad probe
 static int run_wgrad(const char* name, int N, int H, int W, int n_strips, int n_taps, int strip_rows, int strip_dh,
-                     const int* strip_dw, const int* tap_row, int n_blocks, bool strided_dy, int iters) {
+                     const int* strip_dw, const int* tap_row, int n_blocks, bool strided_dy, int iters, bool fused3 = false) {
   const int Cout = n_blocks * 64;
   std::vector<uint16_t> x(size_t(N) * H * W * 64), dy(size_t(N) * H * W * Cout);
   for (auto& v : x) v = f2bf(frand());
@@ -308,7 +308,8 @@ static int run_wgrad(const char* name, int N, int H, int W, int n_strips, int n_
   for (int s = 0; s < n_strips; ++s) a.strip_dw[s] = strip_dw[s];
   for (int r = 0; r < n_taps; ++r) a.tap_row[r] = tap_row[r];
   int splits = 0;
-  const int pf = wgrad_partials_floats(a, &splits);
+  const int pf = fused3 ? wgrad3x3_partials_floats(a, &splits) : wgrad_partials_floats(a, &splits);
+  if (fused3) printf("[%s] partial sets = %d\n", name, splits);
   CK(cudaMalloc(&dpart, size_t(pf) * 4));
   a.partials = dpart;
   const int T = n_strips * n_taps, n_pairs = (T + 1) / 2;
@@ -318,12 +319,14 @@ static int run_wgrad(const char* name, int N, int H, int W, int n_strips, int n_
   for (int t = 0; t < T; ++t) for (int ci = 0; ci < 64; ++ci) for (int co = 0; co < Cout; ++co) {
     const int nb = co / 64, pr = t / 2, row = (t & 1) * 64 + ci;
     idx[(t * 64 + ci) * Cout + co] = ((nb * n_pairs + pr) * 128 + row) * 64 + (co % 64);
+    if (fused3) idx[(t * 64 + ci) * Cout + co] = ((nb * 3 + t / 3) * 192 + (2 - t % 3) * 64 + (co % 64)) * 64 + ci;
   }
+  const size_t split_stride = fused3 ? size_t(n_blocks) * 3 * 64 * 192 : size_t(n_blocks) * n_pairs * 128 * 64;
   CK(cudaMalloc(&didx, n_out * 4)); CK(cudaMalloc(&dout, n_out * 4));
   CK(cudaMemcpy(didx, idx.data(), n_out * 4, cudaMemcpyHostToDevice));
-  int rc = launch_wgrad_gemm(a, 0);
+  int rc = fused3 ? launch_wgrad3x3(a, 0) : launch_wgrad_gemm(a, 0);
   if (rc) { printf("[%s] launch rc=%d %s\n", name, rc, last_error()); return 1; }
-  rc = launch_wgrad_reduce(dpart, didx, dout, n_out, splits, size_t(n_blocks) * n_pairs * 128 * 64, 0, 0);
+  rc = launch_wgrad_reduce(dpart, didx, dout, n_out, splits, split_stride, 0, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess || rc) { printf("[%s] kernel failed: %s\n", name, cudaGetErrorString(e)); exit(3); }
   std::vector<float> out(n_out);
@@ -353,11 +356,16 @@ static int run_wgrad(const char* name, int N, int H, int W, int n_strips, int n_
   printf("[%s] checked=%zu bad=%zu max_abs_err=%.5f max_ref=%.3f %s\n", name, checked, bad, max_err, max_ref, bad == 0 ? "OK" : "FAIL");
   if (iters > 0) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) { launch_wgrad_gemm(a, 0); launch_wgrad_reduce(dpart, didx, dout, n_out, splits, size_t(n_blocks) * n_pairs * 128 * 64, 0, 0); }
+    for (int i = 0; i < 3; ++i) { fused3 ? launch_wgrad3x3(a, 0) : launch_wgrad_gemm(a, 0); }
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) { launch_wgrad_gemm(a, 0); launch_wgrad_reduce(dpart, didx, dout, n_out, splits, size_t(n_blocks) * n_pairs * 128 * 64, 0, 0); }
+    for (int i = 0; i < iters; ++i) { fused3 ? launch_wgrad3x3(a, 0) : launch_wgrad_gemm(a, 0); }
     cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    printf("[%s] %.3f us/launch (gemm only)\n", name, ms * 1000 / iters);
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) { fused3 ? launch_wgrad3x3(a, 0) : launch_wgrad_gemm(a, 0); launch_wgrad_reduce(dpart, didx, dout, n_out, splits, split_stride, 0, 0); }
+    cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1);
     const double flops = 2.0 * N * H * W * double(T) * 64 * Cout;
     printf("[%s] %.3f us/launch (gemm+reduce)  %.1f TFLOP/s useful\n", name, ms * 1000 / iters, flops / (ms / iters * 1e-3) / 1e12);
   }
@@ -373,10 +381,16 @@ int main(int argc, char** argv) {
     fails += run_wgrad("wg3x3_small", 2, 32, 24, 3, 3, 18, -1, dw3, tr3, 1, false, 0);
     fails += run_wgrad("wg3x3_ragged", 3, 40, 20, 3, 3, 18, -1, dw3, tr3, 1, false, 0);
     fails += run_wgrad("wg3x3_cout256_ps", 2, 32, 16, 3, 3, 18, -1, dw3, tr3, 4, true, 0);
+    fails += run_wgrad("wg3_fused_ragged", 3, 40, 20, 3, 3, 18, -1, dw3, tr3, 1, false, 0, true);
+    fails += run_wgrad("wg3_fused_128tiles", 16, 32, 32, 3, 3, 18, -1, dw3, tr3, 1, false, 0, true);
+    fails += run_wgrad("wg3_fused_296tiles", 4, 96, 48, 3, 3, 18, -1, dw3, tr3, 1, false, 0, true);
+    fails += run_wgrad("wg3_fused_cout256_ps", 2, 32, 16, 3, 3, 18, -1, dw3, tr3, 4, true, 0, true);
     const int dw1[1] = {0}, tr5[5] = {0, 2, 4, 6, 8};
     fails += run_wgrad("wg9_pairs", 2, 32, 16, 1, 5, 24, -3, dw1, tr5, 1, false, 0);
     if (iters > 0) {
       fails += run_wgrad("perf_wg_trunk_16x96x96", 16, 96, 96, 3, 3, 18, -1, dw3, tr3, 1, false, iters);
+      fails += run_wgrad("perf_wg3_trunk_16x96x96", 16, 96, 96, 3, 3, 18, -1, dw3, tr3, 1, false, iters, true);
+      fails += run_wgrad("perf_wg3_up3_16x192x192", 16, 192, 192, 3, 3, 18, -1, dw3, tr3, 4, true, iters, true);
       fails += run_wgrad("perf_wg_up3_16x192x192", 16, 192, 192, 3, 3, 18, -1, dw3, tr3, 4, true, iters);
     }
   }
