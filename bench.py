@@ -332,7 +332,7 @@ def run_ours(a):
     except Exception:
         pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, cfg2 geometry)", "kernel": "conv_gemm_kernel<64,3> (3x3 64->64 fprop/dgrad implicit GEMM)",
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, cfg2 geometry)", "kernel": "conv3_il_kernel (3x3 64->64 fprop/dgrad implicit GEMM, row-interleaved N=128 tcgen05 MMAs)",
                 "launches_timed": k_n, "avg_launch_us": avg_ms * 1e3, "kernel_share_of_step": (k_ms / prof_steps) / ms_per_step,
                 "flop_per_launch": flop_per_launch, "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "timed_over": f"{prof_steps} extra steps right after the timed region (per-launch CUDA events on the launch stream)"}

@@ -13,6 +13,7 @@
 #include "ptx.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -442,21 +443,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
 
 // =====================================================================================================================
-// 3x3 convolution with the three row taps of every strip fused into one N = 192 MMA ("fuse_taps").
+// 3x3 stride-1 convolution, 64 input channels, with ROW-INTERLEAVED accumulator blocks ("conv3_il").
 //
-// Measured on B200 (tools/mma_probe.cu): an SS-mode M128 x K16 tcgen05.mma costs ~69 cycles for N = 64 and for N = 128
-// and 128 cycles for N = 256 -- a ~64-cycle floor per instruction -- so the N = 64 MMAs of the generic kernel run the
-// tensor pipe at 46 %.  Here ONE 16-row x 8-pixel input window per column shift is multiplied by the stacked weights of
-// its three row taps, B = [W_kh0 | W_kh1 | W_kh2] (192 rows): 12 MMAs of 96 cycles per tile instead of 36 of 69.
-// Accumulator column group kh holds E_kh[m] = W_kh . x[window pixel m]; the output is
-//     out[m] = E_0[m - 8] + E_1[m] + E_2[m + 8]        (8 = tile width: one image row up / down)
-// re-aligned in the epilogue with warp shuffles (+ a small shared-memory exchange at warp boundaries).  Window rows 0
-// and 15 have no complete sum, so tiles advance by 14 rows (87.5 % of the MMA rows are useful).
+// Measured on B200 (tools/mma_probe.cu): an SS-mode M128 x K16 tcgen05.mma costs ~69 cycles for N = 64 AND for N = 128
+// (a ~64-cycle floor per instruction), so the N = 64 MMAs of the generic kernel run the tensor pipe at 46 %.  Pairing
+// two taps in one N = 128 MMA is free -- if both halves of the accumulator are complete outputs, i.e. nothing has to be
+// re-aligned in registers afterwards.  This kernel gets there through the A descriptor instead of the epilogue:
+//
+//   * a tile is 32 image rows x 8 pixels; TMEM block E (64 columns) holds the EVEN rows h0+2g, block O (the next 64
+//     columns) the ODD rows h0+2g+1, g = 0..15 = the MMA's 8-lane row groups;
+//   * the input is loaded through two row-parity views, so a "half strip" is 17 dense rows of one parity;
+//   * an A window starting at image row h0+rho (rho = -1..2, stepping 2 rows per lane group) contributes tap
+//     kh = rho+1 to block E and tap kh = rho to block O:
+//         rho = -1: E += W[kh0]                  (N = 64)       rho = 0: [E | O] += [W[kh1] | W[kh0]]   (N = 128)
+//         rho =  1: [E | O] += [W[kh2] | W[kh1]] (N = 128)      rho = 2: O += W[kh2]                    (N = 64)
+//     with the weights of one column shift resident in shared memory as 192 rows [kh2 ; kh1 ; kh0].
+//
+// 256 pixels x 9 taps cost 3 x 4 windows x 4 K-steps = 48 MMAs instead of 72, every accumulator lane is a finished
+// output pixel, and the two blocks go to two independent 8-warp epilogue groups (the generic kernel's epilogue needs
+// ~1600 cycles per 128 pixels, which would otherwise become the limiter).  Output / residual / mask tiles move through
+// row-parity TMA views as well (16 rows x 8 pixels per block).
 // =====================================================================================================================
-constexpr uint32_t kFuseBTile = 192 * 128;            // bytes of one fused weight k-block (3 taps x 64 cout x 64 k)
-constexpr uint32_t kXchgBytes = 2 * 2 * 4 * 2 * 8 * 16 * 4;   // [buf 2][hf 2][q 4][kind 2][8 lanes][16 cols] floats
+struct IlKParams {
+  CUtensorMap in_map[2];     // [image-row parity] 64-channel input view
+  CUtensorMap w_map;
+  CUtensorMap out_map[8];    // [n-block (pixel shuffle) or 0][row parity]
+  CUtensorMap aux_map[2];    // [row parity] residual / mask tensor
+  int N, H, W;
+  int tiles_h, tiles_w, tiles_total;
+  int strip_dw[3];
+  int cout_total, n_blocks, ctas_per_block;
+  int n_stages;
+  const float* bias;
+  int act;
+  float slope;
+  int aux_mode;              // 0 none, 1 add (residual), 2 mask (zero where aux <= 0)
+  int out_mode;
+  float* stats;              // per-CTA channel sums / sums of squares
+  const uint32_t* stats_y;   // optional second factor (bf16 pairs, the output's geometry): sum(out * stats_y) replaces sum(out^2)
+  long long* prof;
+};
 
-__global__ void __launch_bounds__(kThreads, 1) conv3_fused_kernel(const __grid_constant__ ConvKParams p) {
+constexpr int kIlThreads = 64 + 512;            // warp 0 producer, warp 1 MMA, warps 2-9 block E, warps 10-17 block O
+constexpr uint32_t kIlHalfStrip = 17 * 8 * 128; // 17 rows x 8 pixels x 64 bf16
+constexpr uint32_t kIlWBytes = 9 * 64 * 128;    // resident filter: [kw 3][kh2 ; kh1 ; kh0][64 cout][64 cin]
+
+__global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_constant__ IlKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = uniform_warp_idx();
@@ -464,28 +496,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_fused_kernel(const __grid_c
   pdl_trigger();
 
   uint8_t* w_smem = smem;
-  uint8_t* stages = smem + p.w_resident_bytes;
-  uint8_t* out_stage = stages + size_t(p.n_stages) * p.stage_bytes;   // 2 x 16 KB
-  uint8_t* aux_stage = out_stage + 2 * kTileOutBytes;                  // 2 x 16 KB (aux_mode != 0)
+  uint8_t* stages = w_smem + kIlWBytes;
+  uint8_t* out_stage = stages + size_t(p.n_stages) * kIlHalfStrip;       // [block 2][16 KB]
+  uint8_t* aux_stage = out_stage + 2 * kTileOutBytes;                     // [block 2][16 KB] (aux_mode != 0)
   uint8_t* tail = aux_stage + (p.aux_mode ? 2 * kTileOutBytes : 0);
-  float* xchg = reinterpret_cast<float*>(tail);                        // boundary-row exchange
-  uint8_t* tail2 = tail + kXchgBytes;
-  float* s_bias = reinterpret_cast<float*>(tail2);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail2 + 256);
-  uint64_t* full = bars;
+  float* s_bias = reinterpret_cast<float*>(tail);                         // 64 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 256);
+  uint64_t* full = bars;                                                  // [n_stages <= 8]
   uint64_t* empty = bars + 8;
   uint64_t* wfull = bars + 16;
-  uint64_t* tfull = bars + 17;
-  uint64_t* tempty = bars + 19;
-  uint64_t* auxfull = bars + 21;
-  uint64_t* auxempty = bars + 23;
+  uint64_t* tfull = bars + 17;                                            // [2]
+  uint64_t* tempty = bars + 19;                                           // [2]
+  uint64_t* auxfull = bars + 21;                                          // [block 2]
+  uint64_t* auxempty = bars + 23;                                         // [block 2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
-  float* s_stats = reinterpret_cast<float*>(tail2 + 512);
+  float* s_stats = reinterpret_cast<float*>(tail + 512);                  // [16][128] floats (p.stats only)
 
   const int nblk = blockIdx.x % p.n_blocks;
   const int tile0 = blockIdx.x / p.n_blocks;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
-  const int kb_total = p.n_chunks * p.n_strips;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.n_stages; ++i) {
@@ -495,18 +524,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_fused_kernel(const __grid_c
     mbar_init(wfull, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpiThreads);
+      mbar_init(&tempty[i], 512);
       mbar_init(&auxfull[i], 1);
-      mbar_init(&auxempty[i], kEpiThreads);
+      mbar_init(&auxempty[i], 256);
     }
     fence_barrier_init();
-    for (int v = 0; v < kMaxInMaps; ++v) tma_prefetch_desc(&p.in_map[v]);
+    tma_prefetch_desc(&p.in_map[0]);
+    tma_prefetch_desc(&p.in_map[1]);
     tma_prefetch_desc(&p.w_map);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  if (warp >= 2) {
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp >= 2 && warp < 4) {
     const int t = threadIdx.x - 64;
-    if (t < 64) s_bias[t] = p.bias != nullptr ? p.bias[nblk * 64 + t] : 0.f;
+    s_bias[t] = p.bias != nullptr ? p.bias[nblk * 64 + t] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -518,50 +548,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_fused_kernel(const __grid_c
   if (warp == 0) {
     // =============================================================== TMA producer
     if (elect_one()) {
-      if (p.resident) {
-        mbar_expect_tx(wfull, uint32_t(kb_total) * kFuseBTile);
-        for (int kb = 0; kb < kb_total; ++kb)
-          tma_load_2d(w_smem + size_t(kb) * kFuseBTile, &p.w_map, wfull, 0, (kb * p.n_blocks + nblk) * 192);
-      }
-      pdl_wait();
-      int stage = 0, ab = 0;
+      // generic packing is k-block (kw*3 + kh); shared memory wants [kw][kh2 ; kh1 ; kh0]
+      mbar_expect_tx(wfull, kIlWBytes);
+      for (int s = 0; s < 3; ++s)
+        for (int r = 0; r < 3; ++r)
+          tma_load_2d(w_smem + size_t(s * 3 + (2 - r)) * 8192, &p.w_map, wfull, 0, (s * 3 + r) * p.cout_total + nblk * 64);
+      pdl_wait();      // the activations (and aux tensor) come from the previous kernel; the weights above do not
+      int stage = 0;
       uint32_t phase = 0, aux_phase = 0;
       for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
         const int n = tile / tiles_per_img;
         const int rem = tile - n * tiles_per_img;
-        const int h0 = (rem / p.tiles_w) * 14 - 1;     // window row 0 (output rows h0+1 .. h0+14)
-        const int w0 = (rem % p.tiles_w) * p.TW;
-        if (p.aux_mode) {
-          mbar_wait(&auxempty[ab], aux_phase ^ 1);
-          mbar_expect_tx(&auxfull[ab], kTileOutBytes);
-          tma_load_4d(aux_stage + ab * kTileOutBytes, &p.aux_map, &auxfull[ab], nblk * 64, w0, h0, n);
-          ab ^= 1;
-          if (ab == 0) aux_phase ^= 1;
-        }
-        for (int c = 0; c < p.n_chunks; ++c) {
-          const int view = c / p.chunks_per_view;
-          const int coff = (c - view * p.chunks_per_view) * 64;
-          for (int s = 0; s < p.n_strips; ++s) {
+        const int hh = (rem / p.tiles_w) * 16;       // tile origin in parity-view rows (h0 / 2)
+        const int w0 = (rem % p.tiles_w) * 8;
+        for (int s = 0; s < 3; ++s) {
+#pragma unroll
+          for (int par = 1; par >= 0; --par) {       // odd image rows h0-1+2j first, then even rows h0+2j (j = 0..16)
             { long long t0_ = clock64(); mbar_wait(&empty[stage], phase ^ 1); prof_acc[0] += clock64() - t0_; }
-            uint8_t* dst = stages + size_t(stage) * p.stage_bytes;
-            mbar_expect_tx(&full[stage], p.resident ? p.strip_bytes : p.stage_bytes);
-            tma_load_4d(dst, &p.in_map[view], &full[stage], coff, w0 + p.strip_dw[s], h0, n);
-            if (!p.resident)
-              tma_load_2d(dst + p.strip_bytes, &p.w_map, &full[stage], 0, ((c * p.n_strips + s) * p.n_blocks + nblk) * 192);
+            mbar_expect_tx(&full[stage], kIlHalfStrip);
+            tma_load_4d(stages + size_t(stage) * kIlHalfStrip, &p.in_map[par], &full[stage], 0, w0 + p.strip_dw[s],
+                        hh - par, n);
             if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
           }
+        }
+        if (p.aux_mode) {
+          // single-buffered per block, issued AFTER this tile's strips so that waiting for the previous tile's
+          // epilogue never holds back the operand prefetch
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            mbar_wait(&auxempty[b], aux_phase ^ 1);
+            mbar_expect_tx(&auxfull[b], kTileOutBytes);
+            tma_load_4d(aux_stage + b * kTileOutBytes, &p.aux_map[b], &auxfull[b], nblk * 64, w0, hh, n);
+          }
+          aux_phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(128, 192, 0, 0);
+    constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc128 = make_idesc_bf16(128, 128, 0, 0);
     const uint64_t desc_hi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
     const uint32_t stage0_lo = smem_u32(stages) >> 4;
-    const uint32_t stage_lo_stride = p.stage_bytes >> 4;
     const uint32_t w_lo = smem_u32(w_smem) >> 4;
-    const uint32_t strip_lo = p.strip_bytes >> 4;
-    if (p.resident) mbar_wait(wfull, 0);
+    mbar_wait(wfull, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -569,28 +599,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_fused_kernel(const __grid_c
     for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
       { long long t0_ = clock64(); mbar_wait(&tempty[acc], acc_phase ^ 1); prof_acc[1] += clock64() - t0_; }
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + uint32_t(acc * 192);
-      uint32_t accumulate = 0;
-      uint32_t kb = 0;
-      for (int c = 0; c < p.n_chunks; ++c) {
-        for (int s = 0; s < p.n_strips; ++s) {
+      const uint32_t d_e = tmem_base + uint32_t(acc * 128);
+      const uint32_t d_o = d_e + 64;
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) {
+        const uint32_t wb = w_lo + uint32_t(s) * (3 * 8192 >> 4);     // [kh2 ; kh1 ; kh0] of this column shift
+#pragma unroll
+        for (int par = 1; par >= 0; --par) {
           { long long t0_ = clock64(); mbar_wait(&full[stage], phase); prof_acc[2] += clock64() - t0_; }
           tc_fence_after();
-          const uint32_t a_lo = stage0_lo + uint32_t(stage) * stage_lo_stride;
-          const uint32_t b_lo = p.resident ? w_lo + kb * (kFuseBTile >> 4) : a_lo + strip_lo;
+          const uint32_t a_lo = stage0_lo + uint32_t(stage) * (kIlHalfStrip >> 4);
           if (elect_one()) {
-            const uint64_t adesc = desc_hi | uint64_t(a_lo);
-            const uint64_t bdesc = desc_hi | uint64_t(b_lo);
+            if (par == 1) {
+              // odd rows: window rho = 1 (rows h0+1+2g = half-strip row g+1): E += kh2, O += kh1; first MMA of the tile
+              const uint64_t a1 = desc_hi | uint64_t(a_lo + (1024 >> 4));
+              const uint64_t b1 = desc_hi | uint64_t(wb);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_e, a1 + uint64_t(2 * k), b1 + uint64_t(2 * k), idesc128, (s > 0 || k > 0) ? 1u : 0u);
+              // window rho = -1 (rows h0-1+2g = half-strip row g): E += kh0
+              const uint64_t a0 = desc_hi | uint64_t(a_lo);
+              const uint64_t b0 = desc_hi | uint64_t(wb + (2 * 8192 >> 4));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d_e, a0 + uint64_t(2 * k), b0 + uint64_t(2 * k), idesc64, 1u);
+            } else {
+              // even rows: window rho = 0 (rows h0+2g = half-strip row g): E += kh1, O += kh0
+              const uint64_t a0 = desc_hi | uint64_t(a_lo);
+              const uint64_t b0 = desc_hi | uint64_t(wb + (8192 >> 4));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d_e, a0 + uint64_t(2 * k), b0 + uint64_t(2 * k), idesc128, 1u);
+              // window rho = 2 (rows h0+2+2g = half-strip row g+1): O += kh2
+              const uint64_t a1 = desc_hi | uint64_t(a_lo + (1024 >> 4));
+              const uint64_t b1 = desc_hi | uint64_t(wb);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d_o, a1 + uint64_t(2 * k), b1 + uint64_t(2 * k), idesc64, 1u);
             }
             umma_commit(&empty[stage]);
           }
           __syncwarp();
-          accumulate = 1;
-          kb += 1;
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -600,81 +646,61 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_fused_kernel(const __grid_c
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // =================================================================== epilogue
-    const int q = warp & 3;            // TMEM lane quadrant
-    const int m = q * 32 + lane;       // window pixel: row r = m / 8 (0..15), column m % 8
-    const int hf = (warp - 2) >> 2;    // 32-channel half
-    const int etid = threadIdx.x - 64;
-    int acc = 0, ob = 0, ab = 0, xb = 0;
+    // =================================================================== epilogue: two independent 8-warp groups
+    const int blk = (warp - 2) >> 3;           // 0: even rows (block E), 1: odd rows (block O)
+    const int gw = (warp - 2) & 7;
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may read
+    const int m = q * 32 + lane;               // GEMM row: lane group g = m >> 3 is image row h0 + 2g + blk
+    const int hf = gw >> 2;                    // which 32-column half of the block's 64 columns
+    const int gtid = gw * 32 + lane;           // thread index inside the group
+    const int bar_a = 1 + 2 * blk, bar_b = 2 + 2 * blk;
+    uint8_t* my_out = out_stage + blk * kTileOutBytes;
+    const uint8_t* my_aux = aux_stage + blk * kTileOutBytes;
+    int acc = 0;
     uint32_t acc_phase = 0, aux_phase = 0;
     float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;
     for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
-      const int h0 = (rem / p.tiles_w) * 14 - 1;
-      const int w0 = (rem % p.tiles_w) * p.TW;
+      const int hh = (rem / p.tiles_w) * 16;
+      const int w0 = (rem % p.tiles_w) * 8;
       { long long t0_ = clock64(); mbar_wait(&tfull[acc], acc_phase); prof_acc[3] += clock64() - t0_; }
       tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 128 + blk * 64 + hf * 32);
+      uint32_t v[32];
+      tmem_ld32(t_addr, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+
       float f[32];
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 192 + hf * 32 + pass * 16);
-        uint32_t e0[16], e1[16], e2[16];
-        tmem_ld16(t_addr, e0);
-        tmem_ld16(t_addr + 64, e1);
-        tmem_ld16(t_addr + 128, e2);
-        tmem_ld_wait();
-        if (pass == 1) {
-          tc_fence_before();
-          mbar_arrive(&tempty[acc]);
-        }
-        // rows at warp boundaries: publish what the neighbouring quadrants need
-        float* xw = xchg + size_t(((xb * 2 + hf) * 4 + q) * 2) * 128;
-        if (lane >= 24) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) xw[(lane - 24) * 16 + j] = __uint_as_float(e0[j]);          // kind 0: E_0 of my last row
-        }
-        if (lane < 8) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) xw[128 + lane * 16 + j] = __uint_as_float(e2[j]);           // kind 1: E_2 of my first row
-        }
-        named_bar_sync(4, kEpiThreads);
-        const float* up_w = xchg + size_t(((xb * 2 + hf) * 4 + ((q + 3) & 3)) * 2) * 128;           // quadrant q-1, kind 0
-        const float* dn_w = xchg + size_t(((xb * 2 + hf) * 4 + ((q + 1) & 3)) * 2) * 128 + 128;     // quadrant q+1, kind 1
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[j]), 8);
-          float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[j]), 8);
-          if (lane < 8) up = up_w[lane * 16 + j];             // (window row 0 reads junk: never stored)
-          if (lane >= 24) dn = dn_w[(lane - 24) * 16 + j];    // (window row 15 likewise)
-          f[pass * 16 + j] = __uint_as_float(e1[j]) + up + dn;
-        }
-        xb ^= 1;
-      }
       {
         const float4* bp = reinterpret_cast<const float4*>(s_bias + hf * 32);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 b = bp[g];
-          f[4 * g + 0] += b.x; f[4 * g + 1] += b.y; f[4 * g + 2] += b.z; f[4 * g + 3] += b.w;
+          f[4 * g + 0] = __uint_as_float(v[4 * g + 0]) + b.x;
+          f[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b.y;
+          f[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b.z;
+          f[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b.w;
         }
       }
       if (p.act == ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        for (int j = 0; j < 32; ++j) f[j] = apply_act<ACT_RELU>(f[j], 0.f);
       } else if (p.act == ACT_LRELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
+        for (int j = 0; j < 32; ++j) f[j] = apply_act<ACT_LRELU>(f[j], p.slope);
       }
       const uint32_t row_off = uint32_t(m) * 128u;
       const uint32_t sw = uint32_t(m & 7);
       if (p.aux_mode) {
-        mbar_wait(&auxfull[ab], aux_phase);
-        const uint8_t* ap = aux_stage + ab * kTileOutBytes + row_off;
+        mbar_wait(&auxfull[blk], aux_phase);
+        const uint8_t* ap = my_aux + row_off;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const uint4 rr = *reinterpret_cast<const uint4*>(ap + (((uint32_t(hf * 4 + g)) ^ sw) << 4));
-          const uint32_t ws[4] = {rr.x, rr.y, rr.z, rr.w};
+          const uint4 r = *reinterpret_cast<const uint4*>(ap + (((uint32_t(hf * 4 + g)) ^ sw) << 4));
+          const uint32_t ws[4] = {r.x, r.y, r.z, r.w};
           if (p.aux_mode == 1) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -689,13 +715,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_fused_kernel(const __grid_c
             }
           }
         }
-        mbar_arrive(&auxempty[ab]);
-        ab ^= 1;
-        if (ab == 0) aux_phase ^= 1;
+        mbar_arrive(&auxempty[blk]);
+        aux_phase ^= 1;
       }
-      if (etid == 0) tma_store_wait_read<1>();
-      named_bar_sync(1, kEpiThreads);
-      uint8_t* op = out_stage + ob * kTileOutBytes + row_off;
+      // stage the bf16 block (128B-swizzled rows) and hand it to the TMA store engine; one staging buffer per group
+      if (gtid == 0) tma_store_wait_read<0>();      // this group's previous store has drained the buffer
+      named_bar_sync(bar_a, 256);
+      uint8_t* op = my_out + row_off;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint4 o;
@@ -706,55 +732,67 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_fused_kernel(const __grid_c
         *reinterpret_cast<uint4*>(op + (((uint32_t(hf * 4 + g)) ^ sw) << 4)) = o;
       }
       fence_proxy_async_smem();
-      named_bar_sync(2, kEpiThreads);
-      if (etid == 0) {
-        // window rows 1..14 -> output rows h0+1 .. h0+14: staging bytes [1024, 15360)
+      // second factor of the product statistics (BatchNorm backward: sum dz * y): 16 coalesced loads per thread, issued
+      // before the barrier so that they land while the group synchronises and the store is handed to the TMA engine
+      uint32_t yv[16];
+      if (p.stats_y != nullptr) {
+        const int c2 = gtid & 31, part = gtid >> 5;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int mm = part * 16 + r;
+          const int hr = 2 * (hh + (mm >> 3)) + blk, wc = w0 + (mm & 7);
+          yv[r] = (hr < p.H && wc < p.W) ? __ldg(p.stats_y + ((size_t(n) * p.H + hr) * p.W + wc) * 32 + c2) : 0u;
+        }
+      }
+      named_bar_sync(bar_b, 256);
+      if (gtid == 0) {
         const bool ps = p.out_mode == OUT_PIXEL_SHUFFLE;
-        tma_store_4d(&p.out_map[ps ? nblk : 0], out_stage + ob * kTileOutBytes + 1024, ps ? 0 : nblk * 64, w0, h0 + 1, n);
+        tma_store_4d(&p.out_map[(ps ? nblk : 0) * 2 + blk], my_out, ps ? 0 : nblk * 64, w0, hh, n);
         tma_store_commit();
       }
       if (p.stats != nullptr) {
-        const int c2 = etid & 31, part = etid >> 5;
-        const uint8_t* sp = out_stage + ob * kTileOutBytes;
-#pragma unroll 4
-        for (int rr = 0; rr < 16; ++rr) {
-          const int mm = part * 16 + rr;
-          const int wr = mm >> 3;
-          if (wr >= 1 && wr <= 14 && h0 + wr < p.H && w0 + (mm & 7) < p.W) {
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(sp + mm * 128 + ((((c2 >> 2)) ^ (mm & 7)) << 4) + (c2 & 3) * 4);
-            const float a0 = bf16_lo(v), a1 = bf16_hi(v);
+        // column sums of the staged bf16 block (exactly the values BatchNorm will normalise)
+        const int c2 = gtid & 31, part = gtid >> 5;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int mm = part * 16 + r;
+          if (2 * (hh + (mm >> 3)) + blk < p.H && w0 + (mm & 7) < p.W) {
+            const uint32_t sv = *reinterpret_cast<const uint32_t*>(my_out + mm * 128 + ((((c2 >> 2)) ^ (mm & 7)) << 4) + (c2 & 3) * 4);
+            const float a0 = bf16_lo(sv), a1 = bf16_hi(sv);
+            float b0 = a0, b1 = a1;
+            if (p.stats_y != nullptr) { b0 = bf16_lo(yv[r]); b1 = bf16_hi(yv[r]); }
             st_s0 += a0; st_s1 += a1;
-            st_q0 = fmaf(a0, a0, st_q0); st_q1 = fmaf(a1, a1, st_q1);
+            st_q0 = fmaf(a0, b0, st_q0); st_q1 = fmaf(a1, b1, st_q1);
           }
         }
       }
-      ob ^= 1;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (etid == 0) tma_store_wait_all<0>();
+    if (gtid == 0) tma_store_wait_all<0>();
     if (p.stats != nullptr) {
-      const int c2 = etid & 31, part = etid >> 5;
+      const int c2 = gtid & 31, part = blk * 8 + (gtid >> 5);
       s_stats[part * 128 + 2 * c2] = st_s0;
       s_stats[part * 128 + 2 * c2 + 1] = st_s1;
       s_stats[part * 128 + 64 + 2 * c2] = st_q0;
       s_stats[part * 128 + 64 + 2 * c2 + 1] = st_q1;
-      named_bar_sync(3, kEpiThreads);
-      if (etid < 128) {
+      named_bar_sync(5, 512);
+      if (blk == 0 && gtid < 128) {
         float t = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) t += s_stats[g * 128 + etid];
-        p.stats[size_t(blockIdx.x) * 128 + etid] = t;
+        for (int g = 0; g < 16; ++g) t += s_stats[g * 128 + gtid];
+        p.stats[size_t(blockIdx.x) * 128 + gtid] = t;
       }
     }
   }
+
   if (p.prof != nullptr && lane == 0 && (warp <= 2)) {
     long long* d = p.prof + (size_t(blockIdx.x) * 3 + warp) * 6;
     d[0] = prof_acc[0]; d[1] = prof_acc[1]; d[2] = prof_acc[2]; d[3] = prof_acc[3]; d[4] = clock64() - t_start; d[5] = t_start;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 // ----------------------------------------------------------- host launcher
@@ -819,110 +857,118 @@ static int launch_instance(const ConvKParams& p, dim3 grid, size_t smem_bytes, c
   return 0;
 }
 
-static int launch_conv3_fused(const ConvGemmArgs& a, cudaStream_t stream) {
-  if (a.TH != 16 || a.TW != 8 || a.n_taps != 3 || a.block_n != 64 || a.n_strips < 1 || a.n_strips > kMaxStrips) {
-    set_error("conv3_fused: needs a 16x8 tile, 3 row taps and 64-channel n-blocks"); return -30;
+// conv3_il applies to the plain 3x3 / 64-input-channel launches (trunk fprop + dgrad, up-conv fprop); everything else
+// (multi-view inputs, 9x9 row pairs, fold9, fp32 outputs, product statistics) stays on the generic kernel.
+static bool conv3_il_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* ev = getenv("SRG_CONV_IL");
+    on = (ev != nullptr && ev[0] == '0') ? 0 : 1;
   }
-  if (a.out_mode != OUT_NHWC && a.out_mode != OUT_PIXEL_SHUFFLE) { set_error("conv3_fused: bf16 NHWC / pixel-shuffle output only"); return -31; }
+  return on != 0;
+}
+static bool use_conv3_il(const ConvGemmArgs& a) {
+  if (a.variant == 1 || (a.variant == 0 && !conv3_il_enabled())) return false;
+  return a.TH == 16 && a.TW == 8 && a.block_n == 64 && a.n_strips == 3 && a.n_taps == 3 && a.strip_dh == -1 &&
+         a.strip_rows == 18 && a.tap_row[0] == 0 && a.tap_row[1] == 1 && a.tap_row[2] == 2 && a.n_views == 1 &&
+         a.views[0].channels == 64 && a.in_H == a.H && a.in_W == a.W && a.H >= 2 &&
+         (a.out_mode == OUT_NHWC || a.out_mode == OUT_PIXEL_SHUFFLE) &&
+         a.cout_total % 64 == 0 && a.cout_total <= 256;
+}
+
+// row-parity view of a [N, H, W, C] tensor given by element strides: rows 2j + par
+static int encode_parity_map(CUtensorMap* map, const void* base, int C, int W, int H, int N, int64_t stride_w,
+                             int64_t stride_h, int64_t stride_n, int par, uint32_t box_rows) {
+  const __nv_bfloat16* ptr = reinterpret_cast<const __nv_bfloat16*>(base) + size_t(par) * stride_h;
+  uint64_t dims[4] = {uint64_t(C), uint64_t(W), uint64_t((H - par + 1) / 2), uint64_t(N)};
+  uint64_t strides[3] = {uint64_t(stride_w) * 2, uint64_t(stride_h) * 4, uint64_t(stride_n) * 2};
+  uint32_t box[4] = {64, 8, box_rows, 1};
+  return encode_map_bf16(map, ptr, 4, dims, strides, box);
+}
+
+static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   if (a.residual != nullptr && a.mask_src != nullptr) { set_error("conv_gemm: residual and mask are exclusive"); return -11; }
   const bool has_aux = a.residual != nullptr || a.mask_src != nullptr;
   if (has_aux && a.out_mode != OUT_NHWC) { set_error("conv_gemm: residual/mask need OUT_NHWC"); return -12; }
   if (a.out_mode == OUT_PIXEL_SHUFFLE && a.cout_total != 256) { set_error("conv_gemm: pixel shuffle needs cout 256"); return -13; }
-  if (a.stats != nullptr && (a.out_mode != OUT_NHWC || a.cout_total != 64)) { set_error("conv_gemm: fused statistics need 64 channels"); return -16; }
-  if (a.cout_total % 64 != 0 || a.n_views < 1 || a.n_views > kMaxInMaps) { set_error("conv3_fused: bad channel/view count"); return -3; }
-  ConvKParams p;
+  if (a.stats != nullptr && (a.out_mode != OUT_NHWC || a.cout_total != 64)) {
+    set_error("conv_gemm: fused statistics need OUT_NHWC with 64 output channels"); return -16;
+  }
+  IlKParams p;
   memset(&p, 0, sizeof(p));
-  p.N = a.N; p.H = a.H; p.W = a.W; p.TH = 16; p.TW = 8;
-  p.tile_step_w = 8; p.tile_w_org = 0;
-  p.tiles_h = (a.H + 13) / 14;
+  p.N = a.N; p.H = a.H; p.W = a.W;
+  p.tiles_h = (a.H + 31) / 32;
   p.tiles_w = (a.W + 7) / 8;
   p.tiles_total = a.N * p.tiles_h * p.tiles_w;
   if (p.tiles_total == 0) return 0;
-  int total_ch = 0;
-  for (int v = 0; v < a.n_views; ++v) {
-    if (a.views[v].channels % 64 != 0 || a.views[v].channels != a.views[0].channels) { set_error("conv_gemm: view channels must be equal multiples of 64"); return -8; }
-    total_ch += a.views[v].channels;
-  }
-  p.n_chunks = total_ch / 64;
-  p.chunks_per_view = a.views[0].channels / 64;
-  p.n_strips = a.n_strips; p.strip_rows = 16; p.strip_dh = 0;
-  for (int s = 0; s < a.n_strips; ++s) p.strip_dw[s] = a.strip_dw[s];
+  for (int s = 0; s < 3; ++s) p.strip_dw[s] = a.strip_dw[s];
   p.cout_total = a.cout_total;
   p.n_blocks = a.cout_total / 64;
-  const int sms = num_sms();
-  p.ctas_per_block = sms / p.n_blocks;
+  p.ctas_per_block = num_sms() / p.n_blocks;
   if (p.ctas_per_block < 1) p.ctas_per_block = 1;
   if (p.ctas_per_block > p.tiles_total) p.ctas_per_block = p.tiles_total;
-  const int kb_total = p.n_chunks * a.n_strips;
-  p.strip_bytes = 16 * 8 * 128u;
-  const uint32_t w_all = uint32_t(kb_total) * kFuseBTile;
   p.aux_mode = a.residual ? 1 : (a.mask_src ? 2 : 0);
-  const uint32_t fixed_bytes = 2 * kTileOutBytes + (has_aux ? 2 * kTileOutBytes : 0) + kXchgBytes + 512 + 8 * 128 * 4;
-  const uint32_t budget = 227 * 1024 - 1024 - fixed_bytes;
-  p.resident = (w_all + 3 * p.strip_bytes <= budget) ? 1 : 0;
-  p.w_resident_bytes = p.resident ? w_all : 0;
-  p.stage_bytes = p.strip_bytes + (p.resident ? 0 : kFuseBTile);
-  int stages = int((budget - p.w_resident_bytes) / p.stage_bytes);
+  const uint32_t fixed_bytes = kIlWBytes + 2 * kTileOutBytes + (has_aux ? 2 * kTileOutBytes : 0) + 512 +
+                               (a.stats != nullptr ? 16 * 128 * 4 : 0);
+  int stages = int((227 * 1024 - 1024 - fixed_bytes) / kIlHalfStrip);
   if (stages > 8) stages = 8;
-  if (stages < 2) { set_error("conv3_fused: shared memory too small for 2 stages"); return -10; }
+  if (stages < 2) { set_error("conv3_il: shared memory too small"); return -10; }
   p.n_stages = stages;
-  const size_t smem_bytes = 1024 + p.w_resident_bytes + size_t(stages) * p.stage_bytes + fixed_bytes;
-  for (int v = 0; v < a.n_views; ++v) {
-    const InView& iv = a.views[v];
-    uint64_t dims[4] = {uint64_t(iv.channels), uint64_t(a.in_W), uint64_t(a.in_H), uint64_t(a.N)};
-    uint64_t strides[3] = {uint64_t(iv.stride_w) * 2, uint64_t(iv.stride_h) * 2, uint64_t(iv.stride_n) * 2};
-    uint32_t box[4] = {64, 8, 16, 1};
-    int rc = encode_map_bf16(&p.in_map[v], iv.ptr, 4, dims, strides, box);
+  const size_t smem_bytes = 1024 + fixed_bytes + size_t(stages) * kIlHalfStrip;
+
+  const InView& iv = a.views[0];
+  for (int par = 0; par < 2; ++par) {
+    int rc = encode_parity_map(&p.in_map[par], iv.ptr, 64, a.in_W, a.in_H, a.N, iv.stride_w, iv.stride_h, iv.stride_n, par, 17);
     if (rc) return rc;
   }
-  for (int v = a.n_views; v < kMaxInMaps; ++v) p.in_map[v] = p.in_map[0];
   {
-    uint64_t dims[2] = {64, uint64_t(kb_total) * p.n_blocks * 192};
+    uint64_t dims[2] = {64, uint64_t(9) * a.cout_total};
     uint64_t strides[1] = {128};
-    uint32_t box[2] = {64, 192};
+    uint32_t box[2] = {64, 64};
     int rc = encode_map_bf16(&p.w_map, a.weights, 2, dims, strides, box);
     if (rc) return rc;
   }
-  {
-    uint32_t box[4] = {64, 8, 14, 1};
-    if (a.out_mode == OUT_PIXEL_SHUFFLE) {
-      for (int q = 0; q < 4; ++q) {
-        const int i = q >> 1, j = q & 1;
-        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a.out) + (size_t(i) * 2 * a.W + j) * 64;
-        uint64_t dims[4] = {64, uint64_t(a.W), uint64_t(a.H), uint64_t(a.N)};
-        uint64_t strides[3] = {128 * 2, uint64_t(4) * a.W * 64 * 2, uint64_t(4) * a.H * a.W * 64 * 2};
-        int rc = encode_map_bf16(&p.out_map[q], base, 4, dims, strides, box);
+  if (a.out_mode == OUT_PIXEL_SHUFFLE) {
+    // view q=(i,j) of the HR tensor [N,2H,2W,64]: pixel (2h+i, 2w+j)
+    for (int q = 0; q < 4; ++q) {
+      const int i = q >> 1, j = q & 1;
+      const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a.out) + (size_t(i) * 2 * a.W + j) * 64;
+      for (int par = 0; par < 2; ++par) {
+        int rc = encode_parity_map(&p.out_map[q * 2 + par], base, 64, a.W, a.H, a.N, 128, int64_t(4) * a.W * 64,
+                                   int64_t(4) * a.H * a.W * 64, par, 16);
         if (rc) return rc;
-      }
-      p.aux_map = p.out_map[0];
-    } else {
-      uint64_t dims[4] = {uint64_t(a.cout_total), uint64_t(a.W), uint64_t(a.H), uint64_t(a.N)};
-      uint64_t strides[3] = {uint64_t(a.cout_total) * 2, uint64_t(a.W) * a.cout_total * 2, uint64_t(a.H) * a.W * a.cout_total * 2};
-      int rc = encode_map_bf16(&p.out_map[0], a.out, 4, dims, strides, box);
-      if (rc) return rc;
-      for (int q = 1; q < 4; ++q) p.out_map[q] = p.out_map[0];
-      if (has_aux) {
-        uint32_t abox[4] = {64, 8, 16, 1};
-        rc = encode_map_bf16(&p.aux_map, a.residual ? a.residual : a.mask_src, 4, dims, strides, abox);
-        if (rc) return rc;
-      } else {
-        p.aux_map = p.out_map[0];
       }
     }
+    p.aux_map[0] = p.aux_map[1] = p.out_map[0];
+  } else {
+    const int64_t C = a.cout_total;
+    for (int par = 0; par < 2; ++par) {
+      int rc = encode_parity_map(&p.out_map[par], a.out, int(C), a.W, a.H, a.N, C, int64_t(a.W) * C, int64_t(a.H) * a.W * C, par, 16);
+      if (rc) return rc;
+      if (has_aux) {
+        rc = encode_parity_map(&p.aux_map[par], a.residual ? a.residual : a.mask_src, int(C), a.W, a.H, a.N, C,
+                               int64_t(a.W) * C, int64_t(a.H) * a.W * C, par, 16);
+        if (rc) return rc;
+      } else {
+        p.aux_map[par] = p.out_map[par];
+      }
+    }
+    for (int q = 2; q < 8; ++q) p.out_map[q] = p.out_map[q & 1];
   }
   p.bias = a.bias; p.act = a.act; p.slope = a.slope;
-  p.out = a.out; p.out_mode = a.out_mode;
+  p.out_mode = a.out_mode;
   p.stats = a.stats;
+  p.stats_y = reinterpret_cast<const uint32_t*>(a.stats_y);
   p.prof = reinterpret_cast<long long*>(a.prof);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv3_il_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     attr_set = true;
   }
-  cudaError_t e = launch_pdl(conv3_fused_kernel, dim3(p.ctas_per_block * p.n_blocks), dim3(kThreads), smem_bytes, stream, p);
+  cudaError_t e = launch_pdl(conv3_il_kernel, dim3(p.ctas_per_block * p.n_blocks), dim3(kIlThreads), smem_bytes, stream, p);
   if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error("conv3_fused launch: %s", cudaGetErrorString(e)); return int(e); }
+  if (e != cudaSuccess) { set_error("conv3_il launch: %s", cudaGetErrorString(e)); return int(e); }
   count_launch();
   return 0;
 }
@@ -930,7 +976,7 @@ static int launch_conv3_fused(const ConvGemmArgs& a, cudaStream_t stream) {
 int conv_gemm_grid(const ConvGemmArgs& a) {
   const bool fold = a.out_mode == OUT_FOLD9_NCHW;
   const int step_w = fold ? a.TW - 8 : a.TW;
-  const int step_h = a.fuse_taps ? 14 : a.TH;
+  const int step_h = use_conv3_il(a) ? 32 : a.TH;
   const int tiles = a.N * ((a.H + step_h - 1) / step_h) * ((a.W + step_w - 1) / step_w);
   const int n_blocks = a.cout_total / a.block_n;
   int per = num_sms() / n_blocks;
@@ -940,7 +986,7 @@ int conv_gemm_grid(const ConvGemmArgs& a) {
 }
 
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
-  if (a.fuse_taps) return launch_conv3_fused(a, stream);
+  if (use_conv3_il(a)) return launch_conv3_il(a, stream);
   if (a.TH * a.TW != 128 || a.TW % 8 != 0) { set_error("conv_gemm: tile must be 128 pixels with TW%%8==0"); return -1; }
   if (a.block_n != 64 && a.block_n != 32) { set_error("conv_gemm: block_n must be 32 or 64"); return -2; }
   if (a.cout_total % a.block_n != 0) { set_error("conv_gemm: cout_total %% block_n != 0"); return -3; }

@@ -56,9 +56,8 @@ struct ConvGemmArgs {
   const void* mask_src;      // bf16, same layout as out: out = (mask_src > 0) ? out : 0  (ReLU backward)
   void* out;
   int out_mode;
-  int fuse_taps;             // 3x3 only: the three row taps of a strip share ONE A window and one N=192 MMA; their
-                             // partial products are re-aligned (+-1 image row) in the epilogue.  Weights must be packed
-                             // [chunk][strip][n-block][tap][64 cout][64 k]; tiles step 14 rows (16-row window).
+  int variant;               // 0: pick the kernel automatically (row-interleaved conv3_il for plain 3x3 / 64-channel launches
+                             // unless SRG_CONV_IL=0), 1: force the generic strip kernel, 2: conv3_il where applicable
   float* stats;              // optional (OUT_NHWC, cout 64): per-CTA column sums of the STORED bf16 tile values,
                              // float [conv_gemm_grid(a)][128] = {sum over valid pixels [64], sum of squares [64]}
   const void* stats_y;       // optional with `stats`: bf16 tensor of the output's geometry; the second 64 columns then hold

@@ -7,6 +7,7 @@
 #include "generator.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_gemm.cuh"
@@ -304,6 +305,10 @@ GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up) {
   if (N < 1 || H < 1 || W < 1 || n_res < 0 || n_up < 0 || n_up > 4) { set_error("generator_create: bad geometry"); return nullptr; }
   EngineImpl* e = new EngineImpl();
   e->N = N; e->H = H; e->W = W; e->n_res = n_res; e->n_up = n_up;
+  {
+    const char* ev = getenv("SRG_FUSE_BWD_STATS");
+    e->fuse_bwd_stats = !(ev != nullptr && ev[0] == '0');
+  }
   // ---- parameters in the reference's registration order (src/models.py:53-78)
   add_param(*e, "conv1.weight", {64, 3, 9, 9});
   add_param(*e, "conv1.bias", {64});
@@ -687,8 +692,9 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     a.in_H = gh; a.in_W = gw;
     a.weights = packed + w_off; a.cout_total = 64; a.block_n = 64;
     a.bias = nullptr; a.act = ACT_NONE; a.residual = residual; a.mask_src = mask; a.out = out; a.out_mode = OUT_NHWC;
-    // Measured (profiles/r01_notes.md): the extra epilogue work costs more than the separate 7 us reduction pass it
-    // replaces (13.1 vs 12.8 ms per 3-generator step), so the fusion is off unless e->fuse_bwd_stats is set.
+    // With the generic kernel's single epilogue group this fusion cost more than the separate 7 us reduction pass it
+    // replaces (profiles/r01_notes.md); conv3_il has two independent epilogue groups with slack, so it is on by default
+    // (SRG_FUSE_BWD_STATS=0 restores the separate chan_reduce pass).
     if (stats_y != nullptr && e->fuse_bwd_stats) { a.stats = partials; a.stats_y = stats_y; bwd_stats_rows = conv_gemm_grid(a); }
     e->launches += 1;
     if (dy_ps) return launch_conv_gemm(a, st);

@@ -61,7 +61,7 @@ struct GeneratorEngine {
   int world = 1;
   long long launches = 0;  // kernels launched so far (bench bookkeeping)
   // optional CUDA-event timing of the dominant kernel class (3x3 64->64 fprop/dgrad conv_gemm launches)
-  bool fuse_bwd_stats = false;  // BatchNorm-backward sums in the dgrad epilogue instead of a separate pass (slower, see .cu)
+  bool fuse_bwd_stats = true;   // BatchNorm-backward sums in the dgrad epilogue instead of a separate pass (SRG_FUSE_BWD_STATS=0: off)
   bool keep_grads = false; // debug: keep every inter-layer gradient in its own named buffer (parity tests)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)

@@ -51,7 +51,7 @@ struct Problem {
   bool residual, mask;
   int out_mode;
   bool stats;                // exercise the fused BatchNorm-statistics epilogue (timing only)
-  bool fuse;                 // fused-tap 3x3 kernel (weights repacked [c][s][nb][r][64][64])
+  int variant;               // ConvGemmArgs::variant: 1 = generic strip kernel, 2 = row-interleaved conv3_il
 };
 
 static int run(const Problem& pr, int timing_iters) {
@@ -96,21 +96,7 @@ static int run(const Problem& pr, int timing_iters) {
   CK(cudaMalloc(&dmsk, out_elems * 2));
   CK(cudaMalloc(&dbias, bias.size() * 4));
   CK(cudaMemcpy(dx, xphys.data(), xphys.size() * 2, cudaMemcpyHostToDevice));
-  if (pr.fuse) {
-    std::vector<uint16_t> wf(wp.size());
-    const int nbk = pr.cout_total / 64;
-    for (int c = 0; c < n_chunks; ++c)
-      for (int s = 0; s < pr.n_strips; ++s)
-        for (int nb = 0; nb < nbk; ++nb)
-          for (int r = 0; r < 3; ++r)
-            for (int nl = 0; nl < 64; ++nl)
-              for (int k = 0; k < 64; ++k)
-                wf[(((((size_t(c) * pr.n_strips + s) * nbk + nb) * 3 + r) * 64 + nl) * 64) + k] =
-                    wp[((size_t((c * pr.n_strips + s) * 3 + r) * pr.cout_total) + nb * 64 + nl) * 64 + k];
-    CK(cudaMemcpy(dw, wf.data(), wf.size() * 2, cudaMemcpyHostToDevice));
-  } else {
-    CK(cudaMemcpy(dw, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
-  }
+  CK(cudaMemcpy(dw, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dres, res.data(), out_elems * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dmsk, msk.data(), out_elems * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dbias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
@@ -142,7 +128,7 @@ static int run(const Problem& pr, int timing_iters) {
   a.weights = dw; a.cout_total = pr.cout_total; a.block_n = pr.block_n;
   a.bias = pr.bias ? dbias : nullptr; a.act = pr.act; a.slope = 0.2f;
   a.residual = pr.residual ? dres : nullptr; a.mask_src = pr.mask ? dmsk : nullptr;
-  a.out = dout; a.out_mode = pr.out_mode; a.fuse_taps = pr.fuse ? 1 : 0;
+  a.out = dout; a.out_mode = pr.out_mode; a.variant = pr.variant;
   float* dstats = nullptr;
   if (pr.stats) { CK(cudaMalloc(&dstats, 148 * 128 * 4)); a.stats = dstats; }
 
@@ -267,6 +253,7 @@ static Problem conv3x3(const char* name, int N, int H, int W, int cout, bool ps)
   for (int r = 0; r < 3; ++r) p.tap_row[r] = r;
   p.cout_total = cout; p.block_n = 64; p.bias = true; p.act = ACT_NONE;
   p.out_mode = ps ? OUT_PIXEL_SHUFFLE : OUT_NHWC;
+  p.variant = 1;
   return p;
 }
 
@@ -435,15 +422,21 @@ int main(int argc, char** argv) {
     p.block_n = 32; p.out_mode = OUT_FOLD9_NCHW;
     fails += run(p, 0);
   }
-  {
-    Problem p = conv3x3("fused_small", 2, 32, 24, 64, false); p.fuse = true; fails += run(p, 0);
-    Problem q = conv3x3("fused_ragged_res", 3, 37, 20, 64, false); q.fuse = true; q.residual = true; q.act = ACT_LRELU; fails += run(q, 0);
-    Problem u = conv3x3("fused_relu_ps", 2, 30, 16, 256, true); u.fuse = true; u.act = ACT_RELU; fails += run(u, 0);
-    Problem v = conv3x3("fused_cin256_views_mask", 2, 32, 16, 64, false); v.fuse = true; v.n_views = 4; v.strided_views = true; v.mask = true; fails += run(v, 0);
+  {  // row-interleaved 3x3 kernel (conv3_il): same problems, 32-row tiles, parity views
+    Problem p = conv3x3("il_small", 2, 32, 24, 64, false); p.variant = 2; fails += run(p, 0);
+    Problem r = conv3x3("il_ragged", 3, 40, 20, 64, false); r.variant = 2; fails += run(r, 0);
+    Problem o = conv3x3("il_odd_rows", 2, 37, 13, 64, false); o.variant = 2; o.act = ACT_RELU; fails += run(o, 0);
+    Problem q = conv3x3("il_ragged_res", 3, 37, 20, 64, false); q.variant = 2; q.residual = true; q.act = ACT_LRELU; fails += run(q, 0);
+    Problem m = conv3x3("il_mask_ragged", 2, 24, 20, 64, false); m.variant = 2; m.mask = true; fails += run(m, 0);
+    Problem u = conv3x3("il_relu_ps", 2, 30, 16, 256, true); u.variant = 2; u.act = ACT_RELU; fails += run(u, 0);
+    Problem t = conv3x3("il_many_tiles", 5, 96, 96, 64, false); t.variant = 2; t.residual = true; fails += run(t, 0);
   }
   if (iters > 0) {
-    { Problem p = conv3x3("perf_fused_trunk_16x96x96", 16, 96, 96, 64, false); p.fuse = true; fails += run(p, iters); }
-    { Problem p = conv3x3("perf_fused_up3_16x192x192", 16, 192, 192, 256, true); p.fuse = true; p.act = ACT_RELU; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_il_trunk_16x96x96", 16, 96, 96, 64, false); p.variant = 2; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_il_trunk_stats", 16, 96, 96, 64, false); p.variant = 2; p.stats = true; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_il_trunk_mask", 16, 96, 96, 64, false); p.variant = 2; p.mask = true; p.bias = false; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_il_trunk_residual", 16, 96, 96, 64, false); p.variant = 2; p.residual = true; p.bias = false; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_il_up3_16x192x192", 16, 192, 192, 256, true); p.variant = 2; p.act = ACT_RELU; fails += run(p, iters); }
     fails += run(conv3x3("perf_trunk_16x96x96", 16, 96, 96, 64, false), iters);
     { Problem p = conv3x3("perf_trunk_stats", 16, 96, 96, 64, false); p.stats = true; fails += run(p, iters); }
     { Problem p = conv3x3("perf_trunk_mask", 16, 96, 96, 64, false); p.mask = true; p.bias = false; fails += run(p, iters); }
