@@ -92,6 +92,22 @@ int launch_wgrad_gemm(const WgradArgs& a, cudaStream_t stream);
 // 3x3 stride-1 specialisation (taps fused along M and N): partials [splits][n_blocks][kw 3][(2-kh)*64 + co][ci 64]
 int wgrad3x3_partials_floats(const WgradArgs& a, int* splits_out);
 int launch_wgrad3x3(const WgradArgs& a, cudaStream_t stream);
+// All same-shape 3x3 / 64->64 layers in one launch (+ one reduce launch).  Layer l reads x at x_base + l * x_layer_stride
+// and dy at dy_base + l * dy_layer_stride (dense NHWC bf16 tensors [N,H,W,64]); its OIHW gradient is written to
+// grads + out_off[l] through `inv` (partial element -> output element, the map launch_wgrad_reduce_inv uses).
+struct WgradBatchArgs {
+  int N, H, W, n_layers;
+  const void* x_base;
+  int64_t x_layer_stride_bytes;
+  const void* dy_base;
+  int64_t dy_layer_stride_bytes;
+  float* partials;           // wgrad3_batched_partials_floats(a) floats
+  const int* inv;            // device, 3*192*64 ints
+  float* grads;
+  const long long* out_off;  // device, n_layers element offsets into grads
+};
+size_t wgrad3_batched_partials_floats(const WgradBatchArgs& a);
+int launch_wgrad3x3_batched(const WgradBatchArgs& a, cudaStream_t stream);
 int launch_wgrad_reduce(const float* partials, const int* idx, float* out, int n_out, int splits, size_t split_stride,
                         int accumulate_into, cudaStream_t stream);
 

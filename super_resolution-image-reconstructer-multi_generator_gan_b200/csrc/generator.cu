@@ -34,6 +34,8 @@ struct Carver {
 // ------------------------------------------------------------------ workspace layout
 struct Layout {
   size_t packed, bias, bncoef, bwdcoef, partials, sums, ticket, wg_partials, ps_scratch, loss_scratch;
+  size_t dyall = 0, slot = 0;             // per-layer output gradients of the trunk convs: slot l = 2*block + conv, last = conv2
+  size_t wgb_partials = 0, wgb_floats = 0;  // partial sets of the batched trunk weight-gradient kernel
   size_t U1, out1, trunk;
   std::vector<size_t> y1, z1, y2, out;   // per residual block (eval: aliases of 4 rotating buffers)
   std::vector<size_t> up;                // per upsample stage
@@ -52,6 +54,16 @@ int64_t wgrad_max_floats(int n_up) {
   // splits * n_blocks * n_pairs * 8192, with splits = SMs / n_blocks  => <= 148 * n_pairs * 8192
   (void)n_up;
   return int64_t(148) * 5 * 8192;
+}
+
+// upper bound of wgrad3_batched_partials_floats() for the trunk (148 SMs; the launcher re-checks against the device)
+size_t wgrad_batched_floats(const GeneratorEngine& e) {
+  const int64_t T = int64_t(e.N) * ((e.H + 15) / 16) * ((e.W + 7) / 8);
+  const int64_t layers = 2 * e.n_res + 1;
+  int64_t per = (T * layers + 147) / 148;
+  if (per < 1) per = 1;
+  const int64_t max_slots = (T + per - 1) / per + 1;
+  return size_t(layers * max_slots) * 3 * 192 * 64;
 }
 
 Layout make_layout(const GeneratorEngine& e, bool training) {
@@ -86,7 +98,13 @@ Layout make_layout(const GeneratorEngine& e, bool training) {
     L.wg_partials = c.take(size_t(wgrad_max_floats(e.n_up)) * 4);
     L.ps_scratch = c.take(size_t(e.N) * (size_t(e.H) << e.n_up) * 128 * 4);
     L.loss_scratch = c.take(size_t(loss_scratch_doubles()) * 8);
-    for (int i = 0; i < 4; ++i) L.g[i] = c.take(t64(P));
+    for (int i = 0; i < 3; ++i) L.g[i] = c.take(t64(P));
+    // every trunk conv's output gradient stays alive until the batched weight-gradient kernel at the end of backward
+    L.slot = (t64(P) + 1023) & ~size_t(1023);
+    L.dyall = c.take(L.slot * size_t(2 * e.n_res + 1));
+    L.g[3] = L.dyall + L.slot * size_t(2 * e.n_res);        // d(trunk) = output gradient of conv2
+    L.wgb_floats = wgrad_batched_floats(e);
+    L.wgb_partials = c.take(L.wgb_floats * 4);
     for (int j = 0; j < e.n_up; ++j) L.dup[j] = c.take(t64(P << (2 * (j + 1))));
     const int64_t Hs = int64_t(e.H) << e.n_up, Ws = int64_t(e.W) << e.n_up;
     L.Ud = c.take(size_t(e.N) * (Hs + 1) * Ws * 128);
@@ -94,7 +112,8 @@ Layout make_layout(const GeneratorEngine& e, bool training) {
     if (e.keep_grads) {
       L.kd_y2.resize(e.n_res); L.kd_p1.resize(e.n_res); L.kd_y1.resize(e.n_res); L.kd_in.resize(e.n_res);
       for (int b = 0; b < e.n_res; ++b) {
-        L.kd_y2[b] = c.take(t64(P)); L.kd_p1[b] = c.take(t64(P)); L.kd_y1[b] = c.take(t64(P)); L.kd_in[b] = c.take(t64(P));
+        L.kd_y2[b] = L.dyall + L.slot * size_t(2 * b + 1); L.kd_y1[b] = L.dyall + L.slot * size_t(2 * b);
+        L.kd_p1[b] = c.take(t64(P)); L.kd_in[b] = c.take(t64(P));
       }
       L.kd_last = c.take(t64(P));
       L.kd_c1 = c.take(t64(P));
@@ -298,7 +317,7 @@ int generator_profile_read(GeneratorEngine* g, double* ms_sum, long long* count)
 GeneratorEngine::~GeneratorEngine() {
   for (cudaEvent_t ev : prof_events) cudaEventDestroy(ev);
   cudaFree(d_pack_idx); cudaFree(d_bias_idx); cudaFree(d_wg_idx_c3x3); cudaFree(d_wg_idx_up);
-  cudaFree(d_wg_idx_conv1); cudaFree(d_wg_idx_conv3);
+  cudaFree(d_wg_idx_conv1); cudaFree(d_wg_idx_conv3); cudaFree(d_wgb_off);
 }
 
 GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up) {
@@ -308,6 +327,8 @@ GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up) {
   {
     const char* ev = getenv("SRG_FUSE_BWD_STATS");
     e->fuse_bwd_stats = !(ev != nullptr && ev[0] == '0');
+    ev = getenv("SRG_WGRAD_BATCHED");
+    e->wgrad_batched = !(ev != nullptr && ev[0] == '0');
   }
   // ---- parameters in the reference's registration order (src/models.py:53-78)
   add_param(*e, "conv1.weight", {64, 3, 9, 9});
@@ -435,6 +456,21 @@ int generator_bind(GeneratorEngine* g, float* master, float* grads, float* bn_bu
     e->d_wg_idx_up = upload(e->h_wg_up);
     e->d_wg_idx_conv1 = upload(e->h_wg_conv1);
     e->d_wg_idx_conv3 = upload(e->h_wg_conv3);
+    {
+      std::vector<long long> off;
+      char wn[96];
+      for (int b = 0; b < e->n_res; ++b)
+        for (int k = 0; k < 2; ++k) {
+          snprintf(wn, sizeof(wn), "residual_blocks.%d.conv%d.weight", b, k + 1);
+          off.push_back((long long)poff(*e, wn));
+        }
+      off.push_back((long long)poff(*e, "conv2.weight"));
+      if (cudaMalloc(&e->d_wgb_off, off.size() * sizeof(long long)) != cudaSuccess ||
+          cudaMemcpy(e->d_wgb_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("generator_bind: device allocation of the wgrad offset table failed");
+        return -23;
+      }
+    }
     if (!e->d_pack_idx || !e->d_bias_idx || !e->d_wg_idx_c3x3 || !e->d_wg_idx_up || !e->d_wg_idx_conv1 || !e->d_wg_idx_conv3) {
       set_error("generator_bind: device allocation of index maps failed: %s", cudaGetErrorString(cudaGetLastError()));
       return -29;
@@ -739,7 +775,16 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
   // ---- conv2 (trunk = conv2(x_last) + out1)
   const void* x_last = e->n_res > 0 ? ws + L.out[e->n_res - 1] : ws + L.out1;
   RC(bias_grad(d_trunk, P, "conv2.bias"));
-  RC(wgrad(plain_view(x_last, H, W), H, W, false, H, W, d_trunk, 1, false, e->d_wg_idx_c3x3, "conv2.weight"));
+  // The 2*n_res + 1 trunk weight gradients run as ONE batched launch at the end of backward (wgrad3_batched_kernel):
+  // x of layer l = 2*block + conv sits at out1 + l * 2 * slot (out[b-1] | z1[b] are two slots apart, conv2 reads out[last]),
+  // dy of layer l at dyall + l * slot.  SRG_WGRAD_BATCHED=0 (or a non-uniform layout) keeps one launch per layer.
+  bool batched = e->wgrad_batched && e->n_res > 0;
+  for (int b = 0; b < e->n_res && batched; ++b) {
+    const size_t x1 = b > 0 ? L.out[b - 1] : L.out1;
+    if (x1 != L.out1 + size_t(2 * b) * 2 * L.slot || L.z1[b] != L.out1 + size_t(2 * b + 1) * 2 * L.slot) batched = false;
+  }
+  if (batched && L.out[e->n_res - 1] != L.out1 + size_t(2 * e->n_res) * 2 * L.slot) batched = false;
+  if (!batched) RC(wgrad(plain_view(x_last, H, W), H, W, false, H, W, d_trunk, 1, false, e->d_wg_idx_c3x3, "conv2.weight"));
   const bool keep = e->keep_grads;
   void* dout = keep ? ws + L.kd_last : ws + L.g[0];
   void* dother = ws + L.g[1];
@@ -778,19 +823,19 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
   };
   for (int b = e->n_res - 1; b >= 0; --b) {
     const void* x_in = b > 0 ? ws + L.out[b - 1] : ws + L.out1;
-    void* d_y2 = keep ? ws + L.kd_y2[b] : dmid;
+    void* d_y2 = ws + L.dyall + L.slot * size_t(2 * b + 1);
     void* d_p1 = keep ? ws + L.kd_p1[b] : dother;
-    void* d_y1 = keep ? ws + L.kd_y1[b] : dmid;
+    void* d_y1 = ws + L.dyall + L.slot * size_t(2 * b);
     void* d_in = keep ? ws + L.kd_in[b] : dother;
     // out = bn2(y2) + x
     RC(bn_backward(b, 1, dout, ws + L.y2[b], d_y2));
     snprintf(nm, sizeof(nm), "residual_blocks.%d.conv2.weight", b);
-    RC(wgrad(plain_view(ws + L.z1[b], H, W), H, W, false, H, W, d_y2, 1, false, e->d_wg_idx_c3x3, nm));
+    if (!batched) RC(wgrad(plain_view(ws + L.z1[b], H, W), H, W, false, H, W, d_y2, 1, false, e->d_wg_idx_c3x3, nm));
     RC(dgrad3x3(d_y2, H, W, false, po.rb_d[1][b], nullptr, ws + L.z1[b], d_p1, ws + L.y1[b]));   // ReLU backward via mask
     // z1 = relu(bn1(y1))
     RC(bn_backward(b, 0, d_p1, ws + L.y1[b], d_y1));
     snprintf(nm, sizeof(nm), "residual_blocks.%d.conv1.weight", b);
-    RC(wgrad(plain_view(x_in, H, W), H, W, false, H, W, d_y1, 1, false, e->d_wg_idx_c3x3, nm));
+    if (!batched) RC(wgrad(plain_view(x_in, H, W), H, W, false, H, W, d_y1, 1, false, e->d_wg_idx_c3x3, nm));
     RC(dgrad3x3(d_y1, H, W, false, po.rb_d[0][b], dout, nullptr, d_in, b > 0 ? ws + L.y2[b - 1] : nullptr));   // + skip gradient
     if (keep) { dout = d_in; } else { void* t = dout; dout = dother; dother = t; }
   }
@@ -800,6 +845,17 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
   e->launches += 1;
   RC(bias_grad(dmid, P, "conv1.bias"));
   RC(wgrad(plain_view(ws + L.U1, H + 1, W), H + 1, W, true, H, W, dmid, 1, false, e->d_wg_idx_conv1, "conv1.weight"));
+  if (batched) {
+    WgradBatchArgs a; memset(&a, 0, sizeof(a));
+    a.N = N; a.H = H; a.W = W; a.n_layers = 2 * e->n_res + 1;
+    a.x_base = ws + L.out1; a.x_layer_stride_bytes = int64_t(2 * L.slot);
+    a.dy_base = ws + L.dyall; a.dy_layer_stride_bytes = int64_t(L.slot);
+    a.partials = reinterpret_cast<float*>(ws + L.wgb_partials);
+    a.inv = e->d_wg_idx_c3x3; a.grads = e->grads; a.out_off = e->d_wgb_off;
+    if (wgrad3_batched_partials_floats(a) > L.wgb_floats) { set_error("batched wgrad partials exceed workspace"); return -27; }
+    RC(launch_wgrad3x3_batched(a, st));
+    e->launches += 2;
+  }
   return 0;
 }
 

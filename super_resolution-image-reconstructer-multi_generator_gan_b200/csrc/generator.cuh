@@ -47,6 +47,7 @@ struct GeneratorEngine {
   int* d_wg_idx_up = nullptr;     // 64->256 3x3 (pixel-shuffle order)
   int* d_wg_idx_conv1 = nullptr;  // 9x9 3->64
   int* d_wg_idx_conv3 = nullptr;  // 9x9 64->3
+  long long* d_wgb_off = nullptr; // gradient-buffer offsets of the trunk conv weights, layer order 2*block + conv, conv2 last
   // bound memory
   float* master = nullptr;
   float* grads = nullptr;
@@ -62,6 +63,7 @@ struct GeneratorEngine {
   long long launches = 0;  // kernels launched so far (bench bookkeeping)
   // optional CUDA-event timing of the dominant kernel class (3x3 64->64 fprop/dgrad conv_gemm launches)
   bool fuse_bwd_stats = true;   // BatchNorm-backward sums in the dgrad epilogue instead of a separate pass (SRG_FUSE_BWD_STATS=0: off)
+  bool wgrad_batched = true;    // trunk weight gradients in one batched launch at the end of backward (SRG_WGRAD_BATCHED=0: off)
   bool keep_grads = false; // debug: keep every inter-layer gradient in its own named buffer (parity tests)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)

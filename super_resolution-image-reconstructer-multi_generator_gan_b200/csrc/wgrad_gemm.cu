@@ -235,6 +235,7 @@ int wgrad_partials_floats(const WgradArgs& a, int* splits_out);
 // MMA costs max(~64, N/2) cycles), and one dy tile + three x tiles per 128 pixels instead of one dy + three haloed x.
 // Partials: [split][n-block][kw 3][(2 - kh) * 64 + co][ci 64] fp32 (ci fastest: the lanes of a warp store contiguously).
 // =====================================================================================================================
+constexpr int kW3Elems = 3 * 192 * 64;          // one partial set: [kw 3][(2-kh)*64 + co 192][ci 64] fp32 (147 KB)
 constexpr uint32_t kW3DyBytes = 18 * 8 * 128;   // 18 KB haloed dy strip
 constexpr uint32_t kW3XBytes = 16 * 8 * 128;    // 16 KB x strip
 constexpr uint32_t kW3Stage = kW3DyBytes + 3 * kW3XBytes;
@@ -396,6 +397,262 @@ int launch_wgrad3x3(const WgradArgs& a, cudaStream_t stream) {
   cudaError_t e = launch_pdl(wgrad3_kernel, dim3(p.n_blocks * p.splits), dim3(kWgThreads), smem_bytes, stream, p);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("wgrad3x3 launch: %s", cudaGetErrorString(e)); return int(e); }
+  count_launch();
+  return 0;
+}
+
+
+// =====================================================================================================================
+// Batched 3x3 weight gradients: ALL same-shape layers (the generator trunk: 2 x 16 residual convs + conv2) in ONE launch.
+//
+// A trunk layer at training sizes is ~10 GFLOP: launched alone it needs all 148 SMs as split-K workers, i.e. 148 partial
+// sets of 147 KB per layer (21.8 MB written and re-read by a reduce kernel) plus a launch ramp / TMEM drain / tail per
+// layer that is as long as the MMA work itself.  Nothing consumes a weight gradient before the optimizer step, so the
+// engine keeps every layer's output gradient (uniformly strided slots) and runs this kernel once at the end of the
+// backward pass: the flattened (layer, pixel tile) space is cut into one contiguous range per CTA, a CTA drains its
+// TMEM accumulators only when its range crosses a layer boundary, and a layer receives <= ceil(T/R)+1 partial sets
+// (6 at cfg2 instead of 148).  Inputs and output gradients are addressed through two 5-D tensor maps whose last
+// dimension is the layer.
+// Partials: [layer][slot][kw 3][(2 - kh) * 64 + co][ci 64] fp32, slot = CTA - first CTA that touches the layer.
+// =====================================================================================================================
+struct WgradBatchKParams {
+  CUtensorMap x_map;       // {64, W, H, N, layers}
+  CUtensorMap dy_map;      // {64, W, H, N, layers}
+  int tiles_h, tiles_w, tiles_per_img, tiles_per_layer;
+  int n_layers, total_tiles, per_cta, max_slots;
+  int n_stages;
+  float* partials;
+};
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad3_batched_kernel(const __grid_constant__ WgradBatchKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  uint8_t* stages = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + size_t(p.n_stages) * kW3Stage);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 4;
+  uint64_t* done = bars + 8;       // MMA -> epilogue: the accumulators of one layer segment are complete
+  uint64_t* drained = bars + 9;    // epilogue -> MMA: TMEM may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int begin = blockIdx.x * p.per_cta;
+  const int end = min(begin + p.per_cta, p.total_tiles);
+
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    mbar_init(drained, 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.x_map);
+    tma_prefetch_desc(&p.dy_map);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      pdl_wait();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int flat = begin; flat < end; ++flat) {
+        const int layer = flat / p.tiles_per_layer;
+        const int tile = flat - layer * p.tiles_per_layer;
+        const int n = tile / p.tiles_per_img;
+        const int rem = tile - n * p.tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * 16;
+        const int w0 = (rem % p.tiles_w) * 8;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* dst = stages + size_t(stage) * kW3Stage;
+        mbar_expect_tx(&full[stage], kW3Stage);
+        tma_load_5d(dst, &p.dy_map, &full[stage], 0, w0, h0 - 1, n, layer);
+        for (int kw = 0; kw < 3; ++kw)
+          tma_load_5d(dst + kW3DyBytes + size_t(kw) * kW3XBytes, &p.x_map, &full[stage], 0, w0 + kw - 1, h0, n, layer);
+        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 192, 1, 1);
+    const uint64_t hi_common = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+    const uint64_t a_hi = hi_common | (uint64_t((kW3XBytes >> 4) & 0x3FFF) << 16);   // M atoms: two x strips
+    const uint64_t b_hi = hi_common | (uint64_t((1024 >> 4) & 0x3FFF) << 16);        // N atoms: dy windows one row apart
+    int stage = 0;
+    uint32_t phase = 0, drained_phase = 0;
+    uint32_t accumulate = 0;
+    int cur_layer = begin / p.tiles_per_layer;
+    for (int flat = begin; flat < end; ++flat) {
+      const int layer = flat / p.tiles_per_layer;
+      if (layer != cur_layer) {
+        // layer boundary inside this CTA's range: hand the finished accumulators to the epilogue, wait for the drain
+        if (elect_one()) umma_commit(done);
+        __syncwarp();
+        mbar_wait(drained, drained_phase);
+        drained_phase ^= 1;
+        tc_fence_after();
+        accumulate = 0;
+        cur_layer = layer;
+      }
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t base = smem_u32(stages + size_t(stage) * kW3Stage);
+      if (elect_one()) {
+        const uint64_t bdesc = b_hi | uint64_t(base >> 4);
+        const uint64_t a1 = a_hi | uint64_t((base + kW3DyBytes) >> 4);               // [kw0; kw1]
+        const uint64_t a2 = a_hi | uint64_t((base + kW3DyBytes + kW3XBytes) >> 4);   // [kw1; kw2]
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // 16 pixels (2 image rows = 2048 bytes) per MMA
+          umma_bf16(tmem_base, a1 + uint64_t(128 * k), bdesc + uint64_t(128 * k), idesc, (k > 0) ? 1u : accumulate);
+          umma_bf16(tmem_base + 192, a2 + uint64_t(128 * k), bdesc + uint64_t(128 * k), idesc, (k > 0) ? 1u : accumulate);
+        }
+        umma_commit(&empty[stage]);
+      }
+      __syncwarp();
+      accumulate = 1;
+      if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
+  } else {
+    // epilogue: one drain per layer segment of this CTA's range
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    pdl_wait();
+    uint32_t done_phase = 0;
+    const int first_layer = begin / p.tiles_per_layer;
+    const int last_layer = (end - 1) / p.tiles_per_layer;
+    for (int layer = first_layer; layer <= last_layer; ++layer) {
+      mbar_wait(done, done_phase);
+      done_phase ^= 1;
+      tc_fence_after();
+      const int slot = int(blockIdx.x) - (layer * p.tiles_per_layer) / p.per_cta;
+      float* dst = p.partials + (size_t(layer) * p.max_slots + slot) * kW3Elems;
+      for (int chain = 0; chain < 2; ++chain) {
+        if (chain == 1 && q < 2) continue;
+        const int kw = chain == 0 ? (m >> 6) : 2;
+        float* col0 = dst + size_t(kw) * 192 * 64 + (m & 63);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 192; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(chain * 192 + c0), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) col0[size_t(c0 + j) * 64] = __uint_as_float(v[j]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(drained);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// out[layer] element inv[j] = sum over the layer's slots of partial element j (fixed order => deterministic)
+__global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const float4* __restrict__ partials, const int* __restrict__ inv,
+                                                                   float* __restrict__ grads, const long long* __restrict__ out_off,
+                                                                   int n_part4, int tiles_per_layer, int per_cta, int max_slots) {
+  pdl_trigger();
+  pdl_wait();
+  const int layer = blockIdx.y;
+  const int j4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j4 >= n_part4) return;
+  const int c_first = (layer * tiles_per_layer) / per_cta;
+  const int c_last = ((layer + 1) * tiles_per_layer - 1) / per_cta;
+  const float4* p = partials + size_t(layer) * max_slots * n_part4 + j4;
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s <= c_last - c_first; ++s) {
+    const float4 v = __ldcs(p + size_t(s) * n_part4);
+    t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+  }
+  float* out = grads + out_off[layer];
+  const int4 o = *reinterpret_cast<const int4*>(inv + 4 * j4);
+  if (o.x >= 0) out[o.x] = t.x;
+  if (o.y >= 0) out[o.y] = t.y;
+  if (o.z >= 0) out[o.z] = t.z;
+  if (o.w >= 0) out[o.w] = t.w;
+}
+
+static void wgrad3_batched_plan(const WgradBatchArgs& a, int* tiles_per_layer, int* grid, int* per_cta, int* max_slots) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int T = a.N * ((a.H + 15) / 16) * ((a.W + 7) / 8);
+  const long long total = (long long)T * a.n_layers;
+  int per = int((total + sms - 1) / sms);
+  if (per < 1) per = 1;
+  const int g = int((total + per - 1) / per);
+  *tiles_per_layer = T; *grid = g; *per_cta = per;
+  *max_slots = (T + per - 1) / per + 1;
+}
+
+size_t wgrad3_batched_partials_floats(const WgradBatchArgs& a) {
+  int T, g, per, ms;
+  wgrad3_batched_plan(a, &T, &g, &per, &ms);
+  return size_t(a.n_layers) * ms * kW3Elems;
+}
+
+int launch_wgrad3x3_batched(const WgradBatchArgs& a, cudaStream_t stream) {
+  if (a.n_layers < 1 || a.N < 1 || a.H < 1 || a.W < 1) { set_error("wgrad3x3_batched: bad geometry"); return -1; }
+  WgradBatchKParams p;
+  memset(&p, 0, sizeof(p));
+  int T, grid, per, ms;
+  wgrad3_batched_plan(a, &T, &grid, &per, &ms);
+  p.tiles_h = (a.H + 15) / 16;
+  p.tiles_w = (a.W + 7) / 8;
+  p.tiles_per_img = p.tiles_h * p.tiles_w;
+  p.tiles_per_layer = T;
+  p.n_layers = a.n_layers;
+  p.total_tiles = T * a.n_layers;
+  p.per_cta = per;
+  p.max_slots = ms;
+  p.n_stages = 3;
+  p.partials = a.partials;
+  {
+    uint64_t dims[5] = {64, uint64_t(a.W), uint64_t(a.H), uint64_t(a.N), uint64_t(a.n_layers)};
+    uint64_t xs[4] = {128, uint64_t(a.W) * 128, uint64_t(a.H) * a.W * 128, uint64_t(a.x_layer_stride_bytes)};
+    uint32_t xbox[5] = {64, 8, 16, 1, 1};
+    int rc = encode_map_bf16(&p.x_map, a.x_base, 5, dims, xs, xbox);
+    if (rc) return rc;
+    uint64_t ds[4] = {128, uint64_t(a.W) * 128, uint64_t(a.H) * a.W * 128, uint64_t(a.dy_layer_stride_bytes)};
+    uint32_t dbox[5] = {64, 8, 18, 1, 1};
+    rc = encode_map_bf16(&p.dy_map, a.dy_base, 5, dims, ds, dbox);
+    if (rc) return rc;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad3_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    attr = true;
+  }
+  const size_t smem_bytes = 1024 + size_t(p.n_stages) * kW3Stage + 256;
+  cudaError_t e = launch_pdl(wgrad3_batched_kernel, dim3(grid), dim3(kWgThreads), smem_bytes, stream, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("wgrad3x3_batched launch: %s", cudaGetErrorString(e)); return int(e); }
+  count_launch();
+  // reduce: [layer][slot] partial sets -> OIHW gradients through the inverse index map shared by all layers
+  const int n4 = kW3Elems / 4;
+  e = launch_pdl(wgrad_reduce_batched_kernel, dim3((n4 + 255) / 256, a.n_layers), dim3(256), 0, stream,
+                 reinterpret_cast<const float4*>(a.partials), a.inv, a.grads, a.out_off, n4, T, per, ms);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("wgrad_reduce_batched launch: %s", cudaGetErrorString(e)); return int(e); }
   count_launch();
   return 0;
 }

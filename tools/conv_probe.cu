@@ -360,6 +360,70 @@ static int run_wgrad(const char* name, int N, int H, int W, int n_strips, int n_
   return bad == 0 ? 0 : 1;
 }
 
+// ------------------------------------------------------------------ batched 3x3 wgrad probe (all layers in one launch)
+static int run_wgrad_batched(const char* name, int L, int N, int H, int W, int iters) {
+  const size_t S = size_t(N) * H * W * 64;            // elements per tensor
+  const size_t xs = 2 * S + 512, ds = S + 1024;       // layer strides (elements): x two slots apart, padded
+  std::vector<uint16_t> x(xs * L), dy(ds * L);
+  for (auto& v : x) v = f2bf(frand());
+  for (auto& v : dy) v = f2bf(frand());
+  std::vector<int> inv(3 * 192 * 64);
+  for (int kw = 0; kw < 3; ++kw) for (int kh = 0; kh < 3; ++kh) for (int co = 0; co < 64; ++co) for (int ci = 0; ci < 64; ++ci)
+    inv[((kw * 192) + (2 - kh) * 64 + co) * 64 + ci] = ((co * 64 + ci) * 3 + kh) * 3 + kw;
+  std::vector<long long> off(L);
+  for (int l = 0; l < L; ++l) off[l] = (long long)l * 36864;
+  void *dx, *ddy; int* dinv; long long* doff; float *dpart, *dgr;
+  CK(cudaMalloc(&dx, x.size() * 2)); CK(cudaMalloc(&ddy, dy.size() * 2));
+  CK(cudaMalloc(&dinv, inv.size() * 4)); CK(cudaMalloc(&doff, L * 8)); CK(cudaMalloc(&dgr, size_t(L) * 36864 * 4));
+  CK(cudaMemcpy(dx, x.data(), x.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ddy, dy.data(), dy.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dinv, inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(doff, off.data(), L * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dgr, 0, size_t(L) * 36864 * 4));
+  WgradBatchArgs a; memset(&a, 0, sizeof(a));
+  a.N = N; a.H = H; a.W = W; a.n_layers = L;
+  a.x_base = dx; a.x_layer_stride_bytes = int64_t(xs) * 2; a.dy_base = ddy; a.dy_layer_stride_bytes = int64_t(ds) * 2;
+  const size_t pf = wgrad3_batched_partials_floats(a);
+  CK(cudaMalloc(&dpart, pf * 4));
+  a.partials = dpart; a.inv = dinv; a.grads = dgr; a.out_off = doff;
+  int rc = launch_wgrad3x3_batched(a, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc || e != cudaSuccess) { printf("[%s] failed rc=%d %s %s\n", name, rc, last_error(), cudaGetErrorString(e)); exit(3); }
+  std::vector<float> g(size_t(L) * 36864);
+  CK(cudaMemcpy(g.data(), dgr, g.size() * 4, cudaMemcpyDeviceToHost));
+  size_t checked = 0, bad = 0; double max_err = 0, max_ref = 0;
+  for (int l = 0; l < L; ++l)
+    for (int s = 0; s < 40; ++s) {
+      const int co = (s * 7 + l) % 64, ci = (s * 13 + 5 * l) % 64, kh = s % 3, kw = (s / 3) % 3;
+      double ref = 0;
+      for (int n = 0; n < N; ++n) for (int h = 0; h < H; ++h) for (int w = 0; w < W; ++w) {
+        const int hi = h + kh - 1, wi = w + kw - 1;
+        if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+        ref += double(bf2f(x[xs * l + ((size_t(n) * H + hi) * W + wi) * 64 + ci])) * bf2f(dy[ds * l + ((size_t(n) * H + h) * W + w) * 64 + co]);
+      }
+      const double got = g[size_t(l) * 36864 + ((co * 64 + ci) * 3 + kh) * 3 + kw];
+      const double err = fabs(got - ref);
+      if (err > max_err) max_err = err;
+      if (fabs(ref) > max_ref) max_ref = fabs(ref);
+      if (err > 1e-3 * fabs(ref) + 5e-4 * sqrt(double(N) * H * W)) ++bad;   // fp32 accumulation over N*H*W products
+      ++checked;
+    }
+  printf("[%s] checked=%zu bad=%zu max_abs_err=%.5f max_ref=%.3f %s\n", name, checked, bad, max_err, max_ref, bad == 0 ? "OK" : "FAIL");
+  if (iters > 0) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 2; ++i) launch_wgrad3x3_batched(a, 0);
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) launch_wgrad3x3_batched(a, 0);
+    cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * L * N * H * W * 9.0 * 64 * 64;
+    printf("[%s] %.3f us/launch (gemm+reduce, %d layers: %.3f us/layer)  %.1f TFLOP/s useful\n", name, ms * 1000 / iters, L,
+           ms * 1000 / iters / L, flops / (ms / iters * 1e-3) / 1e12);
+  }
+  cudaFree(dx); cudaFree(ddy); cudaFree(dinv); cudaFree(doff); cudaFree(dpart); cudaFree(dgr);
+  return bad == 0 ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 0;
   int fails = 0;
@@ -372,6 +436,10 @@ int main(int argc, char** argv) {
     fails += run_wgrad("wg3_fused_128tiles", 16, 32, 32, 3, 3, 18, -1, dw3, tr3, 1, false, 0, true);
     fails += run_wgrad("wg3_fused_296tiles", 4, 96, 48, 3, 3, 18, -1, dw3, tr3, 1, false, 0, true);
     fails += run_wgrad("wg3_fused_cout256_ps", 2, 32, 16, 3, 3, 18, -1, dw3, tr3, 4, true, 0, true);
+    fails += run_wgrad_batched("wgb_3layers_ragged", 3, 2, 40, 20, 0);
+    fails += run_wgrad_batched("wgb_5layers", 5, 4, 96, 48, 0);
+    fails += run_wgrad_batched("wgb_1layer_tiny", 1, 1, 9, 5, 0);
+    if (iters > 0) fails += run_wgrad_batched("perf_wgb_trunk_33x16x96x96", 33, 16, 96, 96, iters / 10 > 0 ? iters / 10 : 1);
     const int dw1[1] = {0}, tr5[5] = {0, 2, 4, 6, 8};
     fails += run_wgrad("wg9_pairs", 2, 32, 16, 1, 5, 24, -3, dw1, tr5, 1, false, 0);
     if (iters > 0) {
