@@ -487,7 +487,16 @@ struct IlKParams {
 constexpr int kIlThreads = 64 + 512;            // warp 0 producer, warp 1 MMA, warps 2-9 block E, warps 10-17 block O
 constexpr uint32_t kIlHalfStrip = 17 * 8 * 128; // 17 rows x 8 pixels x 64 bf16
 constexpr uint32_t kIlWBytes = 9 * 64 * 128;    // resident filter: [kw 3][kh2 ; kh1 ; kh0][64 cout][64 cin]
+// WIDE: ONE 10-pixel-wide half strip (17 rows x 10 pixels, row pitch 1280 B) serves all three column shifts: the A
+// descriptor starts kw * 128 B into it with a stride (SBO) of 1280 B between 8-pixel row groups.  Measured on B200
+// (tools/conv_probe il_* cases): the UMMA 128B swizzle is a function of the ABSOLUTE shared-memory address bits, exactly
+// like the TMA write side, so a start address / group stride that is only 128-byte aligned reads the right data with
+// base_offset = 0 (setting base_offset = (addr >> 7) & 7 gives wrong results).  One third of the L2->SM operand traffic
+// and of the stage footprint of the three-strip form, so the same shared memory holds a 2x deeper prefetch.
+constexpr uint32_t kIlWidePitch = 10 * 128;
+constexpr uint32_t kIlWideStage = 22 * 1024;    // 17 x 1280 = 21760 B, rounded up to the 1024-byte swizzle period
 
+template <bool WIDE>
 __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_constant__ IlKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -497,7 +506,8 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
 
   uint8_t* w_smem = smem;
   uint8_t* stages = w_smem + kIlWBytes;
-  uint8_t* out_stage = stages + size_t(p.n_stages) * kIlHalfStrip;       // [block 2][16 KB]
+  constexpr uint32_t kStage = WIDE ? kIlWideStage : kIlHalfStrip;
+  uint8_t* out_stage = stages + size_t(p.n_stages) * kStage;             // [block 2][16 KB]
   uint8_t* aux_stage = out_stage + 2 * kTileOutBytes;                     // [block 2][16 KB] (aux_mode != 0)
   uint8_t* tail = aux_stage + (p.aux_mode ? 2 * kTileOutBytes : 0);
   float* s_bias = reinterpret_cast<float*>(tail);                         // 64 floats
@@ -561,14 +571,23 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
         const int rem = tile - n * tiles_per_img;
         const int hh = (rem / p.tiles_w) * 16;       // tile origin in parity-view rows (h0 / 2)
         const int w0 = (rem % p.tiles_w) * 8;
-        for (int s = 0; s < 3; ++s) {
+        if constexpr (WIDE) {
 #pragma unroll
           for (int par = 1; par >= 0; --par) {       // odd image rows h0-1+2j first, then even rows h0+2j (j = 0..16)
             { long long t0_ = clock64(); mbar_wait(&empty[stage], phase ^ 1); prof_acc[0] += clock64() - t0_; }
-            mbar_expect_tx(&full[stage], kIlHalfStrip);
-            tma_load_4d(stages + size_t(stage) * kIlHalfStrip, &p.in_map[par], &full[stage], 0, w0 + p.strip_dw[s],
-                        hh - par, n);
+            mbar_expect_tx(&full[stage], 17 * kIlWidePitch);
+            tma_load_4d(stages + size_t(stage) * kStage, &p.in_map[par], &full[stage], 0, w0 + p.strip_dw[0], hh - par, n);
             if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          }
+        } else {
+          for (int s = 0; s < 3; ++s) {
+#pragma unroll
+            for (int par = 1; par >= 0; --par) {
+              { long long t0_ = clock64(); mbar_wait(&empty[stage], phase ^ 1); prof_acc[0] += clock64() - t0_; }
+              mbar_expect_tx(&full[stage], kIlHalfStrip);
+              tma_load_4d(stages + size_t(stage) * kStage, &p.in_map[par], &full[stage], 0, w0 + p.strip_dw[s], hh - par, n);
+              if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            }
           }
         }
         if (p.aux_mode) {
@@ -601,6 +620,45 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
       tc_fence_after();
       const uint32_t d_e = tmem_base + uint32_t(acc * 128);
       const uint32_t d_o = d_e + 64;
+      if constexpr (WIDE) {
+        // descriptor high part: SBO = 1280 B between 8-pixel row groups, base_offset 0 (see kIlWidePitch)
+        const uint64_t adesc_hi = (uint64_t(kIlWidePitch >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+#pragma unroll
+        for (int par = 1; par >= 0; --par) {
+          { long long t0_ = clock64(); mbar_wait(&full[stage], phase); prof_acc[2] += clock64() - t0_; }
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(stages) + uint32_t(stage) * kStage;     // 1024-byte aligned
+          if (elect_one()) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const uint32_t wb = w_lo + uint32_t(s) * (3 * 8192 >> 4);
+              // window starting at half-strip row 0 / row 1, column shift s pixels
+              const uint32_t st0 = a_base + uint32_t(s) * 128u, st1 = st0 + kIlWidePitch;
+              const uint64_t a0 = adesc_hi | uint64_t((st0 & 0x3FFFFu) >> 4);
+              const uint64_t a1 = adesc_hi | uint64_t((st1 & 0x3FFFFu) >> 4);
+              if (par == 1) {
+                const uint64_t b1 = desc_hi | uint64_t(wb);                         // rho = 1: E += kh2, O += kh1
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d_e, a1 + uint64_t(2 * k), b1 + uint64_t(2 * k), idesc128, (s > 0 || k > 0) ? 1u : 0u);
+                const uint64_t b0 = desc_hi | uint64_t(wb + (2 * 8192 >> 4));       // rho = -1: E += kh0
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d_e, a0 + uint64_t(2 * k), b0 + uint64_t(2 * k), idesc64, 1u);
+              } else {
+                const uint64_t b0 = desc_hi | uint64_t(wb + (8192 >> 4));           // rho = 0: E += kh1, O += kh0
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d_e, a0 + uint64_t(2 * k), b0 + uint64_t(2 * k), idesc128, 1u);
+                const uint64_t b1 = desc_hi | uint64_t(wb);                         // rho = 2: O += kh2
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d_o, a1 + uint64_t(2 * k), b1 + uint64_t(2 * k), idesc64, 1u);
+              }
+            }
+            umma_commit(&empty[stage]);
+          }
+          __syncwarp();
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        }
+      } else {
 #pragma unroll 1
       for (int s = 0; s < 3; ++s) {
         const uint32_t wb = w_lo + uint32_t(s) * (3 * 8192 >> 4);     // [kh2 ; kh1 ; kh0] of this column shift
@@ -639,6 +697,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
           __syncwarp();
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
+      }
       }
       if (elect_one()) umma_commit(&tfull[acc]);
       __syncwarp();
@@ -830,7 +889,25 @@ int encode_map_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t*
   return 0;
 }
 
+// Concurrency share: when K independent launch chains (the K generators' graph branches) run side by side, every
+// persistent kernel sizes its grid for 1/K of the SMs so that the chains really overlap instead of queueing for whole-GPU
+// grids (each kernel pays its launch ramp / pipeline fill / tail while the other chains keep the remaining SMs busy).
+static int g_sm_share = 0;
+void set_sm_share(int k) { g_sm_share = k < 1 ? 1 : k; }
+static int sm_share() {
+  if (g_sm_share == 0) {
+    const char* ev = getenv("SRG_SM_SHARE");
+    g_sm_share = ev ? atoi(ev) : 1;
+    if (g_sm_share < 1) g_sm_share = 1;
+  }
+  return g_sm_share;
+}
 static int g_num_sms = 0;
+static int num_sms();
+int sm_budget() {
+  int b = num_sms() / sm_share();
+  return b < 1 ? 1 : b;
+}
 static int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
@@ -867,6 +944,15 @@ static bool conv3_il_enabled() {
   }
   return on != 0;
 }
+// SRG_CONV_IL_WIDE=0: load one 8-pixel half strip per column shift instead of one 10-pixel strip for all three
+static bool conv3_il_wide_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* ev = getenv("SRG_CONV_IL_WIDE");
+    on = (ev != nullptr && ev[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 static bool use_conv3_il(const ConvGemmArgs& a) {
   if (a.variant == 1 || (a.variant == 0 && !conv3_il_enabled())) return false;
   return a.TH == 16 && a.TW == 8 && a.block_n == 64 && a.n_strips == 3 && a.n_taps == 3 && a.strip_dh == -1 &&
@@ -878,11 +964,11 @@ static bool use_conv3_il(const ConvGemmArgs& a) {
 
 // row-parity view of a [N, H, W, C] tensor given by element strides: rows 2j + par
 static int encode_parity_map(CUtensorMap* map, const void* base, int C, int W, int H, int N, int64_t stride_w,
-                             int64_t stride_h, int64_t stride_n, int par, uint32_t box_rows) {
+                             int64_t stride_h, int64_t stride_n, int par, uint32_t box_rows, uint32_t box_w = 8) {
   const __nv_bfloat16* ptr = reinterpret_cast<const __nv_bfloat16*>(base) + size_t(par) * stride_h;
   uint64_t dims[4] = {uint64_t(C), uint64_t(W), uint64_t((H - par + 1) / 2), uint64_t(N)};
   uint64_t strides[3] = {uint64_t(stride_w) * 2, uint64_t(stride_h) * 4, uint64_t(stride_n) * 2};
-  uint32_t box[4] = {64, 8, box_rows, 1};
+  uint32_t box[4] = {64, box_w, box_rows, 1};
   return encode_map_bf16(map, ptr, 4, dims, strides, box);
 }
 
@@ -904,21 +990,25 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   for (int s = 0; s < 3; ++s) p.strip_dw[s] = a.strip_dw[s];
   p.cout_total = a.cout_total;
   p.n_blocks = a.cout_total / 64;
-  p.ctas_per_block = num_sms() / p.n_blocks;
+  p.ctas_per_block = sm_budget() / p.n_blocks;
   if (p.ctas_per_block < 1) p.ctas_per_block = 1;
   if (p.ctas_per_block > p.tiles_total) p.ctas_per_block = p.tiles_total;
   p.aux_mode = a.residual ? 1 : (a.mask_src ? 2 : 0);
   const uint32_t fixed_bytes = kIlWBytes + 2 * kTileOutBytes + (has_aux ? 2 * kTileOutBytes : 0) + 512 +
                                (a.stats != nullptr ? 16 * 128 * 4 : 0);
-  int stages = int((227 * 1024 - 1024 - fixed_bytes) / kIlHalfStrip);
+  // the wide form needs the three column shifts to be -1, 0, +1 (one 10-pixel strip starting at w0 - 1)
+  const bool wide = (a.variant == 3 || (a.variant == 0 && conv3_il_wide_enabled())) && a.strip_dw[0] == -1 && a.strip_dw[1] == 0 && a.strip_dw[2] == 1;
+  const uint32_t stage_bytes = wide ? kIlWideStage : kIlHalfStrip;
+  int stages = int((227 * 1024 - 1024 - fixed_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("conv3_il: shared memory too small"); return -10; }
   p.n_stages = stages;
-  const size_t smem_bytes = 1024 + fixed_bytes + size_t(stages) * kIlHalfStrip;
+  const size_t smem_bytes = 1024 + fixed_bytes + size_t(stages) * stage_bytes;
 
   const InView& iv = a.views[0];
   for (int par = 0; par < 2; ++par) {
-    int rc = encode_parity_map(&p.in_map[par], iv.ptr, 64, a.in_W, a.in_H, a.N, iv.stride_w, iv.stride_h, iv.stride_n, par, 17);
+    int rc = encode_parity_map(&p.in_map[par], iv.ptr, 64, a.in_W, a.in_H, a.N, iv.stride_w, iv.stride_h, iv.stride_n, par, 17,
+                               wide ? 10 : 8);
     if (rc) return rc;
   }
   {
@@ -962,11 +1052,14 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   p.prof = reinterpret_cast<long long*>(a.prof);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3_il_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv3_il_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     attr_set = true;
   }
-  cudaError_t e = launch_pdl(conv3_il_kernel, dim3(p.ctas_per_block * p.n_blocks), dim3(kIlThreads), smem_bytes, stream, p);
+  const dim3 grid(p.ctas_per_block * p.n_blocks);
+  cudaError_t e = wide ? launch_pdl(conv3_il_kernel<true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
+                       : launch_pdl(conv3_il_kernel<false>, grid, dim3(kIlThreads), smem_bytes, stream, p);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv3_il launch: %s", cudaGetErrorString(e)); return int(e); }
   count_launch();
@@ -979,7 +1072,7 @@ int conv_gemm_grid(const ConvGemmArgs& a) {
   const int step_h = use_conv3_il(a) ? 32 : a.TH;
   const int tiles = a.N * ((a.H + step_h - 1) / step_h) * ((a.W + step_w - 1) / step_w);
   const int n_blocks = a.cout_total / a.block_n;
-  int per = num_sms() / n_blocks;
+  int per = sm_budget() / n_blocks;
   if (per < 1) per = 1;
   if (per > tiles) per = tiles;
   return per * n_blocks;
@@ -1027,7 +1120,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   }
   p.cout_total = a.cout_total;
   p.n_blocks = a.cout_total / a.block_n;
-  const int sms = num_sms();
+  const int sms = sm_budget();
   p.ctas_per_block = sms / p.n_blocks;
   if (p.ctas_per_block < 1) p.ctas_per_block = 1;
   if (p.ctas_per_block > p.tiles_total) p.ctas_per_block = p.tiles_total;

@@ -57,7 +57,8 @@ struct ConvGemmArgs {
   void* out;
   int out_mode;
   int variant;               // 0: pick the kernel automatically (row-interleaved conv3_il for plain 3x3 / 64-channel launches
-                             // unless SRG_CONV_IL=0), 1: force the generic strip kernel, 2: conv3_il where applicable
+                             // unless SRG_CONV_IL=0), 1: force the generic strip kernel, 2: conv3_il with one 8-pixel half strip
+                             // per column shift, 3: conv3_il with one 10-pixel half strip for all three shifts (default form)
   float* stats;              // optional (OUT_NHWC, cout 64): per-CTA column sums of the STORED bf16 tile values,
                              // float [conv_gemm_grid(a)][128] = {sum over valid pixels [64], sum of squares [64]}
   const void* stats_y;       // optional with `stats`: bf16 tensor of the output's geometry; the second 64 columns then hold
@@ -110,6 +111,10 @@ size_t wgrad3_batched_partials_floats(const WgradBatchArgs& a);
 int launch_wgrad3x3_batched(const WgradBatchArgs& a, cudaStream_t stream);
 int launch_wgrad_reduce(const float* partials, const int* idx, float* out, int n_out, int splits, size_t split_stride,
                         int accumulate_into, cudaStream_t stream);
+
+// SMs a persistent kernel may size its grid for: device SM count / concurrency share (set_sm_share, SRG_SM_SHARE)
+int sm_budget();
+void set_sm_share(int k);
 
 // total kernels launched by this library in this process (bench bookkeeping: "gpu_launches")
 void count_launch(int n = 1);

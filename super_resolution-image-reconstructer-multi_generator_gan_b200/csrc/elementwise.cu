@@ -44,7 +44,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 int reduce_blocks(int64_t pixels) {
   int64_t b = (pixels + 32 * 8 - 1) / (32 * 8);
   if (b < 1) b = 1;
-  if (b > kRedBlocksMax) b = kRedBlocksMax;
+  const int cap = 2 * sm_budget() < kRedBlocksMax ? 2 * sm_budget() : kRedBlocksMax;
+  if (b > cap) b = cap;
   return int(b);
 }
 
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
 }
 static int ew_blocks(int64_t n_vec) {
   int64_t b = (n_vec + 255) / 256;
-  if (b > 148 * 8) b = 148 * 8;
+  if (b > sm_budget() * 8) b = sm_budget() * 8;
   if (b < 1) b = 1;
   return int(b);
 }

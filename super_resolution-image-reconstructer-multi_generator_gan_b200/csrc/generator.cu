@@ -326,7 +326,7 @@ GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up) {
   e->N = N; e->H = H; e->W = W; e->n_res = n_res; e->n_up = n_up;
   {
     const char* ev = getenv("SRG_FUSE_BWD_STATS");
-    e->fuse_bwd_stats = !(ev != nullptr && ev[0] == '0');
+    e->fuse_bwd_stats = ev != nullptr && ev[0] == '1';
     ev = getenv("SRG_WGRAD_BATCHED");
     e->wgrad_batched = !(ev != nullptr && ev[0] == '0');
   }
@@ -728,9 +728,9 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     a.in_H = gh; a.in_W = gw;
     a.weights = packed + w_off; a.cout_total = 64; a.block_n = 64;
     a.bias = nullptr; a.act = ACT_NONE; a.residual = residual; a.mask_src = mask; a.out = out; a.out_mode = OUT_NHWC;
-    // With the generic kernel's single epilogue group this fusion cost more than the separate 7 us reduction pass it
-    // replaces (profiles/r01_notes.md); conv3_il has two independent epilogue groups with slack, so it is on by default
-    // (SRG_FUSE_BWD_STATS=0 restores the separate chan_reduce pass).
+    // Measured twice (profiles/r01_notes.md): with the generic kernel's single epilogue group the fusion was slower than
+    // the separate 7 us reduction pass; with conv3_il's two epilogue groups the step time is unchanged within noise
+    // (11.4-11.5 ms either way) while the dgrad launches get 4 us longer, so it stays off unless SRG_FUSE_BWD_STATS=1.
     if (stats_y != nullptr && e->fuse_bwd_stats) { a.stats = partials; a.stats_y = stats_y; bwd_stats_rows = conv_gemm_grid(a); }
     e->launches += 1;
     if (dy_ps) return launch_conv_gemm(a, st);

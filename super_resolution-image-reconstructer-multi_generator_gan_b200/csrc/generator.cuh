@@ -62,7 +62,7 @@ struct GeneratorEngine {
   int world = 1;
   long long launches = 0;  // kernels launched so far (bench bookkeeping)
   // optional CUDA-event timing of the dominant kernel class (3x3 64->64 fprop/dgrad conv_gemm launches)
-  bool fuse_bwd_stats = true;   // BatchNorm-backward sums in the dgrad epilogue instead of a separate pass (SRG_FUSE_BWD_STATS=0: off)
+  bool fuse_bwd_stats = false;  // BatchNorm-backward sums in the dgrad epilogue instead of a separate pass (SRG_FUSE_BWD_STATS=1: on)
   bool wgrad_batched = true;    // trunk weight gradients in one batched launch at the end of backward (SRG_WGRAD_BATCHED=0: off)
   bool keep_grads = false; // debug: keep every inter-layer gradient in its own named buffer (parity tests)
   bool prof_on = false;

@@ -590,10 +590,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const float4*
 }
 
 static void wgrad3_batched_plan(const WgradBatchArgs& a, int* tiles_per_layer, int* grid, int* per_cta, int* max_slots) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (sms <= 0) sms = 148;
+  const int sms = sm_budget();
   const int T = a.N * ((a.H + 15) / 16) * ((a.W + 7) / 8);
   const long long total = (long long)T * a.n_layers;
   int per = int((total + sms - 1) / sms);
@@ -658,10 +655,7 @@ int launch_wgrad3x3_batched(const WgradBatchArgs& a, cudaStream_t stream) {
 }
 
 int wgrad_partials_floats(const WgradArgs& a, int* splits_out) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (sms <= 0) sms = 148;
+  const int sms = sm_budget();
   const int tiles = a.N * ((a.H + a.TH - 1) / a.TH) * ((a.W + a.TW - 1) / a.TW);
   int splits = sms / a.n_blocks;
   if (splits < 1) splits = 1;

@@ -490,21 +490,25 @@ int main(int argc, char** argv) {
     p.block_n = 32; p.out_mode = OUT_FOLD9_NCHW;
     fails += run(p, 0);
   }
-  {  // row-interleaved 3x3 kernel (conv3_il): same problems, 32-row tiles, parity views
-    Problem p = conv3x3("il_small", 2, 32, 24, 64, false); p.variant = 2; fails += run(p, 0);
-    Problem r = conv3x3("il_ragged", 3, 40, 20, 64, false); r.variant = 2; fails += run(r, 0);
-    Problem o = conv3x3("il_odd_rows", 2, 37, 13, 64, false); o.variant = 2; o.act = ACT_RELU; fails += run(o, 0);
-    Problem q = conv3x3("il_ragged_res", 3, 37, 20, 64, false); q.variant = 2; q.residual = true; q.act = ACT_LRELU; fails += run(q, 0);
-    Problem m = conv3x3("il_mask_ragged", 2, 24, 20, 64, false); m.variant = 2; m.mask = true; fails += run(m, 0);
-    Problem u = conv3x3("il_relu_ps", 2, 30, 16, 256, true); u.variant = 2; u.act = ACT_RELU; fails += run(u, 0);
-    Problem t = conv3x3("il_many_tiles", 5, 96, 96, 64, false); t.variant = 2; t.residual = true; fails += run(t, 0);
+  for (int var = 2; var <= 3; ++var) {  // row-interleaved 3x3 kernel (conv3_il): 2 = one 8-pixel strip per shift, 3 = one 10-pixel strip
+    printf("-- conv3_il variant %d\n", var);
+    Problem p = conv3x3("il_small", 2, 32, 24, 64, false); p.variant = var; fails += run(p, 0);
+    Problem r = conv3x3("il_ragged", 3, 40, 20, 64, false); r.variant = var; fails += run(r, 0);
+    Problem o = conv3x3("il_odd_rows", 2, 37, 13, 64, false); o.variant = var; o.act = ACT_RELU; fails += run(o, 0);
+    Problem q = conv3x3("il_ragged_res", 3, 37, 20, 64, false); q.variant = var; q.residual = true; q.act = ACT_LRELU; fails += run(q, 0);
+    Problem m = conv3x3("il_mask_ragged", 2, 24, 20, 64, false); m.variant = var; m.mask = true; fails += run(m, 0);
+    Problem u = conv3x3("il_relu_ps", 2, 30, 16, 256, true); u.variant = var; u.act = ACT_RELU; fails += run(u, 0);
+    Problem t = conv3x3("il_many_tiles", 5, 96, 96, 64, false); t.variant = var; t.residual = true; fails += run(t, 0);
   }
   if (iters > 0) {
-    { Problem p = conv3x3("perf_il_trunk_16x96x96", 16, 96, 96, 64, false); p.variant = 2; fails += run(p, iters); }
-    { Problem p = conv3x3("perf_il_trunk_stats", 16, 96, 96, 64, false); p.variant = 2; p.stats = true; fails += run(p, iters); }
-    { Problem p = conv3x3("perf_il_trunk_mask", 16, 96, 96, 64, false); p.variant = 2; p.mask = true; p.bias = false; fails += run(p, iters); }
-    { Problem p = conv3x3("perf_il_trunk_residual", 16, 96, 96, 64, false); p.variant = 2; p.residual = true; p.bias = false; fails += run(p, iters); }
-    { Problem p = conv3x3("perf_il_up3_16x192x192", 16, 192, 192, 256, true); p.variant = 2; p.act = ACT_RELU; fails += run(p, iters); }
+    for (int var = 2; var <= 3; ++var) {
+      printf("-- conv3_il variant %d\n", var);
+      { Problem p = conv3x3("perf_il_trunk_16x96x96", 16, 96, 96, 64, false); p.variant = var; fails += run(p, iters); }
+      { Problem p = conv3x3("perf_il_trunk_stats", 16, 96, 96, 64, false); p.variant = var; p.stats = true; fails += run(p, iters); }
+      { Problem p = conv3x3("perf_il_trunk_mask", 16, 96, 96, 64, false); p.variant = var; p.mask = true; p.bias = false; fails += run(p, iters); }
+      { Problem p = conv3x3("perf_il_trunk_residual", 16, 96, 96, 64, false); p.variant = var; p.residual = true; p.bias = false; fails += run(p, iters); }
+      { Problem p = conv3x3("perf_il_up3_16x192x192", 16, 192, 192, 256, true); p.variant = var; p.act = ACT_RELU; fails += run(p, iters); }
+    }
     fails += run(conv3x3("perf_trunk_16x96x96", 16, 96, 96, 64, false), iters);
     { Problem p = conv3x3("perf_trunk_stats", 16, 96, 96, 64, false); p.stats = true; fails += run(p, iters); }
     { Problem p = conv3x3("perf_trunk_mask", 16, 96, 96, 64, false); p.mask = true; p.bias = false; fails += run(p, iters); }
