@@ -854,6 +854,205 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
   if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
+// =====================================================================================================================
+// 9x9 convolution with 3 output channels (conv3 of the generator, the last layer at 4x resolution): "conv9_rows".
+//
+// The generic fold9 instance folds the 9 horizontal taps into N = 27 (+5) and issues one N = 32 MMA per row tap and
+// K-step: with the ~64-cycle floor of an M128 MMA that is 4 % of the tensor rate.  Here one MMA consumes ONE image row
+// segment (128 pixels x 64 channels) and feeds up to 8 output rows at once: TMEM block j (32 columns) is output row
+// h0 + j, and the input row h0 + rho contributes row tap kh = rho - j + 4 to every block with 0 <= kh <= 8.  With the
+// filter resident as 288 rows [kh8 ; kh7 ; ... ; kh0] (32 rows = 9 column taps x 3 channels each), the blocks a row
+// touches are CONTIGUOUS in both the B operand and the accumulator, so one MMA of N = 32 x (number of blocks, <= 256)
+// covers them: 16 input rows x 4 K-steps (+7 first-touch splits) = 71 MMAs per 8 x 120 output pixels instead of 360,
+// 4.5x fewer tensor-pipe cycles.  The epilogue (two 4-warp groups, 4 blocks each) shift-accumulates the 9 column taps
+// through shared memory and writes fp32 NCHW.  Tiles are 128 pixels wide with a 4-pixel halo on each side.
+// =====================================================================================================================
+struct C9KParams {
+  CUtensorMap in_map;        // {64, W, H, N}, box {64, 128, 1, 1}
+  CUtensorMap w_map;         // {64, 9*32}, box {64, 32}
+  int N, H, W;
+  int tiles_h, tiles_w, tiles_total, n_ctas;
+  int n_stages;
+  const float* bias;         // [3] or null
+  float* out;                // fp32 [N,3,H,W]
+  long long* prof;
+};
+
+constexpr int kC9Threads = 64 + 256;            // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups
+constexpr uint32_t kC9Row = 128 * 128;          // one image-row segment: 128 pixels x 64 bf16
+constexpr uint32_t kC9WBytes = 9 * 32 * 128;    // resident filter
+
+__global__ void __launch_bounds__(kC9Threads, 1) conv9_rows_kernel(const __grid_constant__ C9KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  pdl_trigger();
+
+  uint8_t* w_smem = smem;                                   // 36 KB
+  uint8_t* stages = w_smem + kC9WBytes;                     // n_stages x 16 KB
+  float* fold_buf = reinterpret_cast<float*>(stages + size_t(p.n_stages) * kC9Row);   // [group 2][128][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(fold_buf) + 2 * 128 * kFoldPad * 4);
+  uint64_t* full = bars;                                    // [n_stages <= 10]
+  uint64_t* empty = bars + 10;
+  uint64_t* wfull = bars + 20;
+  uint64_t* tfull = bars + 21;                              // [2]
+  uint64_t* tempty = bars + 23;                             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(wfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 256);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.in_map);
+    tma_prefetch_desc(&p.w_map);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long prof_acc[4] = {0, 0, 0, 0};
+  const long long t_start = clock64();
+
+  if (warp == 0) {
+    // =============================================================== TMA producer: one image-row segment per stage
+    if (elect_one()) {
+      mbar_expect_tx(wfull, kC9WBytes);
+      for (int r = 0; r < 9; ++r) tma_load_2d(w_smem + size_t(8 - r) * 4096, &p.w_map, wfull, 0, r * 32);
+      pdl_wait();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.tiles_total; tile += p.n_ctas) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * 8;
+        const int w0 = (rem % p.tiles_w) * 120 - 4;
+        for (int ri = 0; ri < 16; ++ri) {
+          { long long t0_ = clock64(); mbar_wait(&empty[stage], phase ^ 1); prof_acc[0] += clock64() - t0_; }
+          mbar_expect_tx(&full[stage], kC9Row);
+          tma_load_4d(stages + size_t(stage) * kC9Row, &p.in_map, &full[stage], 0, w0, h0 + ri - 4, n);
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    constexpr uint32_t idesc0 = make_idesc_bf16(128, 0, 0, 0);        // N field (bits 17-22) filled per MMA
+    const uint64_t desc_hi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+    const uint32_t stage0_lo = smem_u32(stages) >> 4;
+    const uint32_t w_lo = smem_u32(w_smem) >> 4;
+    mbar_wait(wfull, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.tiles_total; tile += p.n_ctas) {
+      { long long t0_ = clock64(); mbar_wait(&tempty[acc], acc_phase ^ 1); prof_acc[1] += clock64() - t0_; }
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + uint32_t(acc * 256);
+#pragma unroll 1
+      for (int ri = 0; ri < 16; ++ri) {          // input row h0 + ri - 4
+        { long long t0_ = clock64(); mbar_wait(&full[stage], phase); prof_acc[2] += clock64() - t0_; }
+        tc_fence_after();
+        const int jlo = ri > 8 ? ri - 8 : 0;     // output rows (blocks) this input row reaches: kh = ri - j in [0, 8]
+        const int jhi = ri < 7 ? ri : 7;
+        const bool fresh = ri <= 7;              // block jhi = ri sees its first tap (kh = 0) here
+        const uint64_t adesc = desc_hi | uint64_t(stage0_lo + uint32_t(stage) * (kC9Row >> 4));
+        const uint64_t b_all = desc_hi | uint64_t(w_lo + uint32_t(8 - ri + jlo) * (4096 >> 4));   // slot of block jlo
+        const uint64_t b_kh0 = desc_hi | uint64_t(w_lo + 8u * (4096 >> 4));
+        if (elect_one()) {
+          const uint32_t n_all = uint32_t(jhi - jlo + 1) * 32u;
+          if (fresh) {
+            // K-step 0: the fresh block must overwrite (accumulate = 0), the older blocks accumulate
+            if (jhi > jlo) umma_bf16(d_base + uint32_t(jlo * 32), adesc, b_all, idesc0 | (((n_all - 32u) >> 3) << 17), 1u);
+            umma_bf16(d_base + uint32_t(jhi * 32), adesc, b_kh0, idesc0 | ((32u >> 3) << 17), 0u);
+          } else {
+            umma_bf16(d_base + uint32_t(jlo * 32), adesc, b_all, idesc0 | ((n_all >> 3) << 17), 1u);
+          }
+#pragma unroll
+          for (int k = 1; k < 4; ++k)
+            umma_bf16(d_base + uint32_t(jlo * 32), adesc + uint64_t(2 * k), b_all + uint64_t(2 * k), idesc0 | ((n_all >> 3) << 17), 1u);
+          umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // =================================================================== epilogue: two 4-warp groups, 4 blocks each
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int m = q * 32 + lane;               // pixel within the 128-wide tile
+    float* fb = fold_buf + grp * 128 * kFoldPad;
+    const float b0 = p.bias ? p.bias[0] : 0.f, b1 = p.bias ? p.bias[1] : 0.f, b2 = p.bias ? p.bias[2] : 0.f;
+    const size_t plane = size_t(p.H) * p.W;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.tiles_total; tile += p.n_ctas) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * 8;
+      const int w0 = (rem % p.tiles_w) * 120 - 4;
+      const int w = w0 + m;
+      { long long t0_ = clock64(); mbar_wait(&tfull[acc], acc_phase); prof_acc[3] += clock64() - t0_; }
+      tc_fence_after();
+#pragma unroll 1
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = grp + 2 * jj;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 256 + j * 32), v);
+        tmem_ld_wait();
+        if (jj == 3) {
+          tc_fence_before();
+          mbar_arrive(&tempty[acc]);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) fb[m * kFoldPad + c] = __uint_as_float(v[c]);
+        named_bar_sync(1 + 2 * grp, 128);
+        const int h = h0 + j;
+        if (m >= 4 && m < 124 && h < p.H && w < p.W) {
+          float o0 = b0, o1 = b1, o2 = b2;
+#pragma unroll
+          for (int s = 0; s < 9; ++s) {
+            const float* row = fb + (m + s - 4) * kFoldPad + s * 3;
+            o0 += row[0];
+            o1 += row[1];
+            o2 += row[2];
+          }
+          const size_t base = (size_t(n) * 3) * plane + size_t(h) * p.W + w;
+          p.out[base] = o0;
+          p.out[base + plane] = o1;
+          p.out[base + 2 * plane] = o2;
+        }
+        named_bar_sync(2 + 2 * grp, 128);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  if (p.prof != nullptr && lane == 0 && (warp <= 2)) {
+    long long* d = p.prof + (size_t(blockIdx.x) * 3 + warp) * 6;
+    d[0] = prof_acc[0]; d[1] = prof_acc[1]; d[2] = prof_acc[2]; d[3] = prof_acc[3]; d[4] = clock64() - t_start; d[5] = t_start;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // ----------------------------------------------------------- host launcher
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1066,6 +1265,62 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+// conv9_rows replaces the fold9 instance of the generic kernel for the plain case (one 64-channel view, 9 row taps
+// starting 4 rows above the tile); ConvGemmArgs::variant == 1 keeps the generic kernel.
+static bool use_conv9_rows(const ConvGemmArgs& a) {
+  if (a.variant == 1 || a.out_mode != OUT_FOLD9_NCHW) return false;
+  if (a.variant == 0 && !conv3_il_enabled()) return false;
+  if (a.block_n != 32 || a.cout_total != 32 || a.n_strips != 1 || a.n_taps != 9 || a.strip_dh != -4 || a.strip_dw[0] != 0) return false;
+  for (int r = 0; r < 9; ++r) if (a.tap_row[r] != r) return false;
+  return a.n_views == 1 && a.views[0].channels == 64 && a.in_H == a.H && a.in_W == a.W && a.residual == nullptr &&
+         a.mask_src == nullptr && a.stats == nullptr && a.act == ACT_NONE;
+}
+
+static int launch_conv9_rows(const ConvGemmArgs& a, cudaStream_t stream) {
+  C9KParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a.N; p.H = a.H; p.W = a.W;
+  p.tiles_h = (a.H + 7) / 8;
+  p.tiles_w = (a.W + 119) / 120;
+  p.tiles_total = a.N * p.tiles_h * p.tiles_w;
+  if (p.tiles_total == 0) return 0;
+  p.n_ctas = sm_budget() < p.tiles_total ? sm_budget() : p.tiles_total;
+  const uint32_t fixed_bytes = kC9WBytes + 2 * 128 * kFoldPad * 4 + 512;
+  int stages = int((227 * 1024 - 1024 - fixed_bytes) / kC9Row);
+  if (stages > 10) stages = 10;
+  p.n_stages = stages;
+  const size_t smem_bytes = 1024 + fixed_bytes + size_t(stages) * kC9Row;
+  {
+    const InView& iv = a.views[0];
+    uint64_t dims[4] = {64, uint64_t(a.in_W), uint64_t(a.in_H), uint64_t(a.N)};
+    uint64_t strides[3] = {uint64_t(iv.stride_w) * 2, uint64_t(iv.stride_h) * 2, uint64_t(iv.stride_n) * 2};
+    uint32_t box[4] = {64, 128, 1, 1};
+    int rc = encode_map_bf16(&p.in_map, iv.ptr, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {64, uint64_t(9) * 32};
+    uint64_t strides[1] = {128};
+    uint32_t box[2] = {64, 32};
+    int rc = encode_map_bf16(&p.w_map, a.weights, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  p.bias = a.bias;
+  p.out = reinterpret_cast<float*>(a.out);
+  p.prof = reinterpret_cast<long long*>(a.prof);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv9_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    attr_set = true;
+  }
+  cudaError_t e = launch_pdl(conv9_rows_kernel, dim3(p.n_ctas), dim3(kC9Threads), smem_bytes, stream, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("conv9_rows launch: %s", cudaGetErrorString(e)); return int(e); }
+  count_launch();
+  return 0;
+}
+
 int conv_gemm_grid(const ConvGemmArgs& a) {
   const bool fold = a.out_mode == OUT_FOLD9_NCHW;
   const int step_w = fold ? a.TW - 8 : a.TW;
@@ -1080,6 +1335,7 @@ int conv_gemm_grid(const ConvGemmArgs& a) {
 
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   if (use_conv3_il(a)) return launch_conv3_il(a, stream);
+  if (use_conv9_rows(a)) return launch_conv9_rows(a, stream);
   if (a.TH * a.TW != 128 || a.TW % 8 != 0) { set_error("conv_gemm: tile must be 128 pixels with TW%%8==0"); return -1; }
   if (a.block_n != 64 && a.block_n != 32) { set_error("conv_gemm: block_n must be 32 or 64"); return -2; }
   if (a.cout_total % a.block_n != 0) { set_error("conv_gemm: cout_total %% block_n != 0"); return -3; }

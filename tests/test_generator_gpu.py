@@ -292,6 +292,31 @@ def test_ragged_and_odd_geometries(S, O):
         assert maxrel(g.conv3.weight.grad, gr) < 2e-2, (n, h, w, res, f)
 
 
+def test_batched_trunk_weight_gradients_match_per_layer_launches(S, monkeypatch):
+    """wgrad3_batched_kernel (all trunk 3x3 weight gradients in one launch at the end of backward) against one
+    wgrad3_kernel launch per layer (SRG_WGRAD_BATCHED=0, read when the engine is created): same bf16 operands, fp32
+    accumulation in a different split order, so equal to fp32 rounding; every other gradient must be bit-identical."""
+    def grads(batched, shape):
+        monkeypatch.setenv("SRG_WGRAD_BATCHED", "1" if batched else "0")
+        torch.manual_seed(31)
+        g = S.SRResNet(num_residuals=3).cuda().train()
+        torch.manual_seed(32)
+        x = torch.rand(*shape).cuda()
+        y = g(x)
+        y.backward(torch.cos(torch.arange(y.numel(), device="cuda", dtype=torch.float32)).reshape(y.shape) * 1e-3)
+        torch.cuda.synchronize()
+        return {k: p.grad.detach().clone() for k, p in g.named_parameters()}
+    for shape in [(2, 3, 40, 20), (3, 3, 33, 17), (1, 3, 16, 8)]:      # ragged tiles, layer boundaries inside CTA ranges
+        a, b = grads(True, shape), grads(False, shape)
+        for k in a:
+            trunk = (k.startswith("residual_blocks") and ".conv" in k and k.endswith("weight")) or k == "conv2.weight"
+            if trunk:
+                assert maxrel(a[k], b[k]) < 1e-5, (shape, k, maxrel(a[k], b[k]))
+                assert float(a[k].abs().max()) > 0
+            else:
+                assert torch.equal(a[k], b[k]), (shape, k)
+
+
 def test_errors_are_python_exceptions(S):
     g = S.SRResNet(num_residuals=1).cuda()
     with pytest.raises(RuntimeError):

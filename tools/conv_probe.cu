@@ -490,6 +490,17 @@ int main(int argc, char** argv) {
     p.block_n = 32; p.out_mode = OUT_FOLD9_NCHW;
     fails += run(p, 0);
   }
+  {  // conv3 through conv9_rows (one image row per MMA, up to 8 output rows per MMA)
+    const int geo[5][3] = {{2, 24, 56}, {3, 37, 130}, {1, 5, 7}, {2, 8, 120}, {1, 19, 245}};
+    for (int g = 0; g < 5; ++g) {
+      Problem p = conv3x3("c9rows", geo[g][0], geo[g][1], geo[g][2], 32, false);
+      p.TH = 4; p.TW = 32;
+      p.n_strips = 1; p.n_taps = 9; p.strip_rows = 4 + 8; p.strip_dh = -4; p.strip_dw[0] = 0;
+      for (int r = 0; r < 9; ++r) p.tap_row[r] = r;
+      p.block_n = 32; p.out_mode = OUT_FOLD9_NCHW; p.variant = 2;
+      fails += run(p, 0);
+    }
+  }
   for (int var = 2; var <= 3; ++var) {  // row-interleaved 3x3 kernel (conv3_il): 2 = one 8-pixel strip per shift, 3 = one 10-pixel strip
     printf("-- conv3_il variant %d\n", var);
     Problem p = conv3x3("il_small", 2, 32, 24, 64, false); p.variant = var; fails += run(p, 0);
@@ -516,6 +527,13 @@ int main(int argc, char** argv) {
     Problem p = conv3x3("perf_up3_16x192x192", 16, 192, 192, 256, true);
     p.act = ACT_RELU;
     fails += run(p, iters);
+    {
+      Problem f = conv3x3("perf_c9rows_16x384x384", 16, 384, 384, 32, false);
+      f.TH = 4; f.TW = 32; f.n_strips = 1; f.n_taps = 9; f.strip_rows = 12; f.strip_dh = -4; f.strip_dw[0] = 0;
+      for (int r = 0; r < 9; ++r) f.tap_row[r] = r;
+      f.block_n = 32; f.out_mode = OUT_FOLD9_NCHW; f.variant = 2;
+      fails += run(f, iters);
+    }
     Problem f = conv3x3("perf_fold9_16x384x384", 16, 384, 384, 32, false);
     f.TH = 4; f.TW = 32; f.n_strips = 1; f.n_taps = 9; f.strip_rows = 12; f.strip_dh = -4; f.strip_dw[0] = 0;
     for (int r = 0; r < 9; ++r) f.tap_row[r] = r;
