@@ -327,7 +327,7 @@ def run_ours(a):
     try:
         if not (a.workload == "cfg2" and B == 16 and LH == 96 and LW == 96):
             raise ValueError("ncu capture was taken at the cfg2 geometry")
-        with open(os.path.join(ROOT, "profiles", "r01_conv_gemm_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01_conv3_il_traffic.json")) as f:
             traffic = json.load(f)["dram_bytes_per_launch"]       # dram__bytes_read.sum + dram__bytes_write.sum (ncu)
     except Exception:
         pass
