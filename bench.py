@@ -280,15 +280,17 @@ def run_ours(a):
     def step_resident():
         trainer.step(lr_dev, hr_dev)
 
-    lr_stage, hr_stage = torch.empty_like(lr_dev), torch.empty_like(hr_dev)
     d2h_bytes = [0]
+    e2e_steps = [a.steps]
 
-    def step_e2e():
-        lr_stage.copy_(lr_host, non_blocking=True)
-        hr_stage.copy_(hr_host, non_blocking=True)
-        out = trainer.step(lr_stage, hr_stage)
-        host = out.cpu()                       # the step's result (losses) back on the host
-        d2h_bytes[0] = host.numel() * host.element_size()
+    def loop_e2e():
+        # the batch loop a user writes: pinned host batches -> DevicePrefetcher (copy of batch t+1 overlaps the kernels
+        # of batch t; exactly one H2D copy of (hr, lr) per step, all inside the timed region) -> step -> losses to host
+        batches = ((hr_host, lr_host) for _ in range(e2e_steps[0]))
+        for hr_d, lr_d in S.DevicePrefetcher(batches, dev):
+            out = trainer.step(lr_d, hr_d)
+            host = out.cpu()                   # the step's result (losses) back on the host
+            d2h_bytes[0] = host.numel() * host.element_size()
 
     for _ in range(max(a.warmup, 3)):
         step_resident()
@@ -341,12 +343,13 @@ def run_ours(a):
 
     e2e = None
     if not a.no_e2e:
-        for _ in range(2):
-            step_e2e()
-        e2e_ms = timed(step_e2e, a.steps) / a.steps
+        e2e_steps[0] = 2
+        loop_e2e()
+        e2e_steps[0] = a.steps
+        e2e_ms = timed(loop_e2e, 1) / a.steps
         e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(lr_host.numel() * 4 + hr_host.numel() * 4), "d2h_bytes_per_step": int(d2h_bytes[0]),
-               "ms_per_step": e2e_ms, "api": "MultiGeneratorGAN.step(lr, hr) after pinned-host -> device copies, losses read back"}
+               "ms_per_step": e2e_ms, "api": "for hr, lr in DevicePrefetcher(pinned host batches): MultiGeneratorGAN.step(lr, hr); losses read back every step"}
     last = trainer.step(lr_dev, hr_dev).cpu().tolist()
 
     cpu_baseline = None

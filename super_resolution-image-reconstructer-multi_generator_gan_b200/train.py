@@ -82,6 +82,50 @@ def train_discriminator_async(discriminator, generator, hr_imgs, lr_imgs, d_opti
     return d_loss.detach()
 
 
+class DevicePrefetcher:
+    """Host -> device staging for the batch loop (the reference copies every batch synchronously from pageable memory,
+    src/train.py:152-153): wraps an iterable of (hr, lr) PINNED host tensors and yields device tensors, issuing the copy
+    of batch t+1 on a side stream while the kernels of batch t run.  Two staging slots; a slot is refilled only after
+    the consumer's stream has passed the point where ``release()`` was called for it."""
+
+    def __init__(self, loader, device, depth: int = 2):
+        self.loader, self.device, self.depth = loader, device, max(int(depth), 2)
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [None] * self.depth
+        self.ready = [torch.cuda.Event() for _ in range(self.depth)]
+        self.freed = [torch.cuda.Event() for _ in range(self.depth)]
+
+    def _stage(self, slot, batch):
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.freed[slot])          # no-op until the slot has been released once
+            if self.slots[slot] is None:
+                self.slots[slot] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in batch]
+            for dst, src in zip(self.slots[slot], batch):
+                dst.copy_(src, non_blocking=True)
+            self.ready[slot].record(self.stream)
+
+    def __iter__(self):
+        it = iter(self.loader)
+        i = 0
+        try:
+            self._stage(0, next(it))
+        except StopIteration:
+            return
+        while True:
+            slot = i % self.depth
+            try:
+                self._stage((i + 1) % self.depth, next(it))   # next batch's copy overlaps this batch's kernels
+                more = True
+            except StopIteration:
+                more = False
+            torch.cuda.current_stream().wait_event(self.ready[slot])
+            yield tuple(self.slots[slot])
+            self.freed[slot].record(torch.cuda.current_stream())   # everything enqueued for this batch precedes the refill
+            i += 1
+            if not more:
+                return
+
+
 def train_one_epoch(generator, train_loader, g_optimizer, vgg_extractor, g_criterion, device, epoch, num_epochs,
                     discriminator, d_optimizer, prefix, verbose: bool = True) -> float:
     """Batch loop of src/train.py:142-172 (D update commented out upstream, kept off here)."""

@@ -317,6 +317,22 @@ def test_batched_trunk_weight_gradients_match_per_layer_launches(S, monkeypatch)
                 assert torch.equal(a[k], b[k]), (shape, k)
 
 
+def test_device_prefetcher_yields_every_batch_in_order(S):
+    """DevicePrefetcher (host -> device staging of the batch loop): every batch arrives intact and in order although
+    the two staging slots are refilled while earlier batches are still being consumed; empty and single-batch loaders."""
+    dev = torch.device("cuda:0")
+    assert list(S.DevicePrefetcher([], dev)) == []
+    for n in (1, 2, 5):
+        host = [(torch.full((2, 3, 8, 8), float(i)).pin_memory(), torch.full((2, 3, 2, 2), float(-i)).pin_memory())
+                for i in range(n)]
+        seen = []
+        for hr_d, lr_d in S.DevicePrefetcher(host, dev):
+            assert hr_d.is_cuda and lr_d.is_cuda
+            torch.cuda._sleep(2_000_000)                       # keep the consumer busy so that refills really overlap
+            seen.append((float(hr_d.sum()) / hr_d.numel(), float(lr_d.sum()) / lr_d.numel()))
+        assert seen == [(float(i), float(-i)) for i in range(n)], seen
+
+
 def test_errors_are_python_exceptions(S):
     g = S.SRResNet(num_residuals=1).cuda()
     with pytest.raises(RuntimeError):
