@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 256);
   uint64_t* full = bars;                                                  // [n_stages <= 8]
   uint64_t* empty = bars + 8;
-  uint64_t* wfull = bars + 16;
+  uint64_t* wfull = bars + 26;                                            // [kw 3]: the filter arrives per column shift
   uint64_t* tfull = bars + 17;                                            // [2]
   uint64_t* tempty = bars + 19;                                           // [2]
   uint64_t* auxfull = bars + 21;                                          // [block 2]
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(wfull, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&wfull[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 512);
@@ -559,10 +559,11 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
     // =============================================================== TMA producer
     if (elect_one()) {
       // generic packing is k-block (kw*3 + kh); shared memory wants [kw][kh2 ; kh1 ; kh0]
-      mbar_expect_tx(wfull, kIlWBytes);
-      for (int s = 0; s < 3; ++s)
+      for (int s = 0; s < 3; ++s) {
+        mbar_expect_tx(&wfull[s], kIlWBytes / 3);
         for (int r = 0; r < 3; ++r)
-          tma_load_2d(w_smem + size_t(s * 3 + (2 - r)) * 8192, &p.w_map, wfull, 0, (s * 3 + r) * p.cout_total + nblk * 64);
+          tma_load_2d(w_smem + size_t(s * 3 + (2 - r)) * 8192, &p.w_map, &wfull[s], 0, (s * 3 + r) * p.cout_total + nblk * 64);
+      }
       pdl_wait();      // the activations (and aux tensor) come from the previous kernel; the weights above do not
       int stage = 0;
       uint32_t phase = 0, aux_phase = 0;
@@ -610,11 +611,11 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
     const uint64_t desc_hi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
     const uint32_t stage0_lo = smem_u32(stages) >> 4;
     const uint32_t w_lo = smem_u32(w_smem) >> 4;
-    mbar_wait(wfull, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    bool w_ready = false;            // first tile: wait for each column shift's weights right before their first use
     for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
       { long long t0_ = clock64(); mbar_wait(&tempty[acc], acc_phase ^ 1); prof_acc[1] += clock64() - t0_; }
       tc_fence_after();
@@ -628,9 +629,10 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
           { long long t0_ = clock64(); mbar_wait(&full[stage], phase); prof_acc[2] += clock64() - t0_; }
           tc_fence_after();
           const uint32_t a_base = smem_u32(stages) + uint32_t(stage) * kStage;     // 1024-byte aligned
-          if (elect_one()) {
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
+          for (int s = 0; s < 3; ++s) {
+            if (!w_ready) mbar_wait(&wfull[s], 0);      // first tile only: this column shift's 24 KB of weights have landed
+            if (elect_one()) {
               const uint32_t wb = w_lo + uint32_t(s) * (3 * 8192 >> 4);
               // window starting at half-strip row 0 / row 1, column shift s pixels
               const uint32_t st0 = a_base + uint32_t(s) * 128u, st1 = st0 + kIlWidePitch;
@@ -652,15 +654,17 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16(d_o, a1 + uint64_t(2 * k), b1 + uint64_t(2 * k), idesc64, 1u);
               }
+              if (s == 2) umma_commit(&empty[stage]);
             }
-            umma_commit(&empty[stage]);
+            __syncwarp();
           }
-          __syncwarp();
+          w_ready = true;
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
       } else {
 #pragma unroll 1
       for (int s = 0; s < 3; ++s) {
+        if (!w_ready) mbar_wait(&wfull[s], 0);
         const uint32_t wb = w_lo + uint32_t(s) * (3 * 8192 >> 4);     // [kh2 ; kh1 ; kh0] of this column shift
 #pragma unroll
         for (int par = 1; par >= 0; --par) {
@@ -699,6 +703,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
         }
       }
       }
+      w_ready = true;
       if (elect_one()) umma_commit(&tfull[acc]);
       __syncwarp();
       acc ^= 1;
