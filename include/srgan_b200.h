@@ -75,6 +75,11 @@ int srg_generator_tensor_info(const srg_generator_t* g, int i, char* name, int n
 int srg_generator_set_keep_grads(srg_generator_t* g, int keep);
 long long srg_generator_launch_count(const srg_generator_t* g); /* kernels enqueued so far by this engine */
 long long srg_total_launches(void);                             /* kernels enqueued so far by the whole library */
+/* parity-test / A-B aid: which convolution kernels later launches use.  0 = default (conv3_il for plain 3x3 / 64-channel
+ * launches, conv9_rows for conv3; honours SRG_CONV_IL), 1 = the generic strip kernel for everything, 2 = conv3_il with one
+ * 8-pixel strip per column shift, 3 = conv3_il with one 10-pixel strip.  Returns the previous value.  Affects kernels
+ * enqueued afterwards (a captured CUDA graph keeps what it was captured with). */
+int srg_set_conv_variant(int variant);
 /* CUDA-event timing of the dominant kernel class (the 3x3 64->64 forward / data-gradient conv_gemm launches, 66 per
  * generator fwd+bwd): enable, run steps, then read the summed device time (ms) and launch count since the last read
  * (read synchronises on the recorded events and resets the counters). */

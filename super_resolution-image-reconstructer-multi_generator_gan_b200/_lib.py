@@ -90,6 +90,7 @@ EXPORTS = {
     "srg_generator_launch_count": (c_longlong, [c_void_p]),
     "srg_generator_set_keep_grads": (c_int, [c_void_p, c_int]),
     "srg_total_launches": (c_longlong, []),
+    "srg_set_conv_variant": (c_int, [c_int]),
     "srg_generator_profile_enable": (c_int, [c_void_p, c_int]),
     "srg_generator_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
     "srg_generator_set_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),

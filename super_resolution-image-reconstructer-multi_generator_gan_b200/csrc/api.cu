@@ -139,6 +139,7 @@ int srg_generator_tensor_info(const srg_generator_t* g, int i, char* name, int n
 }
 long long srg_generator_launch_count(const srg_generator_t* g) { return G(g)->launches; }
 long long srg_total_launches(void) { return total_launches(); }
+int srg_set_conv_variant(int variant) { return set_conv_variant(variant); }
 int srg_generator_set_keep_grads(srg_generator_t* g, int keep) { return generator_set_keep_grads(G(g), keep); }
 int srg_generator_profile_enable(srg_generator_t* g, int on) { return generator_profile_enable(G(g), on); }
 int srg_generator_profile_read(srg_generator_t* g, double* ms_sum, long long* count) {

@@ -1157,8 +1157,16 @@ static bool conv3_il_wide_enabled() {
   }
   return on != 0;
 }
+static int g_variant_override = 0;
+int set_conv_variant(int variant) {
+  const int old = g_variant_override;
+  g_variant_override = (variant >= 0 && variant <= 3) ? variant : 0;
+  return old;
+}
+static int effective_variant(const ConvGemmArgs& a) { return a.variant != 0 ? a.variant : g_variant_override; }
 static bool use_conv3_il(const ConvGemmArgs& a) {
-  if (a.variant == 1 || (a.variant == 0 && !conv3_il_enabled())) return false;
+  const int variant = effective_variant(a);
+  if (variant == 1 || (variant == 0 && !conv3_il_enabled())) return false;
   return a.TH == 16 && a.TW == 8 && a.block_n == 64 && a.n_strips == 3 && a.n_taps == 3 && a.strip_dh == -1 &&
          a.strip_rows == 18 && a.tap_row[0] == 0 && a.tap_row[1] == 1 && a.tap_row[2] == 2 && a.n_views == 1 &&
          a.views[0].channels == 64 && a.in_H == a.H && a.in_W == a.W && a.H >= 2 &&
@@ -1201,7 +1209,8 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   const uint32_t fixed_bytes = kIlWBytes + 2 * kTileOutBytes + (has_aux ? 2 * kTileOutBytes : 0) + 512 +
                                (a.stats != nullptr ? 16 * 128 * 4 : 0);
   // the wide form needs the three column shifts to be -1, 0, +1 (one 10-pixel strip starting at w0 - 1)
-  const bool wide = (a.variant == 3 || (a.variant == 0 && conv3_il_wide_enabled())) && a.strip_dw[0] == -1 && a.strip_dw[1] == 0 && a.strip_dw[2] == 1;
+  const int variant = effective_variant(a);
+  const bool wide = (variant == 3 || (variant == 0 && conv3_il_wide_enabled())) && a.strip_dw[0] == -1 && a.strip_dw[1] == 0 && a.strip_dw[2] == 1;
   const uint32_t stage_bytes = wide ? kIlWideStage : kIlHalfStrip;
   // Leave 44 KB of the SM's shared memory to CTAs of other graph branches (chan_reduce, finalize, loss passes need 8-18 KB):
   // measured 11.27 -> 11.14 ms per cfg2 step; the shallower pipeline (3 / 2 stages) costs nothing (profiles/r01_notes.md).
@@ -1277,8 +1286,9 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
 // conv9_rows replaces the fold9 instance of the generic kernel for the plain case (one 64-channel view, 9 row taps
 // starting 4 rows above the tile); ConvGemmArgs::variant == 1 keeps the generic kernel.
 static bool use_conv9_rows(const ConvGemmArgs& a) {
-  if (a.variant == 1 || a.out_mode != OUT_FOLD9_NCHW) return false;
-  if (a.variant == 0 && !conv3_il_enabled()) return false;
+  const int variant = effective_variant(a);
+  if (variant == 1 || a.out_mode != OUT_FOLD9_NCHW) return false;
+  if (variant == 0 && !conv3_il_enabled()) return false;
   if (a.block_n != 32 || a.cout_total != 32 || a.n_strips != 1 || a.n_taps != 9 || a.strip_dh != -4 || a.strip_dw[0] != 0) return false;
   for (int r = 0; r < 9; ++r) if (a.tap_row[r] != r) return false;
   return a.n_views == 1 && a.views[0].channels == 64 && a.in_H == a.H && a.in_W == a.W && a.residual == nullptr &&

@@ -112,6 +112,9 @@ int launch_wgrad3x3_batched(const WgradBatchArgs& a, cudaStream_t stream);
 int launch_wgrad_reduce(const float* partials, const int* idx, float* out, int n_out, int splits, size_t split_stride,
                         int accumulate_into, cudaStream_t stream);
 
+// process-wide override of ConvGemmArgs::variant for launches that leave it 0 (parity tests, A/B runs); returns the old value
+int set_conv_variant(int variant);
+
 // SMs a persistent kernel may size its grid for: device SM count / concurrency share (set_sm_share, SRG_SM_SHARE)
 int sm_budget();
 void set_sm_share(int k);

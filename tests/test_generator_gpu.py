@@ -516,6 +516,45 @@ def test_full_size_properties_cfg2(S):
     assert rel < 2e-2, rel                                     # linear up to bf16 rounding of the scaled gradients
 
 
+def test_kernel_families_agree_at_full_size_cfg2(S):
+    """The specialised convolution kernels (conv3_il in both strip forms, conv9_rows, batched weight gradients) against
+    the generic strip kernel at the BASELINE configs[1] geometry: same bf16 operands and fp32 accumulation in a
+    different tap order; every one of the 37 layers stores bf16, so a different accumulation order flips roundings
+    and the families agree to bf16 storage noise compounded over the depth (measured 47 dB), not to fp32 noise."""
+    L = S.lib()
+    torch.manual_seed(7)
+    g = S.SRResNet().cuda()
+    lr = torch.rand(16, 3, 96, 96).cuda()
+    dsr = (torch.randn(16, 3, 384, 384, generator=torch.Generator().manual_seed(8)) * 1e-4).cuda()
+    state = {k: v.clone() for k, v in g.state_dict().items()}
+    outs, grads = {}, {}
+    try:
+        for variant in (1, 2, 3):
+            L.srg_set_conv_variant(variant)
+            g.load_state_dict(state)
+            g.eval()
+            with torch.no_grad():
+                outs[variant] = g(lr).clone()
+            g.train()
+            g.zero_grad()
+            y = g(lr)
+            y.backward(dsr)
+            torch.cuda.synchronize()
+            grads[variant] = g.flat_grads().clone()
+    finally:
+        L.srg_set_conv_variant(0)
+    for variant in (2, 3):
+        mse = float(((outs[variant] - outs[1]).double() ** 2).mean())
+        assert mse < 1e-4 * float((outs[1].double() ** 2).mean()), (variant, mse)               # > 40 dB
+        assert maxrel(outs[variant], outs[1]) < 5e-2, (variant, maxrel(outs[variant], outs[1]))
+        # end-to-end gradients of two bf16 paths differ like bf16 vs fp32 does (DESIGN.md section 4: ReLU masks are taken
+        # on slightly different activations, O(10 %) in deep layers; measured 12 %); the strict bound is per layer
+        # (test_backward_layers_isolated), here only gross disagreement is excluded
+        rel = float((grads[variant] - grads[1]).norm() / grads[1].norm())
+        assert rel < 0.3, (variant, rel)
+    assert maxrel(outs[2], outs[3]) < 5e-2      # same operands, MMAs issued in a different order (strip-major vs parity-major)
+
+
 def test_setup_training_linear_lr_and_resume_protocol(S, tmp_path):
     """a9: the reference's optimiser / scheduler set-up (src/train.py:40-41,61-62,70-71) and resume protocol (:51-59)
     on top of the flat capturable Adam: LinearLR changes must reach the device-side learning rate."""
