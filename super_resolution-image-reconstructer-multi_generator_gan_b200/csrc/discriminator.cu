@@ -58,32 +58,42 @@ int ew_grid(int64_t items) {
 
 // ------------------------------------------------------------------------------------------------ stage-0 unfold
 // U0[n][h'][w'][ch], ch = ((v*2+a)*2+b)*3+c  <-  x[n][c][2h'+a-2][2(w'+v)+b-2]   (zero outside / ch >= 48)
+// The 12 values of column pair j = w'+v, T[j] = {x[c][2h'+a-2][2j-2+b]}, are shared by four neighbouring pixels
+// (pixel w' = [T[w'], T[w'+1], T[w'+2], T[w'+3], 16 zeros]).  One block per (n, h'): phase 1 builds T for the whole row in
+// shared memory (coalesced reads along the image row, 24 bytes of bf16 per j), phase 2 writes the output row as
+// consecutive 16-byte vectors copied from 96 contiguous shared-memory bytes per pixel.
 __global__ void __launch_bounds__(256) d_unfold0_kernel(const float* __restrict__ x, int N, int H, int W, int Hs, int Ws,
                                                         uint4* __restrict__ dst) {
-  const int64_t total = int64_t(N) * Hs * Ws * 8;
+  extern __shared__ uint2 sT[];                 // [(Ws + 3)][3] uint2 = 12 bf16 per column pair
+  const int hq = blockIdx.x % Hs, n = blockIdx.x / Hs;
   const int64_t plane = int64_t(H) * W;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int cg = int(i & 7);
-    const int64_t pix = i >> 3;
-    const int wq = int(pix % Ws);
-    const int64_t t = pix / Ws;
-    const int hq = int(t % Hs);
-    const int n = int(t / Hs);
-    float f[8];
+  const float* xn = x + int64_t(n) * 3 * plane;
+  for (int j = threadIdx.x; j < Ws + 3; j += blockDim.x) {
+    float f[12];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int ch = cg * 8 + e;
-      float val = 0.f;
-      if (ch < 48) {
-        const int v = ch / 12, rem = ch - v * 12, a = rem / 6, b = (rem % 6) / 3, c = rem % 3;
-        const int yy = 2 * hq + a - 2, xx = 2 * (wq + v) + b - 2;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(x + (int64_t(n) * 3 + c) * plane + int64_t(yy) * W + xx);
+    for (int a = 0; a < 2; ++a) {
+      const int yy = 2 * hq + a - 2;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int xx = 2 * j - 2 + b;
+        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f[a * 6 + b * 3 + c] = ok ? __ldg(xn + c * plane + int64_t(yy) * W + xx) : 0.f;
       }
-      f[e] = val;
     }
-    uint4 o;
-    o.x = bpack2(f[0], f[1]); o.y = bpack2(f[2], f[3]); o.z = bpack2(f[4], f[5]); o.w = bpack2(f[6], f[7]);
-    dst[i] = o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sT[j * 3 + k] = make_uint2(bpack2(f[4 * k], f[4 * k + 1]), bpack2(f[4 * k + 2], f[4 * k + 3]));
+  }
+  __syncthreads();
+  uint4* row = dst + (int64_t(n) * Hs + hq) * Ws * 8;
+  for (int u = threadIdx.x; u < Ws * 8; u += blockDim.x) {
+    const int wq = u >> 3, k = u & 7;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (k < 6) {
+      const uint2 lo = sT[wq * 3 + 2 * k], hi = sT[wq * 3 + 2 * k + 1];     // bytes 24*wq + 16*k .. + 16
+      o = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
+    row[u] = o;
   }
 }
 // dx[n][c][y][x] = sum_v dU0[n][(y+2)>>1][((x+2)>>1) - v][ch(v, (y+2)&1, (x+2)&1, c)]
@@ -255,42 +265,83 @@ __global__ void d_apply_sigmoid_kernel(const float* __restrict__ P, const float*
 }
 // dY[n][ho][wo][c] (bf16) = sum over pooled windows (hp, wp) containing (ho, wo) whose argmax is (ho, wo) of
 //   inv * (g - c1 - xhat * c2)         (InstanceNorm backward + MaxPool backward, gather form: no atomics)
+// One thread = a 2x2 block of outputs x 8 channels: the four pooling windows (hp in {i-1, i}, wp in {j-1, j}) that can
+// route into it are read ONCE (9 window reads per block in the one-output-per-thread form), every argmax code is
+// decoded to its target inside the block.
 __global__ void __launch_bounds__(256) d_pool_bwd_kernel(const float* __restrict__ G, const float* __restrict__ P,
                                                          const uint8_t* __restrict__ idx, const float* __restrict__ stats,
                                                          const float* __restrict__ stats2, int Ho, int Wo, int Hp, int Wp,
                                                          int C, int N, uint4* __restrict__ dY) {
   const int groups = C / 8;
-  const int64_t total = int64_t(N) * Ho * Wo * groups;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int gq = int(i % groups);
-    int64_t t = i / groups;
-    const int wo = int(t % Wo);
-    t /= Wo;
-    const int ho = int(t % Ho);
-    const int n = int(t / Ho);
+  const int Hb = (Ho + 1) / 2, Wb = (Wo + 1) / 2;
+  const int64_t total = int64_t(N) * Hb * Wb * groups;
+  for (int64_t t0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t0 < total; t0 += int64_t(gridDim.x) * blockDim.x) {
+    const int gq = int(t0 % groups);
+    int64_t t = t0 / groups;
+    const int j = int(t % Wb);
+    t /= Wb;
+    const int i = int(t % Hb);
+    const int n = int(t / Hb);
     const int c0 = gq * 8;
-    float f[8];
+    float f[4][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = 0.f;
-    const int hp_lo = max(0, (ho - 1) >> 1), hp_hi = min(Hp - 1, ho >> 1);
-    const int wp_lo = max(0, (wo - 1) >> 1), wp_hi = min(Wp - 1, wo >> 1);
-    for (int hp = hp_lo; hp <= hp_hi; ++hp)
-      for (int wp = wp_lo; wp <= wp_hi; ++wp) {
-        const int rel = (ho - 2 * hp) * 3 + (wo - 2 * wp);
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[q][e] = 0.f;
+    // per-(n, channel) statistics of this thread's 8 channels: {mean, inv} and {c1, c2} pairs, 128-bit loads
+    const float4* s1 = reinterpret_cast<const float4*>(stats + (int64_t(n) * C + c0) * 2);
+    const float4* s2 = reinterpret_cast<const float4*>(stats2 + (int64_t(n) * C + c0) * 2);
+    float mean[8], inv[8], k1[8], k2[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = __ldg(s1 + q), b = __ldg(s2 + q);
+      mean[2 * q] = a.x; inv[2 * q] = a.y; mean[2 * q + 1] = a.z; inv[2 * q + 1] = a.w;
+      k1[2 * q] = b.x; k2[2 * q] = b.y; k1[2 * q + 1] = b.z; k2[2 * q + 1] = b.w;
+    }
+#pragma unroll
+    for (int wi = 0; wi < 2; ++wi) {
+      const int hp = i - 1 + wi;
+      if (hp < 0 || hp >= Hp) continue;
+#pragma unroll
+      for (int wj = 0; wj < 2; ++wj) {
+        const int wp = j - 1 + wj;
+        if (wp < 0 || wp >= Wp) continue;
         const int64_t po = ((int64_t(n) * Hp + hp) * Wp + wp) * C + c0;
+        const uint2 iv = *reinterpret_cast<const uint2*>(idx + po);           // 8 argmax codes r*3 + c (C % 8 == 0)
+        // target inside the block: di = r - 2*(1 - wi), dj = c - 2*(1 - wj), both must be 0 or 1
+        int tgt[8];
+        bool any = false;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          if (idx[po + e] == rel) {
-            const int64_t sc = (int64_t(n) * C + c0 + e) * 2;
-            const float inv = stats[sc + 1];
-            const float xhat = (P[po + e] - stats[sc]) * inv;
-            f[e] += inv * (G[po + e] - stats2[sc] - xhat * stats2[sc + 1]);
-          }
+          const int code = int(((e < 4 ? iv.x : iv.y) >> (8 * (e & 3))) & 0xFFu);
+          const int r = code / 3, c = code - 3 * r;
+          const int di = r - 2 * (1 - wi), dj = c - 2 * (1 - wj);
+          tgt[e] = (di >= 0 && di <= 1 && dj >= 0 && dj <= 1) ? di * 2 + dj : -1;
+          any |= tgt[e] >= 0;
+        }
+        if (!any) continue;
+        const float4 p0 = *reinterpret_cast<const float4*>(P + po), p1 = *reinterpret_cast<const float4*>(P + po + 4);
+        const float4 g0 = *reinterpret_cast<const float4*>(G + po), g1 = *reinterpret_cast<const float4*>(G + po + 4);
+        const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xhat = (pv[e] - mean[e]) * inv[e];
+          const float val = inv[e] * (gv[e] - k1[e] - xhat * k2[e]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) f[q][e] += (tgt[e] == q) ? val : 0.f;
         }
       }
-    uint4 o;
-    o.x = bpack2(f[0], f[1]); o.y = bpack2(f[2], f[3]); o.z = bpack2(f[4], f[5]); o.w = bpack2(f[6], f[7]);
-    dY[i] = o;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ho = 2 * i + (q >> 1), wo = 2 * j + (q & 1);
+      if (ho < Ho && wo < Wo) {
+        uint4 o;
+        o.x = bpack2(f[q][0], f[q][1]); o.y = bpack2(f[q][2], f[q][3]); o.z = bpack2(f[q][4], f[q][5]); o.w = bpack2(f[q][6], f[q][7]);
+        dY[((int64_t(n) * Ho + ho) * Wo + wo) * groups + gq] = o;
+      }
+    }
   }
 }
 // per-channel sums of a bf16 [pixels][C] tensor: partials[block][C], then out[c] = sum over blocks (fixed order)
@@ -585,8 +636,7 @@ int discriminator_forward(DiscriminatorEngine* d, const float* x, float* out, in
   float* partials = reinterpret_cast<float*>(ws + L.partials);
   {
     const DiscStage& s = e->st[0];
-    const int64_t total = int64_t(N) * s.Hs * s.Ws * 8;
-    d_unfold0_kernel<<<ew_grid(total), 256, 0, st>>>(x, N, e->H, e->W, s.Hs, s.Ws, reinterpret_cast<uint4*>(ws + L.X[0]));
+    d_unfold0_kernel<<<N * s.Hs, 256, size_t(s.Ws + 3) * 24, st>>>(x, N, e->H, e->W, s.Hs, s.Ws, reinterpret_cast<uint4*>(ws + L.X[0]));
     D_LAUNCH_CHECK("d_unfold0");
   }
   for (int l = 0; l < 4; ++l) {
@@ -666,7 +716,7 @@ int discriminator_backward(DiscriminatorEngine* d, const float* dout, int param_
     D_LAUNCH_CHECK("d_in_bwd_finalize");
     // ---- InstanceNorm + MaxPool backward -> d(conv output), bf16
     {
-      const int64_t total = int64_t(N) * s.Ho * s.Wo * (s.Cout / 8);
+      const int64_t total = int64_t(N) * ((s.Ho + 1) / 2) * ((s.Wo + 1) / 2) * (s.Cout / 8);
       d_pool_bwd_kernel<<<ew_grid(total), 256, 0, st>>>(G, reinterpret_cast<const float*>(ws + L.P[l]), ws + L.idx[l], stats,
                                                        stats2, s.Ho, s.Wo, s.Hp, s.Wp, s.Cout, N,
                                                        reinterpret_cast<uint4*>(ws + L.dY[l]));
