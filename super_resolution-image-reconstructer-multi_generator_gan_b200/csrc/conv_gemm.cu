@@ -6,8 +6,14 @@
 // input element crosses L2->SM  n_strips times instead of n_strips*n_taps times.  Because TW % 8 == 0 every tap's
 // A operand starts on a 1024-byte swizzle-atom boundary: canonical K-major SWIZZLE_128B descriptors throughout.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue.
 // Persistent CTAs; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Three kernels live in this file, all behind launch_conv_gemm():
+//   conv_gemm_kernel<BLOCK_N, NT>  the generic strip kernel described above (one N = 64 / 32 MMA per tap and K-step);
+//   conv3_il_kernel<WIDE>          plain 3x3 / 64-input-channel launches: row-interleaved accumulator blocks so that two
+//                                  taps share one N = 128 MMA (the ~64-cycle floor of an M128 MMA makes that free);
+//   conv9_rows_kernel              the 9x9 / 3-output-channel conv3: one image row per MMA feeding up to 8 output rows.
 #include "conv_gemm.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
