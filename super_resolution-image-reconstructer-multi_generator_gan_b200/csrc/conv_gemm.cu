@@ -57,6 +57,7 @@ struct ConvKParams {
   int resident, n_stages;
   uint32_t strip_bytes, stage_bytes, w_resident_bytes;
   const float* bias;
+  const float* scale;  // optional per-channel multiplier of the accumulator (folded eval-mode BatchNorm)
   int act;
   float slope;
   int aux_mode;  // 0 none, 1 add (residual), 2 mask (zero where aux <= 0)
@@ -96,8 +97,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint8_t* tail = aux_stage + (p.aux_mode ? 2 * kTileOutBytes : 0);
   float* fold_buf = reinterpret_cast<float*>(tail);       // 128*33 floats (fold9 only)
   uint8_t* tail2 = tail + (kFold ? 128 * kFoldPad * 4 : 0);
-  float* s_bias = reinterpret_cast<float*>(tail2);        // BLOCK_N floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail2 + 256);
+  float* s_bias = reinterpret_cast<float*>(tail2);        // BLOCK_N floats bias, then BLOCK_N floats scale (128 + 128 B used of 512)
+  float* s_scale = s_bias + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail2 + 512);
   uint64_t* full = bars;                                  // [n_stages]
   uint64_t* empty = bars + 8;                             // [n_stages]
   uint64_t* wfull = bars + 16;
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* auxfull = bars + 21;                          // [2]
   uint64_t* auxempty = bars + 23;                         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
-  float* s_stats = reinterpret_cast<float*>(tail2 + 512);  // [8][128] floats (p.stats only)
+  float* s_stats = reinterpret_cast<float*>(tail2 + 768);  // [8][128] floats (p.stats only)
 
   const int nblk = blockIdx.x % p.n_blocks;
   const int tile0 = blockIdx.x / p.n_blocks;
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       float b = 0.f;
       if (p.bias != nullptr && !kFold) b = p.bias[nblk * BLOCK_N + t];
       s_bias[t] = b;
+      s_scale[t] = (p.scale != nullptr && !kFold) ? p.scale[nblk * BLOCK_N + t] : 1.f;
     }
   }
   tc_fence_before();
@@ -320,13 +323,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         float f[32];
         {
           const float4* bp = reinterpret_cast<const float4*>(s_bias + hf * 32);
+          const float4* sp4 = reinterpret_cast<const float4*>(s_scale + hf * 32);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 b = bp[g];
-            f[4 * g + 0] = __uint_as_float(v[4 * g + 0]) + b.x;
-            f[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b.y;
-            f[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b.z;
-            f[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b.w;
+            const float4 sc = sp4[g];
+            f[4 * g + 0] = fmaf(__uint_as_float(v[4 * g + 0]), sc.x, b.x);
+            f[4 * g + 1] = fmaf(__uint_as_float(v[4 * g + 1]), sc.y, b.y);
+            f[4 * g + 2] = fmaf(__uint_as_float(v[4 * g + 2]), sc.z, b.z);
+            f[4 * g + 3] = fmaf(__uint_as_float(v[4 * g + 3]), sc.w, b.w);
           }
         }
         if (p.act == ACT_RELU) {
@@ -481,6 +486,7 @@ struct IlKParams {
   int cout_total, n_blocks, ctas_per_block;
   int n_stages;
   const float* bias;
+  const float* scale;        // optional per-channel multiplier of the accumulator (folded eval-mode BatchNorm)
   int act;
   float slope;
   int aux_mode;              // 0 none, 1 add (residual), 2 mask (zero where aux <= 0)
@@ -516,8 +522,9 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
   uint8_t* out_stage = stages + size_t(p.n_stages) * kStage;             // [block 2][16 KB]
   uint8_t* aux_stage = out_stage + 2 * kTileOutBytes;                     // [block 2][16 KB] (aux_mode != 0)
   uint8_t* tail = aux_stage + (p.aux_mode ? 2 * kTileOutBytes : 0);
-  float* s_bias = reinterpret_cast<float*>(tail);                         // 64 floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 256);
+  float* s_bias = reinterpret_cast<float*>(tail);                         // 64 floats bias, 64 floats scale
+  float* s_scale = s_bias + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 512);
   uint64_t* full = bars;                                                  // [n_stages <= 8]
   uint64_t* empty = bars + 8;
   uint64_t* wfull = bars + 26;                                            // [kw 3]: the filter arrives per column shift
@@ -526,7 +533,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
   uint64_t* auxfull = bars + 21;                                          // [block 2]
   uint64_t* auxempty = bars + 23;                                         // [block 2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
-  float* s_stats = reinterpret_cast<float*>(tail + 512);                  // [16][128] floats (p.stats only)
+  float* s_stats = reinterpret_cast<float*>(tail + 768);                  // [16][128] floats (p.stats only)
 
   const int nblk = blockIdx.x % p.n_blocks;
   const int tile0 = blockIdx.x / p.n_blocks;
@@ -553,6 +560,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
   if (warp >= 2 && warp < 4) {
     const int t = threadIdx.x - 64;
     s_bias[t] = p.bias != nullptr ? p.bias[nblk * 64 + t] : 0.f;
+    s_scale[t] = p.scale != nullptr ? p.scale[nblk * 64 + t] : 1.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -746,13 +754,15 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
       float f[32];
       {
         const float4* bp = reinterpret_cast<const float4*>(s_bias + hf * 32);
+        const float4* sp4 = reinterpret_cast<const float4*>(s_scale + hf * 32);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 b = bp[g];
-          f[4 * g + 0] = __uint_as_float(v[4 * g + 0]) + b.x;
-          f[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b.y;
-          f[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b.z;
-          f[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b.w;
+          const float4 sc = sp4[g];
+          f[4 * g + 0] = fmaf(__uint_as_float(v[4 * g + 0]), sc.x, b.x);
+          f[4 * g + 1] = fmaf(__uint_as_float(v[4 * g + 1]), sc.y, b.y);
+          f[4 * g + 2] = fmaf(__uint_as_float(v[4 * g + 2]), sc.z, b.z);
+          f[4 * g + 3] = fmaf(__uint_as_float(v[4 * g + 3]), sc.w, b.w);
         }
       }
       if (p.act == ACT_RELU) {
@@ -1212,7 +1222,7 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   if (p.ctas_per_block < 1) p.ctas_per_block = 1;
   if (p.ctas_per_block > p.tiles_total) p.ctas_per_block = p.tiles_total;
   p.aux_mode = a.residual ? 1 : (a.mask_src ? 2 : 0);
-  const uint32_t fixed_bytes = kIlWBytes + 2 * kTileOutBytes + (has_aux ? 2 * kTileOutBytes : 0) + 512 +
+  const uint32_t fixed_bytes = kIlWBytes + 2 * kTileOutBytes + (has_aux ? 2 * kTileOutBytes : 0) + 768 +
                                (a.stats != nullptr ? 16 * 128 * 4 : 0);
   // the wide form needs the three column shifts to be -1, 0, +1 (one 10-pixel strip starting at w0 - 1)
   const int variant = effective_variant(a);
@@ -1268,7 +1278,7 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
     }
     for (int q = 2; q < 8; ++q) p.out_map[q] = p.out_map[q & 1];
   }
-  p.bias = a.bias; p.act = a.act; p.slope = a.slope;
+  p.bias = a.bias; p.scale = a.scale; p.act = a.act; p.slope = a.slope;
   p.out_mode = a.out_mode;
   p.stats = a.stats;
   p.stats_y = reinterpret_cast<const uint32_t*>(a.stats_y);
@@ -1298,7 +1308,7 @@ static bool use_conv9_rows(const ConvGemmArgs& a) {
   if (a.block_n != 32 || a.cout_total != 32 || a.n_strips != 1 || a.n_taps != 9 || a.strip_dh != -4 || a.strip_dw[0] != 0) return false;
   for (int r = 0; r < 9; ++r) if (a.tap_row[r] != r) return false;
   return a.n_views == 1 && a.views[0].channels == 64 && a.in_H == a.H && a.in_W == a.W && a.residual == nullptr &&
-         a.mask_src == nullptr && a.stats == nullptr && a.act == ACT_NONE;
+         a.mask_src == nullptr && a.stats == nullptr && a.act == ACT_NONE && a.scale == nullptr;
 }
 
 static int launch_conv9_rows(const ConvGemmArgs& a, cudaStream_t stream) {
@@ -1415,7 +1425,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   if (a.stats != nullptr && (a.out_mode != OUT_NHWC || a.cout_total != 64 || a.TW != 8)) {
     set_error("conv_gemm: fused statistics need OUT_NHWC with 64 output channels and 8-pixel-wide tiles"); return -16;
   }
-  const uint32_t fixed_bytes = (fold ? 128 * kFoldPad * 4 : 2 * kTileOutBytes) + (has_aux ? 2 * kTileOutBytes : 0) + 256 + 256 +
+  const uint32_t fixed_bytes = (fold ? 128 * kFoldPad * 4 : 2 * kTileOutBytes) + (has_aux ? 2 * kTileOutBytes : 0) + 512 + 256 +
                                (a.stats != nullptr ? 8 * 128 * 4 : 0);
   const uint32_t budget = 227 * 1024 - 1024 - fixed_bytes;
   p.resident = (w_all + 3 * p.strip_bytes <= budget) ? 1 : 0;
@@ -1475,7 +1485,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     for (int q = 0; q < 4; ++q) p.out_map[q] = p.in_map[0];
     p.aux_map = p.in_map[0];
   }
-  p.bias = a.bias; p.act = a.act; p.slope = a.slope;
+  p.bias = a.bias; p.scale = a.scale; p.act = a.act; p.slope = a.slope;
   p.out = a.out; p.out_mode = a.out_mode;
   p.stats = a.stats;
   p.stats_y = reinterpret_cast<const uint32_t*>(a.stats_y);

@@ -50,6 +50,8 @@ struct ConvGemmArgs {
   int block_n;               // 32 (fold9 only) or 64
   // epilogue
   const float* bias;         // [cout_total] (GEMM n order) or nullptr; OUT_FOLD9: [3]
+  const float* scale;        // optional [cout_total]: out = act(acc * scale + bias) (eval-mode BatchNorm folded into the
+                             // epilogue: scale = gamma / sqrt(var + eps), bias = beta + (conv bias - mean) * scale)
   int act;
   float slope;
   const void* residual;      // bf16, same layout as out (OUT_NHWC only), added after activation

@@ -286,15 +286,16 @@ int launch_bn_finalize(const double* sums, double count, const float* gamma, con
 }
 
 __global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
-                                      float* scale, float* shift) {
+                                      const float* conv_bias, float* scale, float* shift) {
   const int c = threadIdx.x;
   const float sc = gamma[c] * rsqrtf(rv[c] + eps);
   scale[c] = sc;
-  shift[c] = beta[c] - rm[c] * sc;
+  // conv_bias != null: the shift absorbs the producing conv's bias, bn(conv + b) = conv * sc + (beta + (b - mean) * sc)
+  shift[c] = beta[c] + ((conv_bias != nullptr ? conv_bias[c] : 0.f) - rm[c]) * sc;
 }
 int launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
-                          float eps, float* scale, float* shift, cudaStream_t st) {
-  bn_eval_coeffs_kernel<<<1, 64, 0, st>>>(gamma, beta, running_mean, running_var, eps, scale, shift);
+                          float eps, float* scale, float* shift, cudaStream_t st, const float* conv_bias) {
+  bn_eval_coeffs_kernel<<<1, 64, 0, st>>>(gamma, beta, running_mean, running_var, eps, conv_bias, scale, shift);
   SRG_LAUNCH_CHECK("bn_eval_coeffs");
   return 0;
 }

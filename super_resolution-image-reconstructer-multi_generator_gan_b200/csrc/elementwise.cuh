@@ -48,8 +48,11 @@ int launch_bn_finalize(const double* sums, double count, const float* gamma, con
                        float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                        float* save_mean, float* save_inv, cudaStream_t st);
 // eval mode: scale/shift from running statistics
+// conv_bias (optional): fold the producing conv's bias into the shift, for the fused epilogue form
+// out = act(acc * scale + shift) of ConvGemmArgs::scale
 int launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
-                          const float* running_var, float eps, float* scale, float* shift, cudaStream_t st);
+                          const float* running_var, float eps, float* scale, float* shift, cudaStream_t st,
+                          const float* conv_bias = nullptr);
 // out = act(scale*y + shift) (+ skip);  relu: 0/1
 int launch_bn_apply(const void* y, const float* scale, const float* shift, const void* skip, int relu, void* out,
                     int64_t pixels, cudaStream_t st);

@@ -554,12 +554,13 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
   e->launches += 2;
 
   int stats_rows = 0;
-  auto conv3x3 = [&](const void* in, int64_t w_off, const float* bias, const void* residual, void* out, bool stats) -> int {
+  auto conv3x3 = [&](const void* in, int64_t w_off, const float* bias, const void* residual, void* out, bool stats,
+                     const float* scale = nullptr, int act = ACT_NONE) -> int {
     ConvGemmArgs a; memset(&a, 0, sizeof(a));
     a.N = N; a.H = H; a.W = W; set_taps_3x3(a);
     a.n_views = 1; a.views[0] = plain_view(in, H, W); a.in_H = H; a.in_W = W;
     a.weights = packed + w_off; a.cout_total = 64; a.block_n = 64;
-    a.bias = bias; a.act = ACT_NONE; a.residual = residual; a.out = out; a.out_mode = OUT_NHWC;
+    a.bias = bias; a.scale = scale; a.act = act; a.residual = residual; a.out = out; a.out_mode = OUT_NHWC;
     if (stats) { a.stats = reinterpret_cast<float*>(ws + L.partials); stats_rows = conv_gemm_grid(a); }
     e->launches += 1;
     ProfScope ps(e, st);
@@ -576,8 +577,10 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
     float* rm = e->bn_buffers + boff(*e, nm);
     float* rv = rm + 64;
     if (!training) {
+      // eval: the coefficients are known before the conv runs, so BatchNorm (+ReLU / +skip) is folded into the conv
+      // epilogue (out = act(acc * scale + shift') + skip); `y` carries the conv bias to absorb into the shift
       e->launches += 1;
-      return launch_bn_eval_coeffs(gamma, beta, rm, rv, kBnEps, coef, coef + 64, st);
+      return launch_bn_eval_coeffs(gamma, beta, rm, rv, kBnEps, coef, coef + 64, st, reinterpret_cast<const float*>(y));
     }
     float* partials = reinterpret_cast<float*>(ws + L.partials);
     double* sums = reinterpret_cast<double*>(ws + L.sums);
@@ -603,6 +606,17 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
   for (int b = 0; b < e->n_res; ++b) {
     const float* coef1 = reinterpret_cast<const float*>(ws + L.bncoef) + size_t(2 * b) * 256;
     const float* coef2 = coef1 + 256;
+    if (!training) {
+      // eval mode: 2 conv launches per block, BatchNorm folded into their epilogues (no y1 / y2 round trip through HBM)
+      snprintf(nm, sizeof(nm), "residual_blocks.%d.conv1.bias", b);
+      RC(bn_coeffs(b, 0, e->master + poff(*e, nm)));
+      RC(conv3x3(x, po.rb_f[0][b], coef1 + 64, nullptr, ws + L.z1[b], false, coef1, ACT_RELU));
+      snprintf(nm, sizeof(nm), "residual_blocks.%d.conv2.bias", b);
+      RC(bn_coeffs(b, 1, e->master + poff(*e, nm)));
+      RC(conv3x3(ws + L.z1[b], po.rb_f[1][b], coef2 + 64, x, ws + L.out[b], false, coef2, ACT_NONE));
+      x = ws + L.out[b];
+      continue;
+    }
     snprintf(nm, sizeof(nm), "residual_blocks.%d.conv1.bias", b);
     RC(conv3x3(x, po.rb_f[0][b], e->master + poff(*e, nm), nullptr, ws + L.y1[b], training != 0));
     RC(bn_coeffs(b, 0, ws + L.y1[b]));
