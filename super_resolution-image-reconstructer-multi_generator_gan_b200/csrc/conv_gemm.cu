@@ -1232,7 +1232,7 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   // measured 11.27 -> 11.14 ms per cfg2 step; the shallower pipeline (3 / 2 stages) costs nothing (profiles/r01_notes.md).
   static int reserve_kb = -1;
   if (reserve_kb < 0) { const char* ev = getenv("SRG_IL_SMEM_RESERVE_KB"); reserve_kb = ev ? atoi(ev) : 44; }
-  int stages = int((227 * 1024 - reserve_kb * 1024 - 1024 - fixed_bytes) / stage_bytes);
+  int stages = int((227 * 1024 - (a.exclusive ? 0 : reserve_kb) * 1024 - 1024 - fixed_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.n_stages = stages;

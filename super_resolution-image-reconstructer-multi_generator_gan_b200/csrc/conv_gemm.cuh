@@ -58,6 +58,8 @@ struct ConvGemmArgs {
   const void* mask_src;      // bf16, same layout as out: out = (mask_src > 0) ? out : 0  (ReLU backward)
   void* out;
   int out_mode;
+  int exclusive;             // 1: nothing else runs beside this launch (inference): conv3_il takes all shared memory for its
+                             // pipeline instead of leaving 44 KB to co-resident CTAs of other graph branches
   int variant;               // 0: pick the kernel automatically (row-interleaved conv3_il for plain 3x3 / 64-channel launches
                              // unless SRG_CONV_IL=0), 1: force the generic strip kernel, 2: conv3_il with one 8-pixel half strip
                              // per column shift, 3: conv3_il with one 10-pixel half strip for all three shifts (default form)

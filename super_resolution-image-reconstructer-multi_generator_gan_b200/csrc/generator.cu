@@ -561,6 +561,7 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
     a.n_views = 1; a.views[0] = plain_view(in, H, W); a.in_H = H; a.in_W = W;
     a.weights = packed + w_off; a.cout_total = 64; a.block_n = 64;
     a.bias = bias; a.scale = scale; a.act = act; a.residual = residual; a.out = out; a.out_mode = OUT_NHWC;
+    a.exclusive = training ? 0 : 1;
     if (stats) { a.stats = reinterpret_cast<float*>(ws + L.partials); stats_rows = conv_gemm_grid(a); }
     e->launches += 1;
     ProfScope ps(e, st);
@@ -639,6 +640,7 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
     a.n_views = 1; a.views[0] = plain_view(in, Hj, Wj); a.in_H = Hj; a.in_W = Wj;
     a.weights = packed + po.up_f[j]; a.cout_total = 256; a.block_n = 64;
     a.bias = pbias + po.up_bias[j]; a.act = ACT_RELU; a.out = ws + L.up[j]; a.out_mode = OUT_PIXEL_SHUFFLE;
+    a.exclusive = training ? 0 : 1;
     RC(launch_conv_gemm(a, st));
     e->launches += 1;
     in = ws + L.up[j];
