@@ -537,9 +537,63 @@ __global__ void __launch_bounds__(256) unfold9_kernel(const float* __restrict__ 
     }
   }
 }
+// Same result for W % 128 == 0 (every training / inference size): one block = 128 consecutive pixels of one image row.  The
+// two source rows x three planes (+4 halo pixels each side) are read ONCE into shared memory with coalesced loads, every
+// thread assembles its pixel's 54 values from there, and the 16 KB of output go out as fully coalesced 16-byte vectors
+// (the per-thread form issues 54 global loads per pixel and writes 128-byte rows with a 128-byte lane stride).
+__global__ void __launch_bounds__(128) unfold9_tile_kernel(const float* __restrict__ src, int N, int H, int W, float scale,
+                                                           uint4* __restrict__ dst) {
+  __shared__ float tile[6][136];             // [dr * 3 + c][4 + 128 + 4]
+  __shared__ uint4 stage[128 * 8];
+  const int segs = W / 128;
+  const int64_t total = int64_t(N) * (H + 1) * segs;
+  const int64_t plane = int64_t(H) * W;
+  const int tp = threadIdx.x;
+  for (int64_t blk = blockIdx.x; blk < total; blk += gridDim.x) {
+    const int seg = int(blk % segs);
+    const int64_t t = blk / segs;
+    const int hp = int(t % (H + 1));
+    const int n = int(t / (H + 1));
+    const int w0 = seg * 128;
+    for (int i = tp; i < 6 * 136; i += 128) {
+      const int r = i / 136, x = i - r * 136;
+      const int dr = r / 3, c = r - dr * 3;
+      const int hh = hp - 1 + dr, ww = w0 + x - 4;
+      tile[r][x] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(src + (int64_t(n) * 3 + c) * plane + int64_t(hh) * W + ww) * scale : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ch = 8 * g + e;                        // ch = dr * 27 + sft * 3 + c
+        f[e] = ch < 54 ? tile[(ch / 27) * 3 + (ch % 27) % 3][tp + (ch % 27) / 3] : 0.f;
+      }
+      uint4 v;
+      v.x = bpack(f[0], f[1]); v.y = bpack(f[2], f[3]); v.z = bpack(f[4], f[5]); v.w = bpack(f[6], f[7]);
+      stage[tp * 8 + (g ^ (tp & 7))] = v;               // XOR swizzle: the 8 lanes of a quarter-warp hit 8 different columns
+    }
+    __syncthreads();
+    uint4* o = dst + ((int64_t(n) * (H + 1) + hp) * W + w0) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int l = k * 128 + tp;                       // linear 16-byte index inside the block's 16 KB
+      const int pp = l >> 3, g = l & 7;
+      o[l] = stage[pp * 8 + (g ^ (pp & 7))];
+    }
+    __syncthreads();
+  }
+}
 int launch_unfold9(const float* src, int N, int H, int W, float scale, void* dst, cudaStream_t st) {
   const int64_t total = int64_t(N) * (H + 1) * W;
-  unfold9_kernel<<<ew_blocks(total), 256, 0, st>>>(src, N, H, W, scale, reinterpret_cast<uint4*>(dst));
+  if (W % 128 == 0) {
+    int64_t blocks = int64_t(N) * (H + 1) * (W / 128);
+    if (blocks > int64_t(sm_budget()) * 16) blocks = int64_t(sm_budget()) * 16;
+    unfold9_tile_kernel<<<int(blocks), 128, 0, st>>>(src, N, H, W, scale, reinterpret_cast<uint4*>(dst));
+  } else {
+    unfold9_kernel<<<ew_blocks(total), 256, 0, st>>>(src, N, H, W, scale, reinterpret_cast<uint4*>(dst));
+  }
   SRG_LAUNCH_CHECK("unfold9");
   return 0;
 }
