@@ -80,6 +80,11 @@ long long srg_total_launches(void);                             /* kernels enque
  * 8-pixel strip per column shift, 3 = conv3_il with one 10-pixel strip.  Returns the previous value.  Affects kernels
  * enqueued afterwards (a captured CUDA graph keeps what it was captured with). */
 int srg_set_conv_variant(int variant);
+/* host-only: the work split of the batched trunk weight-gradient kernel for `layers` same-shape [N,H,W,64] layers
+ * (no device work, usable without a GPU): CTA c owns flattened (layer, tile) indices [c * per_cta, (c + 1) * per_cta),
+ * layer l = index / tiles_per_layer; its partial set for layer l goes to slot c - (l * tiles_per_layer) / per_cta, and
+ * slot < max_slots.  Returns 0. */
+int srg_wgrad_batched_plan(int N, int H, int W, int layers, int* tiles_per_layer, int* grid, int* per_cta, int* max_slots);
 /* CUDA-event timing of the dominant kernel class (the 3x3 64->64 forward / data-gradient conv_gemm launches, 66 per
  * generator fwd+bwd): enable, run steps, then read the summed device time (ms) and launch count since the last read
  * (read synchronises on the recorded events and resets the counters). */

@@ -91,6 +91,8 @@ EXPORTS = {
     "srg_generator_set_keep_grads": (c_int, [c_void_p, c_int]),
     "srg_total_launches": (c_longlong, []),
     "srg_set_conv_variant": (c_int, [c_int]),
+    "srg_wgrad_batched_plan": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                       POINTER(c_int)]),
     "srg_generator_profile_enable": (c_int, [c_void_p, c_int]),
     "srg_generator_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
     "srg_generator_set_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),

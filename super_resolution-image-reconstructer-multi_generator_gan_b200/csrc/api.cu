@@ -140,6 +140,18 @@ int srg_generator_tensor_info(const srg_generator_t* g, int i, char* name, int n
 long long srg_generator_launch_count(const srg_generator_t* g) { return G(g)->launches; }
 long long srg_total_launches(void) { return total_launches(); }
 int srg_set_conv_variant(int variant) { return set_conv_variant(variant); }
+int srg_wgrad_batched_plan(int N, int H, int W, int layers, int* tiles_per_layer, int* grid, int* per_cta, int* max_slots) {
+  WgradBatchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = N; a.H = H; a.W = W; a.n_layers = layers;
+  int t = 0, g = 0, p = 0, m = 0;
+  wgrad3_batched_plan(a, &t, &g, &p, &m);
+  if (tiles_per_layer) *tiles_per_layer = t;
+  if (grid) *grid = g;
+  if (per_cta) *per_cta = p;
+  if (max_slots) *max_slots = m;
+  return 0;
+}
 int srg_generator_set_keep_grads(srg_generator_t* g, int keep) { return generator_set_keep_grads(G(g), keep); }
 int srg_generator_profile_enable(srg_generator_t* g, int on) { return generator_profile_enable(G(g), on); }
 int srg_generator_profile_read(srg_generator_t* g, double* ms_sum, long long* count) {

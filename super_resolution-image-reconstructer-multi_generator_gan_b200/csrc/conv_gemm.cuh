@@ -111,6 +111,8 @@ struct WgradBatchArgs {
   float* grads;
   const long long* out_off;  // device, n_layers element offsets into grads
 };
+// work split: tiles per layer, CTAs, flattened (layer, tile) indices per CTA, partial-set slots per layer (host arithmetic)
+void wgrad3_batched_plan(const WgradBatchArgs& a, int* tiles_per_layer, int* grid, int* per_cta, int* max_slots);
 size_t wgrad3_batched_partials_floats(const WgradBatchArgs& a);
 int launch_wgrad3x3_batched(const WgradBatchArgs& a, cudaStream_t stream);
 int launch_wgrad_reduce(const float* partials, const int* idx, float* out, int n_out, int splits, size_t split_stride,

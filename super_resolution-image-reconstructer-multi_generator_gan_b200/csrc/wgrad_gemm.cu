@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const float4*
   if (o.w >= 0) out[o.w] = t.w;
 }
 
-static void wgrad3_batched_plan(const WgradBatchArgs& a, int* tiles_per_layer, int* grid, int* per_cta, int* max_slots) {
+void wgrad3_batched_plan(const WgradBatchArgs& a, int* tiles_per_layer, int* grid, int* per_cta, int* max_slots) {
   const int sms = sm_budget();
   const int T = a.N * ((a.H + 15) / 16) * ((a.W + 7) / 8);
   const long long total = (long long)T * a.n_layers;

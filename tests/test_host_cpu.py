@@ -127,3 +127,33 @@ def test_reference_checkpoint_interop(tmp_path):
     for a, b in zip(d.state_dict().values(), d2.state_dict().values()):
         assert torch.equal(a, b)
     assert S.resume_learning_rates(1e-4, 5e-5) == (2e-5, 1e-5)
+
+
+def test_batched_weight_gradient_plan_covers_every_layer_tile_once():
+    """Host arithmetic behind wgrad3_batched_kernel / wgrad_reduce_batched_kernel (srg_wgrad_batched_plan, no device work):
+    the contiguous per-CTA ranges cover every (layer, tile) exactly once, every (layer, slot) partial set has exactly
+    one writer, slots stay below max_slots, and the slots the reduce kernel sums for a layer (first .. last CTA touching
+    it) are exactly the slots that get written."""
+    L = S.lib()
+    for (n, h, w, layers) in [(16, 96, 96, 33), (2, 40, 20, 3), (1, 9, 5, 1), (4, 96, 48, 5), (32, 128, 128, 33), (3, 33, 17, 7),
+                              (1, 16, 8, 33)]:
+        t, g, per, ms = (ctypes.c_int() for _ in range(4))
+        assert L.srg_wgrad_batched_plan(n, h, w, layers, ctypes.byref(t), ctypes.byref(g), ctypes.byref(per), ctypes.byref(ms)) == 0
+        T, G, P, M = t.value, g.value, per.value, ms.value
+        assert T == n * ((h + 15) // 16) * ((w + 7) // 8)
+        total = T * layers
+        assert G >= 1 and (G - 1) * P < total <= G * P              # no empty CTA, everything covered
+        writers = {}
+        covered = 0
+        for c in range(G):
+            lo, hi = c * P, min((c + 1) * P, total)
+            covered += hi - lo
+            for layer in range(lo // T, (hi - 1) // T + 1):
+                slot = c - (layer * T) // P
+                assert 0 <= slot < M, (n, h, w, layers, c, layer, slot, M)
+                assert (layer, slot) not in writers
+                writers[(layer, slot)] = c
+        assert covered == total
+        for layer in range(layers):
+            c_first, c_last = (layer * T) // P, ((layer + 1) * T - 1) // P
+            assert {s_ for (l_, s_) in writers if l_ == layer} == set(range(c_last - c_first + 1)), (n, h, w, layers, layer)
