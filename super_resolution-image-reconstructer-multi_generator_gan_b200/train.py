@@ -105,7 +105,12 @@ class DevicePrefetcher:
             self.ready[slot].record(self.stream)
 
     def __iter__(self):
-        it = iter(self.loader)
+        return self.iterate(self.loader)
+
+    def iterate(self, loader):
+        """Iterate another loader of same-shaped batches through the SAME staging slots / stream / events (an epoch loop
+        constructs the prefetcher once: no device allocation or stream creation per epoch)."""
+        it = iter(loader)
         i = 0
         try:
             self._stage(0, next(it))

@@ -331,6 +331,11 @@ def test_device_prefetcher_yields_every_batch_in_order(S):
             torch.cuda._sleep(2_000_000)                       # keep the consumer busy so that refills really overlap
             seen.append((float(hr_d.sum()) / hr_d.numel(), float(lr_d.sum()) / lr_d.numel()))
         assert seen == [(float(i), float(-i)) for i in range(n)], seen
+    pf = S.DevicePrefetcher(None, dev)                          # one prefetcher, several epochs through the same staging slots
+    for epoch in range(3):
+        host = [(torch.full((1, 3, 4, 4), float(10 * epoch + i)).pin_memory(),) for i in range(3)]
+        got = [float(t.mean()) for (t,) in pf.iterate(host)]
+        assert got == [float(10 * epoch + i) for i in range(3)], (epoch, got)
 
 
 def test_errors_are_python_exceptions(S):
