@@ -84,6 +84,10 @@ int srg_set_conv_variant(int variant);
  * (no device work, usable without a GPU): CTA c owns flattened (layer, tile) indices [c * per_cta, (c + 1) * per_cta),
  * layer l = index / tiles_per_layer; its partial set for layer l goes to slot c - (l * tiles_per_layer) / per_cta, and
  * slot < max_slots.  Returns 0. */
+/* host-only: the conv9_rows schedule (conv3, 9x9 / 3 output channels) for input row ri = 0..15 of a tile: the output rows
+ * (TMEM blocks) jlo..jhi it feeds, the first filter slot (slot 8 - kh of the resident [kh8 ; ... ; kh0] stack, kh = ri - j)
+ * and whether block jhi is touched for the first time.  The kernel evaluates the same inline function. */
+int srg_conv9_rows_window(int ri, int* jlo, int* jhi, int* slot_lo, int* fresh);
 int srg_wgrad_batched_plan(int N, int H, int W, int layers, int* tiles_per_layer, int* grid, int* per_cta, int* max_slots);
 /* CUDA-event timing of the dominant kernel class (the 3x3 64->64 forward / data-gradient conv_gemm launches, 66 per
  * generator fwd+bwd): enable, run steps, then read the summed device time (ms) and launch count since the last read

@@ -91,6 +91,7 @@ EXPORTS = {
     "srg_generator_set_keep_grads": (c_int, [c_void_p, c_int]),
     "srg_total_launches": (c_longlong, []),
     "srg_set_conv_variant": (c_int, [c_int]),
+    "srg_conv9_rows_window": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "srg_wgrad_batched_plan": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                        POINTER(c_int)]),
     "srg_generator_profile_enable": (c_int, [c_void_p, c_int]),

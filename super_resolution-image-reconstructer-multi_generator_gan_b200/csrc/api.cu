@@ -140,6 +140,15 @@ int srg_generator_tensor_info(const srg_generator_t* g, int i, char* name, int n
 long long srg_generator_launch_count(const srg_generator_t* g) { return G(g)->launches; }
 long long srg_total_launches(void) { return total_launches(); }
 int srg_set_conv_variant(int variant) { return set_conv_variant(variant); }
+int srg_conv9_rows_window(int ri, int* jlo, int* jhi, int* slot_lo, int* fresh) {
+  if (ri < 0 || ri > 15) { set_error("conv9_rows_window: ri must be 0..15"); return -1; }
+  const C9Window w = c9_window(ri);
+  if (jlo) *jlo = w.jlo;
+  if (jhi) *jhi = w.jhi;
+  if (slot_lo) *slot_lo = w.slot_lo;
+  if (fresh) *fresh = w.fresh;
+  return 0;
+}
 int srg_wgrad_batched_plan(int N, int H, int W, int layers, int* tiles_per_layer, int* grid, int* per_cta, int* max_slots) {
   WgradBatchArgs a;
   memset(&a, 0, sizeof(a));

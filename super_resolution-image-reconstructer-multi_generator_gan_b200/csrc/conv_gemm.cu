@@ -984,11 +984,11 @@ __global__ void __launch_bounds__(kC9Threads, 1) conv9_rows_kernel(const __grid_
       for (int ri = 0; ri < 16; ++ri) {          // input row h0 + ri - 4
         { long long t0_ = clock64(); mbar_wait(&full[stage], phase); prof_acc[2] += clock64() - t0_; }
         tc_fence_after();
-        const int jlo = ri > 8 ? ri - 8 : 0;     // output rows (blocks) this input row reaches: kh = ri - j in [0, 8]
-        const int jhi = ri < 7 ? ri : 7;
-        const bool fresh = ri <= 7;              // block jhi = ri sees its first tap (kh = 0) here
+        const C9Window win = c9_window(ri);      // output rows (blocks) this input row reaches: kh = ri - j in [0, 8]
+        const int jlo = win.jlo, jhi = win.jhi;
+        const bool fresh = win.fresh != 0;       // block jhi = ri sees its first tap (kh = 0) here
         const uint64_t adesc = desc_hi | uint64_t(stage0_lo + uint32_t(stage) * (kC9Row >> 4));
-        const uint64_t b_all = desc_hi | uint64_t(w_lo + uint32_t(8 - ri + jlo) * (4096 >> 4));   // slot of block jlo
+        const uint64_t b_all = desc_hi | uint64_t(w_lo + uint32_t(win.slot_lo) * (4096 >> 4));     // slot of block jlo
         const uint64_t b_kh0 = desc_hi | uint64_t(w_lo + 8u * (4096 >> 4));
         if (elect_one()) {
           const uint32_t n_all = uint32_t(jhi - jlo + 1) * 32u;

@@ -118,6 +118,20 @@ int launch_wgrad3x3_batched(const WgradBatchArgs& a, cudaStream_t stream);
 int launch_wgrad_reduce(const float* partials, const int* idx, float* out, int n_out, int splits, size_t split_stride,
                         int accumulate_into, cudaStream_t stream);
 
+// conv9_rows schedule (shared by the kernel and by the host-side test entry srg_conv9_rows_window): input row `ri` of a tile
+// (image row h0 + ri - 4, ri = 0..15) reaches the output rows (TMEM blocks) jlo..jhi with row tap kh = ri - j in [0, 8];
+// block j reads filter slot 8 - kh of the resident [kh8 ; ... ; kh0] stack, so the blocks' slots are consecutive from
+// slot_lo; `fresh`: block jhi sees its first tap (kh = 0) on this row and must overwrite instead of accumulate.
+struct C9Window { int jlo, jhi, slot_lo, fresh; };
+__host__ __device__ inline C9Window c9_window(int ri) {
+  C9Window w;
+  w.jlo = ri > 8 ? ri - 8 : 0;
+  w.jhi = ri < 7 ? ri : 7;
+  w.slot_lo = 8 - ri + w.jlo;
+  w.fresh = ri <= 7 ? 1 : 0;
+  return w;
+}
+
 // process-wide override of ConvGemmArgs::variant for launches that leave it 0 (parity tests, A/B runs); returns the old value
 int set_conv_variant(int variant);
 

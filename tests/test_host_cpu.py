@@ -157,3 +157,30 @@ def test_batched_weight_gradient_plan_covers_every_layer_tile_once():
         for layer in range(layers):
             c_first, c_last = (layer * T) // P, ((layer + 1) * T - 1) // P
             assert {s_ for (l_, s_) in writers if l_ == layer} == set(range(c_last - c_first + 1)), (n, h, w, layers, layer)
+
+
+def test_conv9_rows_schedule_applies_every_row_tap_once_per_output_row():
+    """The conv9_rows schedule the kernel evaluates (srg_conv9_rows_window is the same inline function): over the 16
+    input rows of a tile every output row (block) 0..7 receives each of the 9 row taps exactly once, from the input row
+    the convolution prescribes (h_out + kh - 4), through the filter slot that holds tap kh; a block's first touch is
+    the `fresh` one and it is the kh = 0 tap; the blocks of one MMA are contiguous and at most 256 columns wide."""
+    L = S.lib()
+    seen = {j: [] for j in range(8)}
+    first = {}
+    for ri in range(16):
+        jlo, jhi, slot, fresh = (ctypes.c_int() for _ in range(4))
+        assert L.srg_conv9_rows_window(ri, ctypes.byref(jlo), ctypes.byref(jhi), ctypes.byref(slot), ctypes.byref(fresh)) == 0
+        jlo, jhi, slot, fresh = jlo.value, jhi.value, slot.value, fresh.value
+        assert 0 <= jlo <= jhi <= 7 and (jhi - jlo + 1) * 32 <= 256
+        for j in range(jlo, jhi + 1):
+            s_j = slot + (j - jlo)                      # consecutive slots for consecutive blocks
+            kh = 8 - s_j                                # slot s holds tap kh = 8 - s
+            assert 0 <= kh <= 8
+            assert (ri - 4) == j + kh - 4               # input row h0 + ri - 4 == output row h0 + j shifted by tap kh
+            seen[j].append(kh)
+            if j not in first:
+                first[j] = (ri, kh, fresh and j == jhi)
+    for j in range(8):
+        assert sorted(seen[j]) == list(range(9)), (j, seen[j])
+        assert first[j][1] == 0 and first[j][2], (j, first[j])       # first touch = tap kh 0, flagged fresh
+    assert L.srg_conv9_rows_window(16, None, None, None, None) != 0
