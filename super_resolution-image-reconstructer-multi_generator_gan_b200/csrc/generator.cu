@@ -800,6 +800,13 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     if (x1 != L.out1 + size_t(2 * b) * 2 * L.slot || L.z1[b] != L.out1 + size_t(2 * b + 1) * 2 * L.slot) batched = false;
   }
   if (batched && L.out[e->n_res - 1] != L.out1 + size_t(2 * e->n_res) * 2 * L.slot) batched = false;
+  if (batched) {
+    // the partial-set workspace was sized for 148 SMs at create time: a device that splits the work differently keeps
+    // the per-layer launches instead of overrunning it
+    WgradBatchArgs probe; memset(&probe, 0, sizeof(probe));
+    probe.N = N; probe.H = H; probe.W = W; probe.n_layers = 2 * e->n_res + 1;
+    if (wgrad3_batched_partials_floats(probe) > L.wgb_floats) batched = false;
+  }
   if (!batched) RC(wgrad(plain_view(x_last, H, W), H, W, false, H, W, d_trunk, 1, false, e->d_wg_idx_c3x3, "conv2.weight"));
   const bool keep = e->keep_grads;
   void* dout = keep ? ws + L.kd_last : ws + L.g[0];
