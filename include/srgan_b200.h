@@ -94,6 +94,29 @@ int srg_wgrad_batched_plan(int N, int H, int W, int layers, int* tiles_per_layer
  * (read synchronises on the recorded events and resets the counters). */
 int srg_generator_profile_enable(srg_generator_t* g, int on);
 int srg_generator_profile_read(srg_generator_t* g, double* ms_sum, long long* count);
+/* Fused trunk kernel (csrc/trunk_fused.cu): the 2*n_res+1 3x3 / 64->64 convolutions of one direction of the residual trunk
+ * (src/models.py:10-25 ResidualBlock x 16, :66 conv2) with their training-mode BatchNorm steps in ONE cooperative launch.
+ * srg_set_trunk_fused(0) makes later forward / backward calls use one launch per layer again (A/B and parity aid;
+ * SRG_TRUNK_FUSED=0 does the same); returns the previous value.  srg_generator_trunk_layers: trunk conv layers covered by
+ * the engine's last profiled launch (1 = per-layer launches).  srg_generator_trunk_error: non-zero if a bounded in-kernel
+ * wait of the fused kernel ever gave up (bit 0 cross-CTA flag / barrier, bit 1 mbarrier, bit 2 peer GPU); synchronises. */
+int srg_set_trunk_fused(int on);
+/* Split execution of one generator pass, for the multi-generator step (readme.md:2-10: K generators trained on the same
+ * batch): phases is a bit mask, 1 = PRE (forward: conv1 + LeakyReLU, src/models.py:81; backward: conv3 and the upsample
+ * stages), 2 = TRUNK (the 16 residual blocks + conv2, src/models.py:82-84, forward or backward), 4 = POST (forward:
+ * upsample + conv3, src/models.py:85-86; backward: conv1 gradients and the batched trunk weight gradients); 7 = the whole
+ * pass (= srg_generator_forward / srg_generator_backward).  srg_generators_trunk runs the TRUNK phase of n <= 4 engines of
+ * identical geometry as ONE launch that interleaves their layers, so the BatchNorm barrier latency of one generator is
+ * hidden behind the tensor work of the others.  Engines must be bound for training; split execution is only available
+ * where the fused trunk kernel applies (otherwise these return an error and the caller uses the whole-pass entry points). */
+int srg_generator_forward_phases(srg_generator_t* g, const float* lr_nchw, float* sr_nchw, int training, int update_running,
+                                 int phases, void* stream);
+int srg_generator_backward_phases(srg_generator_t* g, const float* dsr_nchw, int phases, void* stream);
+int srg_generators_trunk(srg_generator_t* const* gs, int n, int backward, int update_running, void* stream);
+/* developer aid (SRG_TRUNK_PROF=1): cycle counters [cta][role: producer, MMA issuer, epilogue][6] of the last fused launch */
+int srg_debug_trunk_prof(long long* host, int n);
+int srg_generator_trunk_layers(const srg_generator_t* g);
+int srg_generator_trunk_error(srg_generator_t* g);
 
 /* SyncBatchNorm hook: called between the local per-channel sums and the BatchNorm finalize in forward and
  * backward with a device buffer of `n` doubles to be summed in place across `world` ranks on `stream`. */

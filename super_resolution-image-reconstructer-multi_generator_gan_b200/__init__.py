@@ -13,12 +13,12 @@ from .loss import ReconstructionLoss, bce_loss, l1_loss, mse_loss, tanh_mean
 from .optim import Adam
 from .policy import (GAN, PIXEL, MultiGeneratorPolicy, PolicyConfig, decide, gan_probability, interpolate_models,
                      shuffle_lists_in_same_order)
-from .train import (DevicePrefetcher, GraphedDiscriminatorStep, GraphedGeneratorStep, GraphedMultiGeneratorStep, MultiGeneratorGAN, train_discriminator, train_discriminator_async, train_generator,
+from .train import (DevicePrefetcher, GraphedDiscriminatorStep, GraphedGeneratorStep, GraphedMultiGeneratorStep, MultiGeneratorGAN, joint_pixel_generator_steps, train_discriminator, train_discriminator_async, train_generator,
                     train_generator_async, train_one_epoch, setup_training)
 from . import parallel
 from .evaluation import (ImageEnhancer, calculate_psnr, load_reference_checkpoint, resume_learning_rates,
                          save_reference_checkpoint, strip_module_prefix)
 
-__all__ = ["SRResNet", "ResidualBlock", "Discriminator", "ReconstructionLoss", "tanh_mean", "Adam", "train_generator",
+__all__ = ["joint_pixel_generator_steps", "SRResNet", "ResidualBlock", "Discriminator", "ReconstructionLoss", "tanh_mean", "Adam", "train_generator",
            "train_discriminator", "train_one_epoch", "DevicePrefetcher", "MultiGeneratorGAN", "GraphedGeneratorStep", "MultiGeneratorPolicy", "PolicyConfig",
            "build", "lib", "parallel"]

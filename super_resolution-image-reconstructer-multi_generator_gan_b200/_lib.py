@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "libsrgan_b200.so")
-SOURCES = ["conv_gemm.cu", "wgrad_gemm.cu", "elementwise.cu", "peer_sync.cu", "generator.cu", "discriminator.cu", "api.cu"]
+SOURCES = ["conv_gemm.cu", "trunk_fused.cu", "wgrad_gemm.cu", "elementwise.cu", "peer_sync.cu", "generator.cu", "discriminator.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
@@ -96,6 +96,13 @@ EXPORTS = {
                                        POINTER(c_int)]),
     "srg_generator_profile_enable": (c_int, [c_void_p, c_int]),
     "srg_generator_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
+    "srg_set_trunk_fused": (c_int, [c_int]),
+    "srg_generator_forward_phases": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "srg_generator_backward_phases": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "srg_generators_trunk": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p]),
+    "srg_debug_trunk_prof": (c_int, [POINTER(c_longlong), c_int]),
+    "srg_generator_trunk_layers": (c_int, [c_void_p]),
+    "srg_generator_trunk_error": (c_int, [c_void_p]),
     "srg_generator_set_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "srg_nccl_unique_id": (c_int, [c_void_p]),
     "srg_nccl_comm_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),

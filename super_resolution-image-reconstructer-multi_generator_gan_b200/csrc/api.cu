@@ -10,6 +10,7 @@
 #include "discriminator.cuh"
 #include "generator.cuh"
 #include "peer_sync.cuh"
+#include "trunk_fused.cuh"
 
 using namespace srg;
 
@@ -166,6 +167,24 @@ int srg_generator_profile_enable(srg_generator_t* g, int on) { return generator_
 int srg_generator_profile_read(srg_generator_t* g, double* ms_sum, long long* count) {
   return generator_profile_read(G(g), ms_sum, count);
 }
+
+int srg_generator_forward_phases(srg_generator_t* g, const float* lr, float* sr, int training, int update_running, int phases,
+                                 void* stream) {
+  return generator_forward_phases(G(g), lr, sr, training, update_running, phases, S(stream));
+}
+int srg_generator_backward_phases(srg_generator_t* g, const float* dsr, int phases, void* stream) {
+  return generator_backward_phases(G(g), dsr, phases, S(stream));
+}
+int srg_generators_trunk(srg_generator_t* const* gs, int n, int backward, int update_running, void* stream) {
+  GeneratorEngine* es[8];
+  if (n < 1 || n > 8) { set_error("srg_generators_trunk: bad engine count"); return -62; }
+  for (int i = 0; i < n; ++i) es[i] = G(gs[i]);
+  return generators_trunk(es, n, backward, update_running, S(stream));
+}
+int srg_set_trunk_fused(int on) { return set_trunk_fused(on); }
+int srg_debug_trunk_prof(long long* host, int n) { return trunk_prof_read(host, n); }
+int srg_generator_trunk_layers(const srg_generator_t* g) { return generator_prof_layers(G(g)); }
+int srg_generator_trunk_error(srg_generator_t* g) { return generator_trunk_error(G(g)); }
 
 int srg_generator_set_allreduce(srg_generator_t* g, srg_allreduce_f64_fn fn, void* ctx, int world) {
   if (world < 1) { set_error("set_allreduce: world < 1"); return -4; }

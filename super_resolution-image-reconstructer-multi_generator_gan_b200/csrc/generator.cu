@@ -13,6 +13,7 @@
 #include "conv_gemm.cuh"
 #include "elementwise.cuh"
 #include "peer_sync.cuh"
+#include "trunk_fused.cuh"
 
 namespace srg {
 
@@ -36,6 +37,7 @@ struct Layout {
   size_t packed, bias, bncoef, bwdcoef, partials, sums, ticket, wg_partials, ps_scratch, loss_scratch;
   size_t dyall = 0, slot = 0;             // per-layer output gradients of the trunk convs: slot l = 2*block + conv, last = conv2
   size_t wgb_partials = 0, wgb_floats = 0;  // partial sets of the batched trunk weight-gradient kernel
+  size_t trunk_sync = 0, trunk_tab = 0;     // trunk_fused: flags / barrier words, the two TrunkLayer tables (fwd | bwd)
   size_t U1, out1, trunk;
   std::vector<size_t> y1, z1, y2, out;   // per residual block (eval: aliases of 4 rotating buffers)
   std::vector<size_t> up;                // per upsample stage
@@ -77,6 +79,8 @@ Layout make_layout(const GeneratorEngine& e, bool training) {
   L.partials = c.take(size_t(kRedBlocksMax) * 128 * 4);
   L.sums = c.take(128 * 8);
   L.ticket = c.take(256);
+  L.trunk_sync = c.take(trunk_sync_bytes(e.N, e.H, e.W));
+  L.trunk_tab = c.take(size_t(2) * (2 * e.n_res + 1) * sizeof(TrunkLayer));
   L.U1 = c.take(size_t(e.N) * (e.H + 1) * e.W * 128);
   L.out1 = c.take(t64(P));
   L.y1.resize(e.n_res); L.z1.resize(e.n_res); L.y2.resize(e.n_res); L.out.resize(e.n_res);
@@ -103,11 +107,8 @@ Layout make_layout(const GeneratorEngine& e, bool training) {
     L.slot = (t64(P) + 1023) & ~size_t(1023);
     L.dyall = c.take(L.slot * size_t(2 * e.n_res + 1));
     L.g[3] = L.dyall + L.slot * size_t(2 * e.n_res);        // d(trunk) = output gradient of conv2
-    L.wgb_floats = wgrad_batched_floats(e);
-    L.wgb_partials = c.take(L.wgb_floats * 4);
-    for (int j = 0; j < e.n_up; ++j) L.dup[j] = c.take(t64(P << (2 * (j + 1))));
-    const int64_t Hs = int64_t(e.H) << e.n_up, Ws = int64_t(e.W) << e.n_up;
-    L.Ud = c.take(size_t(e.N) * (Hs + 1) * Ws * 128);
+    // debug buffers directly behind dyall: g[0..2] | dyall | kd_* form ONE uniformly strided "gradient region" that the
+    // fused trunk kernel addresses by buffer index
     L.kd_last = L.kd_c1 = 0;
     if (e.keep_grads) {
       L.kd_y2.resize(e.n_res); L.kd_p1.resize(e.n_res); L.kd_y1.resize(e.n_res); L.kd_in.resize(e.n_res);
@@ -118,6 +119,11 @@ Layout make_layout(const GeneratorEngine& e, bool training) {
       L.kd_last = c.take(t64(P));
       L.kd_c1 = c.take(t64(P));
     }
+    L.wgb_floats = wgrad_batched_floats(e);
+    L.wgb_partials = c.take(L.wgb_floats * 4);
+    for (int j = 0; j < e.n_up; ++j) L.dup[j] = c.take(t64(P << (2 * (j + 1))));
+    const int64_t Hs = int64_t(e.H) << e.n_up, Ws = int64_t(e.W) << e.n_up;
+    L.Ud = c.take(size_t(e.N) * (Hs + 1) * Ws * 128);
   }
   L.total = c.off;
   return L;
@@ -233,6 +239,11 @@ struct EngineImpl : GeneratorEngine {
   Layout L;
   // host copies of the constant index maps; uploaded at the first bind (create() needs no device)
   std::vector<int> h_pack_idx, h_bias_idx, h_wg_c3x3, h_wg_up, h_wg_conv1, h_wg_conv3;
+  // fused trunk (trunk_fused.cu): set at bind when the workspace layout is uniformly strided and the geometry fits
+  bool trunk_ok = false;
+  int trunk_act_buffers = 0, trunk_grad_buffers = 0;
+  size_t trunk_act_slot = 0;
+  int trunk_dout_idx = 0;       // gradient-region buffer that holds d(out1) of the block chain after the backward kernel
 };
 
 #define RC(x)                  \
@@ -289,6 +300,174 @@ struct ProfScope {
   }
 };
 }  // namespace
+
+// ---- fused trunk: per-layer tables for both directions (see TrunkLayer) and the uniform-stride checks they rely on
+namespace {
+bool build_trunk_tables(EngineImpl& e, std::vector<TrunkLayer>& fwd, std::vector<TrunkLayer>& bwd) {
+  const Layout& L = e.L;
+  const PackOffsets& po = e.po;
+  const int R = e.n_res;
+  if (R < 1 || trunk_grid(e.N, e.H, e.W) == 0) return false;
+  // activation region: out1 | (y1 z1 y2 out) x R | trunk, one slot apart
+  const size_t Sa = L.y1[0] - L.out1;
+  if (Sa != L.slot) return false;
+  for (int b = 0; b < R; ++b) {
+    if (L.y1[b] != L.out1 + size_t(4 * b + 1) * Sa || L.z1[b] != L.out1 + size_t(4 * b + 2) * Sa ||
+        L.y2[b] != L.out1 + size_t(4 * b + 3) * Sa || L.out[b] != L.out1 + size_t(4 * b + 4) * Sa) return false;
+  }
+  if (L.trunk != L.out1 + size_t(4 * R + 1) * Sa) return false;
+  // gradient region: g0 g1 g2 | dyall (2R+1) | [keep: (kd_p1 kd_in) x R, kd_last, kd_c1]
+  if (L.g[1] != L.g[0] + L.slot || L.g[2] != L.g[0] + 2 * L.slot || L.dyall != L.g[0] + 3 * L.slot) return false;
+  const int kd0 = 3 + 2 * R + 1;
+  if (e.keep_grads) {
+    for (int b = 0; b < R; ++b)
+      if (L.kd_p1[b] != L.g[0] + size_t(kd0 + 2 * b) * L.slot || L.kd_in[b] != L.g[0] + size_t(kd0 + 2 * b + 1) * L.slot) return false;
+    if (L.kd_last != L.g[0] + size_t(kd0 + 2 * R) * L.slot) return false;
+  }
+  // packed filters: (fwd, dgrad) pairs of 576 rows each, layer order 2*block + conv, conv2 last
+  const int64_t w0 = po.rb_f[0][0], set = 36864;
+  for (int b = 0; b < R; ++b)
+    for (int k = 0; k < 2; ++k)
+      if (po.rb_f[k][b] != w0 + int64_t(2 * (2 * b + k)) * set || po.rb_d[k][b] != w0 + int64_t(2 * (2 * b + k) + 1) * set) return false;
+  if (po.conv2_f != w0 + int64_t(4 * R) * set || po.conv2_d != w0 + int64_t(4 * R + 1) * set) return false;
+  if (e.param_elems > (int64_t(1) << 30)) return false;
+
+  char nm[96];
+  auto P = [&](const char* fmt, int b, int k) { snprintf(nm, sizeof(nm), fmt, b, k); return int(poff(e, nm)); };
+  auto clear = [](TrunkLayer& t) {
+    memset(&t, 0, sizeof(t));
+    t.st1_idx = t.st2_idx = t.aux1_idx = t.aux2_idx = t.y_idx = t.mask_bn = t.bn = t.bias_off = -1;
+  };
+  fwd.assign(size_t(2 * R + 1), TrunkLayer());
+  for (int l = 0; l < 2 * R; ++l) {
+    const int b = l / 2, k = l % 2;
+    TrunkLayer& t = fwd[size_t(l)];
+    clear(t);
+    t.in_idx = 4 * b + 2 * k; t.st1_idx = 4 * b + 1 + 2 * k; t.st2_idx = 4 * b + 2 + 2 * k;
+    t.aux2_idx = k ? 4 * b : -1; t.bn = l; t.relu = k ? 0 : 1; t.w_row = 2 * l * 576;
+    t.bias_off = P("residual_blocks.%d.conv%d.bias", b, k + 1);
+    t.gamma_off = P("residual_blocks.%d.bn%d.weight", b, k + 1);
+    t.beta_off = P("residual_blocks.%d.bn%d.bias", b, k + 1);
+    snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.running_mean", b, k + 1);
+    t.rm_off = int(boff(e, nm));
+  }
+  {
+    TrunkLayer& t = fwd[size_t(2 * R)];
+    clear(t);
+    t.in_idx = 4 * R; t.st1_idx = 4 * R + 1; t.aux1_idx = 0; t.w_row = 4 * R * 576; t.bias_off = int(poff(e, "conv2.bias"));
+  }
+  const bool keep = e.keep_grads;
+  const int i_last = kd0 + 2 * R;
+  auto i_p1 = [&](int b) { return kd0 + 2 * b; };
+  auto i_in = [&](int b) { return kd0 + 2 * b + 1; };
+  bwd.clear();
+  {
+    TrunkLayer t;
+    clear(t);
+    t.in_idx = 3 + 2 * R; t.st1_idx = keep ? i_last : 0; t.st2_idx = 3 + 2 * (R - 1) + 1;
+    t.y_idx = 4 * (R - 1) + 3; t.bn = 2 * (R - 1) + 1; t.w_row = (4 * R + 1) * 576;
+    t.gamma_off = P("residual_blocks.%d.bn%d.weight", R - 1, 2); t.beta_off = P("residual_blocks.%d.bn%d.bias", R - 1, 2);
+    bwd.push_back(t);
+  }
+  for (int b = R - 1; b >= 0; --b) {
+    TrunkLayer t;
+    clear(t);                                   // conv2 of block b: d(z1) -> ReLU mask -> BatchNorm 1 backward
+    t.in_idx = 3 + 2 * b + 1; t.st1_idx = keep ? i_p1(b) : 1; t.st2_idx = 3 + 2 * b;   // raw masked gradient: scratch g[1]
+    t.y_idx = 4 * b + 1; t.mask_bn = 2 * b; t.bn = 2 * b; t.w_row = (2 * (2 * b + 1) + 1) * 576;
+    t.gamma_off = P("residual_blocks.%d.bn%d.weight", b, 1); t.beta_off = P("residual_blocks.%d.bn%d.bias", b, 1);
+    bwd.push_back(t);
+    clear(t);                                   // conv1 of block b: + skip gradient -> BatchNorm 2 backward of block b-1
+    t.in_idx = 3 + 2 * b;
+    t.aux1_idx = keep ? (b == R - 1 ? i_last : i_in(b + 1)) : 0;
+    t.st1_idx = keep ? i_in(b) : 0;
+    t.w_row = (2 * (2 * b) + 1) * 576;
+    if (b > 0) {
+      t.y_idx = 4 * (b - 1) + 3; t.bn = 2 * (b - 1) + 1; t.st2_idx = 3 + 2 * (b - 1) + 1;
+      t.gamma_off = P("residual_blocks.%d.bn%d.weight", b - 1, 2); t.beta_off = P("residual_blocks.%d.bn%d.bias", b - 1, 2);
+    }
+    bwd.push_back(t);
+  }
+  e.trunk_act_buffers = 4 * R + 2;
+  e.trunk_grad_buffers = kd0 + (keep ? 2 * R + 2 : 0);
+  e.trunk_act_slot = Sa;
+  e.trunk_dout_idx = keep ? i_in(0) : 0;
+  return true;
+}
+
+// the fused trunk applies to training passes on one GPU, or under data parallelism with the peer-memory SyncBatchNorm
+// transport (the NCCL transport keeps the per-layer launches)
+bool use_trunk_fused(const EngineImpl& e) {
+  if (!e.trunk_ok || !trunk_fused_enabled()) return false;
+  if (e.peer != nullptr) return true;
+  return e.allreduce == nullptr && e.world == 1;
+}
+
+void fill_trunk_gen(EngineImpl* e, TrunkGen& t) {
+  const Layout& L = e->L;
+  uint8_t* ws = e->ws;
+  t.act_base = ws + L.out1;
+  t.grad_base = ws + L.g[0];
+  t.weights = reinterpret_cast<const uint16_t*>(ws + L.packed) + e->po.rb_f[0][0];
+  t.master = e->master; t.grads = e->grads; t.bn_buffers = e->bn_buffers;
+  t.bncoef = reinterpret_cast<float*>(ws + L.bncoef);
+  t.gpart = reinterpret_cast<float*>(ws + L.partials);
+  t.sync = reinterpret_cast<unsigned int*>(ws + L.trunk_sync);
+  t.err = reinterpret_cast<unsigned int*>(ws + L.ticket + 128);
+  t.peer = e->peer;
+}
+
+// one launch for the trunks of `n` engines of identical geometry / configuration (n = 1: the nn.Module path)
+int run_trunk_multi(EngineImpl* const* es, int n, int bwd, int update_running, cudaStream_t st) {
+  EngineImpl* e = es[0];
+  const Layout& L = e->L;
+  const int64_t P = int64_t(e->N) * e->H * e->W;
+  TrunkArgs a; memset(&a, 0, sizeof(a));
+  a.bwd = bwd; a.N = e->N; a.H = e->H; a.W = e->W; a.n_layers = 2 * e->n_res + 1;
+  a.layers = reinterpret_cast<const TrunkLayer*>(e->ws + L.trunk_tab) + (bwd ? a.n_layers : 0);
+  a.act_slot = int64_t(e->trunk_act_slot); a.act_buffers = e->trunk_act_buffers;
+  a.grad_slot = int64_t(L.slot); a.grad_buffers = e->trunk_grad_buffers;
+  a.weight_rows = int64_t(4 * e->n_res + 2) * 576;
+  a.count = double(P) * e->world; a.eps = kBnEps; a.momentum = kBnMomentum; a.update_running = update_running;
+  a.param_grad_scale = 1.f / float(e->world);
+  a.n_gen = n;
+  for (int i = 0; i < n; ++i) {
+    EngineImpl* o = es[i];
+    if (!o->trunk_ok || o->N != e->N || o->H != e->H || o->W != e->W || o->n_res != e->n_res || o->keep_grads != e->keep_grads ||
+        o->world != e->world || o->L.slot != L.slot || o->trunk_act_slot != e->trunk_act_slot) {
+      set_error("trunk_fused: the engines of a joint launch must share geometry and configuration");
+      return -65;
+    }
+    fill_trunk_gen(o, a.gen[i]);
+    o->prof_layers = a.n_layers;
+  }
+  e->launches += 1;
+  ProfScope ps(e, st);
+  return launch_trunk(a, st);
+}
+int run_trunk(EngineImpl* e, int bwd, int update_running, cudaStream_t st) { return run_trunk_multi(&e, 1, bwd, update_running, st); }
+}  // namespace
+
+int generators_trunk(GeneratorEngine* const* gs, int n, int bwd, int update_running, cudaStream_t st) {
+  if (n < 1 || n > kTrunkMaxGen) { set_error("generators_trunk: 1..%d engines", kTrunkMaxGen); return -62; }
+  EngineImpl* es[kTrunkMaxGen];
+  for (int i = 0; i < n; ++i) {
+    es[i] = static_cast<EngineImpl*>(gs[i]);
+    if (!es[i]->ws || !es[i]->ws_training || !use_trunk_fused(*es[i]) || (bwd && !es[i]->wgrad_batched)) {
+      set_error("generators_trunk: engine %d is not bound for training on the fused trunk path", i);
+      return -66;
+    }
+  }
+  return run_trunk_multi(es, n, bwd, update_running, st);
+}
+
+int generator_trunk_error(GeneratorEngine* g) {
+  EngineImpl* e = static_cast<EngineImpl*>(g);
+  if (!e->ws) return 0;
+  unsigned int v = 0;
+  if (cudaMemcpy(&v, e->ws + e->L.ticket + 128, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return int(v);
+}
+int generator_prof_layers(const GeneratorEngine* g) { return g->prof_layers; }
 
 int generator_set_keep_grads(GeneratorEngine* g, int keep) {
   EngineImpl* e = static_cast<EngineImpl*>(g);
@@ -480,6 +659,18 @@ int generator_bind(GeneratorEngine* g, float* master, float* grads, float* bn_bu
   e->ws = reinterpret_cast<uint8_t*>(ws); e->ws_bytes = ws_bytes; e->ws_training = training != 0;
   e->L = make_layout(*e, training != 0);
   if (cudaMemset(e->ws + e->L.ticket, 0, 256) != cudaSuccess) { set_error("generator_bind: memset failed"); return -29; }
+  e->trunk_ok = false;
+  if (training) {
+    std::vector<TrunkLayer> tf, tb;
+    if (build_trunk_tables(*e, tf, tb)) {
+      tf.insert(tf.end(), tb.begin(), tb.end());
+      if (cudaMemcpy(e->ws + e->L.trunk_tab, tf.data(), tf.size() * sizeof(TrunkLayer), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("generator_bind: upload of the trunk layer tables failed");
+        return -29;
+      }
+      e->trunk_ok = true;
+    }
+  }
   // named tensors for parity tests
   e->tensors.clear();
   auto reg = [&](const std::string& name, size_t off, int n, int h, int w, int c, int dtype) {
@@ -528,6 +719,11 @@ int generator_pack(GeneratorEngine* g, cudaStream_t st) {
 
 // ------------------------------------------------------------------ forward
 int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int training, int update_running, cudaStream_t st) {
+  return generator_forward_phases(g, lr, sr, training, update_running, kPhaseAll, st);
+}
+
+int generator_forward_phases(GeneratorEngine* g, const float* lr, float* sr, int training, int update_running, int phases,
+                             cudaStream_t st) {
   EngineImpl* e = static_cast<EngineImpl*>(g);
   if (!e->ws) { set_error("generator_forward: not bound"); return -23; }
   if (training && !e->ws_training) { set_error("generator_forward: bound workspace is eval-sized"); return -24; }
@@ -540,7 +736,12 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
   const int64_t P = int64_t(N) * H * W;
   char nm[96];
 
+  if (phases != kPhaseAll && !(training && use_trunk_fused(*e))) {
+    set_error("generator_forward_phases: split execution needs the fused trunk path (training, supported configuration)");
+    return -31;
+  }
   // conv1: 9x9, 3->64, LeakyReLU(0.2)  (src/models.py:56-57,81)
+  if (phases & kPhasePre) {
   RC(launch_unfold9(lr, N, H, W, 1.f, ws + L.U1, st));
   {
     ConvGemmArgs a; memset(&a, 0, sizeof(a));
@@ -552,6 +753,7 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
     RC(launch_conv_gemm(a, st));
   }
   e->launches += 2;
+  }
 
   int stats_rows = 0;
   auto conv3x3 = [&](const void* in, int64_t w_off, const float* bias, const void* residual, void* out, bool stats,
@@ -604,7 +806,10 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
   };
 
   const void* x = ws + L.out1;
-  for (int b = 0; b < e->n_res; ++b) {
+  const bool fused = training && use_trunk_fused(*e);
+  e->prof_layers = 1;
+  if (fused && (phases & kPhaseTrunk)) RC(run_trunk(e, 0, update_running, st));
+  for (int b = 0; b < e->n_res && !fused; ++b) {
     const float* coef1 = reinterpret_cast<const float*>(ws + L.bncoef) + size_t(2 * b) * 256;
     const float* coef2 = coef1 + 256;
     if (!training) {
@@ -630,7 +835,8 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
     x = ws + L.out[b];
   }
   // conv2 + global skip (src/models.py:83-84)
-  RC(conv3x3(x, po.conv2_f, e->master + poff(*e, "conv2.bias"), ws + L.out1, ws + L.trunk, false));
+  if (!fused) RC(conv3x3(x, po.conv2_f, e->master + poff(*e, "conv2.bias"), ws + L.out1, ws + L.trunk, false));
+  if (!(phases & kPhasePost)) return 0;
   // upsample stages: conv 64->256, PixelShuffle(2), ReLU (src/models.py:69-75,85)
   const void* in = ws + L.trunk;
   for (int j = 0; j < e->n_up; ++j) {
@@ -663,6 +869,10 @@ int generator_forward(GeneratorEngine* g, const float* lr, float* sr, int traini
 
 // ------------------------------------------------------------------ backward
 int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
+  return generator_backward_phases(g, dsr, kPhaseAll, st);
+}
+
+int generator_backward_phases(GeneratorEngine* g, const float* dsr, int phases, cudaStream_t st) {
   EngineImpl* e = static_cast<EngineImpl*>(g);
   if (!e->ws || !e->ws_training) { set_error("generator_backward: needs a training-sized bound workspace"); return -25; }
   const Layout& L = e->L;
@@ -677,7 +887,8 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
   float* wgp = reinterpret_cast<float*>(ws + L.wg_partials);
   char nm[96];
 
-  if (cudaMemsetAsync(e->grads, 0, size_t(e->param_elems) * 4, st) != cudaSuccess) { set_error("memset grads failed"); return -26; }
+  const bool pre = (phases & kPhasePre) != 0, mid = (phases & kPhaseTrunk) != 0, post = (phases & kPhasePost) != 0;
+  if (pre && cudaMemsetAsync(e->grads, 0, size_t(e->param_elems) * 4, st) != cudaSuccess) { set_error("memset grads failed"); return -26; }
 
   auto wgrad = [&](InView xv, int in_H, int in_W, bool pairs, int gh, int gw, const void* dy_base, int n_blocks,
                    bool dy_ps, const int* idx, const std::string& wname) -> int {
@@ -754,17 +965,18 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     return launch_conv_gemm(a, st);
   };
 
+  const void* conv3_in = S > 0 ? ws + L.up[S - 1] : ws + L.trunk;
+  void* d_trunk = ws + L.g[3];
+  if (pre) {
   // ---- conv3 (9x9, 64->3): unfold d(SR) once; it feeds the bias sum, wgrad and dgrad
   RC(launch_unfold9(dsr, N, Hs, Ws, 1.f, ws + L.Ud, st));
   RC(launch_nchw_chan_sum(dsr, N, 3, int64_t(Hs) * Ws, reinterpret_cast<double*>(ws + L.loss_scratch),
                           e->grads + poff(*e, "conv3.bias"), 1.f, st));
   e->launches += 3;
-  const void* conv3_in = S > 0 ? ws + L.up[S - 1] : ws + L.trunk;
   {
     InView uv = plain_view(ws + L.Ud, Hs + 1, Ws);
     RC(wgrad(uv, Hs + 1, Ws, true, Hs, Ws, conv3_in, 1, false, e->d_wg_idx_conv3, "conv3.weight"));
   }
-  void* d_trunk = ws + L.g[3];
   {
     ConvGemmArgs a; memset(&a, 0, sizeof(a));
     a.N = N; a.H = Hs; a.W = Ws; set_taps_pairs(a);
@@ -788,9 +1000,10 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     RC(wgrad(plain_view(in_j, Hj, Wj), Hj, Wj, false, Hj, Wj, ws + L.dup[j], 4, true, e->d_wg_idx_up, nm));
     RC(dgrad3x3(ws + L.dup[j], Hj, Wj, true, po.up_d[j], nullptr, j > 0 ? in_j : nullptr, j > 0 ? ws + L.dup[j - 1] : d_trunk, nullptr));
   }
+  }
   // ---- conv2 (trunk = conv2(x_last) + out1)
   const void* x_last = e->n_res > 0 ? ws + L.out[e->n_res - 1] : ws + L.out1;
-  RC(bias_grad(d_trunk, P, "conv2.bias"));
+  if (pre) RC(bias_grad(d_trunk, P, "conv2.bias"));
   // The 2*n_res + 1 trunk weight gradients run as ONE batched launch at the end of backward (wgrad3_batched_kernel):
   // x of layer l = 2*block + conv sits at out1 + l * 2 * slot (out[b-1] | z1[b] are two slots apart, conv2 reads out[last]),
   // dy of layer l at dyall + l * slot.  SRG_WGRAD_BATCHED=0 (or a non-uniform layout) keeps one launch per layer.
@@ -807,12 +1020,20 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     probe.N = N; probe.H = H; probe.W = W; probe.n_layers = 2 * e->n_res + 1;
     if (wgrad3_batched_partials_floats(probe) > L.wgb_floats) batched = false;
   }
-  if (!batched) RC(wgrad(plain_view(x_last, H, W), H, W, false, H, W, d_trunk, 1, false, e->d_wg_idx_c3x3, "conv2.weight"));
+  if (!batched && pre) RC(wgrad(plain_view(x_last, H, W), H, W, false, H, W, d_trunk, 1, false, e->d_wg_idx_c3x3, "conv2.weight"));
   const bool keep = e->keep_grads;
   void* dout = keep ? ws + L.kd_last : ws + L.g[0];
   void* dother = ws + L.g[1];
   void* dmid = ws + L.g[2];
-  RC(dgrad3x3(d_trunk, H, W, false, po.conv2_d, nullptr, nullptr, dout, e->n_res > 0 ? ws + L.y2[e->n_res - 1] : nullptr));
+  // the whole dgrad chain of the trunk (conv2, then every block's BatchNorm / ReLU / conv backward) in one launch
+  const bool fused = batched && use_trunk_fused(*e);
+  if (phases != kPhaseAll && !fused) { set_error("generator_backward_phases: split execution needs the fused trunk path"); return -31; }
+  if (fused) {
+    if (mid) RC(run_trunk(e, 1, 0, st));
+    dout = ws + L.g[0] + L.slot * size_t(e->trunk_dout_idx);
+  } else {
+    RC(dgrad3x3(d_trunk, H, W, false, po.conv2_d, nullptr, nullptr, dout, e->n_res > 0 ? ws + L.y2[e->n_res - 1] : nullptr));
+  }
   // ---- residual blocks, last to first (src/models.py:21-25)
   float* bwd = reinterpret_cast<float*>(ws + L.bwdcoef);
   auto bn_backward = [&](int b, int k, const void* dz, const void* y, void* dy) -> int {
@@ -844,7 +1065,7 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     }
     return launch_bn_bwd_apply(dz, y, bwd, bwd + 64, bwd + 128, dy, P, st);
   };
-  for (int b = e->n_res - 1; b >= 0; --b) {
+  for (int b = e->n_res - 1; b >= 0 && !fused; --b) {
     const void* x_in = b > 0 ? ws + L.out[b - 1] : ws + L.out1;
     void* d_y2 = ws + L.dyall + L.slot * size_t(2 * b + 1);
     void* d_p1 = keep ? ws + L.kd_p1[b] : dother;
@@ -862,6 +1083,7 @@ int generator_backward(GeneratorEngine* g, const float* dsr, cudaStream_t st) {
     RC(dgrad3x3(d_y1, H, W, false, po.rb_d[0][b], dout, nullptr, d_in, b > 0 ? ws + L.y2[b - 1] : nullptr));   // + skip gradient
     if (keep) { dout = d_in; } else { void* t = dout; dout = dother; dother = t; }
   }
+  if (!post) return 0;
   // ---- conv1: out1 = lrelu(conv1(x)); d(out1) = block-chain gradient + trunk skip gradient
   if (keep) dmid = ws + L.kd_c1;
   RC(launch_lrelu_bwd_add2(dout, d_trunk, ws + L.out1, kSlope, dmid, P, st));

@@ -68,6 +68,7 @@ struct GeneratorEngine {
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
   size_t prof_used = 0;
+  int prof_layers = 1;     // trunk conv layers covered by one profiled launch (1: per-layer launches, 2*n_res+1: fused trunk kernel)
 
   virtual ~GeneratorEngine();
 };
@@ -79,9 +80,21 @@ int generator_pack(GeneratorEngine* g, cudaStream_t st);
 int generator_forward(GeneratorEngine* g, const float* lr_nchw, float* sr_nchw, int training, int update_running,
                       cudaStream_t st);
 int generator_backward(GeneratorEngine* g, const float* dsr_nchw, cudaStream_t st);
+// Split execution for the multi-generator step: PRE = everything before the residual trunk, TRUNK = the trunk itself,
+// POST = everything after it (forward: conv1 | blocks + conv2 | upsample + conv3; backward: conv3 + upsample stages |
+// trunk dgrad chain | conv1 gradients + the batched trunk weight gradients).  The TRUNK phases of several engines of equal
+// geometry run as ONE interleaved launch through generators_trunk() (csrc/trunk_fused.cu).
+enum GeneratorPhase : int { kPhasePre = 1, kPhaseTrunk = 2, kPhasePost = 4, kPhaseAll = 7 };
+int generator_forward_phases(GeneratorEngine* g, const float* lr_nchw, float* sr_nchw, int training, int update_running,
+                             int phases, cudaStream_t st);
+int generator_backward_phases(GeneratorEngine* g, const float* dsr_nchw, int phases, cudaStream_t st);
+int generators_trunk(GeneratorEngine* const* gs, int n, int bwd, int update_running, cudaStream_t st);
 // dominant-kernel timing: enable/disable; read() synchronises on the recorded events, returns the summed duration
 // (ms) and launch count since the last read and resets.
 int generator_set_keep_grads(GeneratorEngine* g, int keep);
+// non-zero if a bounded in-kernel wait of the fused trunk kernel ever gave up (synchronises the device)
+int generator_trunk_error(GeneratorEngine* g);
+int generator_prof_layers(const GeneratorEngine* g);
 int generator_profile_enable(GeneratorEngine* g, int on);
 int generator_profile_read(GeneratorEngine* g, double* ms_sum, long long* count);
 

@@ -190,6 +190,15 @@ int peer_sync_error(PeerSync* ps) {
   return v;
 }
 int peer_sync_world(const PeerSync* ps) { return ps->world; }
+int peer_sync_device_view(PeerSync* ps, PeerDeviceView* out) {
+  memset(out, 0, sizeof(*out));
+  for (int r = 0; r < ps->world; ++r) {
+    if (ps->peers[r] == nullptr) { set_error("peer_sync: rank %d not connected", r); return -2; }
+    out->peers[r] = ps->peers[r];
+  }
+  out->world = ps->world; out->rank = ps->rank; out->seq = ps->d_seq; out->err = ps->d_err;
+  return 0;
+}
 
 int launch_peer_finalize(PeerSync* ps, const float* partials, int rows, const ReduceFinalize& f, cudaStream_t st) {
   if (f.mode != RF_BN_FWD && f.mode != RF_BN_BWD) { set_error("peer_finalize: unsupported mode"); return -1; }

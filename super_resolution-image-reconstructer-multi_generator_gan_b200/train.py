@@ -309,9 +309,106 @@ class GraphedDiscriminatorStep:
         return self.loss
 
 
+def joint_pixel_generator_steps(generators, g_criterion, g_optimizers, lr_imgs: torch.Tensor, hr_imgs: torch.Tensor,
+                                streams: Sequence[torch.cuda.Stream]) -> torch.Tensor:
+    """K pixel-mode ``train_generator`` steps (src/train.py:175-203 with ``loss = com_loss + tv_loss``) on ONE batch with
+    the residual trunks of all K generators executed JOINTLY: every generator runs the part of its pass before / after the
+    trunk on its own stream, the trunks (16 residual blocks + conv2, forward and backward) run as one interleaved launch
+    each (``srg_generators_trunk``, csrc/trunk_fused.cu), so the BatchNorm statistics latency of one generator hides
+    behind the tensor work of the others.  Same arithmetic per generator as ``train_generator_async``; the autograd graph
+    is bypassed (engine phases and loss kernels are called directly, ``.grad`` are views of the engines' flat gradient
+    buffers).  Returns a device tensor [K, 4] of (g_loss, com_loss, tv_loss, 0) rows.  Capturable into a CUDA graph."""
+    from ctypes import c_void_p
+    from . import _lib
+    from ._lib import check, stream_ptr
+    from .loss import _scratch
+    L = _lib.lib()
+    K = len(generators)
+    if not (1 <= K <= 4):
+        raise RuntimeError("joint_pixel_generator_steps: 1..4 generators")
+    lr_imgs = lr_imgs.contiguous().float()
+    hr_imgs = hr_imgs.contiguous().float()
+    N, _, H, W = lr_imgs.shape
+    main = torch.cuda.current_stream()
+    PRE, TRUNK, POST = 1, 2, 4
+    engs, srs, work = [], [], []
+    for i, g in enumerate(generators):
+        streams[i].wait_stream(main)
+        with torch.cuda.stream(streams[i]):
+            g.train()
+            g._flatten(lr_imgs.device)
+            rt = g._rt
+            eng = g._engine(N, H, W, True, lr_imgs.device, True)
+            if getattr(eng, "grad_flat", None) is None:
+                eng.grad_flat = torch.empty_like(rt["flat"])
+            eng.bind(rt["flat"], eng.grad_flat, rt["flat_buf"])
+            check(L.srg_generator_pack(eng.handle, stream_ptr()), "srg_generator_pack")
+            rt["last_engine"] = eng
+            if rt["nbt"] is not None and g.num_residuals > 0:
+                rt["nbt"] += 1
+            eng.busy = True
+            sr = torch.empty(N, 3, H << g.num_upsample_stages, W << g.num_upsample_stages, dtype=torch.float32,
+                             device=lr_imgs.device)
+            check(L.srg_generator_forward_phases(eng.handle, c_void_p(lr_imgs.data_ptr()), c_void_p(sr.data_ptr()), 1, 1, PRE,
+                                                 stream_ptr()), "srg_generator_forward_phases(pre)")
+            engs.append(eng)
+            srs.append(sr)
+    for s_ in streams[:K]:
+        main.wait_stream(s_)
+    handles = (c_void_p * K)(*[e.handle for e in engs])
+    check(L.srg_generators_trunk(handles, K, 0, 1, stream_ptr()), "srg_generators_trunk(forward)")
+    rows = []
+    for i, g in enumerate(generators):
+        streams[i].wait_stream(main)
+        with torch.cuda.stream(streams[i]):
+            eng, sr = engs[i], srs[i]
+            check(L.srg_generator_forward_phases(eng.handle, c_void_p(lr_imgs.data_ptr()), c_void_p(sr.data_ptr()), 1, 1, POST,
+                                                 stream_ptr()), "srg_generator_forward_phases(post)")
+            # ReconstructionLoss(hr, sr) forward + backward (src/utils.py:173-241), unit weights on both terms
+            Nn, C, Hh, Ww = sr.shape
+            scratch = _scratch(sr.device)
+            e_buf, g_buf, dsr = torch.empty_like(sr), torch.empty_like(sr), torch.empty_like(sr)
+            losses = torch.empty(2, dtype=torch.float32, device=sr.device)
+            check(L.srg_recon_loss_forward(c_void_p(hr_imgs.data_ptr()), c_void_p(sr.data_ptr()), Nn, C, Hh, Ww,
+                                           c_void_p(scratch.data_ptr()), scratch.numel(), c_void_p(e_buf.data_ptr()),
+                                           c_void_p(g_buf.data_ptr()), c_void_p(losses.data_ptr()), stream_ptr()),
+                  "srg_recon_loss_forward")
+            check(L.srg_recon_loss_backward(c_void_p(hr_imgs.data_ptr()), c_void_p(sr.data_ptr()), Nn, C, Hh, Ww,
+                                            c_void_p(scratch.data_ptr()), c_void_p(e_buf.data_ptr()),
+                                            c_void_p(g_buf.data_ptr()), None, None, c_void_p(dsr.data_ptr()), 1.0,
+                                            stream_ptr()), "srg_recon_loss_backward")
+            flat_g = eng.grad_flat
+            check(L.srg_generator_set_grads(eng.handle, c_void_p(flat_g.data_ptr())))
+            check(L.srg_generator_backward_phases(eng.handle, c_void_p(dsr.data_ptr()), PRE, stream_ptr()),
+                  "srg_generator_backward_phases(pre)")
+            work.append((flat_g, losses, (scratch, e_buf, g_buf, dsr)))
+    for s_ in streams[:K]:
+        main.wait_stream(s_)
+    check(L.srg_generators_trunk(handles, K, 1, 0, stream_ptr()), "srg_generators_trunk(backward)")
+    for i, (g, o) in enumerate(zip(generators, g_optimizers)):
+        streams[i].wait_stream(main)
+        with torch.cuda.stream(streams[i]):
+            eng = engs[i]
+            flat_g, losses, _keep = work[i]
+            check(L.srg_generator_backward_phases(eng.handle, None, POST, stream_ptr()), "srg_generator_backward_phases(post)")
+            eng.busy = False
+            g._after_backward(flat_g)                      # data-parallel gradient all-reduce hook (parallel.py)
+            plist, ptable = g._rt["plist"], g._ptable
+            if plist[0].grad is None or plist[0].grad.data_ptr() != flat_g.data_ptr() + 4 * ptable[0][1]:
+                for p_, (_, off, n, shape) in zip(plist, ptable):      # zero_grad() dropped the views: re-attach them
+                    p_.grad = flat_g[off:off + n].view(shape)
+            o.step()
+            zero = torch.zeros((), dtype=torch.float32, device=losses.device)
+            rows.append(torch.stack([losses[0] + losses[1], losses[0], losses[1], zero]))
+    for s_ in streams[:K]:
+        main.wait_stream(s_)
+    return torch.stack(rows)
+
+
 class GraphedMultiGeneratorStep:
     """K independent pixel-mode generator steps captured as PARALLEL branches of one CUDA graph (one capture stream
-    forks into K side streams and joins them again).
+    forks into K side streams and joins them again).  With ``joint=True`` (default when the fused trunk kernel applies)
+    the residual trunks of the K generators run as one interleaved launch per direction (joint_pixel_generator_steps).
 
     The generators share nothing but the input batch, so their kernel chains may interleave: while one generator's
     persistent tensor-core kernel owns the SMs' shared memory, the HBM-bound passes (BatchNorm apply / backward,
@@ -319,7 +416,7 @@ class GraphedMultiGeneratorStep:
     Results are identical to running the K steps one after the other."""
 
     def __init__(self, generators, g_criterion, g_optimizers, lr_example: torch.Tensor, hr_example: torch.Tensor,
-                 warmup: int = 2):
+                 warmup: int = 2, joint: Optional[bool] = None):
         from . import _lib
         self.generators, self.optimizers = list(generators), list(g_optimizers)
         for o in self.optimizers:
@@ -328,6 +425,11 @@ class GraphedMultiGeneratorStep:
         self.lr = lr_example.detach().clone()
         self.hr = hr_example.detach().clone()
         K = len(self.generators)
+        import os
+        if joint is None:
+            joint = K <= 4 and os.environ.get("SRG_JOINT_TRUNK", "1") != "0" and os.environ.get("SRG_TRUNK_FUSED", "1") != "0"
+        self.joint = bool(joint)
+        self.streams = [torch.cuda.Stream() for _ in range(K)]
         snaps = []
         for g, o in zip(self.generators, self.optimizers):
             flat = g.flat_parameters()
@@ -339,6 +441,16 @@ class GraphedMultiGeneratorStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):
+                if self.joint:
+                    try:
+                        joint_pixel_generator_steps(self.generators, g_criterion, self.optimizers, self.lr, self.hr, self.streams)
+                        continue
+                    except RuntimeError:
+                        self.joint = False       # configuration outside the fused trunk kernel: per-generator branches
+                        for g in self.generators:
+                            for pool in g._rt["engines"].values():
+                                for e in pool:
+                                    e.busy = False
                 for g, o in zip(self.generators, self.optimizers):
                     train_generator_async(g, None, self.lr, self.hr, None, g_criterion, o)
         torch.cuda.current_stream().wait_stream(side)
@@ -356,18 +468,21 @@ class GraphedMultiGeneratorStep:
                 o.zero_grad()
         torch.cuda.synchronize()
         n0 = _lib.lib().srg_total_launches()
-        self.streams = [torch.cuda.Stream() for _ in range(K)]
         self.graph = torch.cuda.CUDAGraph()
         rows = [None] * K
         with torch.cuda.graph(self.graph):
-            main = torch.cuda.current_stream()
-            for i, (g, o) in enumerate(zip(self.generators, self.optimizers)):
-                self.streams[i].wait_stream(main)
-                with torch.cuda.stream(self.streams[i]):
-                    rows[i] = train_generator_async(g, None, self.lr, self.hr, None, g_criterion, o)
-            for s_ in self.streams:
-                main.wait_stream(s_)
-            self.losses = torch.stack(rows)
+            if self.joint:
+                self.losses = joint_pixel_generator_steps(self.generators, g_criterion, self.optimizers, self.lr, self.hr,
+                                                          self.streams)
+            else:
+                main = torch.cuda.current_stream()
+                for i, (g, o) in enumerate(zip(self.generators, self.optimizers)):
+                    self.streams[i].wait_stream(main)
+                    with torch.cuda.stream(self.streams[i]):
+                        rows[i] = train_generator_async(g, None, self.lr, self.hr, None, g_criterion, o)
+                for s_ in self.streams:
+                    main.wait_stream(s_)
+                self.losses = torch.stack(rows)
         self.launches_per_replay = int(_lib.lib().srg_total_launches() - n0)
 
     def __call__(self, lr_imgs: torch.Tensor, hr_imgs: torch.Tensor) -> torch.Tensor:

@@ -295,7 +295,10 @@ def test_ragged_and_odd_geometries(S, O):
 def test_batched_trunk_weight_gradients_match_per_layer_launches(S, monkeypatch):
     """wgrad3_batched_kernel (all trunk 3x3 weight gradients in one launch at the end of backward) against one
     wgrad3_kernel launch per layer (SRG_WGRAD_BATCHED=0, read when the engine is created): same bf16 operands, fp32
-    accumulation in a different split order, so equal to fp32 rounding; every other gradient must be bit-identical."""
+    accumulation in a different split order, so equal to fp32 rounding; every other gradient must be bit-identical.
+    The fused trunk kernel needs the batched form, so both arms run the per-layer dgrad launches here."""
+    old = S.lib().srg_set_trunk_fused(0)
+
     def grads(batched, shape):
         monkeypatch.setenv("SRG_WGRAD_BATCHED", "1" if batched else "0")
         torch.manual_seed(31)
@@ -315,6 +318,45 @@ def test_batched_trunk_weight_gradients_match_per_layer_launches(S, monkeypatch)
                 assert float(a[k].abs().max()) > 0
             else:
                 assert torch.equal(a[k], b[k]), (shape, k)
+    S.lib().srg_set_trunk_fused(old)
+
+
+def test_fused_trunk_kernel_matches_per_layer_launches(S):
+    """csrc/trunk_fused.cu (all 33 trunk convs of a direction + their BatchNorm steps in one cooperative launch) against
+    the per-layer launch path on the same weights and inputs: forward intermediates agree to a bf16 ulp (only the order
+    of the statistics sums differs), gradients to bf16 rounding noise through the 33-layer chain, BatchNorm running
+    statistics to fp32 rounding, and no bounded in-kernel wait ever gave up."""
+    L = S.lib()
+    for shape in [(2, 3, 16, 24), (3, 3, 40, 20), (1, 3, 33, 17), (4, 3, 64, 64)]:   # ragged tiles, 1-4 tiles per CTA
+        res = []
+        for fused in (0, 1):
+            old = L.srg_set_trunk_fused(fused)
+            torch.manual_seed(41)
+            g = S.SRResNet().cuda().train()
+            torch.manual_seed(42)
+            x = torch.rand(*shape).cuda()
+            y = g(x)
+            y.backward(torch.cos(torch.arange(y.numel(), device="cuda", dtype=torch.float32)).reshape(y.shape) * 1e-3)
+            torch.cuda.synchronize()
+            eng = g.last_engine()
+            assert L.srg_generator_trunk_layers(eng.handle) == (33 if fused else 1)
+            assert L.srg_generator_trunk_error(eng.handle) == 0
+            T = {n: eng.named_tensor(n).float().clone() for n in eng.tensor_table()}
+            res.append((y.detach().clone(), T, {k: p.grad.detach().clone() for k, p in g.named_parameters()},
+                        {k: v.clone() for k, v in g.state_dict().items() if "running" in k}))
+            L.srg_set_trunk_fused(old)
+        (y0, T0, G0, R0), (y1, T1, G1, R1) = res
+        assert maxrel(y1, y0) < 2e-2, shape
+        for n in T0:
+            if not n.startswith("d_"):
+                assert maxrel(T1[n], T0[n]) < 1e-2, (shape, n, maxrel(T1[n], T0[n]))
+        for k in R0:
+            assert maxrel(R1[k], R0[k]) < 1e-5, (shape, k)
+        for k in G0:
+            if float(G0[k].abs().max()) > 0:
+                assert maxrel(G1[k], G0[k]) < 5e-2, (shape, k, maxrel(G1[k], G0[k]))
+            else:
+                assert float(G1[k].abs().max()) == 0.0, (shape, k)
 
 
 def test_device_prefetcher_yields_every_batch_in_order(S):
