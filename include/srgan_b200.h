@@ -96,8 +96,9 @@ int srg_generator_profile_enable(srg_generator_t* g, int on);
 int srg_generator_profile_read(srg_generator_t* g, double* ms_sum, long long* count);
 /* Fused trunk kernel (csrc/trunk_fused.cu): the 2*n_res+1 3x3 / 64->64 convolutions of one direction of the residual trunk
  * (src/models.py:10-25 ResidualBlock x 16, :66 conv2) with their training-mode BatchNorm steps in ONE cooperative launch.
- * srg_set_trunk_fused(0) makes later forward / backward calls use one launch per layer again (A/B and parity aid;
- * SRG_TRUNK_FUSED=0 does the same); returns the previous value.  srg_generator_trunk_layers: trunk conv layers covered by
+ * srg_set_trunk_fused(mode): 0 = one launch per layer, 1 = the fused kernel wherever it applies, 2 = automatic (default:
+ * fused when a layer has at most one 32x8-pixel tile per SM, i.e. launch-latency-bound sizes; measured in
+ * profiles/r02_notes.md).  SRG_TRUNK_FUSED=0/1 sets the initial mode.  Returns the previous mode.  srg_generator_trunk_layers: trunk conv layers covered by
  * the engine's last profiled launch (1 = per-layer launches).  srg_generator_trunk_error: non-zero if a bounded in-kernel
  * wait of the fused kernel ever gave up (bit 0 cross-CTA flag / barrier, bit 1 mbarrier, bit 2 peer GPU); synchronises. */
 int srg_set_trunk_fused(int on);

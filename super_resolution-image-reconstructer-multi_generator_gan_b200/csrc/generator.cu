@@ -397,7 +397,7 @@ bool build_trunk_tables(EngineImpl& e, std::vector<TrunkLayer>& fwd, std::vector
 // the fused trunk applies to training passes on one GPU, or under data parallelism with the peer-memory SyncBatchNorm
 // transport (the NCCL transport keeps the per-layer launches)
 bool use_trunk_fused(const EngineImpl& e) {
-  if (!e.trunk_ok || !trunk_fused_enabled()) return false;
+  if (!e.trunk_ok || !trunk_fused_preferred(e.N, e.H, e.W)) return false;
   if (e.peer != nullptr) return true;
   return e.allreduce == nullptr && e.world == 1;
 }

@@ -56,10 +56,11 @@ constexpr uint32_t kTrWBytes = 9 * 64 * 128;    // resident filter [kw 3][kh2 ; 
 constexpr uint32_t kTrPitch = 10 * 128;         // 10-pixel-wide half strip row
 constexpr uint32_t kTrStage = 22 * 1024;        // 17 x 1280 B rounded up to the 1024-byte swizzle period
 constexpr uint32_t kTrTile = 128 * 128;         // one block (128 pixels x 64 bf16) staged for a TMA store
-constexpr uint32_t kTrTailBytes = 2 * 256 + 4 * 256 + 16 * 128 * 4 + 3 * 256 + 512;
+constexpr int kTrMaxLayers = 40;
+constexpr uint32_t kTrTailBytes = 2 * 256 + 4 * 256 + 16 * 128 * 4 + 3 * 256 + 512 + kTrMaxLayers * 64;
 static_assert(1024 + kTrWBytes + 2 * kTrStage + 6 * kTrTile + kTrTailBytes <= 227 * 1024, "backward instance exceeds the shared memory of an SM");
 constexpr int kTraceBase = 148 * 18;            // role timers first, then the event trace [cta][slot 128][event 8]
-constexpr int kTraceSlots = 128, kTraceEvents = 8;
+constexpr int kTraceSlots = 128, kTraceEvents = 16;
 constexpr int kProfWords = kTraceBase + 148 * kTraceSlots * kTraceEvents;
 
 template <bool BWD> constexpr int tr_stages() { return BWD ? 2 : 3; }
@@ -226,7 +227,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint4 ldg_cg_u4(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+// asm volatile: the loads are PREFETCHES issued one tile ahead of their use; a plain __ldcg lets the compiler sink them
+// next to the use to save registers, which puts the HBM latency back on the critical path
+__device__ __forceinline__ uint4 ldg_cg_u4(const uint8_t* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void stg_u4(uint8_t* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
 struct TileCoord { int n, hh, w0; };
@@ -276,6 +283,10 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
   unsigned long long* seq_s = reinterpret_cast<unsigned long long*>(bars + 31);
   unsigned int* s_last = reinterpret_cast<unsigned int*>(bars + 32);
+  int4* s_tile = reinterpret_cast<int4*>(bars + 34);                       // [4] {n, hh, w0, tile} of this CTA's tiles
+  const uint8_t** s_base = reinterpret_cast<const uint8_t**>(bars + 42);   // [generator 4][2] activation / gradient region base
+  TrunkLayer* s_layers = reinterpret_cast<TrunkLayer*>(bars + 64);         // [n_layers <= kTrMaxLayers] copy of the layer table
+  static_assert(sizeof(TrunkLayer) == 64, "TrunkLayer is copied as 16 words");
 
   const int G = int(gridDim.x);
   const int cta = int(blockIdx.x);
@@ -294,6 +305,13 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 512); }
     for (int i = 0; i < 4; ++i) { mbar_init(&staged[i], 256); mbar_init(&freebuf[i], 1); }
     *s_last = 0u;
+    {
+      int ti = 0;
+      for (int t = cta; t < p.tiles_total && ti < 4; t += G, ++ti) {
+        const TileCoord c = tile_coord(p, t);
+        s_tile[ti] = make_int4(c.n, c.hh, c.w0, t);
+      }
+    }
     fence_barrier_init();
     for (int g = 0; g < K; ++g) {
       tma_prefetch_desc(&p.gen[g].ld_map[0]);
@@ -304,6 +322,10 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
     }
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  // hot, dynamically indexed launch constants go to shared memory once: the layer table and the region bases
+  for (int i = threadIdx.x; i < p.n_layers * 16; i += kTrThreads)
+    reinterpret_cast<int*>(s_layers)[i] = reinterpret_cast<const int*>(p.layers)[i];
+  if (threadIdx.x < 2 * K) s_base[threadIdx.x] = (threadIdx.x & 1) ? p.gen[threadIdx.x >> 1].grad_base : p.gen[threadIdx.x >> 1].act_base;
   if (threadIdx.x >= kTrEpi0 && threadIdx.x < kTrEpi0 + 192) {
     // pass-1 coefficients of slot 0 (later slots: loaded one slot ahead)
     const int t = threadIdx.x - kTrEpi0;
@@ -327,8 +349,8 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
     for (int slot = 0; slot < n_slots; ++slot) {
       const int j = slot / K, g = slot - j * K;
       const TrunkGenK& gp = p.gen[g];
-      const int in_idx = p.layers[j].in_idx;
-      const int w_row = p.layers[j].w_row;
+      const int in_idx = s_layers[j].in_idx;
+      const int w_row = s_layers[j].w_row;
       if (lane == 0) {
         // filter of this slot, one column shift at a time, as soon as the previous slot's last MMAs on that shift retired
         for (int s = 0; s < 3; ++s) {
@@ -437,8 +459,10 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
       // back after job n has been issued (wait_group.read 1), and the flag of a pass-2 job is published two jobs later
       // (wait_group 2), when its completion is no longer on anyone's critical path.
       unsigned int* pend_flag[2] = {nullptr, nullptr};   // flag of job jc-1 / jc-2 awaiting completion (index: job & 1)
-      auto job = [&](int g, int idx, int tile, bool flag) {
-        const TileCoord c = tile_coord(p, tile);
+      auto job = [&](int g, int idx, int ti, bool flag) {
+        const int4 tc = s_tile[ti];
+        TileCoord c; c.n = tc.x; c.hh = tc.y; c.w0 = tc.z;
+        const int tile = tc.w;
         const uint32_t b = jc & 1u;
         mbar_wait_b(&staged[blk * 2 + b], (jc >> 1) & 1u, err);
         tma_store_5d(&p.gen[g].st_map[blk], v_stage + size_t(blk * 2 + b) * kTrTile, 0, c.w0, c.hh, c.n, idx);
@@ -464,16 +488,16 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
       };
       for (int slot = 0; slot < n_slots; ++slot) {
         const int j = slot / K, g = slot - j * K;
-        const int st1 = p.layers[j].st1_idx;
+        const int st1 = s_layers[j].st1_idx;
         const int pslot = slot - 1;
         const int pj = pslot >= 0 ? pslot / K : 0, pg = pslot >= 0 ? pslot - pj * K : 0;
-        const int pst2 = (interleave && pslot >= 0) ? p.layers[pj].st2_idx : -1;
-        for (int tile = cta; tile < p.tiles_total; tile += G) {
-          if (pst2 >= 0) job(pg, pst2, tile, true);
-          if (st1 >= 0) job(g, st1, tile, false);
+        const int pst2 = (interleave && pslot >= 0) ? s_layers[pj].st2_idx : -1;
+        for (int ti = 0; ti < n_my; ++ti) {
+          if (pst2 >= 0) job(pg, pst2, ti, true);
+          if (st1 >= 0) job(g, st1, ti, false);
         }
-        if (!interleave && p.layers[j].st2_idx >= 0) {
-          for (int tile = cta; tile < p.tiles_total; tile += G) job(g, p.layers[j].st2_idx, tile, true);
+        if (!interleave && s_layers[j].st2_idx >= 0) {
+          for (int ti = 0; ti < n_my; ++ti) job(g, s_layers[j].st2_idx, ti, true);
           flush();                           // one generator: the next slot needs these tiles now
         }
       }
@@ -496,25 +520,29 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
     uint64_t* my_free = freebuf + blk * 2;
     const uint32_t row_off = uint32_t(m) * 128u;
     const uint32_t sw = uint32_t(m & 7);
-    const int c2 = gtid & 31, part = gtid >> 5;   // column-sum mapping: channel pair c2, rows part*16 .. +15
+    const int cq = gtid & 7, rp4 = gtid >> 3;     // column-sum mapping: 8-channel chunk cq, staged rows rp4*4 .. +3
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
     const uint32_t park_col = 256u + uint32_t(blk * 32 + hf * 16);   // + 64 * tile index: 16 packed columns of this thread
     uint32_t tcount = 0;                         // accumulators consumed (MMA ring)
     uint32_t jc = 0;                             // store jobs issued (staging ring)
 
-    // ---- pass 2 of one tile of slot (pj, pg): parked v -> out, staged for the store thread
-    auto pass2_tile = [&](int pj, int pg, int ti, int tile) {
-      const TrunkLayer& PL = p.layers[pj];
-      const TrunkGenK& pp = p.gen[pg];
-      const TileCoord c = tile_coord(p, tile);
-      const int hr = 2 * (c.hh + (m >> 3)) + blk, wc = c.w0 + (m & 7);
+    // ---- pass 2 of one tile of slot (pj, pg): parked v -> out, staged for the store thread.  `xx` = this thread's 64
+    // bytes of the second operand (forward: the block input added after BatchNorm; backward: the saved conv output y),
+    // prefetched one tile ahead by load_x() so that its HBM latency never sits in front of the tensor-memory read.
+    auto load_x = [&](int pj, int pg, int ti, uint4 (&xx)[4]) {
+      const TrunkLayer& PL = s_layers[pj];
+      const int4 tc = s_tile[ti];
+      const int hr = 2 * (tc.y + (m >> 3)) + blk, wc = tc.z + (m & 7);
       const bool valid = hr < p.H && wc < p.W;
-      const size_t pix_off = ((size_t(c.n) * p.H + hr) * p.W + wc) * 128 + size_t(hf) * 64;
-      const uint8_t* xb = BWD ? pp.act_base + size_t(PL.y_idx) * size_t(p.act_slot)
-                              : (PL.aux2_idx >= 0 ? pp.act_base + size_t(PL.aux2_idx) * size_t(p.act_slot) : nullptr);
-      uint4 xx[4];
+      const uint8_t* act = s_base[2 * pg];
+      const uint8_t* xb = BWD ? act + size_t(PL.y_idx) * size_t(p.act_slot)
+                              : (PL.aux2_idx >= 0 ? act + size_t(PL.aux2_idx) * size_t(p.act_slot) : nullptr);
+      const size_t pix_off = ((size_t(tc.x) * p.H + hr) * p.W + wc) * 128 + size_t(hf) * 64;
 #pragma unroll
       for (int i = 0; i < 4; ++i) xx[i] = (xb != nullptr && valid) ? ldg_cg_u4(xb + pix_off + i * 16) : make_uint4(0, 0, 0, 0);
+    };
+    auto pass2_tile = [&](int pj, int ti, const uint4 (&xx)[4]) {
+      const TrunkLayer& PL = s_layers[pj];
       uint32_t pv[16];
       tmem_ld16(lane_addr + park_col + uint32_t(ti * 64), pv);
       tmem_ld_wait();
@@ -522,10 +550,19 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
       uint8_t* ob = vb0 + size_t(b) * kTrTile + row_off;
       if (jc >= 2) mbar_wait_b(&my_free[b], ((jc >> 1) - 1u) & 1u, err);
       ++jc;
+      const bool relu = !BWD && PL.relu != 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {            // 8 channels per 16-byte chunk
         const uint32_t xw[4] = {xx[i].x, xx[i].y, xx[i].z, xx[i].w};
-        const float* k0 = s_coef + hf * 32 + i * 8;
+        const float4* kq = reinterpret_cast<const float4*>(s_coef + hf * 32 + i * 8);
+        const float4 ka0 = kq[0], ka1 = kq[1], kb0 = kq[16], kb1 = kq[17];
+        const float ka[8] = {ka0.x, ka0.y, ka0.z, ka0.w, ka1.x, ka1.y, ka1.z, ka1.w};
+        const float kb[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
+        float kc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (BWD) {
+          const float4 kc0 = kq[32], kc1 = kq[33];
+          kc[0] = kc0.x; kc[1] = kc0.y; kc[2] = kc0.z; kc[3] = kc0.w; kc[4] = kc1.x; kc[5] = kc1.y; kc[6] = kc1.z; kc[7] = kc1.w;
+        }
         uint32_t ow[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -533,13 +570,13 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
           const float x0 = bf16_lo(xw[e]), x1 = bf16_hi(xw[e]);
           float o0, o1;
           if (!BWD) {
-            o0 = fmaf(v0, k0[2 * e], k0[64 + 2 * e]);
-            o1 = fmaf(v1, k0[2 * e + 1], k0[64 + 2 * e + 1]);
-            if (PL.relu) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
+            o0 = fmaf(v0, ka[2 * e], kb[2 * e]);
+            o1 = fmaf(v1, ka[2 * e + 1], kb[2 * e + 1]);
+            if (relu) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
             o0 += x0; o1 += x1;                // x = 0 when the layer has no skip addend
           } else {
-            o0 = fmaf(k0[2 * e], v0, fmaf(k0[64 + 2 * e], x0, k0[128 + 2 * e]));
-            o1 = fmaf(k0[2 * e + 1], v1, fmaf(k0[64 + 2 * e + 1], x1, k0[128 + 2 * e + 1]));
+            o0 = fmaf(ka[2 * e], v0, fmaf(kb[2 * e], x0, kc[2 * e]));
+            o1 = fmaf(ka[2 * e + 1], v1, fmaf(kb[2 * e + 1], x1, kc[2 * e + 1]));
           }
           ow[e] = pack_bf16(o0, o1);
         }
@@ -551,7 +588,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
 
     // ---- statistics of slot (pj, pg) are complete on every CTA: coefficients into shared memory
     auto finish_barrier = [&](int pslot, int pj, int pg) {
-      const TrunkLayer& PL = p.layers[pj];
+      const TrunkLayer& PL = s_layers[pj];
       const TrunkGenK& pp = p.gen[pg];
       const uint32_t seq = uint32_t(pj);
       double* gs = pp.gsum + size_t(seq & 1u) * 128;
@@ -603,26 +640,38 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
     for (int slot = 0; slot < n_slots; ++slot) {
       const int j = slot / K, g = slot - j * K;
       const TrunkGenK& gp = p.gen[g];
-      const TrunkLayer L = p.layers[j];
+      const TrunkLayer L = s_layers[j];
       const bool has_bn = L.bn >= 0;
-      const uint8_t* aux1_base = L.aux1_idx >= 0 ? (BWD ? gp.grad_base + size_t(L.aux1_idx) * size_t(p.grad_slot)
-                                                        : gp.act_base + size_t(L.aux1_idx) * size_t(p.act_slot))
+      const uint8_t* aux1_base = L.aux1_idx >= 0 ? (BWD ? s_base[2 * g + 1] + size_t(L.aux1_idx) * size_t(p.grad_slot)
+                                                        : s_base[2 * g] + size_t(L.aux1_idx) * size_t(p.act_slot))
                                                  : nullptr;
-      const uint8_t* y_base = (BWD && L.y_idx >= 0) ? gp.act_base + size_t(L.y_idx) * size_t(p.act_slot) : nullptr;
+      const uint8_t* y_base = (BWD && L.y_idx >= 0) ? s_base[2 * g] + size_t(L.y_idx) * size_t(p.act_slot) : nullptr;
       const bool masked = BWD && L.mask_bn >= 0;
       const float* bias_s = s_bias + (slot & 1) * 64;
       const float* mask_s = s_mask + (slot & 1) * 128;
-      float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;
+      float st_s[8], st_q[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { st_s[e] = 0.f; st_q[e] = 0.f; }
       // previous slot (another generator when interleaving): its pass 2 runs here, one tile ahead of our pass 1
       const int pslot = slot - 1;
       const int pj = pslot >= 0 ? pslot / K : 0, pg = pslot >= 0 ? pslot - pj * K : 0;
-      const bool prev_p2 = interleave && pslot >= 0 && p.layers[pj].bn >= 0;
-      if (prev_p2) finish_barrier(pslot, pj, pg);
+      const bool prev_p2 = interleave && pslot >= 0 && s_layers[pj].bn >= 0;
+      uint4 xq[4];
+      if (prev_p2) {
+        load_x(pj, pg, 0, xq);                 // in flight while we wait for the statistics
+        finish_barrier(pslot, pj, pg);
+      }
 
-      int ti = 0;
-      for (int tile = cta; tile < p.tiles_total; tile += G, ++ti, ++tcount) {
-        if (prev_p2) pass2_tile(pj, pg, ti, tile);
-        const TileCoord c = tile_coord(p, tile);
+      for (int ti = 0; ti < n_my; ++ti, ++tcount) {
+        const bool trt = etid == 0 && ti == 1;
+        if (trt) TR_EV(slot, 8);
+        if (prev_p2) {
+          pass2_tile(pj, ti, xq);
+          if (ti + 1 < n_my) load_x(pj, pg, ti + 1, xq);   // lands during this tile's pass 1
+        }
+        if (trt) TR_EV(slot, 9);
+        TileCoord c;
+        { const int4 tc = s_tile[ti]; c.n = tc.x; c.hh = tc.y; c.w0 = tc.z; }
         const int hr = 2 * (c.hh + (m >> 3)) + blk, wc = c.w0 + (m & 7);
         const bool valid = hr < p.H && wc < p.W;
         const size_t pix_off = ((size_t(c.n) * p.H + hr) * p.W + wc) * 128 + size_t(hf) * 64;
@@ -647,10 +696,13 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 4; ++i) a1[i] = ldg_cg_u4(aux1_base + pix_off + i * 16);
         }
+        if (trt) TR_EV(slot, 10);
         mbar_wait_b(&tfull[r], (tcount >> 1) & 1u, err);
         tc_fence_after();
+        if (trt) TR_EV(slot, 11);
         if (jc >= 2) mbar_wait_b(&my_free[b], ((jc >> 1) - 1u) & 1u, err);   // the store of job jc-2 has read the buffer
         ++jc;
+        if (trt) TR_EV(slot, 12);
         const uint32_t t_addr = lane_addr + r * 128u + uint32_t(blk * 64 + hf * 32);
         uint32_t park[16];
 #pragma unroll
@@ -712,46 +764,61 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
           tmem_st16(lane_addr + park_col + uint32_t(ti * 64), park);
           tmem_st_wait();
         }
+        if (trt) TR_EV(slot, 13);
         fence_proxy_async_smem();
         mbar_arrive(&my_staged[b]);
         named_bar_sync(bar_b, 256);
+        if (trt) TR_EV(slot, 14);
         if (has_bn) {
-          // column sums over the staged block: sum v, and sum v*v (forward) or sum v*y (backward).  All 16 loads first,
-          // validity as arithmetic, so the loads pipeline.
-          uint32_t sv[16], yv[16];
+          // column sums over the staged block: sum v, and sum v*v (forward) or sum v*y (backward).  Thread = (8-channel
+          // chunk cq, 4 consecutive staged rows): 128-bit shared loads, 16 running sums per thread.
+          const int mm0 = rp4 * 4;
+          const bool row_ok = 2 * (c.hh + (mm0 >> 3)) + blk < p.H;
 #pragma unroll
-          for (int rr = 0; rr < 16; ++rr) {
-            const int mm = part * 16 + rr;
-            const uint32_t so = uint32_t(mm) * 128u + ((uint32_t(c2 >> 2) ^ uint32_t(mm & 7)) << 4) + uint32_t(c2 & 3) * 4u;
-            sv[rr] = *reinterpret_cast<const uint32_t*>(vb + so);
-            if (BWD) yv[rr] = *reinterpret_cast<const uint32_t*>(yb + so);
-          }
+          for (int i = 0; i < 4; ++i) {
+            const int mm = mm0 + i;
+            const uint32_t so = uint32_t(mm) * 128u + ((uint32_t(cq) ^ uint32_t(mm & 7)) << 4);
+            uint4 a = *reinterpret_cast<const uint4*>(vb + so);
+            if (!(row_ok && c.w0 + (mm & 7) < p.W)) a = make_uint4(0, 0, 0, 0);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+            uint32_t bw[4] = {a.x, a.y, a.z, a.w};
+            if (BWD) {
+              const uint4 bq = *reinterpret_cast<const uint4*>(yb + so);
+              bw[0] = bq.x; bw[1] = bq.y; bw[2] = bq.z; bw[3] = bq.w;
+            }
 #pragma unroll
-          for (int rr = 0; rr < 16; ++rr) {
-            const int mm = part * 16 + rr;
-            const bool ok = 2 * (c.hh + (mm >> 3)) + blk < p.H && c.w0 + (mm & 7) < p.W;
-            const uint32_t s = ok ? sv[rr] : 0u;
-            const float x0 = bf16_lo(s), x1 = bf16_hi(s);
-            float y0 = x0, y1 = x1;
-            if (BWD) { y0 = bf16_lo(yv[rr]); y1 = bf16_hi(yv[rr]); }
-            st_s0 += x0; st_s1 += x1;
-            st_q0 = fmaf(x0, y0, st_q0); st_q1 = fmaf(x1, y1, st_q1);
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = bf16_lo(aw[e]), x1 = bf16_hi(aw[e]);
+              st_s[2 * e] += x0; st_s[2 * e + 1] += x1;
+              st_q[2 * e] = fmaf(x0, bf16_lo(bw[e]), st_q[2 * e]);
+              st_q[2 * e + 1] = fmaf(x1, bf16_hi(bw[e]), st_q[2 * e + 1]);
+            }
           }
         }
+        if (trt) TR_EV(slot, 15);
       }
       if (etid == 0) TR_EV(slot, 4);
 
       // ---------------------------------------------------- end of slot: partial sums out, next slot's coefficients in
       if (has_bn) {
-        s_stats[(blk * 8 + part) * 128 + 2 * c2] = st_s0;
-        s_stats[(blk * 8 + part) * 128 + 2 * c2 + 1] = st_s1;
-        s_stats[(blk * 8 + part) * 128 + 64 + 2 * c2] = st_q0;
-        s_stats[(blk * 8 + part) * 128 + 64 + 2 * c2 + 1] = st_q1;
+        // lanes of a warp = 4 row groups x 8 chunks: fold the row groups, then one row of s_stats per warp
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          st_s[e] += __shfl_xor_sync(0xffffffffu, st_s[e], 8);
+          st_q[e] += __shfl_xor_sync(0xffffffffu, st_q[e], 8);
+          st_s[e] += __shfl_xor_sync(0xffffffffu, st_s[e], 16);
+          st_q[e] += __shfl_xor_sync(0xffffffffu, st_q[e], 16);
+        }
+        if (lane < 8) {
+          float* row = s_stats + (blk * 8 + gw) * 128;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { row[lane * 8 + e] = st_s[e]; row[64 + lane * 8 + e] = st_q[e]; }
+        }
       }
       if (slot + 1 < n_slots && etid >= 256 && etid < 448) {
         const int t = etid - 256;
         const int j1 = (slot + 1) / K, g1 = (slot + 1) - j1 * K;
-        const TrunkLayer& L1 = p.layers[j1];
+        const TrunkLayer& L1 = s_layers[j1];
         if (t < 64) {
           if (!BWD) s_bias[((slot + 1) & 1) * 64 + t] = L1.bias_off >= 0 ? p.gen[g1].master[L1.bias_off + t] : 0.f;
         } else if (BWD && L1.mask_bn >= 0) {
@@ -840,9 +907,13 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
       }
       if (!interleave) {
         // one generator: the next slot consumes this slot's outputs, so pass 2 runs now (serial chain)
+        uint4 xs[4];
+        load_x(j, g, 0, xs);
         finish_barrier(slot, j, g);
-        int t2 = 0;
-        for (int tile = cta; tile < p.tiles_total; tile += G, ++t2) pass2_tile(j, g, t2, tile);
+        for (int t2 = 0; t2 < n_my; ++t2) {
+          pass2_tile(j, t2, xs);
+          if (t2 + 1 < n_my) load_x(j, g, t2 + 1, xs);
+        }
       }
     }
   }
@@ -861,16 +932,29 @@ long long* g_trunk_prof = nullptr;     // SRG_TRUNK_PROF=1: role timers + event 
 
 }  // namespace
 
-bool trunk_fused_enabled() {
+// -1: not read yet, 0: off, 1: on, 2: automatic (default)
+static int trunk_fused_mode() {
   if (g_trunk_fused < 0) {
     const char* ev = getenv("SRG_TRUNK_FUSED");
-    g_trunk_fused = (ev != nullptr && ev[0] == '0') ? 0 : 1;
+    g_trunk_fused = (ev == nullptr || ev[0] == '\0') ? 2 : (ev[0] == '0' ? 0 : 1);
   }
-  return g_trunk_fused != 0;
+  return g_trunk_fused;
+}
+bool trunk_fused_enabled() { return trunk_fused_mode() != 0; }
+// Measured on B200 (profiles/r02_notes.md): with at most one tile per SM and layer the step is launch-latency bound and
+// the fused kernel wins (8x3x64x64: 2.21 vs 2.69 ms per eager generator step); at the cfg2 geometry (4 tiles per SM)
+// its serial statistics -> barrier -> apply chain per layer loses to the per-layer launches, whose gaps the K
+// generators' graph branches fill (12.6 vs 11.0 ms per 3-generator step).  Automatic mode picks accordingly;
+// SRG_TRUNK_FUSED=1 / srg_set_trunk_fused(1) forces the fused kernel wherever it applies.
+bool trunk_fused_preferred(int N, int H, int W) {
+  const int mode = trunk_fused_mode();
+  if (mode != 2) return mode == 1;
+  const int grid = trunk_grid(N, H, W);
+  return grid > 0 && N * ((H + 31) / 32) * ((W + 7) / 8) <= grid;
 }
 int set_trunk_fused(int on) {
-  const int old = trunk_fused_enabled() ? 1 : 0;
-  g_trunk_fused = on ? 1 : 0;
+  const int old = trunk_fused_mode();
+  g_trunk_fused = on < 0 || on > 2 ? 2 : on;
   return old;
 }
 
@@ -900,6 +984,7 @@ int launch_trunk(const TrunkArgs& a, cudaStream_t stream) {
   if (grid == 0) { set_error("trunk_fused: unsupported geometry (more than 4 tiles of 32x8 pixels per SM and layer)"); return -60; }
   if (a.n_gen < 1 || a.n_gen > kTrunkMaxGen) { set_error("trunk_fused: 1..%d generators per launch", kTrunkMaxGen); return -62; }
   if (a.n_layers < 1) return 0;
+  if (a.n_layers > kTrMaxLayers) { set_error("trunk_fused: at most %d layers per chain", kTrMaxLayers); return -67; }
   static TrunkKParams p;            // ~3 KB: keep it off the stack of small host threads; launches are serialized per process
   memset(&p, 0, sizeof(p));
   p.layers = a.layers; p.n_layers = a.n_layers; p.n_gen = a.n_gen;

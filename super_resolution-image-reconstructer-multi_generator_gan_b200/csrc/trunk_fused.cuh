@@ -71,9 +71,11 @@ struct TrunkArgs {
 int trunk_grid(int N, int H, int W);
 size_t trunk_sync_bytes(int N, int H, int W);   // device scratch behind TrunkGen::sync (barrier words, flags, published sums)
 int launch_trunk(const TrunkArgs& a, cudaStream_t stream);
-// process-wide switch (SRG_TRUNK_FUSED=0 disables; tests flip it to compare against the per-layer launch path)
+// process-wide switch: 0 = never, 1 = wherever the kernel applies, 2 = automatic (default; SRG_TRUNK_FUSED=0/1 overrides):
+// fused when a layer has at most one 32x8-pixel tile per SM (launch-latency bound sizes), per-layer launches otherwise
 bool trunk_fused_enabled();
-int set_trunk_fused(int on);   // returns the previous value
+bool trunk_fused_preferred(int N, int H, int W);
+int set_trunk_fused(int mode);   // returns the previous mode
 // SRG_TRUNK_PROF=1: per-CTA role timers of the most recent launch (developer aid)
 int trunk_prof_read(long long* host, int n);
 

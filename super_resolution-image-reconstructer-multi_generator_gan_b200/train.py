@@ -427,7 +427,9 @@ class GraphedMultiGeneratorStep:
         K = len(self.generators)
         import os
         if joint is None:
-            joint = K <= 4 and os.environ.get("SRG_JOINT_TRUNK", "1") != "0" and os.environ.get("SRG_TRUNK_FUSED", "1") != "0"
+            # the joint launch pays off where the fused trunk kernel is the preferred path (see srg_set_trunk_fused);
+            # warm-up falls back to per-generator branches when the engines refuse the split execution
+            joint = K <= 4 and os.environ.get("SRG_JOINT_TRUNK", "1") != "0"
         self.joint = bool(joint)
         self.streams = [torch.cuda.Stream() for _ in range(K)]
         snaps = []

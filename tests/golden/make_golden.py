@@ -48,6 +48,92 @@ def make_enhancer_fixture(models):
                         y1=models.ImageEnhancer().forward(x).numpy(), y05=models.ImageEnhancer(factor=0.5).forward(x).numpy())
 
 
+def make_adversarial_fixture(models, train, utils):
+    """Discriminator step (src/train.py:206-230) and GAN-mode generator term (src/train.py:184-192) at NON-degenerate
+    geometries: HR 940 x 940 (discriminator map 512 x 3 x 3) and the reference's native 512 x 1024 crop (512 x 1 x 3,
+    src/transformers.py:74).  At the minimum valid size (428 x 684) the last InstanceNorm sees two elements and the sigmoid
+    map collapses to a constant, which pins nothing.  python tests/golden/make_golden.py adversarial"""
+    out = {}
+    arrays = {}
+    for tag, (h, w) in (("hr940", (235, 235)), ("native", (128, 256))):
+        # ---- two discriminator updates, generator in eval mode (reference function, unmodified)
+        torch.manual_seed(14)
+        g = models.SRResNet()
+        torch.manual_seed(15)
+        d = models.Discriminator()
+        torch.manual_seed(16)
+        lr = torch.rand(1, 3, h, w)
+        hr = torch.rand(1, 3, 4 * h, 4 * w)
+        d_opt = torch.optim.Adam(d.parameters(), lr=5e-5)
+        with torch.no_grad():
+            g.eval()
+            real0 = d(hr)
+            fake0 = d(g(lr))
+        d_losses = [train.train_discriminator(d, g, hr, lr, d_opt)]
+        torch.autograd.set_detect_anomaly(False)
+        grads = {k: p.grad.detach().clone() for k, p in d.named_parameters()}      # gradients of the FIRST update
+        for _ in range(2):
+            d_losses.append(train.train_discriminator(d, g, hr, lr, d_opt))
+            torch.autograd.set_detect_anomaly(False)
+        arrays[f"{tag}/d_real0"] = real0.numpy()
+        arrays[f"{tag}/d_fake0"] = fake0.numpy()
+        for k in ("model.0.weight", "model.0.bias", "model.4.weight", "model.4.bias"):
+            arrays[f"{tag}/d_grad/{k}"] = grads[k].numpy()
+        for k in ("model.8.weight", "model.12.weight"):
+            arrays[f"{tag}/d_grad_sub/{k}"] = grads[k].flatten()[::97].numpy()      # strided sample of the large tensors
+        rec = {"lr_shape": [1, 3, h, w], "hr_shape": [1, 3, 4 * h, 4 * w], "seeds": {"g": 14, "d": 15, "data": 16},
+               "d_losses": d_losses, "d_grad_norms": {k: float(v.double().norm()) for k, v in grads.items()},
+               "d_param_checksum_after": checksum(d.state_dict())}
+        # ---- GAN-mode generator objective: com + tv + mean(tanh(D(hr) - D(G(lr)))) (the commented reference lines)
+        torch.manual_seed(14)
+        g = models.SRResNet()
+        torch.manual_seed(15)
+        d = models.Discriminator()
+        g.train(); d.eval()
+        sr = g(lr)
+        fake = d(sr)
+        with torch.no_grad():
+            real = d(hr)
+        com, tv = utils.ReconstructionLoss()(hr, sr)
+        g_d = torch.mean(torch.tanh(real - fake))
+        (com + tv + g_d).backward()
+        gg = {k: p.grad.detach() for k, p in g.named_parameters()}
+        # the adversarial term alone (gradient through D into G), for a sharper check of the dgrad chain through D
+        g.zero_grad()
+        sr2 = g(lr)
+        torch.mean(torch.tanh(real - d(sr2))).backward()
+        ga = {k: p.grad.detach() for k, p in g.named_parameters()}
+        for k in ("conv3.weight", "conv3.bias", "upsample.3.bias"):
+            arrays[f"{tag}/g_grad/{k}"] = gg[k].numpy()
+            arrays[f"{tag}/g_grad_adv/{k}"] = ga[k].numpy()
+        rec["gan_mode"] = {"com": com.item(), "tv": tv.item(), "g_d": g_d.item(),
+                           "grad_norms": {k: float(v.double().norm()) for k, v in gg.items()},
+                           "grad_norms_adv": {k: float(v.double().norm()) for k, v in ga.items()}}
+        out[tag] = rec
+        print(tag, "d_losses", d_losses, "g_d", g_d.item(), flush=True)
+    np.savez_compressed(os.path.join(HERE, "adversarial.npz"), **arrays)
+    with open(os.path.join(HERE, "adversarial.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+def make_checkpoint_fixture(models):
+    """A checkpoint written the way the reference writes it under DDP (src/train.py:123-125 saves
+    ``generator.state_dict()`` of the DDP-wrapped model: every key carries the ``module.`` prefix), for the f-1
+    interop test.  Tiny SRResNet (2 residual blocks) to keep the file small.  python tests/golden/make_golden.py checkpoint"""
+    torch.manual_seed(21)
+    g = models.SRResNet(num_residuals=2)
+    g.train()
+    with torch.no_grad():
+        g(torch.rand(1, 3, 8, 8))             # one training-mode pass: BatchNorm buffers / num_batches_tracked move
+    sd = {"module." + k: v for k, v in g.state_dict().items()}
+    torch.save(sd, os.path.join(HERE, "reference_ddp_checkpoint.pth"))
+    g.eval()
+    x = torch.linspace(0, 1, 3 * 12 * 10).reshape(1, 3, 12, 10)
+    with torch.no_grad():
+        y = g(x)
+    np.savez_compressed(os.path.join(HERE, "reference_ddp_checkpoint_io.npz"), x=x.numpy(), y=y.numpy())
+
+
 def main():
     torch.set_num_threads(8)
     models, train, utils = import_reference()
@@ -147,6 +233,8 @@ def main():
                        "grad_norms": {k: float(p.grad.double().norm()) for k, p in g.named_parameters()}}
 
     make_enhancer_fixture(models)
+    make_adversarial_fixture(models, train, utils)
+    make_checkpoint_fixture(models)
 
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, indent=1)
@@ -156,5 +244,10 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "enhancer":
         make_enhancer_fixture(import_reference()[0])
+    elif len(sys.argv) > 1 and sys.argv[1] == "adversarial":
+        torch.set_num_threads(8)
+        make_adversarial_fixture(*import_reference())
+    elif len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
+        make_checkpoint_fixture(import_reference()[0])
     else:
         main()

@@ -25,13 +25,15 @@ def make(K, seed0=0):
 
 
 def main():
-    a = [int(x) for x in sys.argv[1:]]
+    joint_only = "--joint-only" in sys.argv
+    a = [int(x) for x in sys.argv[1:] if not x.startswith("--")]
     K, N, H, W = (a + [3, 16, 96, 96])[:4] if len(a) >= 4 else (3, 16, 96, 96)
+    S.lib().srg_set_trunk_fused(1)          # force the fused trunk kernel (automatic mode picks it for small geometries only)
     crit = S.ReconstructionLoss()
     gen = torch.Generator(device="cpu").manual_seed(7)
     batches = [(torch.rand(N, 3, H, W, generator=gen).cuda(), torch.rand(N, 3, 4 * H, 4 * W, generator=gen).cuda()) for _ in range(3)]
     out = {}
-    for joint in (False, True):
+    for joint in ((True,) if joint_only else (False, True)):
         gens, opts = make(K)
         step = S.GraphedMultiGeneratorStep(gens, crit, opts, batches[0][0], batches[0][1], joint=joint)
         assert step.joint == joint, "joint path was refused"
@@ -55,6 +57,8 @@ def main():
               flush=True)
         if joint:
             prof_dump("joint", K)
+    if joint_only:
+        sys.exit(1 if any(out[True][4]) else 0)
     la, lb = out[False][0], out[True][0]
     for t in range(3):
         print(f"step {t}: losses per-generator-branches {la[t][:, 0].tolist()}  joint {lb[t][:, 0].tolist()}")

@@ -21,14 +21,14 @@ def rel(a, b):
 def prof_dump(tag, K=1):
     import ctypes
     import numpy as np
-    NT = 148 * 18 + 148 * 128 * 8
+    NT = 148 * 18 + 148 * 128 * 16
     buf = (ctypes.c_longlong * NT)()
     n = S.lib().srg_debug_trunk_prof(buf, NT)
     if n <= 0:
         return
     full = np.array(buf[:n], dtype=np.int64)
     tot = full[:148 * 18].reshape(148, 18)[:, 4].max()
-    tr = full[148 * 18:].reshape(148, 128, 8)
+    tr = full[148 * 18:].reshape(148, 128, 16)
     names = ["prod:flags ok", "mma:operands in", "mma:last issued", "st:raw stored", "p1:slot done", "ap:arrive", "ap:sums published",
              "ap:transform start"]
     print(f"  [{tag}] kernel cycles (max over CTAs) {tot}")
@@ -38,6 +38,8 @@ def prof_dump(tag, K=1):
             print(f"    cta {cta} slot {s_}: " + "  ".join(f"{names[e].split(':')[1]}={tr[cta, s_, e] - t0}" for e in (0, 2, 4, 3, 5, 6, 7))
                   + f"  | next slot: flags ok={tr[cta, s_ + 1, 0] - t0} operands in={tr[cta, s_ + 1, 1] - t0}"
                   + (f"  | same generator's next layer: flags ok={tr[cta, s_ + K, 0] - t0} operands in={tr[cta, s_ + K, 1] - t0}" if K > 1 else ""))
+            e = tr[cta, s_, 8:16] - tr[cta, s_, 8]
+            print(f"      tile 1 epilogue: pass2 {e[1]}  bar_a+y {e[2] - e[1]}  wait acc {e[3] - e[2]}  wait buf {e[4] - e[3]}  tmem+stage+park {e[5] - e[4]}  bar_b {e[6] - e[5]}  stats {e[7] - e[6]}  total {e[7]}")
 
 
 def one_pass(g, crit, lr, hr):
