@@ -131,7 +131,9 @@ int srg_nccl_unique_id(void* out128); /* host buffer, 128 bytes */
 int srg_nccl_comm_create(const void* unique_id128, int world, int rank, void** comm_out);
 void srg_nccl_comm_destroy(void* comm);
 int srg_nccl_allreduce_f64(void* comm, double* buf, int n, void* stream);
-int srg_nccl_allreduce_f32(void* comm, float* buf, int64_t n, void* stream); /* flat gradient all-reduce (sum) */
+int srg_nccl_allreduce_f32(void* comm, float* buf, int64_t n, void* stream);
+/* mean over ranks in one collective (ncclAvg): the DDP gradient all-reduce of src/train.py:195 without a scaling pass */
+int srg_nccl_allreduce_mean_f32(void* comm, float* buf, int64_t n, void* stream); /* flat gradient all-reduce (sum) */
 int srg_generator_use_nccl(srg_generator_t* g, void* comm, int world);
 
 /* SyncBatchNorm over NVLink peer memory (preferred to the NCCL hook): the statistics reduction, the exchange with all

@@ -109,6 +109,7 @@ EXPORTS = {
     "srg_nccl_comm_destroy": (None, [c_void_p]),
     "srg_nccl_allreduce_f64": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "srg_nccl_allreduce_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "srg_nccl_allreduce_mean_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "srg_generator_use_nccl": (c_int, [c_void_p, c_void_p, c_int]),
     "srg_peer_sync_create": (c_int, [POINTER(c_void_p), c_int, c_int]),
     "srg_peer_sync_handle": (c_int, [c_void_p, c_void_p]),

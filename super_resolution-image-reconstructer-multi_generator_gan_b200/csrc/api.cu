@@ -39,7 +39,7 @@ struct NcclApi {
   CommDestroyFn comm_destroy = nullptr;
   GetErrorStringFn error_string = nullptr;
 } g_nccl;
-constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0, kNcclAvg = 4;
 
 int nccl_load() {
   if (g_nccl.handle) return 0;
@@ -229,6 +229,10 @@ int srg_nccl_allreduce_f64(void* comm, double* buf, int n, void* stream) {
 int srg_nccl_allreduce_f32(void* comm, float* buf, int64_t n, void* stream) {
   if (comm == nullptr) { set_error("NCCL communicator is null"); return -44; }
   return nccl_check(g_nccl.all_reduce(buf, buf, size_t(n), kNcclFloat32, kNcclSum, comm, S(stream)), "ncclAllReduce");
+}
+int srg_nccl_allreduce_mean_f32(void* comm, float* buf, int64_t n, void* stream) {
+  if (comm == nullptr) { set_error("NCCL communicator is null"); return -44; }
+  return nccl_check(g_nccl.all_reduce(buf, buf, size_t(n), kNcclFloat32, kNcclAvg, comm, S(stream)), "ncclAllReduce(avg)");
 }
 int srg_generator_use_nccl(srg_generator_t* g, void* comm, int world) {
   if (comm == nullptr) { set_error("NCCL communicator is null"); return -44; }

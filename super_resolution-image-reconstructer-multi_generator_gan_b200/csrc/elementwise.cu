@@ -300,6 +300,26 @@ int launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* ru
   return 0;
 }
 
+// every eval-mode BatchNorm of a generator in ONE launch, issued before the first conv of the forward: the convs are
+// launched with programmatic dependent launch and read their folded coefficients in the prologue, BEFORE
+// griddepcontrol.wait, so the coefficients must not come from the immediately preceding kernel (launch.cuh)
+__global__ void bn_eval_coeffs_all_kernel(const float* __restrict__ master, const float* __restrict__ buffers,
+                                          const int4* __restrict__ tab, float eps, float* __restrict__ coef) {
+  const int l = blockIdx.x, c = threadIdx.x;
+  const int4 t = tab[l];                      // {gamma, beta, running_mean, conv bias} offsets
+  const float* rm = buffers + t.z;
+  const float sc = master[t.x + c] * rsqrtf(rm[64 + c] + eps);
+  coef[size_t(l) * 256 + c] = sc;
+  coef[size_t(l) * 256 + 64 + c] = master[t.y + c] + (master[t.w + c] - rm[c]) * sc;
+}
+int launch_bn_eval_coeffs_all(const float* master, const float* buffers, const void* tab, int n_bn, float eps, float* coef,
+                              cudaStream_t st) {
+  if (n_bn <= 0) return 0;
+  bn_eval_coeffs_all_kernel<<<n_bn, 64, 0, st>>>(master, buffers, reinterpret_cast<const int4*>(tab), eps, coef);
+  SRG_LAUNCH_CHECK("bn_eval_coeffs_all");
+  return 0;
+}
+
 template <bool RELU, bool SKIP>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, const uint4* __restrict__ skip,

@@ -53,6 +53,10 @@ int launch_bn_finalize(const double* sums, double count, const float* gamma, con
 int launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
                           const float* running_var, float eps, float* scale, float* shift, cudaStream_t st,
                           const float* conv_bias = nullptr);
+// all `n_bn` eval-mode BatchNorm layers of a model at once: tab[l] = int4{gamma, beta, running_mean (running_var = +64),
+// conv bias} float offsets into master / buffers; coef[l][256] = {scale[64], shift[64] with the conv bias folded in, ...}
+int launch_bn_eval_coeffs_all(const float* master, const float* buffers, const void* tab, int n_bn, float eps, float* coef,
+                              cudaStream_t st);
 // out = act(scale*y + shift) (+ skip);  relu: 0/1
 int launch_bn_apply(const void* y, const float* scale, const float* shift, const void* skip, int relu, void* out,
                     int64_t pixels, cudaStream_t st);

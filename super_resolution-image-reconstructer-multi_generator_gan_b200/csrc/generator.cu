@@ -80,7 +80,7 @@ Layout make_layout(const GeneratorEngine& e, bool training) {
   L.sums = c.take(128 * 8);
   L.ticket = c.take(256);
   L.trunk_sync = c.take(trunk_sync_bytes(e.N, e.H, e.W));
-  L.trunk_tab = c.take(size_t(2) * (2 * e.n_res + 1) * sizeof(TrunkLayer));
+  L.trunk_tab = c.take(size_t(2) * (2 * e.n_res + 1) * sizeof(TrunkLayer));   // eval: 2*n_res int4 BatchNorm offset rows instead
   L.U1 = c.take(size_t(e.N) * (e.H + 1) * e.W * 128);
   L.out1 = c.take(t64(P));
   L.y1.resize(e.n_res); L.z1.resize(e.n_res); L.y2.resize(e.n_res); L.out.resize(e.n_res);
@@ -660,6 +660,22 @@ int generator_bind(GeneratorEngine* g, float* master, float* grads, float* bn_bu
   e->L = make_layout(*e, training != 0);
   if (cudaMemset(e->ws + e->L.ticket, 0, 256) != cudaSuccess) { set_error("generator_bind: memset failed"); return -29; }
   e->trunk_ok = false;
+  if (!training && e->n_res > 0) {
+    // eval mode: offsets of every BatchNorm's parameters / statistics / preceding conv bias for launch_bn_eval_coeffs_all
+    std::vector<int> tab;
+    char nm[96];
+    for (int b = 0; b < e->n_res; ++b)
+      for (int k = 1; k <= 2; ++k) {
+        snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.weight", b, k); tab.push_back(int(poff(*e, nm)));
+        snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.bias", b, k); tab.push_back(int(poff(*e, nm)));
+        snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.running_mean", b, k); tab.push_back(int(boff(*e, nm)));
+        snprintf(nm, sizeof(nm), "residual_blocks.%d.conv%d.bias", b, k); tab.push_back(int(poff(*e, nm)));
+      }
+    if (cudaMemcpy(e->ws + e->L.trunk_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("generator_bind: upload of the BatchNorm offset table failed");
+      return -29;
+    }
+  }
   if (training) {
     std::vector<TrunkLayer> tf, tb;
     if (build_trunk_tables(*e, tf, tb)) {
@@ -740,6 +756,12 @@ int generator_forward_phases(GeneratorEngine* g, const float* lr, float* sr, int
     set_error("generator_forward_phases: split execution needs the fused trunk path (training, supported configuration)");
     return -31;
   }
+  if (!training && e->n_res > 0) {
+    // eval: every BatchNorm's folded coefficients in one launch, two kernels ahead of the first conv that reads them
+    RC(launch_bn_eval_coeffs_all(e->master, e->bn_buffers, ws + L.trunk_tab, 2 * e->n_res, kBnEps,
+                                 reinterpret_cast<float*>(ws + L.bncoef), st));
+    e->launches += 1;
+  }
   // conv1: 9x9, 3->64, LeakyReLU(0.2)  (src/models.py:56-57,81)
   if (phases & kPhasePre) {
   RC(launch_unfold9(lr, N, H, W, 1.f, ws + L.U1, st));
@@ -814,11 +836,7 @@ int generator_forward_phases(GeneratorEngine* g, const float* lr, float* sr, int
     const float* coef2 = coef1 + 256;
     if (!training) {
       // eval mode: 2 conv launches per block, BatchNorm folded into their epilogues (no y1 / y2 round trip through HBM)
-      snprintf(nm, sizeof(nm), "residual_blocks.%d.conv1.bias", b);
-      RC(bn_coeffs(b, 0, e->master + poff(*e, nm)));
       RC(conv3x3(x, po.rb_f[0][b], coef1 + 64, nullptr, ws + L.z1[b], false, coef1, ACT_RELU));
-      snprintf(nm, sizeof(nm), "residual_blocks.%d.conv2.bias", b);
-      RC(bn_coeffs(b, 1, e->master + poff(*e, nm)));
       RC(conv3x3(ws + L.z1[b], po.rb_f[1][b], coef2 + 64, x, ws + L.out[b], false, coef2, ACT_NONE));
       x = ws + L.out[b];
       continue;

@@ -21,6 +21,9 @@ namespace {
 constexpr int kSlots = 4;
 constexpr int kSlotDoubles = 136;   // 128 sums + flag + padding (1088 bytes)
 constexpr int kMaxWorld = 8;
+// ~64 ns per probe: 2^26 probes is minutes, long enough for a peer held up by data loading, checkpoint I/O or a first-time
+// graph capture (the round-1 bound of 2^22 gave up after a few seconds and then normalised with stale sums)
+constexpr long long kPeerWaitSpins = 1ll << 26;
 
 struct PeerParams {
   double* peers[kMaxWorld];   // exchange buffers of all ranks (peers[rank] is the local one)
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(1024) peer_finalize_kernel(const float* __rest
                                                              const PeerParams pp) {
   __shared__ double red[8][128];
   __shared__ unsigned long long seq_s;
+  __shared__ int timed_out;
   // NOTE: pdl_trigger() only AFTER the cross-GPU wait below.  Triggering early would let the dependent kernel's blocks
   // fill every SM while this block spins on a peer; the peer's matching kernel of ANOTHER graph branch could then find
   // no free SM on its GPU and the two GPUs would wait on each other forever.
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(1024) peer_finalize_kernel(const float* __rest
   }
   for (; b < rows; b += 8) a0 += double(partials[size_t(b) * 128 + col]);
   red[rl][col] = (a0 + a1) + (a2 + a3);
-  if (threadIdx.x == 0) seq_s = ++(*pp.seq);
+  if (threadIdx.x == 0) { seq_s = ++(*pp.seq); timed_out = 0; }
   __syncthreads();
   const unsigned long long seq = seq_s;
   const int slot = int(seq % kSlots);
@@ -112,7 +116,9 @@ __global__ void __launch_bounds__(1024) peer_finalize_kernel(const float* __rest
         reinterpret_cast<const unsigned long long*>(pp.peers[pp.rank] + (size_t(slot) * pp.world + r) * kSlotDoubles + 128);
     long long spins = 0;
     while (ld_acquire_sys(flag) != seq) {
-      if (++spins > (1ll << 22)) { *pp.err = 1; break; }   // a few seconds: never hang the GPU on a lost peer
+      // a lost / stalled peer must never hang the GPU -- but it must not go unnoticed either: the statistics are
+      // poisoned below (NaN losses on every rank that missed a contribution) and *err makes the host raise
+      if (++spins > kPeerWaitSpins) { *pp.err = 1; timed_out = 1; break; }
       __nanosleep(64);
     }
   }
@@ -122,6 +128,7 @@ __global__ void __launch_bounds__(1024) peer_finalize_kernel(const float* __rest
   if (rl == 0) {
     double t = 0.0;
     for (int r = 0; r < pp.world; ++r) t += ld_volatile_f64(pp.peers[pp.rank] + (size_t(slot) * pp.world + r) * kSlotDoubles + col);
+    if (timed_out) t = __longlong_as_double(0x7ff8000000000000ll);      // NaN: a missing contribution is never silently used
     red[0][col] = t;
   }
   __syncthreads();

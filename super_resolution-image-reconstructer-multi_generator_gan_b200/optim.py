@@ -74,6 +74,12 @@ class Adam(torch.optim.Optimizer):
                         st["step_dev"] = torch.full((1,), int(st["step"]), dtype=torch.int32, device=flat.device)
                         st["lr_dev"] = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=flat.device)
                         st["lr_host"] = float(group["lr"])
+                    elif st["lr_host"] != float(group["lr"]) and not torch.cuda.is_current_stream_capturing():
+                        # a scheduler moved the learning rate (LinearLR, src/train.py:70-71): refresh the device scalar.
+                        # Under stream capture the value is baked into nothing -- the graph reads lr_dev -- so the
+                        # graphed steps refresh it through sync_lr() right before each replay instead.
+                        st["lr_dev"].fill_(float(group["lr"]))
+                        st["lr_host"] = float(group["lr"])
                     check(L.srg_adam_step_dev(c_void_p(flat.data_ptr()), c_void_p(gflat.data_ptr()),
                                               c_void_p(st["m"].data_ptr()), c_void_p(st["v"].data_ptr()), flat.numel(),
                                               c_void_p(st["lr_dev"].data_ptr()), float(b1), float(b2), float(group["eps"]),
@@ -95,6 +101,40 @@ class Adam(torch.optim.Optimizer):
                 if st is not None and "lr_dev" in st and st["lr_host"] != float(group["lr"]):
                     st["lr_dev"].fill_(float(group["lr"]))
                     st["lr_host"] = float(group["lr"])
+
+    # ---- checkpointing: m / v / step live in flat per-module buffers, not in torch's per-parameter state dict
+    def state_dict(self):
+        sd = super().state_dict()
+        flat = []
+        for group in self.param_groups:
+            for owner in self._owners(group):
+                st = self._flat_state.get(id(owner))
+                if st is None:
+                    flat.append(None)
+                    continue
+                step = int(st["step_dev"].item()) if "step_dev" in st else int(st["step"])
+                flat.append({"m": st["m"].detach().clone(), "v": st["v"].detach().clone(), "step": step})
+        sd["srg_flat_state"] = flat
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat = state_dict.pop("srg_flat_state", None)
+        super().load_state_dict(state_dict)
+        if flat is None:
+            return
+        i = 0
+        for group in self.param_groups:
+            for owner in self._owners(group):
+                src = flat[i] if i < len(flat) else None
+                i += 1
+                if src is None:
+                    continue
+                ref = owner.flat_parameters()
+                st = {"m": src["m"].to(ref.device).clone(), "v": src["v"].to(ref.device).clone(), "step": int(src["step"])}
+                if st["m"].numel() != ref.numel():
+                    raise RuntimeError("optim.Adam.load_state_dict: flat state does not match the module's parameter layout")
+                self._flat_state[id(owner)] = st          # capturable device scalars are re-created lazily by step()
 
     def flat_state(self, owner) -> dict:
         """{"m": exp_avg, "v": exp_avg_sq, "step": int} in the owner's flat layout (checkpointing / tests)."""

@@ -87,6 +87,15 @@ def peer_sync_errors() -> int:
     return sum(int(L.srg_peer_sync_error(p)) for p in _peers)
 
 
+def check_peer_sync() -> None:
+    """Raise if a SyncBatchNorm peer exchange ever gave up waiting for a peer GPU (csrc/peer_sync.cu poisons the
+    statistics of that step with NaN; this turns it into an exception at the next loss read-back).  No-op without
+    peer-sync objects; otherwise one 4-byte device read per object, so call it where the host synchronises anyway."""
+    if _peers and peer_sync_errors():
+        raise RuntimeError("SyncBatchNorm peer exchange timed out: a peer GPU did not deliver its BatchNorm statistics "
+                           "(rank stalled or lost); the affected steps carry NaN statistics")
+
+
 def shutdown_nccl() -> None:
     L = _lib.lib()
     while _comms:
@@ -103,11 +112,12 @@ def average_gradients_hook(group: Optional[dist.ProcessGroup] = None, comm: Opti
         if world == 1:
             return
         if comm is not None:
-            check(_lib.lib().srg_nccl_allreduce_f32(comm, c_void_p(flat_grads.data_ptr()), flat_grads.numel(), stream_ptr()),
-                  "srg_nccl_allreduce_f32")
+            # ncclAvg: sum and 1/world in the collective itself, no extra pass over the gradients
+            check(_lib.lib().srg_nccl_allreduce_mean_f32(comm, c_void_p(flat_grads.data_ptr()), flat_grads.numel(),
+                                                         stream_ptr()), "srg_nccl_allreduce_mean_f32")
         else:
-            dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
-        flat_grads.mul_(1.0 / world)
+            dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)     # gloo (CPU tests) has no averaging op
+            flat_grads.mul_(1.0 / world)
     return hook
 
 

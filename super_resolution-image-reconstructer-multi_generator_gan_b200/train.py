@@ -144,6 +144,8 @@ def train_one_epoch(generator, train_loader, g_optimizer, vgg_extractor, g_crite
         n += 1
     n = max(n, 1)
     avg = float(sums[0]) / n
+    from . import parallel
+    parallel.check_peer_sync()          # a SyncBatchNorm exchange that timed out during the epoch raises here
     if verbose:
         print(f"Epoch [{epoch + 1}/{num_epochs}] {prefix} Loss: {avg:.6f}")
         print(f"com_loss: {float(sums[1]) / n}, tv_loss: {float(sums[2]) / n}, g_d_loss: {float(sums[3]) / n}")
@@ -531,6 +533,9 @@ class MultiGeneratorGAN:
         while len(self._pending) > keep:
             gids, dev_losses = self._pending.pop(0)
             host = dev_losses.tolist()
+            if self.loss_allreduce is not None:
+                from . import parallel
+                parallel.check_peer_sync()       # the host just synchronised: surface a timed-out SyncBatchNorm exchange
             for gid, row in zip(gids, host):
                 self.policy.observe(gid, row[1])
 

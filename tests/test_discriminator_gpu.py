@@ -195,6 +195,106 @@ def test_train_discriminator_and_gan_mode_steps(S, O):
     assert all(p.grad is None or torch.isfinite(p.grad).all() for p in g.parameters())
 
 
+def _cos(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-300)), float(a.norm() / b.norm().clamp_min(1e-300))
+
+
+def test_adversarial_steps_match_reference_fixtures(S, golden_dir):
+    """train_discriminator (src/train.py:206-230) and the GAN-mode generator objective (src/train.py:184-192) against
+    numbers recorded from the UNMODIFIED reference (tests/golden/adversarial.{json,npz}, make_golden.py) at two
+    non-degenerate geometries: HR 940x940 (discriminator map 512x3x3) and the native 512x1024 crop (512x1x3).
+
+    What can be pinned end to end is set by the reference's own conditioning, not by this implementation: its fp32
+    gradient d(g_d)/d(sr) keeps only cos 0.97 (940x940) / 0.54 (native) with itself when its INPUT is merely rounded to
+    bf16 (tests/test_oracle_golden.py::test_discriminator_gradient_conditioning) -- MaxPool argmax flips and an
+    InstanceNorm over 9 / 3 elements amplify 2^-9 perturbations.  So: losses to a few percent, gradient norms to 25 %,
+    directions as far as that conditioning allows; the per-stage tests above carry the 1e-2 bound on identical inputs."""
+    import json
+    import os
+    import numpy as np
+    meta = json.load(open(os.path.join(golden_dir, "adversarial.json")))
+    z = np.load(os.path.join(golden_dir, "adversarial.npz"))
+    bounds = {"hr940": dict(loss=0.05, dcos=0.80, dratio=0.10, gcos=0.98, acos=0.50, aratio=0.20, fwd=0.985),
+              "native": dict(loss=0.12, dcos=0.40, dratio=0.30, gcos=0.85, acos=-1.0, aratio=0.30, fwd=0.95)}
+    for tag, rec in meta.items():
+        b = bounds[tag]
+        torch.manual_seed(14); g = S.SRResNet()
+        torch.manual_seed(15); d = S.Discriminator()
+        torch.manual_seed(16)
+        lr = torch.rand(*rec["lr_shape"]).cuda(); hr = torch.rand(*rec["hr_shape"]).cuda()
+        g, d = g.cuda(), d.cuda()
+        with torch.no_grad():
+            g.eval()
+            real0, fake0 = d(hr).cpu(), d(g(lr)).cpu()
+        assert real0.shape == tuple(z[f"{tag}/d_real0"].shape)
+        assert _cos(real0 - 0.5, torch.from_numpy(z[f"{tag}/d_real0"]) - 0.5)[0] > max(b["fwd"], 0.99), tag
+        assert _cos(fake0 - 0.5, torch.from_numpy(z[f"{tag}/d_fake0"]) - 0.5)[0] > b["fwd"], tag
+        # three discriminator updates: loss trajectory of the reference function
+        d_opt = S.Adam(d.parameters(), lr=5e-5)
+        grads = None
+        for i, ref in enumerate(rec["d_losses"]):
+            loss = S.train_discriminator(d, g, hr, lr, d_opt)
+            assert abs(loss - ref) < b["loss"] * abs(ref) + 1e-4, (tag, i, loss, ref)
+            if i == 0:
+                grads = {k: p.grad.detach().clone() for k, p in d.named_parameters()}
+        for k in ("model.0.weight", "model.4.weight"):
+            c, r = _cos(grads[k], torch.from_numpy(z[f"{tag}/d_grad/{k}"]))
+            assert c > b["dcos"] and abs(r - 1) < b["dratio"], (tag, k, c, r)
+        for k in ("model.8.weight", "model.12.weight"):
+            c, _ = _cos(grads[k].flatten()[::97], torch.from_numpy(z[f"{tag}/d_grad_sub/{k}"]))
+            r = float(grads[k].double().norm()) / rec["d_grad_norms"][k]
+            assert c > b["dcos"] and abs(r - 1) < b["dratio"], (tag, k, c, r)
+        # GAN-mode generator step with the initial discriminator: com + tv + mean(tanh(D(hr) - D(G(lr))))
+        torch.manual_seed(14); g = S.SRResNet().cuda()
+        torch.manual_seed(15); d = S.Discriminator().cuda()
+        g_opt = S.Adam(g.parameters(), lr=1e-4)
+        g_loss, com, tv, g_d = S.train_generator(g, d, lr, hr, None, S.ReconstructionLoss(), g_opt, gan_mode=True)
+        gm = rec["gan_mode"]
+        assert abs(com - gm["com"]) < 1e-3 * gm["com"] and abs(tv - gm["tv"]) < 2e-2 * gm["tv"], (tag, com, tv)
+        assert abs(g_d - gm["g_d"]) < 0.35 * abs(gm["g_d"]) + 1e-4 and g_d * gm["g_d"] > 0, (tag, g_d, gm["g_d"])
+        assert abs(g_loss - (com + tv + g_d)) < 1e-5
+        gg = {k: p.grad.detach().clone() for k, p in g.named_parameters()}
+        for k in ("conv3.weight", "conv3.bias"):
+            c, r = _cos(gg[k], torch.from_numpy(z[f"{tag}/g_grad/{k}"]))
+            assert c > b["gcos"] and abs(r - 1) < 0.05, (tag, k, c, r)
+        for k in ("conv1.weight", "residual_blocks.0.conv1.weight", "upsample.0.weight"):
+            assert abs(float(gg[k].double().norm()) / gm["grad_norms"][k] - 1) < 0.25, (tag, k)
+        # the adversarial term alone: the gradient that flows through D (input-gradient-only backward) into G
+        torch.manual_seed(14); g = S.SRResNet().cuda().train()
+        torch.manual_seed(15); d = S.Discriminator().cuda().eval()
+        sr = g(lr)
+        with d.input_grad_only():
+            fake = d(sr)
+        with torch.no_grad():
+            real = d(hr)
+        S.tanh_mean(real, fake).backward()
+        for k in ("conv3.weight", "upsample.3.bias"):
+            c, r = _cos(dict(g.named_parameters())[k].grad, torch.from_numpy(z[f"{tag}/g_grad_adv/{k}"]))
+            assert c > b["acos"] and abs(r - 1) < b["aratio"], (tag, k, c, r)
+        for k in ("conv1.weight", "residual_blocks.0.conv1.weight", "upsample.0.weight"):
+            n = float(dict(g.named_parameters())[k].grad.double().norm())
+            assert abs(n / gm["grad_norms_adv"][k] - 1) < 0.25, (tag, k, n)
+        assert all(v is None or torch.isfinite(v).all() for v in (p.grad for p in d.parameters()))
+
+
+def test_input_grad_only_backward_equals_full_backward(S):
+    """Composition pin that is free of the reference's ill-conditioning: the input-gradient-only discriminator backward
+    used by the GAN-mode generator step must give exactly the d(sr) of the full backward (same kernels, parameter
+    gradients skipped)."""
+    torch.manual_seed(31)
+    d = S.Discriminator().cuda()
+    x0 = torch.rand(1, 3, 512, 1024).cuda()
+    w = torch.randn(1, 512, 1, 3).cuda() * 1e-2
+    xa = x0.clone().requires_grad_(True)
+    d(xa).backward(w)
+    xb = x0.clone().requires_grad_(True)
+    with d.input_grad_only():
+        out = d(xb)
+    out.backward(w)
+    assert torch.equal(xa.grad, xb.grad)
+
+
 def test_gan_mode_cuda_graphs_match_eager(S):
     """D step + GAN-mode generator steps replayed from CUDA graphs equal the eagerly enqueued steps bit for bit."""
     crit = S.ReconstructionLoss()

@@ -184,3 +184,19 @@ def test_conv9_rows_schedule_applies_every_row_tap_once_per_output_row():
         assert sorted(seen[j]) == list(range(9)), (j, seen[j])
         assert first[j][1] == 0 and first[j][2], (j, first[j])       # first touch = tap kh 0, flagged fresh
     assert L.srg_conv9_rows_window(16, None, None, None, None) != 0
+
+
+def test_reference_written_checkpoint_fixture_loads_on_cpu(golden_dir):
+    """f-1 on the host side: the reference-written DDP checkpoint (module. prefix) maps onto the drop-in module's keys."""
+    import os
+    import torch
+    import srgan_b200 as S
+    g = S.SRResNet(num_residuals=2)
+    sd = torch.load(os.path.join(golden_dir, "reference_ddp_checkpoint.pth"), map_location="cpu", weights_only=True)
+    assert all(k.startswith("module.") for k in sd)
+    res = S.load_reference_checkpoint(g, sd)
+    assert not res.missing_keys and not res.unexpected_keys
+    mine = g.state_dict()
+    assert set(mine) == {k[len("module."):] for k in sd}
+    for k, v in sd.items():
+        assert torch.equal(mine[k[len("module."):]].cpu(), v), k

@@ -140,3 +140,32 @@ def test_image_enhancer_matches_reference(golden_dir):
     x = torch.from_numpy(z["x"])
     np.testing.assert_allclose(O.image_enhancer(x, 1.0).numpy(), z["y1"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(O.image_enhancer(x, 0.5).numpy(), z["y05"], rtol=0, atol=1e-6)
+
+
+def test_discriminator_gradient_conditioning():
+    """Why end-to-end gradient parity through the reference Discriminator cannot be stated at 1e-2: the oracle's OWN fp32
+    gradient of the adversarial term w.r.t. the image keeps a cosine of only ~0.5-0.7 with itself at the native 512x1024
+    geometry when the input image is rounded to bf16 and nothing else changes (last InstanceNorm over 3 elements, MaxPool
+    argmax flips); at 940x940 (9 elements) it stays ~0.97.  The GPU tests therefore bound per-stage errors on identical
+    inputs at 1e-2 and end-to-end directions only as far as this conditioning allows."""
+    import torch
+    from oracle import srgan_oracle as O
+    torch.set_num_threads(max(torch.get_num_threads(), 4))
+    sd = O.init_discriminator_state(15)
+
+    def grad(x, real):
+        x = x.clone().requires_grad_(True)
+        torch.mean(torch.tanh(real - O.discriminator_forward(sd, x))).backward()
+        return x.grad.double().flatten()
+
+    res = {}
+    for (h, w) in ((512, 1024), (940, 940)):
+        torch.manual_seed(16)
+        hr, sr = torch.rand(1, 3, h, w), torch.rand(1, 3, h, w) * 0.2
+        with torch.no_grad():
+            real = O.discriminator_forward(sd, hr)
+        g0, g1 = grad(sr, real), grad(sr.bfloat16().float(), real)
+        res[(h, w)] = float(torch.dot(g0, g1) / (g0.norm() * g1.norm()))
+    assert res[(512, 1024)] < 0.9, res          # ill-conditioned: a bf16-sized input perturbation turns the gradient
+    assert res[(940, 940)] > 0.9, res
+    assert res[(940, 940)] > res[(512, 1024)], res
