@@ -2,14 +2,18 @@
 """Benchmark of the SR-GAN train step (BASELINE.json metric: train LR-patches/sec; conv tensor-pipe roofline).
 
     python bench.py --gpus 1 --steps 20 --warmup 3                 # this repo's CUDA path on cuda:0
-    torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU, batch-sharded (weak scaling)
-    python bench.py --impl reference --steps 3 --warmup 1           # the reference's CPU arithmetic (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU: BASELINE configs[2], global batch 256
+    python bench.py --impl reference --steps 3 --warmup 1           # the UNMODIFIED reference step on the host cores
 
 Workload (N=1): BASELINE.json configs[1] -- K=3 generators (count inferred from src/main.py:28), each doing the
 reference's train_generator step (SRResNet fwd+bwd, ReconstructionLoss, Adam) on one batch of 16x3x96x96 synthetic LR
 patches (HR 16x3x384x384), bf16 operands / fp32 accumulate.  The reference Discriminator raises on 384x384 HR inputs
 (SURVEY Appendix E), so like the reference's HEAD the discriminator step is not part of this configuration.
 One step = all K generator updates on one batch; value = batch patches / step time, summed over ranks.
+
+Workload (N > 1): BASELINE.json configs[2] -- the same step batch-sharded over N GPUs at GLOBAL batch 256 (256/N patches
+per GPU), NCCL gradient all-reduce + SyncBatchNorm; the line also carries the weak-scaling figure at 16 patches per GPU
+("weak16") so that both readings of the scaling question are on record.
 """
 import argparse
 import json
@@ -37,7 +41,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--generators", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16, help="LR patches per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="LR patches per GPU per step (default: 16 on one GPU = "
+                    "configs[1]; 256 / N on N > 1 GPUs = configs[2])")
+    ap.add_argument("--no-weak16", action="store_true", help="N > 1: skip the secondary 16-patches-per-GPU measurement")
+    ap.add_argument("--no-hbm", action="store_true", help="skip the HBM roofline leg (memory-bound kernels timed alone)")
     ap.add_argument("--lr-size", type=int, default=96)
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "gan-native", "infer-1080p"],
                     help="cfg2: BASELINE configs[1] (default).  gan-native: D update + all generators in GAN mode at the "
@@ -56,7 +63,10 @@ def parse():
 
 def geometry(a):
     if a.workload == "gan-native":
-        return 12, 128, 256                  # batch 12 (src/train.py:94), LR 128x256 (src/transformers.py:74)
+        return (a.batch or 12), 128, 256     # batch 12 (src/train.py:94), LR 128x256 (src/transformers.py:74)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.batch is None:
+        return (16 if world == 1 else max(256 // world, 1)), a.lr_size, a.lr_size
     return a.batch, a.lr_size, a.lr_size
 
 
@@ -65,7 +75,9 @@ def workload_name(a):
     if a.workload == "gan-native":
         return (f"gan-native: train_discriminator + {a.generators} generators x train_generator in GAN mode "
                 f"(SRResNet fwd+bwd, ReconstructionLoss + tanh adversarial term through D, Adam), {b}x3x{h}x{w} LR -> x4 HR per GPU")
-    return (f"cfg2: {a.generators} generators x train_generator (SRResNet fwd+bwd + ReconstructionLoss + Adam), "
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = "cfg2" if world == 1 else f"cfg3 (global batch {b * world} over {world} GPUs)"
+    return (f"{cfg}: {a.generators} generators x train_generator (SRResNet fwd+bwd + ReconstructionLoss + Adam), "
             f"{b}x3x{h}x{w} LR -> x4 HR per GPU, pixel-loss mode (reference D invalid at this HR size)")
 
 
@@ -127,55 +139,90 @@ class ClockSampler:
 # CPU arithmetic of the reference (oracle port): used by --impl reference and by the cpu_baseline leg only
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_reference_steps(a, steps, warmup, budget_s=150.0):
+    """K x train_generator on the host cores, on a bounded sample of the batch.  Runs the UNMODIFIED reference
+    (src/train.py:175-203 with src/models.py / src/utils.py, copied verbatim into the git-ignored oracle/_ref by
+    oracle/make_ref.py) when that copy travelled with the snapshot -> kind "reference"; otherwise the oracle's
+    restatement of the same arithmetic -> kind "port".  Returns (patches/s, s/step, cores, sample text, kind, batch)."""
     import torch
-    from oracle import srgan_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # bounded sample: calibrate on one patch, then take the largest sample batch (<= --ref-sample-batch) that keeps
-    # the whole run inside the time budget
-    torch.manual_seed(0)
-    sd0 = O.init_srresnet_state(0)
-    opt0 = O.AdamState([sd0[k] for k in O.trainable_keys(sd0)], lr=1e-4)
-    t0 = time.perf_counter()
-    O.train_generator_step(sd0, opt0, torch.rand(1, 3, a.lr_size, a.lr_size), torch.rand(1, 3, 4 * a.lr_size, 4 * a.lr_size))
-    t_one = (time.perf_counter() - t0) * a.generators
-    b = max(1, min(a.ref_sample_batch, int(budget_s / max((steps + warmup) * t_one, 1e-9))))
-    torch.manual_seed(0)
-    gens = [O.init_srresnet_state(s) for s in range(a.generators)]
-    opts = []
-    for sd in gens:
-        keys = O.trainable_keys(sd)
-        opts.append(O.AdamState([sd[k] for k in keys], lr=1e-4))
-    lr = torch.rand(b, 3, a.lr_size, a.lr_size)
-    hr = torch.rand(b, 3, 4 * a.lr_size, 4 * a.lr_size)
+    size = a.lr_size
+    kind = "port"
+    try:
+        from oracle import make_ref
+        if make_ref.available() or os.path.isdir("/root/reference/src"):
+            models, train, utils = make_ref.import_reference()
+            kind = "reference"
+    except Exception:
+        kind = "port"
+    if kind == "reference":
+        def build():
+            torch.manual_seed(0)
+            gens = []
+            for s_ in range(a.generators):
+                torch.manual_seed(s_)
+                gens.append(models.SRResNet())
+            opts = [torch.optim.Adam(g.parameters(), lr=1e-4) for g in gens]
+            crit = utils.ReconstructionLoss()
+            torch.manual_seed(100)
+            disc = models.Discriminator()          # passed like the reference's loop does; unused at HEAD (g_d_loss = 0)
 
-    def step():
-        for sd, opt in zip(gens, opts):
-            O.train_generator_step(sd, opt, lr, hr)
+            def step(lr, hr):
+                for g, o in zip(gens, opts):
+                    train.train_generator(g, disc, lr, hr, None, crit, o)
+            return step
+        what = "UNMODIFIED reference src/train.py:train_generator (anomaly detection on, as upstream)"
+    else:
+        from oracle import srgan_oracle as O
+
+        def build():
+            gens = [O.init_srresnet_state(s_) for s_ in range(a.generators)]
+            opts = [O.AdamState([sd[k] for k in O.trainable_keys(sd)], lr=1e-4) for sd in gens]
+
+            def step(lr, hr):
+                for sd, opt in zip(gens, opts):
+                    O.train_generator_step(sd, opt, lr, hr)
+            return step
+        what = "oracle restatement of the reference step (oracle/srgan_oracle.py; oracle/_ref not present)"
+    # bounded sample: calibrate on one patch, then the largest sample batch (<= --ref-sample-batch) inside the budget
+    step = build()
+    t0 = time.perf_counter()
+    step(torch.rand(1, 3, size, size), torch.rand(1, 3, 4 * size, 4 * size))
+    t_one = time.perf_counter() - t0
+    b = max(1, min(a.ref_sample_batch, int(budget_s / max((steps + warmup) * t_one, 1e-9))))
+    step = build()
+    torch.manual_seed(0)
+    lr = torch.rand(b, 3, size, size)
+    hr = torch.rand(b, 3, 4 * size, 4 * size)
     for _ in range(warmup):
-        step()
+        step(lr, hr)
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
+        step(lr, hr)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    sample = (f"{a.generators} generators x oracle train_generator_step on {b}x3x{a.lr_size}x{a.lr_size} LR patches per step "
-              f"(bounded sample of the {a.batch}-patch batch), fp32, torch CPU kernels, {cores} threads")
-    return b / dt, dt, cores, sample
+    try:
+        torch.autograd.set_detect_anomaly(False)
+    except Exception:
+        pass
+    sample = (f"{a.generators} generators x {what} on {b}x3x{size}x{size} LR patches per step (a bounded sample of the "
+              f"16-patch cfg2 batch: patches/s = {b} / step time), fp32, torch CPU kernels, {cores} threads")
+    return b / dt, dt, cores, sample, kind, b
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, dt, cores, sample = cpu_reference_steps(a, a.steps, a.warmup)
+    val, dt, cores, sample, kind, b = cpu_reference_steps(a, a.steps, a.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "generators": a.generators, "sample_batch": a.ref_sample_batch,
-                   "note": "reference arithmetic restated on torch CPU kernels (oracle/srgan_oracle.py); the Python "
-                           "reference itself does not travel to the GPU box"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(a), "generators": a.generators, "sample_batch": b,
+                   "note": ("the unmodified reference sources run from oracle/_ref (copied verbatim by oracle/make_ref.py, "
+                            "git-ignored)" if kind == "reference" else
+                            "oracle/_ref did not travel: reference arithmetic restated on torch CPU kernels (oracle/srgan_oracle.py)")},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -191,7 +238,7 @@ def run_infer(a):
     torch.cuda.set_device(0)
     torch.manual_seed(0)
     g = S.SRResNet().cuda().eval()
-    B, H, W = a.batch if a.batch != 16 else 8, 1080, 1920
+    B, H, W = (a.batch or 8), 1080, 1920
     x = torch.rand(B, 3, H, W, device="cuda")
     with torch.no_grad():
         for _ in range(max(a.warmup, 1)):
@@ -213,6 +260,79 @@ def run_infer(a):
                                  "algorithmic_tflops": flop / (ms * 1e-3) / 1e12,
                                  "frac_of_bf16_sustained_peak": flop / (ms * 1e-3) / 1e12 / float(pk["bf16_tflops_sustained"])},
                       "gpu_launches": int(S.lib().srg_total_launches())}), flush=True)
+
+
+def hbm_roofline(S, torch, dev, B, LH, LW, pk):
+    """Achieved HBM GB/s of the memory-bound kernels of the step, each timed ALONE with CUDA events on cfg-shaped
+    tensors through its per-operator C-ABI entry point.  Every launch works on a different one of `nbuf` buffer sets
+    (together far larger than the 126 MB L2), so the algorithmic bytes really come from / go to HBM."""
+    from ctypes import c_void_p
+    L = S.lib()
+    st = c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = B * LH * LW
+    act_bytes = P * 128                                     # one [P][64] bf16 tensor
+    nbuf = max(4, int(600e6 // (3 * act_bytes)) + 1)
+    bufs = [[torch.randn(P, 64, device=dev).to(torch.bfloat16) for _ in range(3)] for _ in range(nbuf)]
+    coef = torch.rand(5, 64, device=dev) + 0.5
+    rows = L.srg_bn_stats_rows(P)
+    partials = torch.empty(rows, 128, device=dev)
+    hr = [torch.rand(B, 3, 4 * LH, 4 * LW, device=dev) for _ in range(2)]
+    sr = [torch.rand(B, 3, 4 * LH, 4 * LW, device=dev) for _ in range(2)]
+    scratch = torch.empty(int(L.srg_recon_loss_scratch_bytes()), dtype=torch.uint8, device=dev)
+    e_buf, g_buf, dsr = torch.empty_like(sr[0]), torch.empty_like(sr[0]), torch.empty_like(sr[0])
+    losses = torch.empty(2, device=dev)
+    img_bytes = hr[0].numel() * 4
+
+    def p(t):
+        return c_void_p(t.data_ptr())
+
+    def k_apply_relu(i):
+        a_, b_, c_ = bufs[i % nbuf]
+        L.srg_bn_apply(p(a_), p(coef[0]), p(coef[1]), None, 1, p(c_), P, st)
+
+    def k_apply_skip(i):
+        a_, b_, c_ = bufs[i % nbuf]
+        L.srg_bn_apply(p(a_), p(coef[0]), p(coef[1]), p(b_), 0, p(c_), P, st)
+
+    def k_stats2(i):
+        a_, b_, c_ = bufs[i % nbuf]
+        L.srg_bn_stats(p(a_), p(b_), P, p(partials), st)
+
+    def k_bwd_apply(i):
+        a_, b_, c_ = bufs[i % nbuf]
+        L.srg_bn_backward_apply(p(a_), p(b_), p(coef[2]), p(coef[3]), p(coef[4]), p(c_), P, st)
+
+    def k_loss(i):
+        h_, s_ = hr[i % 2], sr[i % 2]
+        L.srg_recon_loss_forward(p(h_), p(s_), B, 3, 4 * LH, 4 * LW, p(scratch), scratch.numel(), p(e_buf), p(g_buf), p(losses), st)
+        L.srg_recon_loss_backward(p(h_), p(s_), B, 3, 4 * LH, 4 * LW, p(scratch), p(e_buf), p(g_buf), None, None, p(dsr), 1.0, st)
+
+    cases = [
+        ("bn_apply_kernel<relu> (BatchNorm apply + ReLU, src/models.py:23)", k_apply_relu, 2 * act_bytes),
+        ("bn_apply_kernel<skip> (BatchNorm apply + residual add, src/models.py:24-25)", k_apply_skip, 3 * act_bytes),
+        ("chan_reduce_kernel<two> (BatchNorm backward sums: sum dz, sum dz*y)", k_stats2, 2 * act_bytes),
+        ("bn_bwd_apply_kernel (BatchNorm input gradient)", k_bwd_apply, 3 * act_bytes),
+        ("loss_pass1-3 + stats/final (ReconstructionLoss forward + backward, src/utils.py:173-241; 16 B per HR element "
+         "minimum, SURVEY 8d)", k_loss, 4 * img_bytes),
+    ]
+    peak = float(pk["hbm_gbs"])
+    out = []
+    for name, fn, nbytes in cases:
+        reps = 24
+        for i in range(4):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        gbs = nbytes / (us * 1e-6) / 1e9
+        out.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                    "algorithmic_bytes_per_launch": nbytes, "avg_us": us})
+    return out
 
 
 def run_ours(a):
@@ -350,16 +470,29 @@ def run_ours(a):
     avg_ms = k_ms / max(k_n, 1)
     achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12 if k_n else 0.0
     peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
+    peak_burst = float(pk.get("bf16_tflops", peak))
+    n_layers = 1
+    try:
+        n_layers = max(1, int(S.lib().srg_generator_trunk_layers(gens[0].last_engine().handle)))
+    except Exception:
+        pass
+    flop_per_launch *= n_layers            # a fused trunk launch covers 2*n_res+1 layers
+    achieved *= n_layers
     traffic = None
     try:
         if not (a.workload == "cfg2" and B == 16 and LH == 96 and LW == 96):
             raise ValueError("ncu capture was taken at the cfg2 geometry")
+        if n_layers != 1:
+            raise ValueError("capture is of the per-layer kernel")
         with open(os.path.join(ROOT, "profiles", "r01_conv3_il_traffic.json")) as f:
             traffic = json.load(f)["dram_bytes_per_launch"]       # dram__bytes_read.sum + dram__bytes_write.sum (ncu)
     except Exception:
         pass
+    kname = ("conv3_il_kernel (3x3 64->64 fprop/dgrad implicit GEMM, row-interleaved N=128 tcgen05 MMAs)" if n_layers == 1 else
+             f"trunk_kernel (fused: {n_layers} 3x3 64->64 conv layers of one direction + their BatchNorm steps per launch)")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, cfg2 geometry)", "kernel": "conv3_il_kernel (3x3 64->64 fprop/dgrad implicit GEMM, row-interleaved N=128 tcgen05 MMAs)",
+                "frac_of_burst_peak": achieved / peak_burst, "peak_burst": peak_burst,
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, cfg2 geometry)", "kernel": kname,
                 "launches_timed": k_n, "avg_launch_us": avg_ms * 1e3, "kernel_share_of_step": (k_ms / prof_steps) / ms_per_step,
                 "flop_per_launch": flop_per_launch, "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "timed_over": f"{prof_steps} extra steps right after the timed region (per-launch CUDA events on the launch stream)"}
@@ -377,23 +510,52 @@ def run_ours(a):
                "ms_per_step": e2e_ms, "api": "for hr, lr in DevicePrefetcher(...).iterate(pinned host batches): MultiGeneratorGAN.step(lr, hr); every step's losses copied to pinned host memory and read one step late"}
     last = trainer.step(lr_dev, hr_dev).cpu().tolist()
 
+    # N > 1: the weak-scaling reading (16 patches per GPU, the single-GPU cfg2 batch) next to configs[2]
+    weak16 = None
+    if world > 1 and B != 16 and a.workload == "cfg2" and not a.no_weak16:
+        lr16, hr16 = lr_dev[:16].contiguous(), hr_dev[:16].contiguous()
+
+        def step16():
+            trainer.step(lr16, hr16)
+        for _ in range(3):
+            step16()
+        ms16 = timed(step16, a.steps) / a.steps
+        weak16 = {"value": world * 16 / (ms16 * 1e-3), "unit": UNIT, "ms_per_step": ms16, "batch_per_gpu": 16,
+                  "global_batch": 16 * world, "scaling": "weak"}
+
+    hbm = None
+    if rank == 0 and not a.no_hbm and a.workload == "cfg2":
+        try:
+            hbm = hbm_roofline(S, torch, dev, min(B, 16), LH, LW, pk)
+        except Exception as exc:          # never lose the headline line to the auxiliary leg
+            hbm = [{"error": str(exc)}]
+    if world > 1:
+        dist.barrier()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline and a.workload == "cfg2":
-        v, dt, cores, sample = cpu_reference_steps(a, 2, 1)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "s_per_step": dt}
+        v, dt, cores, sample, kind, bs = cpu_reference_steps(a, 2, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "s_per_step": dt,
+                        "sample_batch": bs}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": ("strong" if (world > 1 and a.batch is None and a.workload == "cfg2") else "weak"), "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(a), "generators": K, "batch_per_gpu": B, "global_batch": B * world,
                        "lr_hw": [LH, LW], "upscale": 4, "cuda_graphs": bool(use_graphs), "parallelism": f"dp{world}", "syncbn": (a.syncbn if world > 1 else None),
                        "peer_sync_timeouts": (S.parallel.peer_sync_errors() if world > 1 else 0),
                        "l2": "per-step working set (~2.5 GB of activations per generator) exceeds the 126 MB L2; no flush needed",
-                       "generator_passes_per_sec": value * K, "whole_step_algorithmic_tflops": whole_step_tflops,
-                       "whole_step_frac_of_bf16_peak": whole_step_tflops / world / peak, "last_losses": last},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+                       "generator_passes_per_sec": value * K,
+                       "whole_step_algorithmic_tflops_per_gpu": whole_step_tflops,
+                       "whole_job_algorithmic_tflops": whole_step_tflops * world,
+                       "whole_step_frac_of_bf16_sustained_peak": whole_step_tflops / peak,
+                       "whole_step_frac_of_bf16_burst_peak": whole_step_tflops / peak_burst,
+                       "trunk_path": ("fused trunk kernel" if n_layers > 1 else "per-layer launches"), "last_losses": last},
+            "roofline": roofline, "roofline_hbm": hbm, "weak16": weak16, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": int(launches),
             "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples", "power_w_max")},
         }
         print(json.dumps(line), flush=True)

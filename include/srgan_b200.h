@@ -181,6 +181,34 @@ int srg_discriminator_tensor_info(const srg_discriminator_t* d, int i, char* nam
                                   int* dims4, int* dtype);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Per-operator entry points for the HBM-bound BatchNorm passes (nn.BatchNorm2d(64) in training mode, src/models.py:16,19,
+ * 23-24, and its autograd backward): the engines above call the same kernels; these exports let a caller (or bench.py's
+ * HBM roofline leg) run them on its own [pixels][64] NHWC bf16 tensors.  All pointers are device pointers; every call
+ * only enqueues on `stream`.
+ *   srg_bn_stats          partials[rows][128] fp32 = per-block {sum a[64], sum a*a[64]} (b == NULL) or {sum a, sum a*b}
+ *                         (BatchNorm backward: a = dout, b = y); rows = srg_bn_stats_rows(pixels) <= 296
+ *   srg_bn_finalize       partial rows -> scale = gamma/sqrt(var+eps), shift = beta - mean*scale, save_mean, save_inv (biased
+ *                         variance, fixed summation order, fp64); running_mean / running_var (may be NULL) updated with
+ *                         `momentum` and the unbiased variance like torch
+ *   srg_bn_apply          out = [relu](y*scale + shift) [+ skip]
+ *   srg_bn_backward_finalize  partial rows of {sum dout, sum dout*y} -> dgamma, dbeta (may be NULL) and the coefficients of
+ *                         dy = A*dout + B*y + C
+ *   srg_bn_backward_apply dy = A*dout + B*y + C
+ * ------------------------------------------------------------------------------------------------------------- */
+int srg_bn_stats_rows(int64_t pixels);
+int srg_bn_stats(const void* a_nhwc_bf16, const void* b_nhwc_bf16, int64_t pixels, float* partials, void* stream);
+int srg_bn_finalize(const float* partials, int rows, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* save_mean,
+                    float* save_inv, void* stream);
+int srg_bn_apply(const void* y_nhwc_bf16, const float* scale, const float* shift, const void* skip_nhwc_bf16, int relu,
+                 void* out_nhwc_bf16, int64_t pixels, void* stream);
+int srg_bn_backward_finalize(const float* partials, int rows, double count, const float* gamma, const float* save_mean,
+                             const float* save_inv, float* dgamma, float* dbeta, float* coef_a, float* coef_b, float* coef_c,
+                             void* stream);
+int srg_bn_backward_apply(const void* dout_nhwc_bf16, const void* y_nhwc_bf16, const float* coef_a, const float* coef_b,
+                          const float* coef_c, void* dy_nhwc_bf16, int64_t pixels, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Losses and optimiser
  * ------------------------------------------------------------------------------------------------------------- */
 /* replaces ReconstructionLoss.forward (src/utils.py:173-241; called at src/train.py:189):

@@ -96,6 +96,14 @@ EXPORTS = {
                                        POINTER(c_int)]),
     "srg_generator_profile_enable": (c_int, [c_void_p, c_int]),
     "srg_generator_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
+    "srg_bn_stats_rows": (c_int, [c_int64]),
+    "srg_bn_stats": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "srg_bn_finalize": (c_int, [c_void_p, c_int, c_double, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "srg_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    "srg_bn_backward_finalize": (c_int, [c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
+    "srg_bn_backward_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "srg_set_trunk_fused": (c_int, [c_int]),
     "srg_generator_forward_phases": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "srg_generator_backward_phases": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

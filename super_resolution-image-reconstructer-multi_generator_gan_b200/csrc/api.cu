@@ -181,6 +181,42 @@ int srg_generators_trunk(srg_generator_t* const* gs, int n, int backward, int up
   for (int i = 0; i < n; ++i) es[i] = G(gs[i]);
   return generators_trunk(es, n, backward, update_running, S(stream));
 }
+// ---- per-operator BatchNorm entry points
+int srg_bn_stats_rows(int64_t pixels) { return reduce_blocks(pixels); }
+int srg_bn_stats(const void* a, const void* b, int64_t pixels, float* partials, void* stream) {
+  if (a == nullptr || partials == nullptr || pixels < 1) { set_error("srg_bn_stats: bad arguments"); return -70; }
+  return launch_chan_reduce(a, b, pixels, partials, S(stream));
+}
+int srg_bn_finalize(const float* partials, int rows, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* save_mean,
+                    float* save_inv, void* stream) {
+  if (!partials || rows < 1 || !gamma || !beta || !scale || !shift || !save_mean || !save_inv) { set_error("srg_bn_finalize: bad arguments"); return -70; }
+  ReduceFinalize f; memset(&f, 0, sizeof(f));
+  f.mode = RF_BN_FWD; f.count = count; f.eps = eps; f.momentum = momentum; f.gamma = gamma; f.beta = beta;
+  f.running_mean = running_mean; f.running_var = running_var;
+  f.out0 = scale; f.out1 = shift; f.out2 = save_mean; f.out3 = save_inv;
+  return launch_partials_finalize(partials, rows, f, S(stream));
+}
+int srg_bn_apply(const void* y, const float* scale, const float* shift, const void* skip, int relu, void* out, int64_t pixels,
+                 void* stream) {
+  if (!y || !scale || !shift || !out || pixels < 1) { set_error("srg_bn_apply: bad arguments"); return -70; }
+  return launch_bn_apply(y, scale, shift, skip, relu, out, pixels, S(stream));
+}
+int srg_bn_backward_finalize(const float* partials, int rows, double count, const float* gamma, const float* save_mean,
+                             const float* save_inv, float* dgamma, float* dbeta, float* coef_a, float* coef_b, float* coef_c,
+                             void* stream) {
+  if (!partials || rows < 1 || !gamma || !save_mean || !save_inv || !coef_a || !coef_b || !coef_c) { set_error("srg_bn_backward_finalize: bad arguments"); return -70; }
+  ReduceFinalize f; memset(&f, 0, sizeof(f));
+  f.mode = RF_BN_BWD; f.count = count; f.gamma = gamma; f.save_mean = save_mean; f.save_inv = save_inv;
+  f.dgamma = dgamma; f.dbeta = dbeta; f.out0 = coef_a; f.out1 = coef_b; f.out2 = coef_c;
+  return launch_partials_finalize(partials, rows, f, S(stream));
+}
+int srg_bn_backward_apply(const void* dout, const void* y, const float* coef_a, const float* coef_b, const float* coef_c,
+                          void* dy, int64_t pixels, void* stream) {
+  if (!dout || !y || !coef_a || !coef_b || !coef_c || !dy || pixels < 1) { set_error("srg_bn_backward_apply: bad arguments"); return -70; }
+  return launch_bn_bwd_apply(dout, y, coef_a, coef_b, coef_c, dy, pixels, S(stream));
+}
+
 int srg_set_trunk_fused(int on) { return set_trunk_fused(on); }
 int srg_debug_trunk_prof(long long* host, int n) { return trunk_prof_read(host, n); }
 int srg_generator_trunk_layers(const srg_generator_t* g) { return generator_prof_layers(G(g)); }
