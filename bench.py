@@ -371,7 +371,7 @@ def run_ours(a):
         S.parallel.data_parallel(gens + ([disc] if disc is not None else []), sync_batchnorm=True, sync_bn_transport=a.syncbn)
         loss_ar = S.parallel.mean_over_ranks()
     policy = S.MultiGeneratorPolicy(S.PolicyConfig(num_generators=K, force=S.GAN if disc is not None else S.PIXEL, seed=0))
-    use_graphs = (not a.no_graphs) and (disc is None or world == 1)
+    use_graphs = not a.no_graphs
     trainer = S.MultiGeneratorGAN(gens, opts, crit, discriminator=disc, d_optimizer=d_opt, policy=policy,
                                   loss_allreduce=loss_ar, use_cuda_graphs=use_graphs)
 

@@ -559,7 +559,9 @@ class MultiGeneratorGAN:
         if any_gan and self.d_optimizer is not None:
             leader_id = plan[0][0]
             leader = self.generators[leader_id]
-            if self.use_cuda_graphs and getattr(self.d_optimizer, "capturable", False) and self.loss_allreduce is None:
+            # (data parallel: the discriminator's gradient all-reduce runs on its own library communicator and is captured
+            # with the step, parallel.average_gradients_hook)
+            if self.use_cuda_graphs and getattr(self.d_optimizer, "capturable", False):
                 dg = self._d_graphs.get(leader_id)
                 if dg is None or dg.lr.shape != lr_imgs.shape:
                     dg = GraphedDiscriminatorStep(self.discriminator, leader, self.d_optimizer, lr_imgs, hr_imgs)
@@ -579,7 +581,7 @@ class MultiGeneratorGAN:
             return out
         rows = []
         for gid, mode in plan:
-            if self.use_cuda_graphs and (mode == PIXEL or self.loss_allreduce is None):
+            if self.use_cuda_graphs:
                 cache = self._graphs if mode == PIXEL else self._gan_graphs
                 gs = cache.get(gid)
                 if gs is None or gs.lr.shape != lr_imgs.shape:
