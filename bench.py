@@ -56,6 +56,8 @@ def parse():
                     "enqueuing the next step (default: read them one step late)")
     ap.add_argument("--syncbn", default="peer", choices=["peer", "nccl"], help="SyncBatchNorm transport for N > 1: fused "
                     "NVLink peer-memory exchange kernel (default) or ncclAllReduce between reduce and finalize kernels")
+    ap.add_argument("--no-stream", action="store_true", help="infer-1080p: one engine call for the whole batch instead of "
+                    "streaming chunks of frames (A/B; materialises every frame's activations)")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from the host instead of replaying "
                     "one captured CUDA graph per generator step")
     return ap.parse_args()
@@ -238,28 +240,37 @@ def run_infer(a):
     torch.cuda.set_device(0)
     torch.manual_seed(0)
     g = S.SRResNet().cuda().eval()
+    if a.no_stream:
+        g.stream_budget_bytes = None
     B, H, W = (a.batch or 8), 1080, 1920
     x = torch.rand(B, 3, H, W, device="cuda")
+    sampler = ClockSampler(0)
     with torch.no_grad():
         for _ in range(max(a.warmup, 1)):
             y = g(x)
         torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
         e0.record()
         for _ in range(a.steps):
             y = g(x)
         e1.record()
         torch.cuda.synchronize()
+        clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / a.steps
     flop = 4436352.0 * H * W * B
     pk, src = peaks()
+    frames_per_call = g.last_engine().N
     print(json.dumps({"metric": "srgan_infer_lr_frames_per_sec", "value": B / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
                       "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                       "config": {"workload": f"infer-1080p: SRResNet eval forward, {B}x3x{H}x{W} LR -> x4", "out_shape": list(y.shape),
                                  "algorithmic_tflops": flop / (ms * 1e-3) / 1e12,
-                                 "frac_of_bf16_sustained_peak": flop / (ms * 1e-3) / 1e12 / float(pk["bf16_tflops_sustained"])},
-                      "gpu_launches": int(S.lib().srg_total_launches())}), flush=True)
+                                 "frac_of_bf16_sustained_peak": flop / (ms * 1e-3) / 1e12 / float(pk["bf16_tflops_sustained"]),
+                                 "frames_per_engine_call": frames_per_call,
+                                 "peak_device_memory_gb": torch.cuda.max_memory_allocated() / 1e9},
+                      "clocks": clocks, "gpu_launches": int(S.lib().srg_total_launches())}), flush=True)
 
 
 def hbm_roofline(S, torch, dev, B, LH, LW, pk):

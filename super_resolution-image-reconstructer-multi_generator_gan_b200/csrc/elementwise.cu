@@ -5,6 +5,7 @@
 #include "elementwise.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_gemm.cuh"
@@ -41,10 +42,19 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 // per-channel reductions: thread = (pixel lane, channel group of 8)
 // ------------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+  const char* ev = getenv(name);
+  return (ev != nullptr && ev[0] != '\0') ? atoi(ev) : dflt;
+}
+// developer knobs (read once): CTAs per SM of the elementwise / reduction passes.  Fewer CTAs leave HBM bandwidth to a
+// tensor-core kernel of another graph branch running beside them (profiles/r02_notes.md)
+static int red_per_sm() { static int v = -1; if (v < 0) v = env_int("SRG_RED_PER_SM", 2); return v < 1 ? 1 : v; }
+static int ew_per_sm() { static int v = -1; if (v < 0) v = env_int("SRG_EW_PER_SM", 4); return v < 1 ? 1 : v; }
+static int fin_per_sm() { static int v = -1; if (v < 0) v = env_int("SRG_FIN_PER_SM", 2); return v < 1 ? 1 : v; }
 int reduce_blocks(int64_t pixels) {
   int64_t b = (pixels + 32 * 8 - 1) / (32 * 8);
   if (b < 1) b = 1;
-  const int cap = 2 * sm_budget() < kRedBlocksMax ? 2 * sm_budget() : kRedBlocksMax;
+  const int cap = red_per_sm() * sm_budget() < kRedBlocksMax ? red_per_sm() * sm_budget() : kRedBlocksMax;
   if (b > cap) b = cap;
   return int(b);
 }
@@ -60,7 +70,30 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const uint4* __restric
   float s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
-  for (int64_t p = int64_t(blockIdx.x) * 32 + lane_p; p < pixels; p += int64_t(gridDim.x) * 32) {
+  // four pixels of a thread in flight per round (8 x 128-bit loads): the kernel is latency-bound otherwise (measured
+  // 2.9 TB/s with one pixel per round); the accumulation order per thread is unchanged
+  const int64_t stride = int64_t(gridDim.x) * 32;
+  int64_t p = int64_t(blockIdx.x) * 32 + lane_p;
+  for (; p + 3 * stride < pixels; p += 4 * stride) {
+    uint4 ra[4], rb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ra[u] = a[(p + u * stride) * 8 + cg];
+      if (TWO) rb[u] = b[(p + u * stride) * 8 + cg];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float fa[8], fb[8];
+      unpack8(ra[u], fa);
+      if (TWO) unpack8(rb[u], fb);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s1[e] += fa[e];
+        s2[e] += TWO ? fa[e] * fb[e] : fa[e] * fa[e];
+      }
+    }
+  }
+  for (; p < pixels; p += stride) {
     float fa[8], fb[8];
     unpack8(a[p * 8 + cg], fa);
     if (TWO) unpack8(b[p * 8 + cg], fb);
@@ -349,7 +382,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
 }
 static int ew_blocks(int64_t n_vec) {
   int64_t b = (n_vec + 255) / 256;
-  if (b > sm_budget() * 8) b = sm_budget() * 8;
+  if (b > sm_budget() * ew_per_sm()) b = sm_budget() * ew_per_sm();
   if (b < 1) b = 1;
   return int(b);
 }
@@ -426,6 +459,205 @@ int launch_bn_bwd_apply(const void* dout, const void* y, const float* coefA, con
   launch_pdl(bn_bwd_apply_kernel, dim3(ew_blocks(n_vec)), dim3(256), 0, st, reinterpret_cast<const uint4*>(dout),
              reinterpret_cast<const uint4*>(y), coefA, coefB, coefC, reinterpret_cast<uint4*>(dy), n_vec);
   SRG_LAUNCH_CHECK("bn_bwd_apply");
+  return 0;
+}
+
+// ---- BatchNorm apply / backward apply with the statistics finalize folded in ---------------------------------------
+// The separate one-block finalize launch between the producer of the [rows][128] partial sums and the apply pass is pure
+// latency on the per-generator dependency chain (measured in the replayed graph: ~5 us of execution + ~5 us of
+// dependent-launch gaps per BatchNorm layer and direction).  Here every CTA of the apply pass re-reduces the partial rows
+// itself (<= 296 x 512 B, L2-resident, fixed order => every CTA and every run gets bit-identical sums), computes the
+// per-channel coefficients into shared memory and goes straight on to the elementwise pass; CTA 0 also writes what
+// later kernels need (coefficients, saved mean / inv-std, running statistics, weight / bias gradients).
+constexpr int kFinThreads = 512;
+__device__ __forceinline__ void block_partial_sums(const float* __restrict__ partials, int rows, double (*red)[128],
+                                                   double* sums) {
+  // 512 threads = 16 row lanes x 32 column quads; row lane rl sums rows rl, rl+16, ... in order (fp64)
+  const int c4 = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  const float4* src = reinterpret_cast<const float4*>(partials) + c4;
+  int r = rl;
+  for (; r + 48 < rows; r += 64) {
+    const float4 v0 = __ldcg(src + size_t(r) * 32), v1 = __ldcg(src + size_t(r + 16) * 32);
+    const float4 v2 = __ldcg(src + size_t(r + 32) * 32), v3 = __ldcg(src + size_t(r + 48) * 32);
+    a0 += double(v0.x); a1 += double(v0.y); a2 += double(v0.z); a3 += double(v0.w);
+    a0 += double(v1.x); a1 += double(v1.y); a2 += double(v1.z); a3 += double(v1.w);
+    a0 += double(v2.x); a1 += double(v2.y); a2 += double(v2.z); a3 += double(v2.w);
+    a0 += double(v3.x); a1 += double(v3.y); a2 += double(v3.z); a3 += double(v3.w);
+  }
+  for (; r < rows; r += 16) {
+    const float4 v = __ldcg(src + size_t(r) * 32);
+    a0 += double(v.x); a1 += double(v.y); a2 += double(v.z); a3 += double(v.w);
+  }
+  red[rl][c4 * 4 + 0] = a0; red[rl][c4 * 4 + 1] = a1; red[rl][c4 * 4 + 2] = a2; red[rl][c4 * 4 + 3] = a3;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += red[i][threadIdx.x];
+    sums[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+template <bool RELU, bool SKIP>
+__global__ void __launch_bounds__(kFinThreads) bn_apply_fin_kernel(const uint4* __restrict__ y, const float* __restrict__ partials,
+                                                                   int rows, const ReduceFinalize f,
+                                                                   const uint4* __restrict__ skip, uint4* __restrict__ out,
+                                                                   int64_t n_vec) {
+  __shared__ double red[16][128];
+  __shared__ double sums[128];
+  __shared__ float coef[2][64];
+  pdl_trigger();
+  pdl_wait();
+  block_partial_sums(partials, rows, red, sums);
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    const double mean = sums[c] / f.count;
+    double var = sums[64 + c] / f.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float inv = float(1.0 / sqrt(var + double(f.eps)));
+    const float sc = f.gamma[c] * inv;
+    const float sh = f.beta[c] - float(mean) * sc;
+    coef[0][c] = sc;
+    coef[1][c] = sh;
+    if (blockIdx.x == 0) {
+      f.out0[c] = sc; f.out1[c] = sh; f.out2[c] = float(mean); f.out3[c] = inv;
+      if (f.running_mean != nullptr) {
+        const double unbiased = f.count > 1.0 ? var * (f.count / (f.count - 1.0)) : var;
+        f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * float(mean);
+        f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * float(unbiased);
+      }
+    }
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 7;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = coef[0][cg * 8 + e]; sh[e] = coef[1][cg * 8 + e]; }
+  const int64_t stride = int64_t(gridDim.x) * kFinThreads;
+  int64_t i = int64_t(blockIdx.x) * kFinThreads + threadIdx.x;
+  for (; i + 3 * stride < n_vec; i += 4 * stride) {
+    uint4 ry[4], rk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ry[u] = y[i + u * stride];
+      if (SKIP) rk[u] = skip[i + u * stride];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8], k[8];
+      unpack8(ry[u], v);
+      if (SKIP) unpack8(rk[u], k);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float o = fmaf(v[e], sc[e], sh[e]);
+        if (RELU) o = fmaxf(o, 0.f);
+        if (SKIP) o += k[e];
+        v[e] = o;
+      }
+      out[i + u * stride] = pack8(v);
+    }
+  }
+  for (; i < n_vec; i += stride) {
+    float v[8], k[8];
+    unpack8(y[i], v);
+    if (SKIP) unpack8(skip[i], k);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float o = fmaf(v[e], sc[e], sh[e]);
+      if (RELU) o = fmaxf(o, 0.f);
+      if (SKIP) o += k[e];
+      v[e] = o;
+    }
+    out[i] = pack8(v);
+  }
+}
+static int fin_blocks(int64_t n_vec) {
+  int64_t b = (n_vec + kFinThreads - 1) / kFinThreads;
+  if (b > fin_per_sm() * sm_budget()) b = fin_per_sm() * sm_budget();
+  if (b < 1) b = 1;
+  return int(b);
+}
+int launch_bn_apply_fin(const void* y, const float* partials, int rows, const ReduceFinalize& f, const void* skip, int relu,
+                        void* out, int64_t pixels, cudaStream_t st) {
+  if (f.mode != RF_BN_FWD) { set_error("bn_apply_fin: needs an RF_BN_FWD finalize descriptor"); return -40; }
+  const int64_t n_vec = pixels * 8;
+  const dim3 grid(fin_blocks(n_vec)), block(kFinThreads);
+  const uint4* yy = reinterpret_cast<const uint4*>(y);
+  const uint4* kk = reinterpret_cast<const uint4*>(skip);
+  uint4* oo = reinterpret_cast<uint4*>(out);
+  if (relu && skip) launch_pdl(bn_apply_fin_kernel<true, true>, grid, block, 0, st, yy, partials, rows, f, kk, oo, n_vec);
+  else if (relu) launch_pdl(bn_apply_fin_kernel<true, false>, grid, block, 0, st, yy, partials, rows, f, kk, oo, n_vec);
+  else if (skip) launch_pdl(bn_apply_fin_kernel<false, true>, grid, block, 0, st, yy, partials, rows, f, kk, oo, n_vec);
+  else launch_pdl(bn_apply_fin_kernel<false, false>, grid, block, 0, st, yy, partials, rows, f, kk, oo, n_vec);
+  SRG_LAUNCH_CHECK("bn_apply_fin");
+  return 0;
+}
+
+__global__ void __launch_bounds__(kFinThreads) bn_bwd_apply_fin_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y,
+                                                                       const float* __restrict__ partials, int rows,
+                                                                       const ReduceFinalize f, uint4* __restrict__ dy,
+                                                                       int64_t n_vec) {
+  __shared__ double red[16][128];
+  __shared__ double sums[128];
+  __shared__ float coef[3][64];
+  pdl_trigger();
+  pdl_wait();
+  block_partial_sums(partials, rows, red, sums);
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    const double s1 = sums[c], s2 = sums[64 + c];
+    const double mean = f.save_mean[c], inv = f.save_inv[c];
+    const double dg = inv * (s2 - mean * s1);
+    const double db = s1;
+    const double sc = double(f.gamma[c]) * inv;
+    const float cA = float(sc), cB = float(-sc * inv * dg / f.count);
+    const float cC = float(-sc * db / f.count + sc * inv * mean * dg / f.count);
+    coef[0][c] = cA; coef[1][c] = cB; coef[2][c] = cC;
+    if (blockIdx.x == 0) {
+      if (f.dgamma) f.dgamma[c] = float(dg);
+      if (f.dbeta) f.dbeta[c] = float(db);
+      f.out0[c] = cA; f.out1[c] = cB; f.out2[c] = cC;
+    }
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 7;
+  float a[8], b[8], c[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a[e] = coef[0][cg * 8 + e]; b[e] = coef[1][cg * 8 + e]; c[e] = coef[2][cg * 8 + e]; }
+  const int64_t stride = int64_t(gridDim.x) * kFinThreads;
+  int64_t i = int64_t(blockIdx.x) * kFinThreads + threadIdx.x;
+  for (; i + 3 * stride < n_vec; i += 4 * stride) {
+    uint4 rd[4], ry[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { rd[u] = dout[i + u * stride]; ry[u] = y[i + u * stride]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float d[8], v[8];
+      unpack8(rd[u], d);
+      unpack8(ry[u], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = fmaf(a[e], d[e], fmaf(b[e], v[e], c[e]));
+      dy[i + u * stride] = pack8(d);
+    }
+  }
+  for (; i < n_vec; i += stride) {
+    float d[8], v[8];
+    unpack8(dout[i], d);
+    unpack8(y[i], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = fmaf(a[e], d[e], fmaf(b[e], v[e], c[e]));
+    dy[i] = pack8(d);
+  }
+}
+int launch_bn_bwd_apply_fin(const void* dout, const void* y, const float* partials, int rows, const ReduceFinalize& f, void* dy,
+                            int64_t pixels, cudaStream_t st) {
+  if (f.mode != RF_BN_BWD) { set_error("bn_bwd_apply_fin: needs an RF_BN_BWD finalize descriptor"); return -40; }
+  const int64_t n_vec = pixels * 8;
+  launch_pdl(bn_bwd_apply_fin_kernel, dim3(fin_blocks(n_vec)), dim3(kFinThreads), 0, st, reinterpret_cast<const uint4*>(dout),
+             reinterpret_cast<const uint4*>(y), partials, rows, f, reinterpret_cast<uint4*>(dy), n_vec);
+  SRG_LAUNCH_CHECK("bn_bwd_apply_fin");
   return 0;
 }
 

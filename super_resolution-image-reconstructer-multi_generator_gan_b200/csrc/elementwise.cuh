@@ -67,6 +67,13 @@ int launch_bn_bwd_finalize(const double* sums, double count, const float* gamma,
                            float* coefC, float param_grad_scale, cudaStream_t st);
 int launch_bn_bwd_apply(const void* dout, const void* y, const float* coefA, const float* coefB, const float* coefC,
                         void* dy, int64_t pixels, cudaStream_t st);
+// The same two passes with the statistics finalize folded in (training, single GPU): every CTA re-reduces the [rows][128]
+// partial sums (fixed order), derives the coefficients and applies them; CTA 0 also writes f.out0..3 (and the running
+// statistics / the BatchNorm weight and bias gradients).  One launch instead of two on the dependency chain.
+int launch_bn_apply_fin(const void* y, const float* partials, int rows, const ReduceFinalize& f, const void* skip, int relu,
+                        void* out, int64_t pixels, cudaStream_t st);
+int launch_bn_bwd_apply_fin(const void* dout, const void* y, const float* partials, int rows, const ReduceFinalize& f, void* dy,
+                            int64_t pixels, cudaStream_t st);
 // d(pre-activation) of LeakyReLU from two incoming gradients: dpre = (ga + gb) * (post > 0 ? 1 : slope)
 int launch_lrelu_bwd_add2(const void* ga, const void* gb, const void* post, float slope, void* dpre, int64_t pixels,
                           cudaStream_t st);

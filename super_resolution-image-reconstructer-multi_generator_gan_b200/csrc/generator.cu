@@ -506,6 +506,8 @@ GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up) {
   {
     const char* ev = getenv("SRG_FUSE_BWD_STATS");
     e->fuse_bwd_stats = ev != nullptr && ev[0] == '1';
+    ev = getenv("SRG_FIN_FUSED");
+    e->fin_fused = ev != nullptr && ev[0] == '1';
     ev = getenv("SRG_WGRAD_BATCHED");
     e->wgrad_batched = !(ev != nullptr && ev[0] == '0');
   }
@@ -827,6 +829,29 @@ int generator_forward_phases(GeneratorEngine* g, const float* lr, float* sr, int
                               update_running ? rv : nullptr, coef, coef + 64, coef + 128, coef + 192, st);
   };
 
+  // training-mode BatchNorm (+ReLU / +skip) behind a conv whose epilogue left the per-CTA statistics in `partials`
+  auto bn_train_apply = [&](int b, int k, const void* y, const void* skip, int relu, void* out) -> int {
+    float* coef = reinterpret_cast<float*>(ws + L.bncoef) + size_t(2 * b + k) * 256;
+    if (e->fin_fused && !e->allreduce && !e->peer) {
+      // single GPU: the finalize runs inside the apply pass (every CTA re-reduces the partial rows): one launch, not two
+      snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.weight", b, k + 1);
+      const float* gamma = e->master + poff(*e, nm);
+      snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.bias", b, k + 1);
+      const float* beta = e->master + poff(*e, nm);
+      snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.running_mean", b, k + 1);
+      float* rm = e->bn_buffers + boff(*e, nm);
+      ReduceFinalize f; memset(&f, 0, sizeof(f));
+      f.mode = RF_BN_FWD; f.count = double(P); f.eps = kBnEps; f.momentum = kBnMomentum; f.gamma = gamma; f.beta = beta;
+      f.running_mean = update_running ? rm : nullptr; f.running_var = update_running ? rm + 64 : nullptr;
+      f.out0 = coef; f.out1 = coef + 64; f.out2 = coef + 128; f.out3 = coef + 192;
+      e->launches += 1;
+      return launch_bn_apply_fin(y, reinterpret_cast<const float*>(ws + L.partials), stats_rows, f, skip, relu, out, P, st);
+    }
+    RC(bn_coeffs(b, k, y));
+    e->launches += 1;
+    return launch_bn_apply(y, coef, coef + 64, skip, relu, out, P, st);
+  };
+
   const void* x = ws + L.out1;
   const bool fused = training && use_trunk_fused(*e);
   e->prof_layers = 1;
@@ -843,13 +868,10 @@ int generator_forward_phases(GeneratorEngine* g, const float* lr, float* sr, int
     }
     snprintf(nm, sizeof(nm), "residual_blocks.%d.conv1.bias", b);
     RC(conv3x3(x, po.rb_f[0][b], e->master + poff(*e, nm), nullptr, ws + L.y1[b], training != 0));
-    RC(bn_coeffs(b, 0, ws + L.y1[b]));
-    RC(launch_bn_apply(ws + L.y1[b], coef1, coef1 + 64, nullptr, 1, ws + L.z1[b], P, st));
+    RC(bn_train_apply(b, 0, ws + L.y1[b], nullptr, 1, ws + L.z1[b]));
     snprintf(nm, sizeof(nm), "residual_blocks.%d.conv2.bias", b);
     RC(conv3x3(ws + L.z1[b], po.rb_f[1][b], e->master + poff(*e, nm), nullptr, ws + L.y2[b], training != 0));
-    RC(bn_coeffs(b, 1, ws + L.y2[b]));
-    RC(launch_bn_apply(ws + L.y2[b], coef2, coef2 + 64, x, 0, ws + L.out[b], P, st));
-    e->launches += 2;
+    RC(bn_train_apply(b, 1, ws + L.y2[b], x, 0, ws + L.out[b]));
     x = ws + L.out[b];
   }
   // conv2 + global skip (src/models.py:83-84)
@@ -1071,6 +1093,10 @@ int generator_backward_phases(GeneratorEngine* g, const float* dsr, int phases, 
       ReduceFinalize f; memset(&f, 0, sizeof(f));
       f.mode = RF_BN_BWD; f.count = double(P) * e->world; f.gamma = e->master + go; f.save_mean = coef + 128; f.save_inv = coef + 192;
       f.dgamma = e->grads + go; f.dbeta = e->grads + bo; f.out0 = bwd; f.out1 = bwd + 64; f.out2 = bwd + 128;
+      if (!e->peer && e->fin_fused) {
+        e->launches += 1;
+        return launch_bn_bwd_apply_fin(dz, y, partials, rows, f, dy, P, st);
+      }
       if (e->peer) RC(launch_peer_finalize(e->peer, partials, rows, f, st));
       else RC(launch_partials_finalize(partials, rows, f, st));
       e->launches += 2;

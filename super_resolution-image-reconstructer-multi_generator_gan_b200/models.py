@@ -313,6 +313,23 @@ class SRResNet(_FlatModule):
     def last_engine(self) -> Optional[_GeneratorEngine]:
         return self._rt["last_engine"]
 
+    #: eval-mode activation budget in bytes: larger batches are streamed in chunks of frames (None: never chunk)
+    stream_budget_bytes: Optional[int] = 6 << 30
+
+    def _stream_chunk(self, N: int, H: int, W: int, device) -> int:
+        """Frames per eval-mode engine call such that the engine workspace stays within ``stream_budget_bytes``."""
+        budget = self.stream_budget_bytes
+        if budget is None:
+            return N
+        rt = self._rt
+        key = ("ws1", H, W)
+        if key not in rt:
+            probe = _GeneratorEngine(1, H, W, self.num_residuals, self.num_upsample_stages, False, device)
+            rt[key] = int(_lib.lib().srg_generator_workspace_bytes(probe.handle, 0))
+            del probe
+        per_frame = max(rt[key], 1)
+        return max(1, min(N, int(budget // per_frame)))
+
     # ---- forward ---------------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
@@ -326,6 +343,20 @@ class SRResNet(_FlatModule):
         self._flatten(x.device)
         rt = self._rt
         need_grad = self.training and torch.is_grad_enabled()
+        if not self.training and N > 1:
+            # Evaluation (src/evaluation.py:48-50, BASELINE configs[3]): frames are independent in eval mode (running
+            # BatchNorm statistics), so a batch whose activations would not fit the streaming budget is run in chunks
+            # of whole frames through ONE smaller engine: peak memory is O(chunk), the arithmetic per frame (and hence
+            # every output bit) is that of the unchunked call.  8 x 1080p would otherwise materialise ~34 GB.
+            chunk = self._stream_chunk(N, H, W, x.device)
+            if chunk < N:
+                sr = torch.empty(N, 3, H << self.num_upsample_stages, W << self.num_upsample_stages, dtype=torch.float32,
+                                 device=x.device)
+                packed = set()                             # engines whose bf16 weight copy is current for THIS call
+                for i in range(0, N, chunk):
+                    j = min(N, i + chunk)
+                    self._eval_into(x[i:j], sr[i:j], packed)   # whole frames of an NCHW batch are contiguous: no copy
+                return sr
         eng = self._engine(N, H, W, self.training, x.device, need_grad)
         if self.training and getattr(eng, "grad_flat", None) is None:
             eng.grad_flat = torch.empty_like(rt["flat"])
@@ -346,6 +377,21 @@ class SRResNet(_FlatModule):
                                       1 if self.training else 0, 1 if self.training else 0, stream_ptr()),
               "srg_generator_forward")
         return sr
+
+    def _eval_into(self, x: torch.Tensor, out: torch.Tensor, packed: set) -> None:
+        """eval-mode forward of a chunk of frames straight into ``out`` (a contiguous slice of the caller's batch)."""
+        assert x.is_contiguous() and out.is_contiguous()
+        n, _, H, W = x.shape
+        rt = self._rt
+        eng = self._engine(n, H, W, False, x.device, False)
+        eng.bind(rt["flat"], None, rt["flat_buf"])
+        L = _lib.lib()
+        if id(eng) not in packed:
+            check(L.srg_generator_pack(eng.handle, stream_ptr()), "srg_generator_pack")
+            packed.add(id(eng))
+        rt["last_engine"] = eng
+        check(L.srg_generator_forward(eng.handle, c_void_p(x.data_ptr()), c_void_p(out.data_ptr()), 0, 0, stream_ptr()),
+              "srg_generator_forward")
 
 
 # ----------------------------------------------------------------------------------------------------------------
