@@ -209,6 +209,29 @@ int srg_bn_backward_apply(const void* dout_nhwc_bf16, const void* y_nhwc_bf16, c
                           const float* coef_c, void* dy_nhwc_bf16, int64_t pixels, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Per-operator convolution (SURVEY 8b "conv2d_{fprop,dgrad,wgrad} ... workspace_bytes"): nn.Conv2d(cin, cout, ksize,
+ * padding=ksize/2) (src/models.py:15,18,56,66,71,78 and the VGG19 stack of src/models.py:126) and its autograd backward
+ * on NHWC bf16 activations [N][H][W][C] with C a multiple of 64; ksize 1 or 3 (wgrad: 3).  The engines above launch the
+ * same tcgen05 kernels; these exports make topologies other than SRResNet / Discriminator reachable.
+ *   srg_conv2d_pack_weights  fp32 OIHW -> the kernels' bf16 operand layout (srg_conv2d_packed_weight_bytes bytes);
+ *                            for_dgrad != 0 packs the transposed, flipped copy the input-gradient launch convolves with
+ *   srg_conv2d_fprop         out = act(conv(x) + bias) (+ residual); act: 0 none, 1 ReLU, 2 LeakyReLU(slope)
+ *   srg_conv2d_dgrad         dx = conv^T(dy) (+ residual), or zeroed where relu_mask_src <= 0 (the ReLU that produced x)
+ *   srg_conv2d_wgrad         dw (fp32 OIHW) = sum over pixels of x (x) dy per tap, dbias (may be NULL) = sum dy; workspace:
+ *                            srg_conv2d_wgrad_workspace_bytes (caller-owned, nothing is allocated inside)
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t srg_conv2d_packed_weight_bytes(int cout, int cin, int ksize);
+int srg_conv2d_pack_weights(const float* w_oihw, int cout, int cin, int ksize, int for_dgrad, void* packed, void* stream);
+int srg_conv2d_fprop(const void* x_nhwc_bf16, int N, int H, int W, int cin, const void* w_packed, int cout, int ksize,
+                     const float* bias, int act, float slope, const void* residual_nhwc_bf16, void* out_nhwc_bf16,
+                     void* stream);
+int srg_conv2d_dgrad(const void* dy_nhwc_bf16, int N, int H, int W, int cout, const void* w_packed_dgrad, int cin, int ksize,
+                     const void* relu_mask_src_nhwc_bf16, const void* residual_nhwc_bf16, void* dx_nhwc_bf16, void* stream);
+size_t srg_conv2d_wgrad_workspace_bytes(int N, int H, int W, int cin, int cout);
+int srg_conv2d_wgrad(const void* x_nhwc_bf16, const void* dy_nhwc_bf16, int N, int H, int W, int cin, int cout,
+                     void* workspace, size_t workspace_bytes, float* dw_oihw, float* dbias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Losses and optimiser
  * ------------------------------------------------------------------------------------------------------------- */
 /* replaces ReconstructionLoss.forward (src/utils.py:173-241; called at src/train.py:189):

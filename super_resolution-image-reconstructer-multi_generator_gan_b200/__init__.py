@@ -7,7 +7,7 @@ All arithmetic runs in hand-written CUDA inside ``libsrgan_b200.so`` (C ABI: inc
 package without that library raises as soon as a kernel is needed -- there is no CPU or PyTorch fallback.
 """
 from . import _lib
-from ._lib import build, lib
+from ._lib import build, check, lib
 from .models import BatchNormParams, ConvParams, Discriminator, ResidualBlock, SRResNet
 from .loss import ReconstructionLoss, bce_loss, l1_loss, mse_loss, tanh_mean
 from .optim import Adam

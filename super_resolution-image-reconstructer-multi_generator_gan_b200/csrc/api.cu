@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "conv_gemm.cuh"
+#include "conv_ops.cuh"
 #include "elementwise.cuh"
 #include "discriminator.cuh"
 #include "generator.cuh"
@@ -409,3 +410,25 @@ int srg_mse(const float* a, const float* b, int64_t n, void* scratch, size_t scr
 }
 
 }  // extern "C"
+
+// ---- per-operator convolution -----------------------------------------------------------------------
+extern "C" size_t srg_conv2d_packed_weight_bytes(int cout, int cin, int ksize) { return conv2d_packed_elems(cout, cin, ksize) * 2; }
+extern "C" int srg_conv2d_pack_weights(const float* w_oihw, int cout, int cin, int ksize, int for_dgrad, void* packed, void* stream) {
+  return launch_conv2d_pack(w_oihw, cout, cin, ksize, for_dgrad, packed, S(stream));
+}
+extern "C" int srg_conv2d_fprop(const void* x, int N, int H, int W, int cin, const void* w_packed, int cout, int ksize,
+                                const float* bias, int act, float slope, const void* residual, void* out, void* stream) {
+  return launch_conv2d(x, N, H, W, cin, w_packed, cout, ksize, bias, act, slope, residual, nullptr, out, S(stream));
+}
+extern "C" int srg_conv2d_dgrad(const void* dy, int N, int H, int W, int cout, const void* w_packed_dgrad, int cin, int ksize,
+                                const void* relu_mask_src, const void* residual, void* dx, void* stream) {
+  if (relu_mask_src != nullptr && residual != nullptr) { set_error("srg_conv2d_dgrad: mask and residual are exclusive"); return -74; }
+  return launch_conv2d(dy, N, H, W, cout, w_packed_dgrad, cin, ksize, nullptr, ACT_NONE, 0.f, residual, relu_mask_src, dx, S(stream));
+}
+extern "C" size_t srg_conv2d_wgrad_workspace_bytes(int N, int H, int W, int cin, int cout) {
+  return conv2d_wgrad_workspace_bytes(N, H, W, cin, cout);
+}
+extern "C" int srg_conv2d_wgrad(const void* x, const void* dy, int N, int H, int W, int cin, int cout, void* workspace,
+                                size_t workspace_bytes, float* dw_oihw, float* dbias, void* stream) {
+  return launch_conv2d_wgrad(x, dy, N, H, W, cin, cout, workspace, workspace_bytes, dw_oihw, dbias, S(stream));
+}
