@@ -232,6 +232,27 @@ int srg_conv2d_wgrad(const void* x_nhwc_bf16, const void* dy_nhwc_bf16, int N, i
                      void* workspace, size_t workspace_bytes, float* dw_oihw, float* dbias, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * VGG19 perceptual loss (src/models.py:123-151 VGGFeatureExtractor, src/utils.py:154-166 perceptal_loss; listed in the
+ * train_generator signature, src/train.py:175): the conv layers go through srg_conv2d_*; these are the passes between
+ * them.  NHWC bf16 activations (C % 8 == 0), NCHW fp32 images.
+ *   srg_unfold3x3_rgb      im2col of the 3-channel first layer: out[N][H][W][64], channel (kh*3 + kw)*3 + c (27 used), so
+ *                          vgg19.features[0] becomes a 1x1 convolution over 64 channels
+ *   srg_fold3x3_rgb        its adjoint: gradient of the unfolded tensor -> d(image) NCHW fp32 (times scale)
+ *   srg_maxpool2x2_*       nn.MaxPool2d(2, 2) forward / backward (gradient to the first maximum, like torch; `add`
+ *                          optionally adds a second gradient of dx's shape: a feature tapped before the pool)
+ *   srg_l1_bf16            out1[0] (+)= weight * mean|a - b| (torch.nn.L1Loss); grad_a (may be NULL) = weight * grad_scale *
+ *                          sign(a - b) / n, zeroed where relu_mask != 0 and a <= 0 (a is a ReLU output)
+ * ------------------------------------------------------------------------------------------------------------- */
+int srg_unfold3x3_rgb(const float* x_nchw, int N, int H, int W, void* out_nhwc64_bf16, void* stream);
+int srg_fold3x3_rgb(const void* d_unfolded_nhwc64_bf16, int N, int H, int W, float scale, float* dx_nchw, void* stream);
+int srg_maxpool2x2_forward(const void* x_nhwc_bf16, int N, int H, int W, int C, void* out_nhwc_bf16, void* stream);
+int srg_maxpool2x2_backward(const void* x_nhwc_bf16, const void* dy_nhwc_bf16, const void* add_nhwc_bf16, int N, int H,
+                            int W, int C, void* dx_nhwc_bf16, void* stream);
+size_t srg_l1_bf16_scratch_bytes(void);
+int srg_l1_bf16(const void* a_bf16, const void* b_bf16, int64_t n, float weight, int accumulate, float grad_scale,
+                int relu_mask, void* grad_a_bf16, void* scratch, size_t scratch_bytes, float* out1, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Losses and optimiser
  * ------------------------------------------------------------------------------------------------------------- */
 /* replaces ReconstructionLoss.forward (src/utils.py:173-241; called at src/train.py:189):

@@ -319,3 +319,57 @@ def init_discriminator_state(seed: int, input_channels=3, num_filters=64):
     sd["model.8.weight"], sd["model.8.bias"] = _conv_init(num_filters * 4, num_filters * 2, 4)
     sd["model.12.weight"], sd["model.12.bias"] = _conv_init(num_filters * 8, num_filters * 4, 4)
     return sd
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# VGG19 perceptual loss (reference: src/models.py:123-151 VGGFeatureExtractor, src/utils.py:154-166 perceptal_loss)
+# ----------------------------------------------------------------------------------------------------------------
+# torchvision vgg19 'E' configuration; module index i of vgg19.features <-> position in this walk
+VGG19_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
+VGG_LAYER_NAMES = {"3": "conv1_2", "8": "conv2_2", "17": "conv3_3", "26": "conv4_3", "35": "conv5_3"}     # src/models.py:128-134
+
+
+def init_vgg19_state(seed: int, prefix: str = "vgg19.") -> Dict[str, Tensor]:
+    """Feature-extractor tensors of torchvision's ``vgg19(weights=None)`` built under ``torch.manual_seed(seed)``: what the
+    reference's VGGFeatureExtractor holds when the ImageNet download is replaced by the default initialisation
+    (tests/golden/make_golden.py:make_vgg_fixture).  The initialiser order inside torchvision (default Conv2d / Linear
+    init, then kaiming_normal_ over all modules) is what fixes the values, so torchvision itself builds them."""
+    import torchvision
+    torch.manual_seed(seed)
+    feats = torchvision.models.vgg19(weights=None).features
+    return {prefix + k: v.detach().clone() for k, v in feats.state_dict().items()}
+
+
+def vgg_features(sd: Dict[str, Tensor], x: Tensor, layers=("conv3_3", "conv4_3"), prefix: str = "vgg19.") -> Dict[str, Tensor]:
+    """VGGFeatureExtractor.forward (src/models.py:140-151): walk vgg19.features, collect the selected (post-ReLU) maps,
+    stop once all are collected."""
+    feats: Dict[str, Tensor] = {}
+    want = [n for n in VGG_LAYER_NAMES.values() if n in layers]
+    idx = 0
+    for v in VGG19_CFG:
+        if v == "M":
+            x = F.max_pool2d(x, 2, 2)
+            steps = [idx]
+            idx += 1
+        else:
+            x = F.conv2d(x, sd[f"{prefix}{idx}.weight"], sd[f"{prefix}{idx}.bias"], padding=1)
+            x = F.relu(x)
+            steps = [idx, idx + 1]
+            idx += 2
+        for s in steps:
+            name = VGG_LAYER_NAMES.get(str(s))
+            if name is not None and name in layers:
+                feats[name] = x
+        if len(feats) == len(want):
+            break
+    return feats
+
+
+def perceptual_loss(sd: Dict[str, Tensor], sr: Tensor, hr: Tensor, layers=("conv3_3", "conv4_3")) -> Tensor:
+    """perceptal_loss (src/utils.py:154-166): sum over the selected layers of mean |features(sr) - features(hr)|."""
+    fr = vgg_features(sd, hr, layers)
+    ff = vgg_features(sd, sr, layers)
+    total = 0
+    for k in fr:
+        total = total + (ff[k] - fr[k]).abs().mean()
+    return total

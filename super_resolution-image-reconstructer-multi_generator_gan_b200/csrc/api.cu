@@ -12,6 +12,7 @@
 #include "generator.cuh"
 #include "peer_sync.cuh"
 #include "trunk_fused.cuh"
+#include "vgg_ops.cuh"
 
 using namespace srg;
 
@@ -431,4 +432,25 @@ extern "C" size_t srg_conv2d_wgrad_workspace_bytes(int N, int H, int W, int cin,
 extern "C" int srg_conv2d_wgrad(const void* x, const void* dy, int N, int H, int W, int cin, int cout, void* workspace,
                                 size_t workspace_bytes, float* dw_oihw, float* dbias, void* stream) {
   return launch_conv2d_wgrad(x, dy, N, H, W, cin, cout, workspace, workspace_bytes, dw_oihw, dbias, S(stream));
+}
+
+// ---- VGG19 perceptual loss helpers (src/models.py:123-151, src/utils.py:154-166) ------------------------------------
+extern "C" int srg_unfold3x3_rgb(const float* x_nchw, int N, int H, int W, void* out, void* stream) {
+  return launch_unfold3(x_nchw, N, H, W, out, S(stream));
+}
+extern "C" int srg_fold3x3_rgb(const void* d_unfolded, int N, int H, int W, float scale, float* dx_nchw, void* stream) {
+  return launch_fold3(d_unfolded, N, H, W, scale, dx_nchw, S(stream));
+}
+extern "C" int srg_maxpool2x2_forward(const void* x, int N, int H, int W, int C, void* out, void* stream) {
+  return launch_maxpool2_forward(x, N, H, W, C, out, S(stream));
+}
+extern "C" int srg_maxpool2x2_backward(const void* x, const void* dy, const void* add, int N, int H, int W, int C, void* dx,
+                                       void* stream) {
+  return launch_maxpool2_backward(x, dy, add, N, H, W, C, dx, S(stream));
+}
+extern "C" size_t srg_l1_bf16_scratch_bytes(void) { return l1_feat_scratch_bytes(); }
+extern "C" int srg_l1_bf16(const void* a, const void* b, int64_t n, float weight, int accumulate, float grad_scale, int relu_mask,
+                           void* grad_a, void* scratch, size_t scratch_bytes, float* out1, void* stream) {
+  if (scratch_bytes < l1_feat_scratch_bytes()) { set_error("srg_l1_bf16: scratch too small"); return -83; }
+  return launch_l1_feat(a, b, n, weight, accumulate, grad_scale, relu_mask, grad_a, scratch, out1, S(stream));
 }

@@ -134,6 +134,52 @@ def make_checkpoint_fixture(models):
     np.savez_compressed(os.path.join(HERE, "reference_ddp_checkpoint_io.npz"), x=x.numpy(), y=y.numpy())
 
 
+def make_vgg_fixture(models, utils):
+    """VGGFeatureExtractor + perceptal_loss (src/models.py:123-151, src/utils.py:154-166), UNMODIFIED, on seeded
+    torchvision-default weights: the reference asks torchvision for the ImageNet checkpoint (a download); the one thing
+    replaced here is that request -- ``torchvision.models.vgg19`` is wrapped to build the same architecture with
+    ``weights=None`` under a fixed seed.  The weights themselves (42 MB for the 12 executed convs) are NOT stored: the
+    test rebuilds them with oracle.init_vgg19_state(seed) and this function checks that both constructions agree.
+    python tests/golden/make_golden.py vgg"""
+    import torchvision
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import srgan_oracle as O
+    real_vgg19 = torchvision.models.vgg19
+
+    def seeded_vgg19(weights=None, **kw):
+        torch.manual_seed(31)
+        return real_vgg19(weights=None, **kw)
+
+    models.models.vgg19 = seeded_vgg19
+    try:
+        fe = models.VGGFeatureExtractor()
+    finally:
+        models.models.vgg19 = real_vgg19
+    sd_ref = {k: v.detach().clone() for k, v in fe.state_dict().items()}
+    # torchvision builds the classifier's Linear layers after the features, so the feature tensors only depend on the
+    # seed and on the conv order: the oracle's own initialiser must reproduce them bit for bit
+    sd_or = O.init_vgg19_state(31)
+    for k, v in sd_or.items():
+        assert torch.equal(v, sd_ref[k]), k
+    torch.manual_seed(32)
+    sr = torch.rand(2, 3, 40, 24, requires_grad=True)
+    hr = torch.rand(2, 3, 40, 24)
+    feats = fe(hr)
+    loss = utils.perceptal_loss(sr, hr, fe)
+    loss.backward()
+    # the oracle restatement against the reference, same weights
+    sr2 = sr.detach().clone().requires_grad_(True)
+    loss_o = O.perceptual_loss(sd_or, sr2, hr)
+    loss_o.backward()
+    assert abs(float(loss_o) - float(loss)) < 1e-7 and torch.allclose(sr2.grad, sr.grad, atol=1e-9)
+    np.savez_compressed(os.path.join(HERE, "vgg_perceptual.npz"), seed=31, sr=sr.detach().numpy(), hr=hr.numpy(),
+                        loss=float(loss), grad=sr.grad.numpy(),
+                        conv3_3=feats["conv3_3"].detach().numpy(), conv4_3=feats["conv4_3"].detach().numpy(),
+                        keys=np.array(sorted(sd_ref.keys())))
+    print("vgg fixture: loss", float(loss), "grad max", float(sr.grad.abs().max()), "feature shapes",
+          {k: tuple(v.shape) for k, v in feats.items()})
+
+
 def main():
     torch.set_num_threads(8)
     models, train, utils = import_reference()
@@ -247,6 +293,10 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "adversarial":
         torch.set_num_threads(8)
         make_adversarial_fixture(*import_reference())
+    elif len(sys.argv) > 1 and sys.argv[1] == "vgg":
+        torch.set_num_threads(8)
+        m, _, u = import_reference()
+        make_vgg_fixture(m, u)
     elif len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
         make_checkpoint_fixture(import_reference()[0])
     else:

@@ -169,3 +169,23 @@ def test_discriminator_gradient_conditioning():
     assert res[(512, 1024)] < 0.9, res          # ill-conditioned: a bf16-sized input perturbation turns the gradient
     assert res[(940, 940)] > 0.9, res
     assert res[(940, 940)] > res[(512, 1024)], res
+
+
+def test_vgg_perceptual_oracle_matches_reference_fixture(golden_dir):
+    """oracle.vgg_features / perceptual_loss (restating src/models.py:123-151, src/utils.py:154-166) against the fixture the
+    unmodified reference produced on torchvision-default weights (tests/golden/make_golden.py vgg)."""
+    import numpy as np
+    import torch
+    from oracle import srgan_oracle as O
+    z = np.load(os.path.join(golden_dir, "vgg_perceptual.npz"))
+    sd = O.init_vgg19_state(int(z["seed"]))
+    assert sorted(sd.keys()) == list(z["keys"])
+    sr = torch.from_numpy(z["sr"]).requires_grad_(True)
+    hr = torch.from_numpy(z["hr"])
+    feats = O.vgg_features(sd, hr)
+    assert np.allclose(feats["conv3_3"].numpy(), z["conv3_3"], atol=1e-6)
+    assert np.allclose(feats["conv4_3"].numpy(), z["conv4_3"], atol=1e-6)
+    loss = O.perceptual_loss(sd, sr, hr)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-7
+    assert np.allclose(sr.grad.numpy(), z["grad"], atol=1e-9)
