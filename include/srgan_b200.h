@@ -296,6 +296,23 @@ int srg_image_enhance(const float* x_nchw, int N, int C, int H, int W, float fac
 /* out1[0] (DEVICE double) = mean((a - b)^2); calculate_psnr (src/utils.py:141-144) = 10 * log10(1 / mse) */
 int srg_mse(const float* a, const float* b, int64_t n, void* scratch, size_t scratch_bytes, double* out1, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Image-size transforms either side of the path (src/transformers.py:73-82, applied per image in src/utils.py:34-47):
+ * transforms.Resize on PIL images = Pillow's ImagingResample (antialiased: the filter support scales with the reduction
+ * factor; separable; 22-bit fixed-point coefficients; uint8 after each pass).  Bit-exact with Pillow for 8-bit RGB.
+ *   srg_resize_plan_ksize  taps per output element for one axis (filter 0 = bilinear, 1 = bicubic), -1 on bad arguments
+ *   srg_resize_plan        HOST arrays bounds[out][2] = (first input index, tap count), coeffs[out][ksize]
+ *   srg_resize_u8          src uint8 [N][H][W][3] -> out_u8 [N][out_h][out_w][3] and / or out_f32 [N][3][out_h][out_w] =
+ *                          v / 255 (ToTensor) + noise * sigma[n] (the degradation of downward_img_quality; both NULL: none).
+ *                          bounds_* / coeffs_* are DEVICE copies of the plans; tmp: uint8 [N][H][out_w][3] when out_w != W
+ * ------------------------------------------------------------------------------------------------------------- */
+int srg_resize_plan_ksize(int in_size, int out_size, int filter);
+int srg_resize_plan(int in_size, int out_size, int filter, int32_t* bounds_host, int32_t* coeffs_host);
+int srg_resize_u8(const uint8_t* src_nhwc, int N, int H, int W, int out_h, int out_w, const int32_t* bounds_w,
+                  const int32_t* coeffs_w, int ksize_w, const int32_t* bounds_h, const int32_t* coeffs_h, int ksize_h,
+                  uint8_t* tmp, uint8_t* out_u8_nhwc, float* out_f32_nchw, const float* noise_nchw,
+                  const float* sigma_per_image, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ from .policy import (GAN, PIXEL, MultiGeneratorPolicy, PolicyConfig, decide, gan
 from .train import (DevicePrefetcher, GraphedDiscriminatorStep, GraphedGeneratorStep, GraphedMultiGeneratorStep, MultiGeneratorGAN, joint_pixel_generator_steps, train_discriminator, train_discriminator_async, train_generator,
                     train_generator_async, train_one_epoch, setup_training)
 from . import parallel
+from . import transformers
 from .vgg import VGGFeatureExtractor, perceptal_loss, perceptual_loss
 from .evaluation import (ImageEnhancer, calculate_psnr, load_reference_checkpoint, resume_learning_rates,
                          save_reference_checkpoint, strip_module_prefix)

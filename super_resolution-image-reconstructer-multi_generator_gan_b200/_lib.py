@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "libsrgan_b200.so")
-SOURCES = ["conv_gemm.cu", "conv_ops.cu", "vgg_ops.cu", "trunk_fused.cu", "wgrad_gemm.cu", "elementwise.cu", "peer_sync.cu", "generator.cu", "discriminator.cu", "api.cu"]
+SOURCES = ["conv_gemm.cu", "conv_ops.cu", "vgg_ops.cu", "resample.cu", "trunk_fused.cu", "wgrad_gemm.cu", "elementwise.cu", "peer_sync.cu", "generator.cu", "discriminator.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
@@ -120,6 +120,10 @@ EXPORTS = {
     "srg_l1_bf16_scratch_bytes": (c_size_t, []),
     "srg_l1_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_int, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p,
                             c_void_p]),
+    "srg_resize_plan_ksize": (c_int, [c_int, c_int, c_int]),
+    "srg_resize_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p]),
+    "srg_resize_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "srg_set_trunk_fused": (c_int, [c_int]),
     "srg_generator_forward_phases": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "srg_generator_backward_phases": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

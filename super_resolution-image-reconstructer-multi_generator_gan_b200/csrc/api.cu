@@ -11,6 +11,7 @@
 #include "discriminator.cuh"
 #include "generator.cuh"
 #include "peer_sync.cuh"
+#include "resample.cuh"
 #include "trunk_fused.cuh"
 #include "vgg_ops.cuh"
 
@@ -453,4 +454,17 @@ extern "C" int srg_l1_bf16(const void* a, const void* b, int64_t n, float weight
                            void* grad_a, void* scratch, size_t scratch_bytes, float* out1, void* stream) {
   if (scratch_bytes < l1_feat_scratch_bytes()) { set_error("srg_l1_bf16: scratch too small"); return -83; }
   return launch_l1_feat(a, b, n, weight, accumulate, grad_scale, relu_mask, grad_a, scratch, out1, S(stream));
+}
+
+// ---- image-size transforms either side of the path (src/transformers.py:73-82) -------------------------------------
+extern "C" int srg_resize_plan_ksize(int in_size, int out_size, int filter) { return resize_plan_ksize(in_size, out_size, filter); }
+extern "C" int srg_resize_plan(int in_size, int out_size, int filter, int32_t* bounds_host, int32_t* coeffs_host) {
+  return resize_plan(in_size, out_size, filter, bounds_host, coeffs_host);
+}
+extern "C" int srg_resize_u8(const uint8_t* src_nhwc, int N, int H, int W, int out_h, int out_w, const int32_t* bounds_w,
+                             const int32_t* coeffs_w, int ksize_w, const int32_t* bounds_h, const int32_t* coeffs_h, int ksize_h,
+                             uint8_t* tmp, uint8_t* out_u8_nhwc, float* out_f32_nchw, const float* noise_nchw,
+                             const float* sigma_per_image, void* stream) {
+  return launch_resize_u8(src_nhwc, N, H, W, out_h, out_w, bounds_w, coeffs_w, ksize_w, bounds_h, coeffs_h, ksize_h, tmp,
+                          out_u8_nhwc, out_f32_nchw, noise_nchw, sigma_per_image, S(stream));
 }
