@@ -15,6 +15,7 @@
 //                                  taps share one N = 128 MMA (the ~64-cycle floor of an M128 MMA makes that free);
 //   conv9_rows_kernel              the 9x9 / 3-output-channel conv3: one image row per MMA feeding up to 8 output rows.
 #include "conv_gemm.cuh"
+#include "elementwise.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
 
@@ -45,6 +46,7 @@ struct ConvKParams {
   CUtensorMap w_map;
   CUtensorMap out_map[4];  // NHWC: [0]; pixel shuffle: one strided view of the HR tensor per n-block
   CUtensorMap aux_map;     // residual / mask tensor (same geometry as out_map[0])
+  uint64_t pol_in;         // L2 eviction priority of the operand / aux loads
   int N, H, W, TH, TW;
   int tiles_h, tiles_w, tiles_total;
   int tile_step_w;  // TW, or TW-8 for the fold9 epilogue
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (p.aux_mode) {
           mbar_wait(&auxempty[ab], aux_phase ^ 1);
           mbar_expect_tx(&auxfull[ab], kTileOutBytes);
-          tma_load_4d(aux_stage + ab * kTileOutBytes, &p.aux_map, &auxfull[ab], nblk * BLOCK_N, w0, h0, n);
+          tma_load_4d_hint(aux_stage + ab * kTileOutBytes, &p.aux_map, &auxfull[ab], nblk * BLOCK_N, w0, h0, n, p.pol_in);
           ab ^= 1;
           if (ab == 0) aux_phase ^= 1;
         }
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             { long long t0_ = clock64(); mbar_wait(&empty[stage], phase ^ 1); prof_acc[0] += clock64() - t0_; }
             uint8_t* dst = stages + size_t(stage) * p.stage_bytes;
             mbar_expect_tx(&full[stage], p.resident ? p.strip_bytes : p.stage_bytes);
-            tma_load_4d(dst, &p.in_map[view], &full[stage], coff, w0 + p.strip_dw[s], h0 + p.strip_dh, n);
+            tma_load_4d_hint(dst, &p.in_map[view], &full[stage], coff, w0 + p.strip_dw[s], h0 + p.strip_dh, n, p.pol_in);
             if (!p.resident) {
               const int kb0 = (c * p.n_strips + s) * NT;
               for (int r = 0; r < NT; ++r)
@@ -493,6 +495,7 @@ struct IlKParams {
   int out_mode;
   float* stats;              // per-CTA channel sums / sums of squares
   const uint32_t* stats_y;   // optional second factor (bf16 pairs, the output's geometry): sum(out * stats_y) replaces sum(out^2)
+  uint64_t pol_out, pol_aux, pol_in; // L2 eviction priorities of the output store / the residual-mask tile loads / the operand strips
   long long* prof;
 };
 
@@ -591,7 +594,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
           for (int par = 1; par >= 0; --par) {       // odd image rows h0-1+2j first, then even rows h0+2j (j = 0..16)
             { long long t0_ = clock64(); mbar_wait(&empty[stage], phase ^ 1); prof_acc[0] += clock64() - t0_; }
             mbar_expect_tx(&full[stage], 17 * kIlWidePitch);
-            tma_load_4d(stages + size_t(stage) * kStage, &p.in_map[par], &full[stage], 0, w0 + p.strip_dw[0], hh - par, n);
+            tma_load_4d_hint(stages + size_t(stage) * kStage, &p.in_map[par], &full[stage], 0, w0 + p.strip_dw[0], hh - par, n, p.pol_in);
             if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
           }
         } else {
@@ -612,7 +615,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
           for (int b = 0; b < 2; ++b) {
             mbar_wait(&auxempty[b], aux_phase ^ 1);
             mbar_expect_tx(&auxfull[b], kTileOutBytes);
-            tma_load_4d(aux_stage + b * kTileOutBytes, &p.aux_map[b], &auxfull[b], nblk * 64, w0, hh, n);
+            tma_load_4d_hint(aux_stage + b * kTileOutBytes, &p.aux_map[b], &auxfull[b], nblk * 64, w0, hh, n, p.pol_aux);
           }
           aux_phase ^= 1;
         }
@@ -827,7 +830,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
       named_bar_sync(bar_b, 256);
       if (gtid == 0) {
         const bool ps = p.out_mode == OUT_PIXEL_SHUFFLE;
-        tma_store_4d(&p.out_map[(ps ? nblk : 0) * 2 + blk], my_out, ps ? 0 : nblk * 64, w0, hh, n);
+        tma_store_4d_hint(&p.out_map[(ps ? nblk : 0) * 2 + blk], my_out, ps ? 0 : nblk * 64, w0, hh, n, p.pol_out);
         tma_store_commit();
       }
       if (p.stats != nullptr) {
@@ -1290,6 +1293,14 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   p.out_mode = a.out_mode;
   p.stats = a.stats;
   p.stats_y = reinterpret_cast<const uint32_t*>(a.stats_y);
+  // training launches (not exclusive): the output is read by the statistics / apply passes right behind this kernel (keep
+  // it in L2 ahead of streaming data); a mask / residual tile is dead after this read
+  const bool hints = !a.exclusive && l2_hints() >= 2;
+  p.pol_out = hints ? kL2EvictLast : kL2EvictNormal;
+  p.pol_aux = hints ? kL2EvictFirst : kL2EvictNormal;
+  // the operand tensor is not read again before the weight gradients at the end of backward (neighbouring tiles re-read
+  // their halo within microseconds, long before capacity pressure evicts it)
+  p.pol_in = (!a.exclusive && l2_hints() >= 3) ? kL2EvictFirst : kL2EvictNormal;
   p.prof = reinterpret_cast<long long*>(a.prof);
   static bool attr_set = false;
   if (!attr_set) {
@@ -1494,6 +1505,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     p.aux_map = p.in_map[0];
   }
   p.bias = a.bias; p.scale = a.scale; p.act = a.act; p.slope = a.slope;
+  p.pol_in = (!a.exclusive && l2_hints() >= 4) ? kL2EvictFirst : kL2EvictNormal;
   p.out = a.out; p.out_mode = a.out_mode;
   p.stats = a.stats;
   p.stats_y = reinterpret_cast<const uint32_t*>(a.stats_y);

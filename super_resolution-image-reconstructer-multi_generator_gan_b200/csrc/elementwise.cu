@@ -10,6 +10,7 @@
 
 #include "conv_gemm.cuh"
 #include "launch.cuh"
+#include "ptx.cuh"
 
 namespace srg {
 
@@ -51,6 +52,11 @@ static int env_int(const char* name, int dflt) {
 static int red_per_sm() { static int v = -1; if (v < 0) v = env_int("SRG_RED_PER_SM", 2); return v < 1 ? 1 : v; }
 static int ew_per_sm() { static int v = -1; if (v < 0) v = env_int("SRG_EW_PER_SM", 4); return v < 1 ? 1 : v; }
 static int fin_per_sm() { static int v = -1; if (v < 0) v = env_int("SRG_FIN_PER_SM", 2); return v < 1 ? 1 : v; }
+// L2 eviction priorities (SRG_L2_HINTS: 0 none, 1 BatchNorm chain, 2 + conv outputs / aux tiles, 3 (default) + conv operands
+// and the block-input read, 4 + weight-gradient and generic-kernel operands).  Per trunk layer the three generators
+// stream ~450 MB through a 126 MB L2; without hints the tensors with a near reuse (the conv output the reduction and the
+// apply pass read next, the apply output the next conv reads) are evicted by data that is dead after its access.
+int l2_hints() { static int v = -1; if (v < 0) v = env_int("SRG_L2_HINTS", 3); return v; }
 int reduce_blocks(int64_t pixels) {
   int64_t b = (pixels + 32 * 8 - 1) / (32 * 8);
   if (b < 1) b = 1;
@@ -61,7 +67,7 @@ int reduce_blocks(int64_t pixels) {
 
 template <bool TWO>
 __global__ void __launch_bounds__(256) chan_reduce_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
-                                                          int64_t pixels, float* __restrict__ partials) {
+                                                          int64_t pixels, float* __restrict__ partials, uint64_t pol) {
   __shared__ float red[32][129];
   pdl_trigger();
   pdl_wait();
@@ -78,8 +84,8 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const uint4* __restric
     uint4 ra[4], rb[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      ra[u] = a[(p + u * stride) * 8 + cg];
-      if (TWO) rb[u] = b[(p + u * stride) * 8 + cg];
+      ra[u] = ldg_hint_u4(a + (p + u * stride) * 8 + cg, pol);
+      if (TWO) rb[u] = ldg_hint_u4(b + (p + u * stride) * 8 + cg, pol);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -153,16 +159,39 @@ __device__ __forceinline__ void finalize_channels(const ReduceFinalize& f, int c
 template <bool TWO>
 __global__ void __launch_bounds__(256) chan_reduce_final_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
                                                                 int64_t pixels, float* __restrict__ partials,
-                                                                unsigned int* __restrict__ ticket, const ReduceFinalize f) {
+                                                                unsigned int* __restrict__ ticket, const ReduceFinalize f,
+                                                                uint64_t pol) {
   __shared__ float red[32][129];
-  __shared__ double dred[2][128];
   __shared__ bool is_last;
+  pdl_trigger();
+  pdl_wait();
   const int cg = threadIdx.x & 7;
   const int lane_p = threadIdx.x >> 3;
   float s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
-  for (int64_t p = int64_t(blockIdx.x) * 32 + lane_p; p < pixels; p += int64_t(gridDim.x) * 32) {
+  const int64_t stride = int64_t(gridDim.x) * 32;
+  int64_t p = int64_t(blockIdx.x) * 32 + lane_p;
+  for (; p + 3 * stride < pixels; p += 4 * stride) {      // same loop (and per-thread accumulation order) as chan_reduce_kernel
+    uint4 ra[4], rb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ra[u] = ldg_hint_u4(a + (p + u * stride) * 8 + cg, pol);
+      if (TWO) rb[u] = ldg_hint_u4(b + (p + u * stride) * 8 + cg, pol);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float fa[8], fb[8];
+      unpack8(ra[u], fa);
+      if (TWO) unpack8(rb[u], fb);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s1[e] += fa[e];
+        s2[e] += TWO ? fa[e] * fb[e] : fa[e] * fa[e];
+      }
+    }
+  }
+  for (; p < pixels; p += stride) {
     float fa[8], fb[8];
     unpack8(a[p * 8 + cg], fa);
     if (TWO) unpack8(b[p * 8 + cg], fb);
@@ -189,16 +218,40 @@ __global__ void __launch_bounds__(256) chan_reduce_final_kernel(const uint4* __r
   if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!is_last) return;
+  // the last block to finish: fixed-order fp64 sum of every block's row (8 row lanes x 32 column quads), then the finalize
   __threadfence();
-  const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
-  double acc = 0.0;
-  for (int blk = half; blk < int(gridDim.x); blk += 2) acc += double(__ldcg(partials + size_t(blk) * 128 + col));
-  dred[half][col] = acc;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    const int c = threadIdx.x;
-    finalize_channels(f, c, dred[0][c] + dred[1][c], dred[0][64 + c] + dred[1][64 + c]);
+  double* dred = reinterpret_cast<double*>(&red[0][0]);        // [8][128] doubles over the dead float rows (16.5 KB)
+  const int c4 = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const float4* src = reinterpret_cast<const float4*>(partials) + c4;
+  const int rows = int(gridDim.x);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int r = rl;
+  for (; r + 32 < rows; r += 40) {
+    const float4 v0 = __ldcg(src + size_t(r) * 32), v1 = __ldcg(src + size_t(r + 8) * 32), v2 = __ldcg(src + size_t(r + 16) * 32);
+    const float4 v3 = __ldcg(src + size_t(r + 24) * 32), v4 = __ldcg(src + size_t(r + 32) * 32);
+    a0 += double(v0.x); a1 += double(v0.y); a2 += double(v0.z); a3 += double(v0.w);
+    a0 += double(v1.x); a1 += double(v1.y); a2 += double(v1.z); a3 += double(v1.w);
+    a0 += double(v2.x); a1 += double(v2.y); a2 += double(v2.z); a3 += double(v2.w);
+    a0 += double(v3.x); a1 += double(v3.y); a2 += double(v3.z); a3 += double(v3.w);
+    a0 += double(v4.x); a1 += double(v4.y); a2 += double(v4.z); a3 += double(v4.w);
   }
+  for (; r < rows; r += 8) {
+    const float4 v = __ldcg(src + size_t(r) * 32);
+    a0 += double(v.x); a1 += double(v.y); a2 += double(v.z); a3 += double(v.w);
+  }
+  __syncthreads();
+  dred[rl * 128 + c4 * 4 + 0] = a0; dred[rl * 128 + c4 * 4 + 1] = a1;
+  dred[rl * 128 + c4 * 4 + 2] = a2; dred[rl * 128 + c4 * 4 + 3] = a3;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 128) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += dred[i * 128 + threadIdx.x];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) dred[threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.x < 64) finalize_channels(f, threadIdx.x, dred[threadIdx.x], dred[64 + threadIdx.x]);
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
@@ -247,11 +300,13 @@ int launch_partials_sums(const float* partials, int rows, double* sums, cudaStre
 int launch_chan_reduce_final(const void* a, const void* b, int64_t pixels, float* partials, unsigned int* ticket,
                              const ReduceFinalize& f, cudaStream_t st) {
   const int blocks = reduce_blocks(pixels);
+  const uint64_t pol = (b && l2_hints()) ? kL2EvictLast : kL2EvictNormal;
   if (b)
-    chan_reduce_final_kernel<true><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
-                                                          pixels, partials, ticket, f);
+    launch_pdl(chan_reduce_final_kernel<true>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint4*>(a),
+               reinterpret_cast<const uint4*>(b), pixels, partials, ticket, f, pol);
   else
-    chan_reduce_final_kernel<false><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(a), nullptr, pixels, partials, ticket, f);
+    launch_pdl(chan_reduce_final_kernel<false>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint4*>(a),
+               static_cast<const uint4*>(nullptr), pixels, partials, ticket, f, pol);
   SRG_LAUNCH_CHECK("chan_reduce_final");
   return 0;
 }
@@ -260,10 +315,10 @@ int launch_chan_reduce(const void* a, const void* b, int64_t pixels, float* part
   const int blocks = reduce_blocks(pixels);
   if (b)
     launch_pdl(chan_reduce_kernel<true>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint4*>(a),
-               reinterpret_cast<const uint4*>(b), pixels, partials);
+               reinterpret_cast<const uint4*>(b), pixels, partials, l2_hints() ? kL2EvictLast : kL2EvictNormal);
   else
     launch_pdl(chan_reduce_kernel<false>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint4*>(a),
-               static_cast<const uint4*>(nullptr), pixels, partials);
+               static_cast<const uint4*>(nullptr), pixels, partials, kL2EvictNormal);
   SRG_LAUNCH_CHECK("chan_reduce");
   return 0;
 }
@@ -356,7 +411,8 @@ int launch_bn_eval_coeffs_all(const float* master, const float* buffers, const v
 template <bool RELU, bool SKIP>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, const uint4* __restrict__ skip,
-                                                       uint4* __restrict__ out, int64_t n_vec) {
+                                                       uint4* __restrict__ out, int64_t n_vec, uint64_t pol_y, uint64_t pol_out,
+                                                       uint64_t pol_skip) {
   pdl_trigger();
   pdl_wait();
   const int cg = threadIdx.x & 7;  // blockDim is a multiple of 8 and the grid stride too
@@ -368,8 +424,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
   }
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += int64_t(gridDim.x) * blockDim.x) {
     float f[8], k[8];
-    unpack8(y[i], f);
-    if (SKIP) unpack8(skip[i], k);
+    unpack8(ldg_hint_u4(y + i, pol_y), f);
+    if (SKIP) unpack8(ldg_hint_u4(skip + i, pol_skip), k);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float v = fmaf(f[e], sc[e], sh[e]);
@@ -377,7 +433,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
       if (SKIP) v += k[e];
       f[e] = v;
     }
-    out[i] = pack8(f);
+    stg_hint_u4(out + i, pack8(f), pol_out);
   }
 }
 static int ew_blocks(int64_t n_vec) {
@@ -393,10 +449,13 @@ int launch_bn_apply(const void* y, const float* scale, const float* shift, const
   const uint4* yy = reinterpret_cast<const uint4*>(y);
   const uint4* kk = reinterpret_cast<const uint4*>(skip);
   uint4* oo = reinterpret_cast<uint4*>(out);
-  if (relu && skip) launch_pdl(bn_apply_kernel<true, true>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec);
-  else if (relu) launch_pdl(bn_apply_kernel<true, false>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec);
-  else if (skip) launch_pdl(bn_apply_kernel<false, true>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec);
-  else launch_pdl(bn_apply_kernel<false, false>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec);
+  // y is not read again before the backward pass (evict first); the output is the next convolution's operand (keep)
+  const uint64_t py = l2_hints() ? kL2EvictFirst : kL2EvictNormal, po = l2_hints() ? kL2EvictLast : kL2EvictNormal;
+  const uint64_t pk = l2_hints() >= 3 ? kL2EvictFirst : kL2EvictNormal;      // the block input: last read of the forward pass
+  if (relu && skip) launch_pdl(bn_apply_kernel<true, true>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk);
+  else if (relu) launch_pdl(bn_apply_kernel<true, false>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk);
+  else if (skip) launch_pdl(bn_apply_kernel<false, true>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk);
+  else launch_pdl(bn_apply_kernel<false, false>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk);
   SRG_LAUNCH_CHECK("bn_apply");
   return 0;
 }
@@ -433,7 +492,7 @@ int launch_bn_bwd_finalize(const double* sums, double count, const float* gamma,
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y,
                                                            const float* __restrict__ cA, const float* __restrict__ cB,
                                                            const float* __restrict__ cC, uint4* __restrict__ dy,
-                                                           int64_t n_vec) {
+                                                           int64_t n_vec, uint64_t pol_in, uint64_t pol_out) {
   pdl_trigger();
   pdl_wait();
   const int cg = threadIdx.x & 7;
@@ -446,18 +505,23 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
   }
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += int64_t(gridDim.x) * blockDim.x) {
     float d[8], v[8];
-    unpack8(dout[i], d);
-    unpack8(y[i], v);
+    unpack8(ldg_hint_u4(dout + i, pol_in), d);
+    unpack8(ldg_hint_u4(y + i, pol_in), v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) d[e] = fmaf(a[e], d[e], fmaf(b[e], v[e], c[e]));
-    dy[i] = pack8(d);
+    stg_hint_u4(dy + i, pack8(d), pol_out);
   }
 }
 int launch_bn_bwd_apply(const void* dout, const void* y, const float* coefA, const float* coefB, const float* coefC,
                         void* dy, int64_t pixels, cudaStream_t st) {
   const int64_t n_vec = pixels * 8;
   launch_pdl(bn_bwd_apply_kernel, dim3(ew_blocks(n_vec)), dim3(256), 0, st, reinterpret_cast<const uint4*>(dout),
-             reinterpret_cast<const uint4*>(y), coefA, coefB, coefC, reinterpret_cast<uint4*>(dy), n_vec);
+             reinterpret_cast<const uint4*>(y), coefA, coefB, coefC, reinterpret_cast<uint4*>(dy), n_vec,
+             // dz and y are (all but) dead after this pass.  Measured: keeping bn2's dz, which the block's conv1 dgrad reads
+             // once more as the skip gradient, at high priority costs 0.15 ms per step, and discarding the dead bn1 dz lines
+             // (discard.global.L2) buys nothing (profiles/r02_notes.md)
+             l2_hints() ? kL2EvictFirst : kL2EvictNormal,
+             l2_hints() ? kL2EvictLast : kL2EvictNormal);      // dy is the next dgrad's operand
   SRG_LAUNCH_CHECK("bn_bwd_apply");
   return 0;
 }

@@ -11,6 +11,7 @@ constexpr int kRedBlocksMax = 296;  // 2 x 148 SMs
 // ---- per-channel reductions over [P pixels][64 ch] bf16 ------------------------------------------
 // partials: float [blocks][128]  ([0,64) = sum a ; [64,128) = sum a*a (b == null) or sum a*b)
 int reduce_blocks(int64_t pixels);
+int l2_hints();   // SRG_L2_HINTS: 0 none, 1 BatchNorm chain, 2 + convolution stores
 int launch_chan_reduce(const void* a, const void* b, int64_t pixels, float* partials, cudaStream_t st);
 // Fused variant: reduction + fixed-order partial sum + per-channel finalize in ONE launch (last block done).
 enum ReduceFinalizeMode : int { RF_BN_FWD = 0, RF_BN_BWD = 1, RF_SUM = 2 };

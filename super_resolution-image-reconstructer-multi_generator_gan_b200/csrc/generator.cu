@@ -506,6 +506,8 @@ GeneratorEngine* generator_create(int N, int H, int W, int n_res, int n_up) {
   {
     const char* ev = getenv("SRG_FUSE_BWD_STATS");
     e->fuse_bwd_stats = ev != nullptr && ev[0] == '1';
+    ev = getenv("SRG_REDUCE_FINAL");
+    e->reduce_final = ev != nullptr && ev[0] == '1';
     ev = getenv("SRG_FIN_FUSED");
     e->fin_fused = ev != nullptr && ev[0] == '1';
     ev = getenv("SRG_WGRAD_BATCHED");
@@ -1084,6 +1086,15 @@ int generator_backward_phases(GeneratorEngine* g, const float* dsr, int phases, 
     const int64_t bo = poff(*e, nm);
     // sum dz and sum dz*y: either accumulated by the dgrad kernel that produced dz (fuse_bwd_stats) or by one pass here
     int rows = bwd_stats_rows;
+    if (!e->fuse_bwd_stats && !e->allreduce && !e->peer && e->reduce_final) {
+      // single GPU: the reduction's last block finalizes (atomic ticket): no finalize launch on the backward chain
+      ReduceFinalize f; memset(&f, 0, sizeof(f));
+      f.mode = RF_BN_BWD; f.count = double(P); f.gamma = e->master + go; f.save_mean = coef + 128; f.save_inv = coef + 192;
+      f.dgamma = e->grads + go; f.dbeta = e->grads + bo; f.out0 = bwd; f.out1 = bwd + 64; f.out2 = bwd + 128;
+      RC(launch_chan_reduce_final(dz, y, P, partials, reinterpret_cast<unsigned int*>(ws + L.ticket), f, st));
+      e->launches += 2;
+      return launch_bn_bwd_apply(dz, y, bwd, bwd + 64, bwd + 128, dy, P, st);
+    }
     if (!e->fuse_bwd_stats) {
       RC(launch_chan_reduce(dz, y, P, partials, st));
       rows = reduce_blocks(P);

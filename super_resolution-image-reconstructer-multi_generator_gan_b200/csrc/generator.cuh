@@ -68,6 +68,9 @@ struct GeneratorEngine {
   // 11.08 -> 11.4-11.7 ms (the fatter apply CTAs take bandwidth from the other branches' tensor-core kernels), so it is off
   // by default
   bool fin_fused = false;
+  // single GPU, backward: the BatchNorm-backward reduction's last block finalizes the coefficients (SRG_REDUCE_FINAL=1).
+  // Measured: 96 fewer launches per 3-generator step, step time unchanged (10.69 vs 10.69-10.72 ms), so the two-launch form stays
+  bool reduce_final = false;
   bool wgrad_batched = true;    // trunk weight gradients in one batched launch at the end of backward (SRG_WGRAD_BATCHED=0: off)
   bool keep_grads = false; // debug: keep every inter-layer gradient in its own named buffer (parity tests)
   bool prof_on = false;

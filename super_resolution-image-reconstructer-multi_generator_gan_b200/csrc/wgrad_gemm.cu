@@ -9,6 +9,7 @@
 // its pixel tiles (split-K over CTAs) and writes one fp32 partial block at the end; wgrad_reduce_kernel sums the
 // partials in a fixed order (deterministic) and scatters them into the OIHW gradient through an index map.
 #include "conv_gemm.cuh"
+#include "elementwise.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
 
@@ -33,6 +34,7 @@ struct WgradKParams {
   uint32_t strip_bytes, stage_bytes;
   int n_stages;
   float* partials;         // [splits][n_blocks][n_pairs][128][64]
+  uint64_t pol_in;         // L2 eviction priority of the operand loads (x and dy are dead after the weight gradient)
 };
 
 constexpr int kWgThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
@@ -85,10 +87,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* dst = stages + size_t(stage) * p.stage_bytes;
         mbar_expect_tx(&full[stage], p.stage_bytes);
-        tma_load_4d(dst, &p.dy_map[nblk], &full[stage], nblk * p.dy_c0_step, w0, h0, n);
+        tma_load_4d_hint(dst, &p.dy_map[nblk], &full[stage], nblk * p.dy_c0_step, w0, h0, n, p.pol_in);
         for (int s = 0; s < p.n_strips; ++s)
-          tma_load_4d(dst + kDyBytes + size_t(s) * p.strip_bytes, &p.x_map, &full[stage], 0, w0 + p.strip_dw[s],
-                      h0 + p.strip_dh, n);
+          tma_load_4d_hint(dst + kDyBytes + size_t(s) * p.strip_bytes, &p.x_map, &full[stage], 0, w0 + p.strip_dw[s],
+                      h0 + p.strip_dh, n, p.pol_in);
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -285,9 +287,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_cons
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* dst = stages + size_t(stage) * kW3Stage;
         mbar_expect_tx(&full[stage], kW3Stage);
-        tma_load_4d(dst, &p.dy_map[nblk], &full[stage], nblk * p.dy_c0_step, w0, h0 - 1, n);
+        tma_load_4d_hint(dst, &p.dy_map[nblk], &full[stage], nblk * p.dy_c0_step, w0, h0 - 1, n, p.pol_in);
         for (int kw = 0; kw < 3; ++kw)
-          tma_load_4d(dst + kW3DyBytes + size_t(kw) * kW3XBytes, &p.x_map, &full[stage], 0, w0 + kw - 1, h0, n);
+          tma_load_4d_hint(dst + kW3DyBytes + size_t(kw) * kW3XBytes, &p.x_map, &full[stage], 0, w0 + kw - 1, h0, n, p.pol_in);
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -371,6 +373,7 @@ int launch_wgrad3x3(const WgradArgs& a, cudaStream_t stream) {
   p.splits = splits;
   p.n_stages = 3;
   p.partials = a.partials;
+  p.pol_in = l2_hints() >= 4 ? kL2EvictFirst : kL2EvictNormal;
   p.dy_c0_step = a.dy_views == 1 ? 64 : 0;
   {
     uint64_t dims[4] = {64, uint64_t(a.in_W), uint64_t(a.in_H), uint64_t(a.N)};
@@ -422,8 +425,17 @@ struct WgradBatchKParams {
   int n_layers, total_tiles, per_cta, max_slots;
   int n_stages;
   float* partials;
+  uint64_t pol_in;
 };
 
+__device__ __forceinline__ void tma_load_5d_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                                 int c4, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2], %8;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
                                             int c4) {
   asm volatile(
@@ -481,9 +493,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_batched_kernel(const __g
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* dst = stages + size_t(stage) * kW3Stage;
         mbar_expect_tx(&full[stage], kW3Stage);
-        tma_load_5d(dst, &p.dy_map, &full[stage], 0, w0, h0 - 1, n, layer);
+        tma_load_5d_hint(dst, &p.dy_map, &full[stage], 0, w0, h0 - 1, n, layer, p.pol_in);
         for (int kw = 0; kw < 3; ++kw)
-          tma_load_5d(dst + kW3DyBytes + size_t(kw) * kW3XBytes, &p.x_map, &full[stage], 0, w0 + kw - 1, h0, n, layer);
+          tma_load_5d_hint(dst + kW3DyBytes + size_t(kw) * kW3XBytes, &p.x_map, &full[stage], 0, w0 + kw - 1, h0, n, layer, p.pol_in);
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -622,6 +634,7 @@ int launch_wgrad3x3_batched(const WgradBatchArgs& a, cudaStream_t stream) {
   p.max_slots = ms;
   p.n_stages = 3;
   p.partials = a.partials;
+  p.pol_in = l2_hints() >= 4 ? kL2EvictFirst : kL2EvictNormal;
   {
     uint64_t dims[5] = {64, uint64_t(a.W), uint64_t(a.H), uint64_t(a.N), uint64_t(a.n_layers)};
     uint64_t xs[4] = {128, uint64_t(a.W) * 128, uint64_t(a.H) * a.W * 128, uint64_t(a.x_layer_stride_bytes)};
@@ -696,6 +709,7 @@ int launch_wgrad_gemm(const WgradArgs& a, cudaStream_t stream) {
   if (stages < 1) { set_error("wgrad: stage does not fit in shared memory (%u B)", p.stage_bytes); return -6; }
   p.n_stages = stages;
   p.partials = a.partials;
+  p.pol_in = l2_hints() >= 4 ? kL2EvictFirst : kL2EvictNormal;
   p.dy_c0_step = a.dy_views == 1 ? 64 : 0;
 
   {
