@@ -14,7 +14,8 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_longl
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SO_PATH = os.path.join(HERE, "libsrgan_b200.so")
+# SRG_LIB_SO: developer override for same-box A/B runs against an older build of the library (never rebuilt)
+SO_PATH = os.environ.get("SRG_LIB_SO") or os.path.join(HERE, "libsrgan_b200.so")
 SOURCES = ["conv_gemm.cu", "conv_ops.cu", "vgg_ops.cu", "resample.cu", "trunk_fused.cu", "wgrad_gemm.cu", "elementwise.cu", "peer_sync.cu", "generator.cu", "discriminator.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
@@ -27,6 +28,8 @@ def _sources():
 
 
 def needs_build() -> bool:
+    if os.environ.get("SRG_LIB_SO"):
+        return False
     if not os.path.exists(SO_PATH):
         return True
     so_m = os.path.getmtime(SO_PATH)

@@ -496,6 +496,8 @@ struct IlKParams {
   float* stats;              // per-CTA channel sums / sums of squares
   const uint32_t* stats_y;   // optional second factor (bf16 pairs, the output's geometry): sum(out * stats_y) replaces sum(out^2)
   uint64_t pol_out, pol_aux, pol_in; // L2 eviction priorities of the output store / the residual-mask tile loads / the operand strips
+  int opt;                   // SRG_IL_OPT bits: 1 = first tile column shift by column shift (filter streams in under the MMAs),
+                             // 2 = leave without waiting for the last store's global writes (only for its shared-memory reads)
   long long* prof;
 };
 
@@ -511,10 +513,19 @@ constexpr uint32_t kIlWBytes = 9 * 64 * 128;    // resident filter: [kw 3][kh2 ;
 constexpr uint32_t kIlWidePitch = 10 * 128;
 constexpr uint32_t kIlWideStage = 22 * 1024;    // 17 x 1280 = 21760 B, rounded up to the 1024-byte swizzle period
 
+// in-kernel stall counters of conv3_il (tools/conv_probe): compiled in only with -DSRG_IL_PROF, they cost ~10 registers
+#ifdef SRG_IL_PROF
+#define IL_PROF(...) __VA_ARGS__
+#define IL_TIMED(slot, ...) { long long t0_ = clock64(); __VA_ARGS__ prof_acc[slot] += clock64() - t0_; }
+#else
+#define IL_PROF(...)
+#define IL_TIMED(slot, ...) { __VA_ARGS__ }
+#endif
 template <bool WIDE>
 __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_constant__ IlKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __builtin_assume(__isShared(smem));      // the integer round-up hides the state space: keep LDS / STS instead of generic accesses
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   pdl_trigger();
@@ -555,9 +566,9 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
       mbar_init(&auxempty[i], 256);
     }
     fence_barrier_init();
-    tma_prefetch_desc(&p.in_map[0]);
-    tma_prefetch_desc(&p.in_map[1]);
     tma_prefetch_desc(&p.w_map);
+    tma_prefetch_desc(&p.in_map[1]);
+    tma_prefetch_desc(&p.in_map[0]);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
   if (warp >= 2 && warp < 4) {
@@ -569,21 +580,27 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  long long prof_acc[4] = {0, 0, 0, 0};
-  const long long t_start = clock64();
+  IL_PROF(long long prof_acc[4] = {0, 0, 0, 0}; const long long t_start = clock64();)
 
   if (warp == 0) {
     // =============================================================== TMA producer
     if (elect_one()) {
       // generic packing is k-block (kw*3 + kh); shared memory wants [kw][kh2 ; kh1 ; kh0]
-      for (int s = 0; s < 3; ++s) {
+      auto load_w = [&](int s) {
         mbar_expect_tx(&wfull[s], kIlWBytes / 3);
         for (int r = 0; r < 3; ++r)
           tma_load_2d(w_smem + size_t(s * 3 + (2 - r)) * 8192, &p.w_map, &wfull[s], 0, (s * 3 + r) * p.cout_total + nblk * 64);
-      }
+      };
+      // WIDE: only the first column shift's 24 KB go out ahead of the first tile's strips; the other two follow them.  All
+      // CTAs start together and fetch the same 72 KB, so the ramp is bound by L2 bandwidth (148 x 72 KB): the first tile's
+      // MMAs run column shift by column shift (see the MMA warp) and start after 45 KB instead of 115 KB have arrived.
+      const bool ramp = WIDE && (p.opt & 1);
+      load_w(0);
+      if (!ramp) { load_w(1); load_w(2); }
       pdl_wait();      // the activations (and aux tensor) come from the previous kernel; the weights above do not
       int stage = 0;
-      uint32_t phase = 0, aux_phase = 0;
+      uint32_t phase = 0;
+      bool first = true;
       for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
         const int n = tile / tiles_per_img;
         const int rem = tile - n * tiles_per_img;
@@ -592,33 +609,45 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
         if constexpr (WIDE) {
 #pragma unroll
           for (int par = 1; par >= 0; --par) {       // odd image rows h0-1+2j first, then even rows h0+2j (j = 0..16)
-            { long long t0_ = clock64(); mbar_wait(&empty[stage], phase ^ 1); prof_acc[0] += clock64() - t0_; }
+            IL_TIMED(0, mbar_wait(&empty[stage], phase ^ 1);)
             mbar_expect_tx(&full[stage], 17 * kIlWidePitch);
             tma_load_4d_hint(stages + size_t(stage) * kStage, &p.in_map[par], &full[stage], 0, w0 + p.strip_dw[0], hh - par, n, p.pol_in);
             if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          }
+          if (first) {
+            if (ramp) { load_w(1); load_w(2); }
+            if (p.aux_mode) {
+              // the first tile's residual / mask blocks go out here, behind everything the first MMAs wait for (the TMA
+              // engine fetches descriptors in order: an aux load issued first would hold the operands back)
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                mbar_expect_tx(&auxfull[b], kTileOutBytes);
+                tma_load_4d_hint(aux_stage + b * kTileOutBytes, &p.aux_map[b], &auxfull[b], nblk * 64, w0, hh, n, p.pol_aux);
+              }
+            }
+            first = false;
           }
         } else {
           for (int s = 0; s < 3; ++s) {
 #pragma unroll
             for (int par = 1; par >= 0; --par) {
-              { long long t0_ = clock64(); mbar_wait(&empty[stage], phase ^ 1); prof_acc[0] += clock64() - t0_; }
+              IL_TIMED(0, mbar_wait(&empty[stage], phase ^ 1);)
               mbar_expect_tx(&full[stage], kIlHalfStrip);
               tma_load_4d(stages + size_t(stage) * kStage, &p.in_map[par], &full[stage], 0, w0 + p.strip_dw[s], hh - par, n);
               if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
           }
-        }
-        if (p.aux_mode) {
-          // single-buffered per block, issued AFTER this tile's strips so that waiting for the previous tile's
-          // epilogue never holds back the operand prefetch
+          if (first && p.aux_mode) {
 #pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            mbar_wait(&auxempty[b], aux_phase ^ 1);
-            mbar_expect_tx(&auxfull[b], kTileOutBytes);
-            tma_load_4d_hint(aux_stage + b * kTileOutBytes, &p.aux_map[b], &auxfull[b], nblk * 64, w0, hh, n, p.pol_aux);
+            for (int b = 0; b < 2; ++b) {
+              mbar_expect_tx(&auxfull[b], kTileOutBytes);
+              tma_load_4d_hint(aux_stage + b * kTileOutBytes, &p.aux_map[b], &auxfull[b], nblk * 64, w0, hh, n, p.pol_aux);
+            }
           }
-          aux_phase ^= 1;
+          first = false;
         }
+        // the residual / mask tiles of the following tiles are loaded by the epilogue groups themselves (one buffer per group, the next tile's load
+        // issued as soon as the group has read the current one): the operand prefetch never waits for an epilogue
       }
     }
   } else if (warp == 1) {
@@ -634,49 +663,92 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
     uint32_t acc_phase = 0;
     bool w_ready = false;            // first tile: wait for each column shift's weights right before their first use
     for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
-      { long long t0_ = clock64(); mbar_wait(&tempty[acc], acc_phase ^ 1); prof_acc[1] += clock64() - t0_; }
+      IL_TIMED(1, mbar_wait(&tempty[acc], acc_phase ^ 1);)
       tc_fence_after();
       const uint32_t d_e = tmem_base + uint32_t(acc * 128);
       const uint32_t d_o = d_e + 64;
       if constexpr (WIDE) {
         // descriptor high part: SBO = 1280 B between 8-pixel row groups, base_offset 0 (see kIlWidePitch)
         const uint64_t adesc_hi = (uint64_t(kIlWidePitch >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+        // the 16 MMAs of one (row parity, column shift) pair; a_base = the half strip's stage (1024-byte aligned)
+        auto issue = [&](int par, int s, uint32_t a_base, bool fresh) {
+          const uint32_t wb = w_lo + uint32_t(s) * (3 * 8192 >> 4);
+          // window starting at half-strip row 0 / row 1, column shift s pixels
+          const uint32_t st0 = a_base + uint32_t(s) * 128u, st1 = st0 + kIlWidePitch;
+          const uint64_t a0 = adesc_hi | uint64_t((st0 & 0x3FFFFu) >> 4);
+          const uint64_t a1 = adesc_hi | uint64_t((st1 & 0x3FFFFu) >> 4);
+          if (par == 1) {
+            const uint64_t b1 = desc_hi | uint64_t(wb);                         // rho = 1: E += kh2, O += kh1
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_e, a1 + uint64_t(2 * k), b1 + uint64_t(2 * k), idesc128, (!fresh || k > 0) ? 1u : 0u);
+            const uint64_t b0 = desc_hi | uint64_t(wb + (2 * 8192 >> 4));       // rho = -1: E += kh0
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d_e, a0 + uint64_t(2 * k), b0 + uint64_t(2 * k), idesc64, 1u);
+          } else {
+            const uint64_t b0 = desc_hi | uint64_t(wb + (8192 >> 4));           // rho = 0: E += kh1, O += kh0
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d_e, a0 + uint64_t(2 * k), b0 + uint64_t(2 * k), idesc128, 1u);
+            const uint64_t b1 = desc_hi | uint64_t(wb);                         // rho = 2: O += kh2
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d_o, a1 + uint64_t(2 * k), b1 + uint64_t(2 * k), idesc64, 1u);
+          }
+        };
+        if (!w_ready && (p.opt & 1)) {
+          // first tile of a training launch: (kw0, odd) (kw0, even) | (kw1, odd) (kw2, odd) -> odd half strip released |
+          // (kw1, even) (kw2, even): the MMAs start once the first 24 KB of the filter and the first half strip have landed
+          // and the rest of the filter streams in underneath them.  Later tiles keep the strip-by-strip order (measured:
+          // the interleaved order costs 4 % in the steady state).  Eval-mode (exclusive) launches never take this path, so an
+          // output pixel's fp32 accumulation order does not depend on the tile slot that computes it and eval results stay
+          // bit-identical between batch layouts.
+          const int st1 = stage; const uint32_t ph1 = phase;
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          const int st0 = stage; const uint32_t ph0 = phase;
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          const uint32_t base1 = smem_u32(stages) + uint32_t(st1) * kStage, base0 = smem_u32(stages) + uint32_t(st0) * kStage;
+          mbar_wait(&wfull[0], 0);
+          IL_TIMED(2, mbar_wait(&full[st1], ph1);)
+          IL_PROF(prof_acc[0] = clock64() - t_start;)     // ramp: launch -> first MMA issue
+          tc_fence_after();
+          if (elect_one()) issue(1, 0, base1, true);
+          __syncwarp();
+          IL_TIMED(2, mbar_wait(&full[st0], ph0);)
+          tc_fence_after();
+          if (elect_one()) issue(0, 0, base0, false);
+          __syncwarp();
+          mbar_wait(&wfull[1], 0);
+          tc_fence_after();
+          if (elect_one()) issue(1, 1, base1, false);
+          __syncwarp();
+          mbar_wait(&wfull[2], 0);
+          tc_fence_after();
+          if (elect_one()) {
+            issue(1, 2, base1, false);
+            umma_commit(&empty[st1]);
+            issue(0, 1, base0, false);
+            issue(0, 2, base0, false);
+            umma_commit(&empty[st0]);
+          }
+          __syncwarp();
+        } else {
 #pragma unroll
         for (int par = 1; par >= 0; --par) {
-          { long long t0_ = clock64(); mbar_wait(&full[stage], phase); prof_acc[2] += clock64() - t0_; }
+          IL_TIMED(2, mbar_wait(&full[stage], phase);)
           tc_fence_after();
           const uint32_t a_base = smem_u32(stages) + uint32_t(stage) * kStage;     // 1024-byte aligned
-#pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            if (!w_ready) mbar_wait(&wfull[s], 0);      // first tile only: this column shift's 24 KB of weights have landed
-            if (elect_one()) {
-              const uint32_t wb = w_lo + uint32_t(s) * (3 * 8192 >> 4);
-              // window starting at half-strip row 0 / row 1, column shift s pixels
-              const uint32_t st0 = a_base + uint32_t(s) * 128u, st1 = st0 + kIlWidePitch;
-              const uint64_t a0 = adesc_hi | uint64_t((st0 & 0x3FFFFu) >> 4);
-              const uint64_t a1 = adesc_hi | uint64_t((st1 & 0x3FFFFu) >> 4);
-              if (par == 1) {
-                const uint64_t b1 = desc_hi | uint64_t(wb);                         // rho = 1: E += kh2, O += kh1
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d_e, a1 + uint64_t(2 * k), b1 + uint64_t(2 * k), idesc128, (s > 0 || k > 0) ? 1u : 0u);
-                const uint64_t b0 = desc_hi | uint64_t(wb + (2 * 8192 >> 4));       // rho = -1: E += kh0
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(d_e, a0 + uint64_t(2 * k), b0 + uint64_t(2 * k), idesc64, 1u);
-              } else {
-                const uint64_t b0 = desc_hi | uint64_t(wb + (8192 >> 4));           // rho = 0: E += kh1, O += kh0
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(d_e, a0 + uint64_t(2 * k), b0 + uint64_t(2 * k), idesc128, 1u);
-                const uint64_t b1 = desc_hi | uint64_t(wb);                         // rho = 2: O += kh2
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(d_o, a1 + uint64_t(2 * k), b1 + uint64_t(2 * k), idesc64, 1u);
-              }
-              if (s == 2) umma_commit(&empty[stage]);
-            }
-            __syncwarp();
+          if (!w_ready) {           // first tile in the plain order: every column shift's weights before its first use
+            mbar_wait(&wfull[0], 0); mbar_wait(&wfull[1], 0); mbar_wait(&wfull[2], 0);
+            IL_PROF(if (par == 1) prof_acc[0] = clock64() - t_start;)
+            tc_fence_after();
           }
-          w_ready = true;
+          if (elect_one()) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) issue(par, s, a_base, s == 0 && par == 1);
+            umma_commit(&empty[stage]);
+          }
+          __syncwarp();
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        }
         }
       } else {
 #pragma unroll 1
@@ -685,7 +757,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
         const uint32_t wb = w_lo + uint32_t(s) * (3 * 8192 >> 4);     // [kh2 ; kh1 ; kh0] of this column shift
 #pragma unroll
         for (int par = 1; par >= 0; --par) {
-          { long long t0_ = clock64(); mbar_wait(&full[stage], phase); prof_acc[2] += clock64() - t0_; }
+          IL_TIMED(2, mbar_wait(&full[stage], phase);)
           tc_fence_after();
           const uint32_t a_lo = stage0_lo + uint32_t(stage) * (kIlHalfStrip >> 4);
           if (elect_one()) {
@@ -723,6 +795,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
       w_ready = true;
       if (elect_one()) umma_commit(&tfull[acc]);
       __syncwarp();
+      IL_PROF(prof_acc[3] = clock64() - t_start;)                              // last commit issued
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -739,13 +812,22 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
     const uint8_t* my_aux = aux_stage + blk * kTileOutBytes;
     int acc = 0;
     uint32_t acc_phase = 0, aux_phase = 0;
-    float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;
+    // statistics: thread (c4 = gtid & 15, rp = gtid >> 4) owns channels 4*c4 .. 4*c4+3 of rows 8*rp .. 8*rp+7 of the block
+    float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
+    const int c4 = gtid & 15, rp = gtid >> 4;
+    auto load_aux = [&](int tile) {           // one thread per group: this group's 16 KB of the residual / mask tile
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      mbar_expect_tx(&auxfull[blk], kTileOutBytes);
+      tma_load_4d_hint(aux_stage + blk * kTileOutBytes, &p.aux_map[blk], &auxfull[blk], nblk * 64, (rem % p.tiles_w) * 8,
+                       (rem / p.tiles_w) * 16, n, p.pol_aux);
+    };
     for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
       const int hh = (rem / p.tiles_w) * 16;
       const int w0 = (rem % p.tiles_w) * 8;
-      { long long t0_ = clock64(); mbar_wait(&tfull[acc], acc_phase); prof_acc[3] += clock64() - t0_; }
+      IL_TIMED(3, mbar_wait(&tfull[acc], acc_phase);) IL_PROF(prof_acc[0] = clock64() - t_start;)
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 128 + blk * 64 + hf * 32);
       uint32_t v[32];
@@ -798,12 +880,12 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
             }
           }
         }
-        mbar_arrive(&auxempty[blk]);
         aux_phase ^= 1;
       }
       // stage the bf16 block (128B-swizzled rows) and hand it to the TMA store engine; one staging buffer per group
       if (gtid == 0) tma_store_wait_read<0>();      // this group's previous store has drained the buffer
-      named_bar_sync(bar_a, 256);
+      named_bar_sync(bar_a, 256);                   // ... and every thread of the group has read its part of the aux tile
+      if (p.aux_mode && gtid == 0 && tile + p.ctas_per_block < p.tiles_total) load_aux(tile + p.ctas_per_block);
       uint8_t* op = my_out + row_off;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -815,18 +897,8 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
         *reinterpret_cast<uint4*>(op + (((uint32_t(hf * 4 + g)) ^ sw) << 4)) = o;
       }
       fence_proxy_async_smem();
-      // second factor of the product statistics (BatchNorm backward: sum dz * y): 16 coalesced loads per thread, issued
-      // before the barrier so that they land while the group synchronises and the store is handed to the TMA engine
-      uint32_t yv[16];
-      if (p.stats_y != nullptr) {
-        const int c2 = gtid & 31, part = gtid >> 5;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const int mm = part * 16 + r;
-          const int hr = 2 * (hh + (mm >> 3)) + blk, wc = w0 + (mm & 7);
-          yv[r] = (hr < p.H && wc < p.W) ? __ldg(p.stats_y + ((size_t(n) * p.H + hr) * p.W + wc) * 32 + c2) : 0u;
-        }
-      }
+      // a tile whose 16 rows x 8 pixels all lie inside the image needs no bounds tests in the statistics loop
+      const bool full_tile = 2 * (hh + 15) + blk < p.H && w0 + 7 < p.W;
       named_bar_sync(bar_b, 256);
       if (gtid == 0) {
         const bool ps = p.out_mode == OUT_PIXEL_SHUFFLE;
@@ -834,31 +906,48 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
         tma_store_commit();
       }
       if (p.stats != nullptr) {
-        // column sums of the staged bf16 block (exactly the values BatchNorm will normalise)
-        const int c2 = gtid & 31, part = gtid >> 5;
+        // column sums of the staged bf16 block (exactly the values BatchNorm will normalise): 8 conflict-free 8-byte
+        // reads per thread (a half warp covers one 128-byte row)
+        const uint8_t* sp = my_out + rp * 1024 + (c4 & 1) * 8;
+        const uint32_t cch = uint32_t(c4 >> 1);
+        const bool row_ok = full_tile || 2 * (hh + rp) + blk < p.H;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const int mm = part * 16 + r;
-          if (2 * (hh + (mm >> 3)) + blk < p.H && w0 + (mm & 7) < p.W) {
-            const uint32_t sv = *reinterpret_cast<const uint32_t*>(my_out + mm * 128 + ((((c2 >> 2)) ^ (mm & 7)) << 4) + (c2 & 3) * 4);
-            const float a0 = bf16_lo(sv), a1 = bf16_hi(sv);
-            float b0 = a0, b1 = a1;
-            if (p.stats_y != nullptr) { b0 = bf16_lo(yv[r]); b1 = bf16_hi(yv[r]); }
-            st_s0 += a0; st_s1 += a1;
-            st_q0 = fmaf(a0, b0, st_q0); st_q1 = fmaf(a1, b1, st_q1);
+        for (int r = 0; r < 8; ++r) {
+          if (row_ok && (full_tile || w0 + r < p.W)) {
+            const uint2 sv = *reinterpret_cast<const uint2*>(sp + r * 128 + ((cch ^ uint32_t(r)) << 4));
+            const float a0 = bf16_lo(sv.x), a1 = bf16_hi(sv.x), a2 = bf16_lo(sv.y), a3 = bf16_hi(sv.y);
+            float b0 = a0, b1 = a1, b2 = a2, b3 = a3;
+            if (p.stats_y != nullptr) {     // second factor of the product statistics (BatchNorm backward: sum dz * y)
+              const uint2 yv = __ldg(reinterpret_cast<const uint2*>(p.stats_y + ((size_t(n) * p.H + 2 * (hh + rp) + blk) * p.W + w0 + r) * 32) + c4);
+              b0 = bf16_lo(yv.x); b1 = bf16_hi(yv.x); b2 = bf16_lo(yv.y); b3 = bf16_hi(yv.y);
+            }
+            st_s[0] += a0; st_s[1] += a1; st_s[2] += a2; st_s[3] += a3;
+            st_q[0] = fmaf(a0, b0, st_q[0]); st_q[1] = fmaf(a1, b1, st_q[1]);
+            st_q[2] = fmaf(a2, b2, st_q[2]); st_q[3] = fmaf(a3, b3, st_q[3]);
           }
         }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (gtid == 0) tma_store_wait_all<0>();
+    IL_PROF(prof_acc[1] = clock64() - t_start;)  // last tile's store handed to the TMA engine (+ statistics loop)
+    if (gtid == 0) {
+      // the shared-memory source must have been read before the CTA retires; the global writes complete with the grid
+      if (p.opt & 2) tma_store_wait_read<0>(); else tma_store_wait_all<0>();
+    }
+    IL_PROF(prof_acc[2] = clock64() - t_start;)
     if (p.stats != nullptr) {
-      const int c2 = gtid & 31, part = blk * 8 + (gtid >> 5);
-      s_stats[part * 128 + 2 * c2] = st_s0;
-      s_stats[part * 128 + 2 * c2 + 1] = st_s1;
-      s_stats[part * 128 + 64 + 2 * c2] = st_q0;
-      s_stats[part * 128 + 64 + 2 * c2 + 1] = st_q1;
+      // lanes l and l+16 hold the same channels of different rows: fold them, then one row of partials per warp
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        st_s[e] += __shfl_xor_sync(0xFFFFFFFFu, st_s[e], 16);
+        st_q[e] += __shfl_xor_sync(0xFFFFFFFFu, st_q[e], 16);
+      }
+      const int part = blk * 8 + (gtid >> 5);
+      if (lane < 16) {
+        *reinterpret_cast<float4*>(s_stats + part * 128 + 4 * c4) = make_float4(st_s[0], st_s[1], st_s[2], st_s[3]);
+        *reinterpret_cast<float4*>(s_stats + part * 128 + 64 + 4 * c4) = make_float4(st_q[0], st_q[1], st_q[2], st_q[3]);
+      }
       named_bar_sync(5, 512);
       if (blk == 0 && gtid < 128) {
         float t = 0.f;
@@ -869,10 +958,12 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
     }
   }
 
+#ifdef SRG_IL_PROF
   if (p.prof != nullptr && lane == 0 && (warp <= 2)) {
     long long* d = p.prof + (size_t(blockIdx.x) * 3 + warp) * 6;
     d[0] = prof_acc[0]; d[1] = prof_acc[1]; d[2] = prof_acc[2]; d[3] = prof_acc[3]; d[4] = clock64() - t_start; d[5] = t_start;
   }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 256);
@@ -1243,7 +1334,15 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   // measured 11.27 -> 11.14 ms per cfg2 step; the shallower pipeline (3 / 2 stages) costs nothing (profiles/r01_notes.md).
   static int reserve_kb = -1;
   if (reserve_kb < 0) { const char* ev = getenv("SRG_IL_SMEM_RESERVE_KB"); reserve_kb = ev ? atoi(ev) : 44; }
-  int stages = int((227 * 1024 - (a.exclusive ? 0 : reserve_kb) * 1024 - 1024 - fixed_bytes) / stage_bytes);
+  // launches with a residual / mask tile keep everything (they would be down to two stages: the operand prefetch of the
+  // next tile could not start before half of the current tile's MMAs have retired; probe: 14.0 -> 12.8 us at cfg2)
+  static int aux_reserve = -1;
+  if (aux_reserve < 0) { const char* ev = getenv("SRG_IL_AUX_RESERVE"); aux_reserve = ev ? atoi(ev) : 0; }
+  const int reserve = a.exclusive ? 0 : ((has_aux && !aux_reserve) ? 0 : reserve_kb);
+  int stages = int((227 * 1024 - reserve * 1024 - 1024 - fixed_bytes) / stage_bytes);
+  static int stage_cap = -1;
+  if (stage_cap < 0) { const char* ev = getenv("SRG_IL_STAGE_CAP"); stage_cap = ev ? atoi(ev) : 8; }
+  if (!a.exclusive && stages > stage_cap) stages = stage_cap;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.n_stages = stages;
@@ -1302,6 +1401,9 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   // their halo within microseconds, long before capacity pressure evicts it)
   p.pol_in = (!a.exclusive && l2_hints() >= 3) ? kL2EvictFirst : kL2EvictNormal;
   p.prof = reinterpret_cast<long long*>(a.prof);
+  static int il_opt = -1;
+  if (il_opt < 0) { const char* ev = getenv("SRG_IL_OPT"); il_opt = ev ? atoi(ev) : 1; }
+  p.opt = a.exclusive ? (il_opt & ~1) : il_opt;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv3_il_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1310,8 +1412,9 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   const dim3 grid(p.ctas_per_block * p.n_blocks);
-  cudaError_t e = wide ? launch_pdl(conv3_il_kernel<true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
-                       : launch_pdl(conv3_il_kernel<false>, grid, dim3(kIlThreads), smem_bytes, stream, p);
+  const bool pdl = a.exclusive || pdl_conv();
+  cudaError_t e = wide ? launch_opt_pdl(pdl, conv3_il_kernel<true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
+                       : launch_opt_pdl(pdl, conv3_il_kernel<false>, grid, dim3(kIlThreads), smem_bytes, stream, p);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv3_il launch: %s", cudaGetErrorString(e)); return int(e); }
   count_launch();

@@ -412,8 +412,8 @@ template <bool RELU, bool SKIP>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, const uint4* __restrict__ skip,
                                                        uint4* __restrict__ out, int64_t n_vec, uint64_t pol_y, uint64_t pol_out,
-                                                       uint64_t pol_skip) {
-  pdl_trigger();
+                                                       uint64_t pol_skip, int late) {
+  if (!late) pdl_trigger();
   pdl_wait();
   const int cg = threadIdx.x & 7;  // blockDim is a multiple of 8 and the grid stride too
   float sc[8], sh[8];
@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
     }
     stg_hint_u4(out + i, pack8(f), pol_out);
   }
+  if (late) pdl_trigger();
 }
 static int ew_blocks(int64_t n_vec) {
   int64_t b = (n_vec + 255) / 256;
@@ -452,10 +453,10 @@ int launch_bn_apply(const void* y, const float* scale, const float* shift, const
   // y is not read again before the backward pass (evict first); the output is the next convolution's operand (keep)
   const uint64_t py = l2_hints() ? kL2EvictFirst : kL2EvictNormal, po = l2_hints() ? kL2EvictLast : kL2EvictNormal;
   const uint64_t pk = l2_hints() >= 3 ? kL2EvictFirst : kL2EvictNormal;      // the block input: last read of the forward pass
-  if (relu && skip) launch_pdl(bn_apply_kernel<true, true>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk);
-  else if (relu) launch_pdl(bn_apply_kernel<true, false>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk);
-  else if (skip) launch_pdl(bn_apply_kernel<false, true>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk);
-  else launch_pdl(bn_apply_kernel<false, false>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk);
+  if (relu && skip) launch_pdl(bn_apply_kernel<true, true>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk, pdl_ew_late());
+  else if (relu) launch_pdl(bn_apply_kernel<true, false>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk, pdl_ew_late());
+  else if (skip) launch_pdl(bn_apply_kernel<false, true>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk, pdl_ew_late());
+  else launch_pdl(bn_apply_kernel<false, false>, dim3(blocks), dim3(256), 0, st, yy, scale, shift, kk, oo, n_vec, py, po, pk, pdl_ew_late());
   SRG_LAUNCH_CHECK("bn_apply");
   return 0;
 }
@@ -492,8 +493,8 @@ int launch_bn_bwd_finalize(const double* sums, double count, const float* gamma,
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y,
                                                            const float* __restrict__ cA, const float* __restrict__ cB,
                                                            const float* __restrict__ cC, uint4* __restrict__ dy,
-                                                           int64_t n_vec, uint64_t pol_in, uint64_t pol_out) {
-  pdl_trigger();
+                                                           int64_t n_vec, uint64_t pol_in, uint64_t pol_out, int late) {
+  if (!late) pdl_trigger();
   pdl_wait();
   const int cg = threadIdx.x & 7;
   float a[8], b[8], c[8];
@@ -511,6 +512,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
     for (int e = 0; e < 8; ++e) d[e] = fmaf(a[e], d[e], fmaf(b[e], v[e], c[e]));
     stg_hint_u4(dy + i, pack8(d), pol_out);
   }
+  if (late) pdl_trigger();
 }
 int launch_bn_bwd_apply(const void* dout, const void* y, const float* coefA, const float* coefB, const float* coefC,
                         void* dy, int64_t pixels, cudaStream_t st) {
@@ -521,7 +523,8 @@ int launch_bn_bwd_apply(const void* dout, const void* y, const float* coefA, con
              // once more as the skip gradient, at high priority costs 0.15 ms per step, and discarding the dead bn1 dz lines
              // (discard.global.L2) buys nothing (profiles/r02_notes.md)
              l2_hints() ? kL2EvictFirst : kL2EvictNormal,
-             l2_hints() ? kL2EvictLast : kL2EvictNormal);      // dy is the next dgrad's operand
+             l2_hints() ? kL2EvictLast : kL2EvictNormal,       // dy is the next dgrad's operand
+             pdl_ew_late());
   SRG_LAUNCH_CHECK("bn_bwd_apply");
   return 0;
 }

@@ -9,6 +9,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include <utility>
 
 namespace srg {
@@ -28,6 +30,27 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+// A/B switches (read once): SRG_PDL_CONV=0 launches the SM-exclusive convolution kernels WITHOUT the attribute (a CTA that
+// is resident early holds ~190 KB of shared memory while it waits for its predecessor, which keeps another graph branch's
+// ready convolution off that SM); SRG_PDL_EW_LATE=1 makes the elementwise producers of a convolution operand trigger their
+// dependents at the END of their loop instead of at the start (the convolution still pre-pays its launch latency).
+inline bool pdl_conv() { static int v = -1; if (v < 0) { const char* e = getenv("SRG_PDL_CONV"); v = (e && e[0] == '0') ? 0 : 1; } return v != 0; }
+inline int pdl_ew_late() { static int v = -1; if (v < 0) { const char* e = getenv("SRG_PDL_EW_LATE"); v = (e && e[0] == '1') ? 1 : 0; } return v; }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_opt_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args&&... args) {
+  if (pdl) return launch_pdl(kernel, grid, block, smem, st, std::forward<Args>(args)...);
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 

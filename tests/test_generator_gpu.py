@@ -355,7 +355,8 @@ def test_fused_trunk_kernel_matches_per_layer_launches(S):
         # ulp, later ones drift apart as rounding decisions flip (the per-layer oracle tests carry the parity bound)
         assert maxrel(y1, y0) < 5e-2, shape
         for n in ("out1", "rb0.y1", "rb0.z1", "rb0.y2", "rb0.out"):
-            assert maxrel(T1[n], T0[n]) < 4e-3, (shape, n, maxrel(T1[n], T0[n]))
+            # one bf16 ulp of an element in the tensor's top binade is 2^-8 .. 2^-7 of the largest entry
+            assert maxrel(T1[n], T0[n]) < 8e-3, (shape, n, maxrel(T1[n], T0[n]))
         for n in T0:
             if not n.startswith("d_"):
                 assert maxrel(T1[n], T0[n]) < 5e-2, (shape, n, maxrel(T1[n], T0[n]))

@@ -215,6 +215,11 @@ static int run(const Problem& pr, int timing_iters) {
     CK(cudaMalloc(&dprof, 1024 * 18 * 8));
     CK(cudaMemset(dprof, 0, 1024 * 18 * 8));
     a.prof = dprof;
+    static void* flush_buf = nullptr;
+    const size_t flush_bytes = size_t(512) << 20;
+    if (!flush_buf) CK(cudaMalloc(&flush_buf, flush_bytes));
+    const bool cold = getenv("PROBE_COLD") != nullptr;
+    if (cold) { CK(cudaMemsetAsync(flush_buf, 1, flush_bytes, 0)); CK(cudaDeviceSynchronize()); }
     launch_conv_gemm(a, 0);
     CK(cudaDeviceSynchronize());
     a.prof = nullptr;
@@ -224,6 +229,32 @@ static int run(const Problem& pr, int timing_iters) {
       printf("  cta %d: producer wait_empty=%lld total=%lld | mma wait_tempty=%lld wait_full=%lld total=%lld | epi wait_tfull=%lld total=%lld\n", b,
              hp[(b * 3 + 0) * 6 + 0], hp[(b * 3 + 0) * 6 + 4], hp[(b * 3 + 1) * 6 + 1], hp[(b * 3 + 1) * 6 + 2], hp[(b * 3 + 1) * 6 + 4],
              hp[(b * 3 + 2) * 6 + 3], hp[(b * 3 + 2) * 6 + 4]);
+    {
+      // averages over all CTAs (cycles): [producer wait_empty, mma wait_tempty, mma wait_full, epi(warp 2) wait_tfull], totals
+      double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+      long long tmin = -1, tmax = 0;
+      int nc = 0;
+      for (int b = 0; b < 148; ++b) {
+        if (hp[(b * 3 + 1) * 6 + 4] == 0) continue;
+        ++nc;
+        acc[0] += hp[(b * 3 + 0) * 6 + 0]; acc[1] += hp[(b * 3 + 1) * 6 + 1]; acc[2] += hp[(b * 3 + 1) * 6 + 2];
+        acc[3] += hp[(b * 3 + 2) * 6 + 3]; acc[4] += hp[(b * 3 + 0) * 6 + 4]; acc[5] += hp[(b * 3 + 1) * 6 + 4]; acc[6] += hp[(b * 3 + 2) * 6 + 4];
+        const long long t0 = hp[(b * 3 + 1) * 6 + 5], t1 = t0 + hp[(b * 3 + 2) * 6 + 4];
+        if (tmin < 0 || t0 < tmin) tmin = t0;
+        if (t1 > tmax) tmax = t1;
+      }
+      {
+        double m0 = 0, m3 = 0, e0 = 0, e1 = 0, e2 = 0;
+        for (int b = 0; b < 148; ++b) {
+          m0 += hp[(b * 3 + 1) * 6 + 0]; m3 += hp[(b * 3 + 1) * 6 + 3];
+          e0 += hp[(b * 3 + 2) * 6 + 0]; e1 += hp[(b * 3 + 2) * 6 + 1]; e2 += hp[(b * 3 + 2) * 6 + 2];
+        }
+        if (nc) printf("  timeline (cycles after the setup barrier): first MMA %.0f | last MMA commit %.0f | last accumulator ready %.0f | last store issued %.0f | store drained %.0f\n",
+                       m0 / nc, m3 / nc, e0 / nc, e1 / nc, e2 / nc);
+      }
+      if (nc) printf("  %s avg over %d CTAs: prod wait_empty=%.0f (total %.0f) | mma wait_tempty=%.0f wait_full=%.0f (total %.0f) | epi wait_tfull=%.0f (total %.0f)\n",
+                     cold ? "COLD" : "warm", nc, acc[0] / nc, acc[4] / nc, acc[1] / nc, acc[2] / nc, acc[5] / nc, acc[3] / nc, acc[6] / nc);
+    }
     cudaFree(dprof);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
@@ -235,6 +266,30 @@ static int run(const Problem& pr, int timing_iters) {
     CK(cudaEventSynchronize(e1));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
+    {
+      // isolated launches: L2 flushed (512 MB memset) before each, no predecessor to overlap with
+      float tot = 0;
+      const int n_iso = 20;
+      for (int i = 0; i < n_iso; ++i) {
+        CK(cudaMemsetAsync(flush_buf, i, flush_bytes, 0));
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        launch_conv_gemm(a, 0);
+        cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1));
+        float t = 0; cudaEventElapsedTime(&t, e0, e1); tot += t;
+      }
+      float tot_h = 0;
+      for (int i = 0; i < n_iso; ++i) {
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        launch_conv_gemm(a, 0);
+        cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1));
+        float t = 0; cudaEventElapsedTime(&t, e0, e1); tot_h += t;
+      }
+      printf("[%s] isolated launch: cold L2 %.2f us, warm L2 %.2f us (events around one launch)\n", pr.name, tot * 1000 / n_iso, tot_h * 1000 / n_iso);
+    }
     const double flops = 2.0 * npix * double(KB) * 64 * pr.cout_total;
     printf("[%s] %.3f us/launch  %.1f TFLOP/s (MMA work incl. padding)\n", pr.name, ms * 1000 / timing_iters,
            flops / (ms / timing_iters * 1e-3) / 1e12);
@@ -427,6 +482,15 @@ static int run_wgrad_batched(const char* name, int L, int N, int H, int W, int i
 int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 0;
   int fails = 0;
+  if (getenv("PROBE_IL_ONLY") != nullptr) {   // quick mode: the cfg2 trunk cases of the row-interleaved kernel only
+    { Problem p = conv3x3("perf_il_trunk_16x96x96", 16, 96, 96, 64, false); p.variant = 3; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_il_trunk_stats", 16, 96, 96, 64, false); p.variant = 3; p.stats = true; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_il_trunk_mask", 16, 96, 96, 64, false); p.variant = 3; p.mask = true; p.bias = false; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_il_trunk_residual", 16, 96, 96, 64, false); p.variant = 3; p.residual = true; p.bias = false; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_il_trunk_48x96x96", 48, 96, 96, 64, false); p.variant = 3; fails += run(p, iters); }
+    printf("PROBE %s (%d failing cases)\n", fails == 0 ? "PASS" : "FAIL", fails);
+    return fails == 0 ? 0 : 1;
+  }
   {
     const int dw3[3] = {-1, 0, 1}, tr3[3] = {0, 1, 2};
     fails += run_wgrad("wg3x3_small", 2, 32, 24, 3, 3, 18, -1, dw3, tr3, 1, false, 0);
