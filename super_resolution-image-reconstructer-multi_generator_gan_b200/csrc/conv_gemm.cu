@@ -86,6 +86,7 @@ template <int BLOCK_N, int NT>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __builtin_assume(__isShared(smem));
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -521,8 +522,21 @@ constexpr uint32_t kIlWideStage = 22 * 1024;    // 17 x 1280 = 21760 B, rounded 
 #define IL_PROF(...)
 #define IL_TIMED(slot, ...) { __VA_ARGS__ }
 #endif
-template <bool WIDE>
-__global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_constant__ IlKParams p) {
+// SRG_IL_MAXREG (compile time): register cap of conv3_il.  576 threads x 96 registers leave 10 K of the SM's 64 K registers,
+// i.e. no 256-thread CTA of the BatchNorm passes (40-56 registers per thread) of another graph branch can be co-resident
+// with a convolution CTA; at 64 registers two of them fit.
+#ifndef SRG_IL_MAXREG
+#define SRG_IL_MAXREG 0
+#endif
+#if SRG_IL_MAXREG > 0
+#define IL_KERNEL_BOUNDS __maxnreg__(SRG_IL_MAXREG)
+#else
+#define IL_KERNEL_BOUNDS __launch_bounds__(kIlThreads, 1)
+#endif
+// YS: the statistics' second factor comes from a global tensor (p.stats_y, BatchNorm-backward product sums); a separate
+// instantiation so that its 16 prefetch registers do not push the common form over the 96-register budget.
+template <bool WIDE, bool YS>
+__global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __builtin_assume(__isShared(smem));      // the integer round-up hides the state space: keep LDS / STS instead of generic accesses
@@ -827,6 +841,17 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
       const int rem = tile - n * tiles_per_img;
       const int hh = (rem / p.tiles_w) * 16;
       const int w0 = (rem % p.tiles_w) * 8;
+      // second factor of the product statistics (BatchNorm backward: sum dz * y): the tensor is cold (written in the forward
+      // pass), so its lines are pulled into L2 here, a tile's worth of MMAs ahead of the loads below (no registers held)
+      if constexpr (YS) {
+        const int hr = 2 * (hh + rp) + blk;     // block row 8*rp + r = image row 2*(hh+rp)+blk, pixel w0+r
+        if (hr < p.H && (c4 & 3) == 0) {          // one prefetch per 32-byte sector
+          const uint2* yp = reinterpret_cast<const uint2*>(p.stats_y + ((size_t(n) * p.H + hr) * p.W + w0) * 32) + c4;
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (w0 + r < p.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + r * 16));
+        }
+      }
       IL_TIMED(3, mbar_wait(&tfull[acc], acc_phase);) IL_PROF(prof_acc[0] = clock64() - t_start;)
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 128 + blk * 64 + hf * 32);
@@ -899,6 +924,15 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
       fence_proxy_async_smem();
       // a tile whose 16 rows x 8 pixels all lie inside the image needs no bounds tests in the statistics loop
       const bool full_tile = 2 * (hh + 15) + blk < p.H && w0 + 7 < p.W;
+      // 8 coalesced 8-byte loads per thread, issued before the barrier so that they land while the group synchronises and
+      // the store is handed to the TMA engine
+      uint2 yv[YS ? 8 : 1];
+      if constexpr (YS) {
+        const int hr = 2 * (hh + rp) + blk;
+        const uint2* yp = reinterpret_cast<const uint2*>(p.stats_y + ((size_t(n) * p.H + hr) * p.W + w0) * 32) + c4;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) yv[r] = (hr < p.H && w0 + r < p.W) ? __ldg(yp + r * 16) : make_uint2(0u, 0u);
+      }
       named_bar_sync(bar_b, 256);
       if (gtid == 0) {
         const bool ps = p.out_mode == OUT_PIXEL_SHUFFLE;
@@ -917,10 +951,7 @@ __global__ void __launch_bounds__(kIlThreads, 1) conv3_il_kernel(const __grid_co
             const uint2 sv = *reinterpret_cast<const uint2*>(sp + r * 128 + ((cch ^ uint32_t(r)) << 4));
             const float a0 = bf16_lo(sv.x), a1 = bf16_hi(sv.x), a2 = bf16_lo(sv.y), a3 = bf16_hi(sv.y);
             float b0 = a0, b1 = a1, b2 = a2, b3 = a3;
-            if (p.stats_y != nullptr) {     // second factor of the product statistics (BatchNorm backward: sum dz * y)
-              const uint2 yv = __ldg(reinterpret_cast<const uint2*>(p.stats_y + ((size_t(n) * p.H + 2 * (hh + rp) + blk) * p.W + w0 + r) * 32) + c4);
-              b0 = bf16_lo(yv.x); b1 = bf16_hi(yv.x); b2 = bf16_lo(yv.y); b3 = bf16_hi(yv.y);
-            }
+            if constexpr (YS) { b0 = bf16_lo(yv[r].x); b1 = bf16_hi(yv[r].x); b2 = bf16_lo(yv[r].y); b3 = bf16_hi(yv[r].y); }
             st_s[0] += a0; st_s[1] += a1; st_s[2] += a2; st_s[3] += a3;
             st_q[0] = fmaf(a0, b0, st_q[0]); st_q[1] = fmaf(a1, b1, st_q[1]);
             st_q[2] = fmaf(a2, b2, st_q[2]); st_q[3] = fmaf(a3, b3, st_q[3]);
@@ -1000,6 +1031,7 @@ constexpr uint32_t kC9WBytes = 9 * 32 * 128;    // resident filter
 __global__ void __launch_bounds__(kC9Threads, 1) conv9_rows_kernel(const __grid_constant__ C9KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __builtin_assume(__isShared(smem));
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   pdl_trigger();
@@ -1406,15 +1438,20 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   p.opt = a.exclusive ? (il_opt & ~1) : il_opt;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3_il_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv3_il_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     attr_set = true;
   }
   const dim3 grid(p.ctas_per_block * p.n_blocks);
   const bool pdl = a.exclusive || pdl_conv();
-  cudaError_t e = wide ? launch_opt_pdl(pdl, conv3_il_kernel<true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
-                       : launch_opt_pdl(pdl, conv3_il_kernel<false>, grid, dim3(kIlThreads), smem_bytes, stream, p);
+  const bool ys = p.stats != nullptr && p.stats_y != nullptr;
+  cudaError_t e = wide ? (ys ? launch_opt_pdl(pdl, conv3_il_kernel<true, true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
+                             : launch_opt_pdl(pdl, conv3_il_kernel<true, false>, grid, dim3(kIlThreads), smem_bytes, stream, p))
+                       : (ys ? launch_opt_pdl(pdl, conv3_il_kernel<false, true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
+                             : launch_opt_pdl(pdl, conv3_il_kernel<false, false>, grid, dim3(kIlThreads), smem_bytes, stream, p));
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv3_il launch: %s", cudaGetErrorString(e)); return int(e); }
   count_launch();

@@ -57,18 +57,29 @@ static int fin_per_sm() { static int v = -1; if (v < 0) v = env_int("SRG_FIN_PER
 // stream ~450 MB through a 126 MB L2; without hints the tensors with a near reuse (the conv output the reduction and the
 // apply pass read next, the apply output the next conv reads) are evicted by data that is dead after its access.
 int l2_hints() { static int v = -1; if (v < 0) v = env_int("SRG_L2_HINTS", 3); return v; }
+static int red_threads() { static int v = -1; if (v < 0) v = env_int("SRG_RED_THREADS", 512) == 256 ? 256 : 512; return v; }
 int reduce_blocks(int64_t pixels) {
   int64_t b = (pixels + 32 * 8 - 1) / (32 * 8);
   if (b < 1) b = 1;
   const int cap = red_per_sm() * sm_budget() < kRedBlocksMax ? red_per_sm() * sm_budget() : kRedBlocksMax;
-  if (b > cap) b = cap;
+  if (b > cap) {
+    // every block the same number of 128-pixel rounds (4 pixels of a thread in flight per round): no block runs a tail of
+    // single-pixel rounds after the others have finished (cfg2: 288 blocks x 4 rounds instead of 296 x 3 + up to 3 singles)
+    const int64_t per_round = red_threads() / 2;      // T / 8 pixels x 4 in flight
+    const int64_t rounds = (pixels + per_round - 1) / per_round;
+    const int64_t per_block = (rounds + cap - 1) / cap;
+    b = (rounds + per_block - 1) / per_block;
+  }
   return int(b);
 }
 
-template <bool TWO>
-__global__ void __launch_bounds__(256) chan_reduce_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
-                                                          int64_t pixels, float* __restrict__ partials, uint64_t pol) {
-  __shared__ float red[32][129];
+// T threads per block = T / 8 pixels per round-slot.  T = 512 (two blocks per SM) keeps 32 warps x 8 loads in flight per SM:
+// at cfg2 every block then runs 2 dependent rounds instead of 4 (the pass is bound by the latency of its rounds).
+template <bool TWO, int T>
+__global__ void __launch_bounds__(T) chan_reduce_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                        int64_t pixels, float* __restrict__ partials, uint64_t pol) {
+  constexpr int PR = T / 8;       // pixels per round-slot
+  __shared__ float red[PR][129];
   pdl_trigger();
   pdl_wait();
   const int cg = threadIdx.x & 7;
@@ -78,8 +89,8 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const uint4* __restric
   for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
   // four pixels of a thread in flight per round (8 x 128-bit loads): the kernel is latency-bound otherwise (measured
   // 2.9 TB/s with one pixel per round); the accumulation order per thread is unchanged
-  const int64_t stride = int64_t(gridDim.x) * 32;
-  int64_t p = int64_t(blockIdx.x) * 32 + lane_p;
+  const int64_t stride = int64_t(gridDim.x) * PR;
+  int64_t p = int64_t(blockIdx.x) * PR + lane_p;
   for (; p + 3 * stride < pixels; p += 4 * stride) {
     uint4 ra[4], rb[4];
 #pragma unroll
@@ -118,7 +129,7 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const uint4* __restric
   if (threadIdx.x < 128) {
     float acc = 0.f;
 #pragma unroll 8
-    for (int l = 0; l < 32; ++l) acc += red[l][threadIdx.x];
+    for (int l = 0; l < PR; ++l) acc += red[l][threadIdx.x];
     partials[size_t(blockIdx.x) * 128 + threadIdx.x] = acc;
   }
 }
@@ -313,12 +324,16 @@ int launch_chan_reduce_final(const void* a, const void* b, int64_t pixels, float
 
 int launch_chan_reduce(const void* a, const void* b, int64_t pixels, float* partials, cudaStream_t st) {
   const int blocks = reduce_blocks(pixels);
-  if (b)
-    launch_pdl(chan_reduce_kernel<true>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint4*>(a),
-               reinterpret_cast<const uint4*>(b), pixels, partials, l2_hints() ? kL2EvictLast : kL2EvictNormal);
-  else
-    launch_pdl(chan_reduce_kernel<false>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint4*>(a),
-               static_cast<const uint4*>(nullptr), pixels, partials, kL2EvictNormal);
+  const uint64_t pol = (b && l2_hints()) ? kL2EvictLast : kL2EvictNormal;
+  const uint4* aa = reinterpret_cast<const uint4*>(a);
+  const uint4* bb = reinterpret_cast<const uint4*>(b);
+  if (red_threads() == 512) {
+    if (b) launch_pdl(chan_reduce_kernel<true, 512>, dim3(blocks), dim3(512), 0, st, aa, bb, pixels, partials, pol);
+    else launch_pdl(chan_reduce_kernel<false, 512>, dim3(blocks), dim3(512), 0, st, aa, bb, pixels, partials, pol);
+  } else {
+    if (b) launch_pdl(chan_reduce_kernel<true, 256>, dim3(blocks), dim3(256), 0, st, aa, bb, pixels, partials, pol);
+    else launch_pdl(chan_reduce_kernel<false, 256>, dim3(blocks), dim3(256), 0, st, aa, bb, pixels, partials, pol);
+  }
   SRG_LAUNCH_CHECK("chan_reduce");
   return 0;
 }
@@ -422,18 +437,35 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
     sc[e] = scale[cg * 8 + e];
     sh[e] = shift[cg * 8 + e];
   }
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += int64_t(gridDim.x) * blockDim.x) {
-    float f[8], k[8];
-    unpack8(ldg_hint_u4(y + i, pol_y), f);
-    if (SKIP) unpack8(ldg_hint_u4(skip + i, pol_skip), k);
+  // U vectors of a thread in flight per round, the last round predicated (the pass is latency-bound with one vector per
+  // round: 4.1 TB/s at cfg2)
+  constexpr int U = SKIP ? 2 : 4;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += U * stride) {
+    uint4 ry[U], rk[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = fmaf(f[e], sc[e], sh[e]);
-      if (RELU) v = fmaxf(v, 0.f);
-      if (SKIP) v += k[e];
-      f[e] = v;
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride < n_vec) {
+        ry[u] = ldg_hint_u4(y + i + u * stride, pol_y);
+        if (SKIP) rk[u] = ldg_hint_u4(skip + i + u * stride, pol_skip);
+      }
     }
-    stg_hint_u4(out + i, pack8(f), pol_out);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride < n_vec) {
+        float f[8], k[8];
+        unpack8(ry[u], f);
+        if (SKIP) unpack8(rk[u], k);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float v = fmaf(f[e], sc[e], sh[e]);
+          if (RELU) v = fmaxf(v, 0.f);
+          if (SKIP) v += k[e];
+          f[e] = v;
+        }
+        stg_hint_u4(out + i + u * stride, pack8(f), pol_out);
+      }
+    }
   }
   if (late) pdl_trigger();
 }
@@ -443,10 +475,19 @@ static int ew_blocks(int64_t n_vec) {
   if (b < 1) b = 1;
   return int(b);
 }
+// grid of a pass whose threads take U vectors per round: every block the same number of rounds (cfg2: 576 blocks x 2 or 4
+// full rounds instead of 592 blocks with a mostly-empty last round)
+static int ew_blocks_rounds(int64_t n_vec, int U) {
+  const int64_t cap = int64_t(sm_budget()) * ew_per_sm();
+  const int64_t rounds = (n_vec + 256 * U - 1) / (256 * U);
+  if (rounds <= cap) return int(rounds < 1 ? 1 : rounds);
+  const int64_t per_block = (rounds + cap - 1) / cap;
+  return int((rounds + per_block - 1) / per_block);
+}
 int launch_bn_apply(const void* y, const float* scale, const float* shift, const void* skip, int relu, void* out,
                     int64_t pixels, cudaStream_t st) {
   const int64_t n_vec = pixels * 8;
-  const int blocks = ew_blocks(n_vec);
+  const int blocks = ew_blocks_rounds(n_vec, skip ? 2 : 4);
   const uint4* yy = reinterpret_cast<const uint4*>(y);
   const uint4* kk = reinterpret_cast<const uint4*>(skip);
   uint4* oo = reinterpret_cast<uint4*>(out);
@@ -504,20 +545,33 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
     b[e] = cB[cg * 8 + e];
     c[e] = cC[cg * 8 + e];
   }
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += int64_t(gridDim.x) * blockDim.x) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += 2 * stride) {
+    // two vectors of each tensor in flight per thread, the second predicated
+    const bool two = i + stride < n_vec;
+    const uint4 rd0 = ldg_hint_u4(dout + i, pol_in), ry0 = ldg_hint_u4(y + i, pol_in);
+    uint4 rd1 = rd0, ry1 = ry0;
+    if (two) { rd1 = ldg_hint_u4(dout + i + stride, pol_in); ry1 = ldg_hint_u4(y + i + stride, pol_in); }
     float d[8], v[8];
-    unpack8(ldg_hint_u4(dout + i, pol_in), d);
-    unpack8(ldg_hint_u4(y + i, pol_in), v);
+    unpack8(rd0, d);
+    unpack8(ry0, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) d[e] = fmaf(a[e], d[e], fmaf(b[e], v[e], c[e]));
     stg_hint_u4(dy + i, pack8(d), pol_out);
+    if (two) {
+      unpack8(rd1, d);
+      unpack8(ry1, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = fmaf(a[e], d[e], fmaf(b[e], v[e], c[e]));
+      stg_hint_u4(dy + i + stride, pack8(d), pol_out);
+    }
   }
   if (late) pdl_trigger();
 }
 int launch_bn_bwd_apply(const void* dout, const void* y, const float* coefA, const float* coefB, const float* coefC,
                         void* dy, int64_t pixels, cudaStream_t st) {
   const int64_t n_vec = pixels * 8;
-  launch_pdl(bn_bwd_apply_kernel, dim3(ew_blocks(n_vec)), dim3(256), 0, st, reinterpret_cast<const uint4*>(dout),
+  launch_pdl(bn_bwd_apply_kernel, dim3(ew_blocks_rounds(n_vec, 2)), dim3(256), 0, st, reinterpret_cast<const uint4*>(dout),
              reinterpret_cast<const uint4*>(y), coefA, coefB, coefC, reinterpret_cast<uint4*>(dy), n_vec,
              // dz and y are (all but) dead after this pass.  Measured: keeping bn2's dz, which the block's conv1 dgrad reads
              // once more as the skip gradient, at high priority costs 0.15 ms per step, and discarding the dead bn1 dz lines

@@ -29,7 +29,13 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  // SRG_PDL=0 (developer switch): plain stream-order launches everywhere, so that a kernel timeline shows each kernel's own
+  // duration instead of a duration that starts while the predecessor is still running
+  // SRG_PDL=2: only grids of at most 8 blocks (the single-block finalize kernels) start early: a big grid that is parked at
+  // griddepcontrol.wait holds registers that another graph branch's ready kernel could use
+  static int pdl_on = -1;
+  if (pdl_on < 0) { const char* e = getenv("SRG_PDL"); pdl_on = e ? atoi(e) : 1; }
+  cfg.numAttrs = (pdl_on == 1 || (pdl_on == 2 && grid.x * grid.y * grid.z <= 8)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 

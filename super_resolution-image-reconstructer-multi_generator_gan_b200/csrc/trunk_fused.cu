@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) trunk_kernel(const __grid_const
   constexpr int kStages = BWD ? 2 : 3;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __builtin_assume(__isShared(smem));
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 

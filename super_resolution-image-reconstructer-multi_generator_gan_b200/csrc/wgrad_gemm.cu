@@ -43,6 +43,7 @@ constexpr uint32_t kDyBytes = 128 * 128;
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __builtin_assume(__isShared(smem));
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   pdl_trigger();
@@ -245,6 +246,7 @@ constexpr uint32_t kW3Stage = kW3DyBytes + 3 * kW3XBytes;
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_constant__ WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __builtin_assume(__isShared(smem));
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   pdl_trigger();
@@ -448,6 +450,7 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_batched_kernel(const __grid_constant__ WgradBatchKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __builtin_assume(__isShared(smem));
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   pdl_trigger();

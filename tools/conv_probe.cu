@@ -131,6 +131,11 @@ static int run(const Problem& pr, int timing_iters) {
   a.out = dout; a.out_mode = pr.out_mode; a.variant = pr.variant;
   float* dstats = nullptr;
   if (pr.stats) { CK(cudaMalloc(&dstats, 148 * 128 * 4)); a.stats = dstats; }
+  static void* dstats_y = nullptr;        // second factor of the product statistics (timing only): a separate tensor of the output's geometry
+  if (pr.stats && getenv("PROBE_STATS_Y") != nullptr) {
+    if (!dstats_y) { CK(cudaMalloc(&dstats_y, size_t(48) * 96 * 96 * 64 * 2)); CK(cudaMemset(dstats_y, 0, size_t(48) * 96 * 96 * 64 * 2)); }
+    a.stats_y = dstats_y;
+  }
 
   int rc = launch_conv_gemm(a, 0);
   if (rc != 0) { printf("[%s] launch rc=%d err=%s\n", pr.name, rc, last_error()); return 1; }
@@ -487,6 +492,7 @@ int main(int argc, char** argv) {
     { Problem p = conv3x3("perf_il_trunk_stats", 16, 96, 96, 64, false); p.variant = 3; p.stats = true; fails += run(p, iters); }
     { Problem p = conv3x3("perf_il_trunk_mask", 16, 96, 96, 64, false); p.variant = 3; p.mask = true; p.bias = false; fails += run(p, iters); }
     { Problem p = conv3x3("perf_il_trunk_residual", 16, 96, 96, 64, false); p.variant = 3; p.residual = true; p.bias = false; fails += run(p, iters); }
+    { Problem p = conv3x3("perf_il_trunk_mask_stats", 16, 96, 96, 64, false); p.variant = 3; p.mask = true; p.bias = false; p.stats = true; fails += run(p, iters); }
     { Problem p = conv3x3("perf_il_trunk_48x96x96", 48, 96, 96, 64, false); p.variant = 3; fails += run(p, iters); }
     printf("PROBE %s (%d failing cases)\n", fails == 0 ? "PASS" : "FAIL", fails);
     return fails == 0 ? 0 : 1;
