@@ -495,7 +495,7 @@ def run_ours(a):
             raise ValueError("ncu capture was taken at the cfg2 geometry")
         if n_layers != 1:
             raise ValueError("capture is of the per-layer kernel")
-        with open(os.path.join(ROOT, "profiles", "r01_conv3_il_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_conv3_il_traffic.json")) as f:
             traffic = json.load(f)["dram_bytes_per_launch"]       # dram__bytes_read.sum + dram__bytes_write.sum (ncu)
     except Exception:
         pass
