@@ -479,23 +479,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 // row-parity TMA views as well (16 rows x 8 pixels per block).
 // =====================================================================================================================
 struct IlKParams {
-  CUtensorMap in_map[2];     // [image-row parity] 64-channel input view
-  CUtensorMap w_map;
-  CUtensorMap out_map[8];    // [n-block (pixel shuffle) or 0][row parity]
-  CUtensorMap aux_map[2];    // [row parity] residual / mask tensor
+  // A launch may carry up to kIlMaxGroups independent problems of one geometry ("groups": the same layer of several
+  // generators, each with its own tensors and filter).  CTA c works for group c % n_groups; with one group the arrays'
+  // first entries are the whole launch.
+  CUtensorMap in_map[2 * kIlMaxGroups];     // [group][image-row parity] 64-channel input view
+  CUtensorMap w_map[kIlMaxGroups];
+  CUtensorMap out_map[8];    // [n-block (pixel shuffle) or group][row parity]
+  CUtensorMap aux_map[2 * kIlMaxGroups];    // [group][row parity] residual / mask tensor
+  int n_groups;
   int N, H, W;
   int tiles_h, tiles_w, tiles_total;
   int strip_dw[3];
   int cout_total, n_blocks, ctas_per_block;
   int n_stages;
-  const float* bias;
-  const float* scale;        // optional per-channel multiplier of the accumulator (folded eval-mode BatchNorm)
+  const float* bias[kIlMaxGroups];
+  const float* scale[kIlMaxGroups];   // optional per-channel multiplier of the accumulator (folded eval-mode BatchNorm)
   int act;
   float slope;
   int aux_mode;              // 0 none, 1 add (residual), 2 mask (zero where aux <= 0)
   int out_mode;
-  float* stats;              // per-CTA channel sums / sums of squares
-  const uint32_t* stats_y;   // optional second factor (bf16 pairs, the output's geometry): sum(out * stats_y) replaces sum(out^2)
+  float* stats[kIlMaxGroups];            // per-CTA channel sums / sums of squares (row = the CTA's index inside its group)
+  const uint32_t* stats_y[kIlMaxGroups]; // optional second factor (bf16 pairs, the output's geometry): sum(out * stats_y) replaces sum(out^2)
   uint64_t pol_out, pol_aux, pol_in; // L2 eviction priorities of the output store / the residual-mask tile loads / the operand strips
   int opt;                   // SRG_IL_OPT bits: 1 = first tile column shift by column shift (filter streams in under the MMAs),
                              // 2 = leave without waiting for the last store's global writes (only for its shared-memory reads)
@@ -535,7 +539,7 @@ constexpr uint32_t kIlWideStage = 22 * 1024;    // 17 x 1280 = 21760 B, rounded 
 #endif
 // YS: the statistics' second factor comes from a global tensor (p.stats_y, BatchNorm-backward product sums); a separate
 // instantiation so that its 16 prefetch registers do not push the common form over the 96-register budget.
-template <bool WIDE, bool YS>
+template <bool WIDE, bool YS, bool GROUPED = false>
 __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -563,8 +567,16 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
   float* s_stats = reinterpret_cast<float*>(tail + 768);                  // [16][128] floats (p.stats only)
 
-  const int nblk = blockIdx.x % p.n_blocks;
-  const int tile0 = blockIdx.x / p.n_blocks;
+  // n_groups > 1 implies n_blocks == 1 (OUT_NHWC, 64 output channels)
+  const int grp = GROUPED ? int(blockIdx.x) % p.n_groups : 0;
+  const int nblk = GROUPED ? 0 : int(blockIdx.x) % p.n_blocks;
+  const int tile0 = int(blockIdx.x) / (GROUPED ? p.n_groups : p.n_blocks);
+  const CUtensorMap* const in_map = &p.in_map[2 * grp];
+  const CUtensorMap* const w_map = &p.w_map[grp];
+  const CUtensorMap* const aux_map = &p.aux_map[2 * grp];
+  const CUtensorMap* const out_map = &p.out_map[GROUPED ? 2 * grp : 0];
+  float* const stats = p.stats[grp];
+  const uint32_t* const stats_y = p.stats_y[grp];
   const int tiles_per_img = p.tiles_h * p.tiles_w;
 
   if (warp == 0 && lane == 0) {
@@ -580,15 +592,15 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
       mbar_init(&auxempty[i], 256);
     }
     fence_barrier_init();
-    tma_prefetch_desc(&p.w_map);
-    tma_prefetch_desc(&p.in_map[1]);
-    tma_prefetch_desc(&p.in_map[0]);
+    tma_prefetch_desc(w_map);
+    tma_prefetch_desc(&in_map[1]);
+    tma_prefetch_desc(&in_map[0]);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
   if (warp >= 2 && warp < 4) {
     const int t = threadIdx.x - 64;
-    s_bias[t] = p.bias != nullptr ? p.bias[nblk * 64 + t] : 0.f;
-    s_scale[t] = p.scale != nullptr ? p.scale[nblk * 64 + t] : 1.f;
+    s_bias[t] = p.bias[grp] != nullptr ? p.bias[grp][nblk * 64 + t] : 0.f;
+    s_scale[t] = p.scale[grp] != nullptr ? p.scale[grp][nblk * 64 + t] : 1.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -603,7 +615,7 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
       auto load_w = [&](int s) {
         mbar_expect_tx(&wfull[s], kIlWBytes / 3);
         for (int r = 0; r < 3; ++r)
-          tma_load_2d(w_smem + size_t(s * 3 + (2 - r)) * 8192, &p.w_map, &wfull[s], 0, (s * 3 + r) * p.cout_total + nblk * 64);
+          tma_load_2d(w_smem + size_t(s * 3 + (2 - r)) * 8192, w_map, &wfull[s], 0, (s * 3 + r) * p.cout_total + nblk * 64);
       };
       // WIDE: only the first column shift's 24 KB go out ahead of the first tile's strips; the other two follow them.  All
       // CTAs start together and fetch the same 72 KB, so the ramp is bound by L2 bandwidth (148 x 72 KB): the first tile's
@@ -625,7 +637,7 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
           for (int par = 1; par >= 0; --par) {       // odd image rows h0-1+2j first, then even rows h0+2j (j = 0..16)
             IL_TIMED(0, mbar_wait(&empty[stage], phase ^ 1);)
             mbar_expect_tx(&full[stage], 17 * kIlWidePitch);
-            tma_load_4d_hint(stages + size_t(stage) * kStage, &p.in_map[par], &full[stage], 0, w0 + p.strip_dw[0], hh - par, n, p.pol_in);
+            tma_load_4d_hint(stages + size_t(stage) * kStage, &in_map[par], &full[stage], 0, w0 + p.strip_dw[0], hh - par, n, p.pol_in);
             if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
           }
           if (first) {
@@ -636,7 +648,7 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
 #pragma unroll
               for (int b = 0; b < 2; ++b) {
                 mbar_expect_tx(&auxfull[b], kTileOutBytes);
-                tma_load_4d_hint(aux_stage + b * kTileOutBytes, &p.aux_map[b], &auxfull[b], nblk * 64, w0, hh, n, p.pol_aux);
+                tma_load_4d_hint(aux_stage + b * kTileOutBytes, &aux_map[b], &auxfull[b], nblk * 64, w0, hh, n, p.pol_aux);
               }
             }
             first = false;
@@ -647,7 +659,7 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
             for (int par = 1; par >= 0; --par) {
               IL_TIMED(0, mbar_wait(&empty[stage], phase ^ 1);)
               mbar_expect_tx(&full[stage], kIlHalfStrip);
-              tma_load_4d(stages + size_t(stage) * kStage, &p.in_map[par], &full[stage], 0, w0 + p.strip_dw[s], hh - par, n);
+              tma_load_4d(stages + size_t(stage) * kStage, &in_map[par], &full[stage], 0, w0 + p.strip_dw[s], hh - par, n);
               if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -655,7 +667,7 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
               mbar_expect_tx(&auxfull[b], kTileOutBytes);
-              tma_load_4d_hint(aux_stage + b * kTileOutBytes, &p.aux_map[b], &auxfull[b], nblk * 64, w0, hh, n, p.pol_aux);
+              tma_load_4d_hint(aux_stage + b * kTileOutBytes, &aux_map[b], &auxfull[b], nblk * 64, w0, hh, n, p.pol_aux);
             }
           }
           first = false;
@@ -833,7 +845,7 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
       mbar_expect_tx(&auxfull[blk], kTileOutBytes);
-      tma_load_4d_hint(aux_stage + blk * kTileOutBytes, &p.aux_map[blk], &auxfull[blk], nblk * 64, (rem % p.tiles_w) * 8,
+      tma_load_4d_hint(aux_stage + blk * kTileOutBytes, &aux_map[blk], &auxfull[blk], nblk * 64, (rem % p.tiles_w) * 8,
                        (rem / p.tiles_w) * 16, n, p.pol_aux);
     };
     for (int tile = tile0; tile < p.tiles_total; tile += p.ctas_per_block) {
@@ -846,7 +858,7 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
       if constexpr (YS) {
         const int hr = 2 * (hh + rp) + blk;     // block row 8*rp + r = image row 2*(hh+rp)+blk, pixel w0+r
         if (hr < p.H && (c4 & 3) == 0) {          // one prefetch per 32-byte sector
-          const uint2* yp = reinterpret_cast<const uint2*>(p.stats_y + ((size_t(n) * p.H + hr) * p.W + w0) * 32) + c4;
+          const uint2* yp = reinterpret_cast<const uint2*>(stats_y + ((size_t(n) * p.H + hr) * p.W + w0) * 32) + c4;
 #pragma unroll
           for (int r = 0; r < 8; ++r)
             if (w0 + r < p.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + r * 16));
@@ -929,17 +941,17 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
       uint2 yv[YS ? 8 : 1];
       if constexpr (YS) {
         const int hr = 2 * (hh + rp) + blk;
-        const uint2* yp = reinterpret_cast<const uint2*>(p.stats_y + ((size_t(n) * p.H + hr) * p.W + w0) * 32) + c4;
+        const uint2* yp = reinterpret_cast<const uint2*>(stats_y + ((size_t(n) * p.H + hr) * p.W + w0) * 32) + c4;
 #pragma unroll
         for (int r = 0; r < 8; ++r) yv[r] = (hr < p.H && w0 + r < p.W) ? __ldg(yp + r * 16) : make_uint2(0u, 0u);
       }
       named_bar_sync(bar_b, 256);
       if (gtid == 0) {
         const bool ps = p.out_mode == OUT_PIXEL_SHUFFLE;
-        tma_store_4d_hint(&p.out_map[(ps ? nblk : 0) * 2 + blk], my_out, ps ? 0 : nblk * 64, w0, hh, n, p.pol_out);
+        tma_store_4d_hint(&out_map[(ps ? nblk : 0) * 2 + blk], my_out, ps ? 0 : nblk * 64, w0, hh, n, p.pol_out);
         tma_store_commit();
       }
-      if (p.stats != nullptr) {
+      if (stats != nullptr) {
         // column sums of the staged bf16 block (exactly the values BatchNorm will normalise): 8 conflict-free 8-byte
         // reads per thread (a half warp covers one 128-byte row)
         const uint8_t* sp = my_out + rp * 1024 + (c4 & 1) * 8;
@@ -967,7 +979,7 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
       if (p.opt & 2) tma_store_wait_read<0>(); else tma_store_wait_all<0>();
     }
     IL_PROF(prof_acc[2] = clock64() - t_start;)
-    if (p.stats != nullptr) {
+    if (stats != nullptr) {
       // lanes l and l+16 hold the same channels of different rows: fold them, then one row of partials per warp
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -984,7 +996,7 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
         float t = 0.f;
 #pragma unroll
         for (int g = 0; g < 16; ++g) t += s_stats[g * 128 + gtid];
-        p.stats[size_t(blockIdx.x) * 128 + gtid] = t;
+        stats[size_t(GROUPED ? tile0 : int(blockIdx.x)) * 128 + gtid] = t;
       }
     }
   }
@@ -1334,7 +1346,24 @@ static int encode_parity_map(CUtensorMap* map, const void* base, int C, int W, i
   return encode_map_bf16(map, ptr, 4, dims, strides, box);
 }
 
-static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
+// `as[0 .. n)`: one problem per group (n = 1: a plain launch).  Groups must agree in everything but the tensors, the filter,
+// the bias / scale vectors and the statistics rows.
+static int launch_conv3_il(const ConvGemmArgs* as, int n, cudaStream_t stream) {
+  const ConvGemmArgs& a = as[0];
+  if (n < 1 || n > kIlMaxGroups) { set_error("conv3_il: 1..%d groups", kIlMaxGroups); return -17; }
+  for (int g = 1; g < n; ++g) {
+    const ConvGemmArgs& o = as[g];
+    if (o.N != a.N || o.H != a.H || o.W != a.W || o.in_H != a.in_H || o.in_W != a.in_W || o.cout_total != 64 || a.cout_total != 64 ||
+        o.out_mode != OUT_NHWC || a.out_mode != OUT_NHWC || o.act != a.act || o.slope != a.slope || o.exclusive != a.exclusive ||
+        (o.residual != nullptr) != (a.residual != nullptr) || (o.mask_src != nullptr) != (a.mask_src != nullptr) ||
+        (o.stats != nullptr) != (a.stats != nullptr) || (o.stats_y != nullptr) != (a.stats_y != nullptr) ||
+        o.views[0].stride_w != a.views[0].stride_w || o.views[0].stride_h != a.views[0].stride_h ||
+        o.views[0].stride_n != a.views[0].stride_n || o.strip_dw[0] != a.strip_dw[0] || o.strip_dw[1] != a.strip_dw[1] ||
+        o.strip_dw[2] != a.strip_dw[2] || effective_variant(o) != effective_variant(a) || a.prof != nullptr) {
+      set_error("conv3_il: the problems of a grouped launch must share geometry, epilogue and layout (OUT_NHWC, 64 channels)");
+      return -18;
+    }
+  }
   if (a.residual != nullptr && a.mask_src != nullptr) { set_error("conv_gemm: residual and mask are exclusive"); return -11; }
   const bool has_aux = a.residual != nullptr || a.mask_src != nullptr;
   if (has_aux && a.out_mode != OUT_NHWC) { set_error("conv_gemm: residual/mask need OUT_NHWC"); return -12; }
@@ -1352,7 +1381,8 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   for (int s = 0; s < 3; ++s) p.strip_dw[s] = a.strip_dw[s];
   p.cout_total = a.cout_total;
   p.n_blocks = a.cout_total / 64;
-  p.ctas_per_block = sm_budget() / p.n_blocks;
+  p.n_groups = n;
+  p.ctas_per_block = sm_budget() / (p.n_blocks * n);      // CTAs per n-block, or per group
   if (p.ctas_per_block < 1) p.ctas_per_block = 1;
   if (p.ctas_per_block > p.tiles_total) p.ctas_per_block = p.tiles_total;
   p.aux_mode = a.residual ? 1 : (a.mask_src ? 2 : 0);
@@ -1380,50 +1410,54 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
   p.n_stages = stages;
   const size_t smem_bytes = 1024 + fixed_bytes + size_t(stages) * stage_bytes;
 
-  const InView& iv = a.views[0];
-  for (int par = 0; par < 2; ++par) {
-    int rc = encode_parity_map(&p.in_map[par], iv.ptr, 64, a.in_W, a.in_H, a.N, iv.stride_w, iv.stride_h, iv.stride_n, par, 17,
-                               wide ? 10 : 8);
-    if (rc) return rc;
-  }
-  {
-    uint64_t dims[2] = {64, uint64_t(9) * a.cout_total};
-    uint64_t strides[1] = {128};
-    uint32_t box[2] = {64, 64};
-    int rc = encode_map_bf16(&p.w_map, a.weights, 2, dims, strides, box);
-    if (rc) return rc;
-  }
-  if (a.out_mode == OUT_PIXEL_SHUFFLE) {
-    // view q=(i,j) of the HR tensor [N,2H,2W,64]: pixel (2h+i, 2w+j)
-    for (int q = 0; q < 4; ++q) {
-      const int i = q >> 1, j = q & 1;
-      const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a.out) + (size_t(i) * 2 * a.W + j) * 64;
-      for (int par = 0; par < 2; ++par) {
-        int rc = encode_parity_map(&p.out_map[q * 2 + par], base, 64, a.W, a.H, a.N, 128, int64_t(4) * a.W * 64,
-                                   int64_t(4) * a.H * a.W * 64, par, 16);
-        if (rc) return rc;
-      }
-    }
-    p.aux_map[0] = p.aux_map[1] = p.out_map[0];
-  } else {
-    const int64_t C = a.cout_total;
+  for (int g = 0; g < n; ++g) {
+    const ConvGemmArgs& ag = as[g];
+    const InView& iv = ag.views[0];
     for (int par = 0; par < 2; ++par) {
-      int rc = encode_parity_map(&p.out_map[par], a.out, int(C), a.W, a.H, a.N, C, int64_t(a.W) * C, int64_t(a.H) * a.W * C, par, 16);
+      int rc = encode_parity_map(&p.in_map[2 * g + par], iv.ptr, 64, a.in_W, a.in_H, a.N, iv.stride_w, iv.stride_h, iv.stride_n, par, 17,
+                                 wide ? 10 : 8);
       if (rc) return rc;
-      if (has_aux) {
-        rc = encode_parity_map(&p.aux_map[par], a.residual ? a.residual : a.mask_src, int(C), a.W, a.H, a.N, C,
-                               int64_t(a.W) * C, int64_t(a.H) * a.W * C, par, 16);
-        if (rc) return rc;
-      } else {
-        p.aux_map[par] = p.out_map[par];
-      }
     }
-    for (int q = 2; q < 8; ++q) p.out_map[q] = p.out_map[q & 1];
+    {
+      uint64_t dims[2] = {64, uint64_t(9) * a.cout_total};
+      uint64_t strides[1] = {128};
+      uint32_t box[2] = {64, 64};
+      int rc = encode_map_bf16(&p.w_map[g], ag.weights, 2, dims, strides, box);
+      if (rc) return rc;
+    }
+    if (a.out_mode == OUT_PIXEL_SHUFFLE) {       // n == 1
+      // view q=(i,j) of the HR tensor [N,2H,2W,64]: pixel (2h+i, 2w+j)
+      for (int q = 0; q < 4; ++q) {
+        const int i = q >> 1, j = q & 1;
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a.out) + (size_t(i) * 2 * a.W + j) * 64;
+        for (int par = 0; par < 2; ++par) {
+          int rc = encode_parity_map(&p.out_map[q * 2 + par], base, 64, a.W, a.H, a.N, 128, int64_t(4) * a.W * 64,
+                                     int64_t(4) * a.H * a.W * 64, par, 16);
+          if (rc) return rc;
+        }
+      }
+      p.aux_map[0] = p.aux_map[1] = p.out_map[0];
+    } else {
+      const int64_t C = a.cout_total;
+      for (int par = 0; par < 2; ++par) {
+        int rc = encode_parity_map(&p.out_map[2 * g + par], ag.out, int(C), a.W, a.H, a.N, C, int64_t(a.W) * C, int64_t(a.H) * a.W * C, par, 16);
+        if (rc) return rc;
+        if (has_aux) {
+          rc = encode_parity_map(&p.aux_map[2 * g + par], ag.residual ? ag.residual : ag.mask_src, int(C), a.W, a.H, a.N, C,
+                                 int64_t(a.W) * C, int64_t(a.H) * a.W * C, par, 16);
+          if (rc) return rc;
+        } else {
+          p.aux_map[2 * g + par] = p.out_map[2 * g + par];
+        }
+      }
+      if (n == 1) for (int q = 2; q < 8; ++q) p.out_map[q] = p.out_map[q & 1];
+    }
+    p.bias[g] = ag.bias; p.scale[g] = ag.scale;
+    p.stats[g] = ag.stats;
+    p.stats_y[g] = reinterpret_cast<const uint32_t*>(ag.stats_y);
   }
-  p.bias = a.bias; p.scale = a.scale; p.act = a.act; p.slope = a.slope;
+  p.act = a.act; p.slope = a.slope;
   p.out_mode = a.out_mode;
-  p.stats = a.stats;
-  p.stats_y = reinterpret_cast<const uint32_t*>(a.stats_y);
   // training launches (not exclusive): the output is read by the statistics / apply passes right behind this kernel (keep
   // it in L2 ahead of streaming data); a mask / residual tile is dead after this read
   const bool hints = !a.exclusive && l2_hints() >= 2;
@@ -1442,13 +1476,18 @@ static int launch_conv3_il(const ConvGemmArgs& a, cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     attr_set = true;
   }
-  const dim3 grid(p.ctas_per_block * p.n_blocks);
+  const dim3 grid(p.ctas_per_block * p.n_blocks * n);
   const bool pdl = a.exclusive || pdl_conv();
-  const bool ys = p.stats != nullptr && p.stats_y != nullptr;
-  cudaError_t e = wide ? (ys ? launch_opt_pdl(pdl, conv3_il_kernel<true, true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
+  const bool ys = a.stats != nullptr && a.stats_y != nullptr;
+  if (n > 1 && ys) { set_error("conv3_il: a grouped launch takes no second statistics factor"); return -18; }
+  cudaError_t e = n > 1 ? (wide ? launch_opt_pdl(pdl, conv3_il_kernel<true, false, true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
+                                : launch_opt_pdl(pdl, conv3_il_kernel<false, false, true>, grid, dim3(kIlThreads), smem_bytes, stream, p))
+                  : wide ? (ys ? launch_opt_pdl(pdl, conv3_il_kernel<true, true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
                              : launch_opt_pdl(pdl, conv3_il_kernel<true, false>, grid, dim3(kIlThreads), smem_bytes, stream, p))
                        : (ys ? launch_opt_pdl(pdl, conv3_il_kernel<false, true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
                              : launch_opt_pdl(pdl, conv3_il_kernel<false, false>, grid, dim3(kIlThreads), smem_bytes, stream, p));
@@ -1527,8 +1566,26 @@ int conv_gemm_grid(const ConvGemmArgs& a) {
   return per * n_blocks;
 }
 
+// Grouped launch: the same 3x3 / 64 -> 64 layer of n <= 3 independent problems (one per generator) in ONE conv3_il launch.
+// Every CTA works for one group (its filter stays resident); with 49 CTAs per group a cfg2 trunk layer is 12 tiles per CTA
+// instead of 4, so the launch ramp, the 72 KB filter load and the last tile's epilogue are paid once per 12 tiles.
+// The statistics rows of a group are its CTAs' rows: conv_gemm_grouped_rows().
+int conv_gemm_grouped_rows(const ConvGemmArgs& a, int n) {
+  const int tiles = a.N * ((a.H + 31) / 32) * ((a.W + 7) / 8);
+  int per = sm_budget() / (n < 1 ? 1 : n);
+  if (per < 1) per = 1;
+  if (per > tiles) per = tiles;
+  return per;
+}
+int launch_conv_gemm_grouped(const ConvGemmArgs* as, int n, cudaStream_t stream) {
+  if (n == 1) return launch_conv_gemm(as[0], stream);
+  for (int g = 0; g < n; ++g)
+    if (!use_conv3_il(as[g]) || as[g].cout_total != 64) { set_error("grouped launch: every problem must be a plain 3x3 64 -> 64 layer"); return -19; }
+  return launch_conv3_il(as, n, stream);
+}
+
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
-  if (use_conv3_il(a)) return launch_conv3_il(a, stream);
+  if (use_conv3_il(a)) return launch_conv3_il(&a, 1, stream);
   if (use_conv9_rows(a)) return launch_conv9_rows(a, stream);
   if (a.TH * a.TW != 128 || a.TW % 8 != 0) { set_error("conv_gemm: tile must be 128 pixels with TW%%8==0"); return -1; }
   if (a.block_n != 64 && a.block_n != 32) { set_error("conv_gemm: block_n must be 32 or 64"); return -2; }

@@ -73,6 +73,10 @@ struct ConvGemmArgs {
 
 // Returns 0 on success, cudaError_t (>0) or a negative argument-check code otherwise.
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream);
+constexpr int kIlMaxGroups = 3;
+// one launch for the same 3x3 / 64 -> 64 layer of n <= kIlMaxGroups independent problems (see conv_gemm.cu); rows of statistics per group
+int launch_conv_gemm_grouped(const ConvGemmArgs* as, int n, cudaStream_t stream);
+int conv_gemm_grouped_rows(const ConvGemmArgs& a, int n);
 // number of CTAs launch_conv_gemm uses for `a` (= rows written to a.stats)
 int conv_gemm_grid(const ConvGemmArgs& a);
 

@@ -445,19 +445,276 @@ int run_trunk_multi(EngineImpl* const* es, int n, int bwd, int update_running, c
   return launch_trunk(a, st);
 }
 int run_trunk(EngineImpl* e, int bwd, int update_running, cudaStream_t st) { return run_trunk_multi(&e, 1, bwd, update_running, st); }
+
+// ------------------------------------------------------------------ grouped per-layer trunk
+// Large geometries (several tiles per SM, where the fused trunk kernel loses to per-layer launches): the SAME trunk layer of
+// n <= 3 generators runs as ONE grouped conv3_il launch (launch_conv_gemm_grouped: 49 CTAs per generator, 12 tiles per CTA
+// at cfg2 instead of 4, so the launch ramp, the 72 KB filter load and the last tile's epilogue drain are paid once per 12
+// tiles), and the BatchNorm passes between two layers run per generator on forked streams (they are HBM-bound and not
+// SM-exclusive, so the n chains overlap) and join again ahead of the next grouped launch.  Arithmetic per generator is the
+// per-layer path's (same kernels, same order).
+bool wgrad_layout_batched(const EngineImpl& e) {
+  const Layout& L = e.L;
+  if (!e.wgrad_batched || e.n_res < 1) return false;
+  for (int b = 0; b < e.n_res; ++b) {
+    const size_t x1 = b > 0 ? L.out[b - 1] : L.out1;
+    if (x1 != L.out1 + size_t(2 * b) * 2 * L.slot || L.z1[b] != L.out1 + size_t(2 * b + 1) * 2 * L.slot) return false;
+  }
+  if (L.out[e.n_res - 1] != L.out1 + size_t(2 * e.n_res) * 2 * L.slot) return false;
+  WgradBatchArgs probe; memset(&probe, 0, sizeof(probe));
+  probe.N = e.N; probe.H = e.H; probe.W = e.W; probe.n_layers = 2 * e.n_res + 1;
+  return wgrad3_batched_partials_floats(probe) <= L.wgb_floats;
+}
+
+bool use_trunk_grouped(const EngineImpl& e) {
+  if (!e.ws || !e.ws_training || e.n_res < 1) return false;
+  if (e.allreduce != nullptr && e.peer == nullptr) return false;      // NCCL SyncBatchNorm transport: per-generator branches
+  if (e.fin_fused || e.reduce_final || e.fuse_bwd_stats) return false;
+  static const bool off = [] { const char* v = getenv("SRG_TRUNK_GROUPED"); return v != nullptr && v[0] == '0'; }();
+  if (off) return false;
+  return wgrad_layout_batched(e);
+}
+
+struct ForkJoin {
+  cudaStream_t side[kIlMaxGroups] = {};
+  cudaEvent_t fork = nullptr, join[kIlMaxGroups] = {};
+  int device = -1;
+};
+// streams[0] = st, streams[1..n) = process-wide side streams; fork() makes them wait for st, join() the other way round
+int fork_join_get(ForkJoin** out) {
+  static ForkJoin fj;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return -70; }
+  if (fj.device != dev) {
+    for (int i = 1; i < kIlMaxGroups; ++i) {
+      if (cudaStreamCreateWithFlags(&fj.side[i], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&fj.join[i], cudaEventDisableTiming) != cudaSuccess) {
+        set_error("grouped trunk: side stream / event creation failed");
+        return -71;
+      }
+    }
+    if (cudaEventCreateWithFlags(&fj.fork, cudaEventDisableTiming) != cudaSuccess) { set_error("grouped trunk: event creation failed"); return -71; }
+    fj.device = dev;
+  }
+  *out = &fj;
+  return 0;
+}
+int fj_fork(ForkJoin* fj, int n, cudaStream_t st) {
+  if (n < 2) return 0;
+  if (cudaEventRecord(fj->fork, st) != cudaSuccess) { set_error("grouped trunk: event record failed"); return -72; }
+  for (int i = 1; i < n; ++i)
+    if (cudaStreamWaitEvent(fj->side[i], fj->fork, 0) != cudaSuccess) { set_error("grouped trunk: stream wait failed"); return -72; }
+  return 0;
+}
+int fj_join(ForkJoin* fj, int n, cudaStream_t st) {
+  for (int i = 1; i < n; ++i)
+    if (cudaEventRecord(fj->join[i], fj->side[i]) != cudaSuccess || cudaStreamWaitEvent(st, fj->join[i], 0) != cudaSuccess) {
+      set_error("grouped trunk: join failed");
+      return -72;
+    }
+  return 0;
+}
+
+struct BnNames { int64_t gamma, beta, rm; };
+BnNames bn_offsets(const EngineImpl& e, int b, int k) {
+  char nm[96];
+  BnNames o;
+  snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.weight", b, k + 1); o.gamma = poff(e, nm);
+  snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.bias", b, k + 1); o.beta = poff(e, nm);
+  snprintf(nm, sizeof(nm), "residual_blocks.%d.bn%d.running_mean", b, k + 1); o.rm = boff(e, nm);
+  return o;
+}
+
+// one grouped 3x3 64 -> 64 launch: problem g reads in[g], writes out[g]
+int grouped_conv3x3(EngineImpl* const* es, int n, const void* const* in, const int64_t* w_off, const float* const* bias,
+                    const void* const* residual, const void* const* mask, void* const* out, bool stats, int* stats_rows,
+                    cudaStream_t st) {
+  ConvGemmArgs as[kIlMaxGroups];
+  for (int g = 0; g < n; ++g) {
+    EngineImpl* e = es[g];
+    ConvGemmArgs& a = as[g];
+    memset(&a, 0, sizeof(a));
+    a.N = e->N; a.H = e->H; a.W = e->W; set_taps_3x3(a);
+    a.n_views = 1; a.views[0] = plain_view(in[g], e->H, e->W); a.in_H = e->H; a.in_W = e->W;
+    a.weights = reinterpret_cast<const uint16_t*>(e->ws + e->L.packed) + w_off[g]; a.cout_total = 64; a.block_n = 64;
+    a.bias = bias ? bias[g] : nullptr; a.act = ACT_NONE;
+    a.residual = residual ? residual[g] : nullptr; a.mask_src = mask ? mask[g] : nullptr;
+    a.out = out[g]; a.out_mode = OUT_NHWC;
+    if (stats) a.stats = reinterpret_cast<float*>(e->ws + e->L.partials);
+  }
+  if (stats) *stats_rows = n > 1 ? conv_gemm_grouped_rows(as[0], n) : conv_gemm_grid(as[0]);
+  es[0]->launches += 1;
+  es[0]->prof_layers = n;
+  ProfScope ps(es[0], st);
+  return launch_conv_gemm_grouped(as, n, st);
+}
+
+int grouped_check(EngineImpl* const* es, int n) {
+  for (int g = 0; g < n; ++g) {
+    const EngineImpl* o = es[g];
+    if (!use_trunk_grouped(*o) || o->N != es[0]->N || o->H != es[0]->H || o->W != es[0]->W || o->n_res != es[0]->n_res ||
+        o->world != es[0]->world) {
+      set_error("grouped trunk: engine %d is not bound for training on the per-layer path or differs in geometry", g);
+      return -67;
+    }
+  }
+  return 0;
+}
+
+int trunk_layers_forward_multi(EngineImpl* const* es, int n, int update_running, cudaStream_t st) {
+  RC(grouped_check(es, n));
+  ForkJoin* fj = nullptr;
+  RC(fork_join_get(&fj));
+  const int R = es[0]->n_res;
+  const int64_t P = int64_t(es[0]->N) * es[0]->H * es[0]->W;
+  const void* x[kIlMaxGroups]; const void* in[kIlMaxGroups]; void* out[kIlMaxGroups];
+  const float* bias[kIlMaxGroups]; const void* res[kIlMaxGroups]; int64_t woff[kIlMaxGroups];
+  char nm[96];
+  for (int g = 0; g < n; ++g) x[g] = es[g]->ws + es[g]->L.out1;
+  // training-mode BatchNorm (+ReLU / +skip) of every generator behind a grouped conv, one forked stream per generator
+  auto bn_stage = [&](int b, int k, int rows) -> int {
+    RC(fj_fork(fj, n, st));
+    for (int g = 0; g < n; ++g) {
+      EngineImpl* e = es[g];
+      const Layout& L = e->L;
+      cudaStream_t sg = g == 0 ? st : fj->side[g];
+      float* coef = reinterpret_cast<float*>(e->ws + L.bncoef) + size_t(2 * b + k) * 256;
+      const BnNames o = bn_offsets(*e, b, k);
+      ReduceFinalize f; memset(&f, 0, sizeof(f));
+      f.mode = RF_BN_FWD; f.count = double(P) * e->world; f.eps = kBnEps; f.momentum = kBnMomentum;
+      f.gamma = e->master + o.gamma; f.beta = e->master + o.beta;
+      f.running_mean = update_running ? e->bn_buffers + o.rm : nullptr;
+      f.running_var = update_running ? e->bn_buffers + o.rm + 64 : nullptr;
+      f.out0 = coef; f.out1 = coef + 64; f.out2 = coef + 128; f.out3 = coef + 192;
+      float* partials = reinterpret_cast<float*>(e->ws + L.partials);
+      if (e->peer) RC(launch_peer_finalize(e->peer, partials, rows, f, sg));
+      else RC(launch_partials_finalize(partials, rows, f, sg));
+      const void* y = e->ws + (k == 0 ? L.y1[b] : L.y2[b]);
+      void* dst = e->ws + (k == 0 ? L.z1[b] : L.out[b]);
+      RC(launch_bn_apply(y, coef, coef + 64, k == 0 ? nullptr : x[g], k == 0 ? 1 : 0, dst, P, sg));
+      e->launches += 2;
+    }
+    return fj_join(fj, n, st);
+  };
+  for (int b = 0; b < R; ++b) {
+    int rows = 0;
+    for (int k = 0; k < 2; ++k) {
+      snprintf(nm, sizeof(nm), "residual_blocks.%d.conv%d.bias", b, k + 1);
+      for (int g = 0; g < n; ++g) {
+        const Layout& L = es[g]->L;
+        in[g] = k == 0 ? x[g] : es[g]->ws + L.z1[b];
+        out[g] = es[g]->ws + (k == 0 ? L.y1[b] : L.y2[b]);
+        woff[g] = es[g]->po.rb_f[k][b];
+        bias[g] = es[g]->master + poff(*es[g], nm);
+      }
+      RC(grouped_conv3x3(es, n, in, woff, bias, nullptr, nullptr, out, true, &rows, st));
+      RC(bn_stage(b, k, rows));
+    }
+    for (int g = 0; g < n; ++g) x[g] = es[g]->ws + es[g]->L.out[b];
+  }
+  // conv2 + global skip (src/models.py:83-84)
+  for (int g = 0; g < n; ++g) {
+    in[g] = x[g]; out[g] = es[g]->ws + es[g]->L.trunk; res[g] = es[g]->ws + es[g]->L.out1;
+    woff[g] = es[g]->po.conv2_f; bias[g] = es[g]->master + poff(*es[g], "conv2.bias");
+  }
+  return grouped_conv3x3(es, n, in, woff, bias, res, nullptr, out, false, nullptr, st);
+}
+
+// buffer that holds d(out1) of the block chain after the per-layer backward loop (the loop alternates g[0] / g[1])
+void* layers_dout(const EngineImpl& e) {
+  if (e.keep_grads) return e.ws + (e.n_res > 0 ? e.L.kd_in[0] : e.L.kd_last);
+  return e.ws + e.L.g[e.n_res % 2 == 0 ? 0 : 1];
+}
+
+int trunk_layers_backward_multi(EngineImpl* const* es, int n, cudaStream_t st) {
+  RC(grouped_check(es, n));
+  ForkJoin* fj = nullptr;
+  RC(fork_join_get(&fj));
+  const int R = es[0]->n_res;
+  const int64_t P = int64_t(es[0]->N) * es[0]->H * es[0]->W;
+  const void* in[kIlMaxGroups]; void* out[kIlMaxGroups]; const void* res[kIlMaxGroups]; const void* mask[kIlMaxGroups];
+  int64_t woff[kIlMaxGroups];
+  void* dout[kIlMaxGroups]; void* dother[kIlMaxGroups];
+  for (int g = 0; g < n; ++g) {
+    const Layout& L = es[g]->L;
+    dout[g] = es[g]->keep_grads ? es[g]->ws + L.kd_last : es[g]->ws + L.g[0];
+    dother[g] = es[g]->ws + L.g[1];
+    in[g] = es[g]->ws + L.g[3]; out[g] = dout[g]; woff[g] = es[g]->po.conv2_d;
+  }
+  RC(grouped_conv3x3(es, n, in, woff, nullptr, nullptr, nullptr, out, false, nullptr, st));
+  // BatchNorm backward of every generator (sums of dz and dz*y, coefficients, apply) on forked streams
+  auto bn_bwd_stage = [&](int b, int k, void* const* dz, void* const* dy) -> int {
+    RC(fj_fork(fj, n, st));
+    for (int g = 0; g < n; ++g) {
+      EngineImpl* e = es[g];
+      const Layout& L = e->L;
+      cudaStream_t sg = g == 0 ? st : fj->side[g];
+      const float* coef = reinterpret_cast<const float*>(e->ws + L.bncoef) + size_t(2 * b + k) * 256;
+      float* bwd = reinterpret_cast<float*>(e->ws + L.bwdcoef);
+      float* partials = reinterpret_cast<float*>(e->ws + L.partials);
+      const BnNames o = bn_offsets(*e, b, k);
+      const void* y = e->ws + (k == 0 ? L.y1[b] : L.y2[b]);
+      RC(launch_chan_reduce(dz[g], y, P, partials, sg));
+      ReduceFinalize f; memset(&f, 0, sizeof(f));
+      f.mode = RF_BN_BWD; f.count = double(P) * e->world; f.gamma = e->master + o.gamma; f.save_mean = coef + 128; f.save_inv = coef + 192;
+      f.dgamma = e->grads + o.gamma; f.dbeta = e->grads + o.beta; f.out0 = bwd; f.out1 = bwd + 64; f.out2 = bwd + 128;
+      if (e->peer) RC(launch_peer_finalize(e->peer, partials, reduce_blocks(P), f, sg));
+      else RC(launch_partials_finalize(partials, reduce_blocks(P), f, sg));
+      RC(launch_bn_bwd_apply(dz[g], y, bwd, bwd + 64, bwd + 128, dy[g], P, sg));
+      e->launches += 3;
+    }
+    return fj_join(fj, n, st);
+  };
+  void* d_y[kIlMaxGroups]; void* d_p1[kIlMaxGroups]; void* d_in[kIlMaxGroups];
+  for (int b = R - 1; b >= 0; --b) {
+    // out = bn2(y2) + x
+    for (int g = 0; g < n; ++g) d_y[g] = es[g]->ws + es[g]->L.dyall + es[g]->L.slot * size_t(2 * b + 1);
+    RC(bn_bwd_stage(b, 1, dout, d_y));
+    for (int g = 0; g < n; ++g) {
+      const Layout& L = es[g]->L;
+      d_p1[g] = es[g]->keep_grads ? es[g]->ws + L.kd_p1[b] : dother[g];
+      in[g] = d_y[g]; out[g] = d_p1[g]; mask[g] = es[g]->ws + L.z1[b]; woff[g] = es[g]->po.rb_d[1][b];   // ReLU backward via mask
+    }
+    RC(grouped_conv3x3(es, n, in, woff, nullptr, nullptr, mask, out, false, nullptr, st));
+    // z1 = relu(bn1(y1))
+    for (int g = 0; g < n; ++g) d_y[g] = es[g]->ws + es[g]->L.dyall + es[g]->L.slot * size_t(2 * b);
+    RC(bn_bwd_stage(b, 0, d_p1, d_y));
+    for (int g = 0; g < n; ++g) {
+      const Layout& L = es[g]->L;
+      d_in[g] = es[g]->keep_grads ? es[g]->ws + L.kd_in[b] : dother[g];
+      in[g] = d_y[g]; out[g] = d_in[g]; res[g] = dout[g]; woff[g] = es[g]->po.rb_d[0][b];               // + skip gradient
+    }
+    RC(grouped_conv3x3(es, n, in, woff, nullptr, res, nullptr, out, false, nullptr, st));
+    for (int g = 0; g < n; ++g) {
+      if (es[g]->keep_grads) { dout[g] = d_in[g]; } else { void* t = dout[g]; dout[g] = dother[g]; dother[g] = t; }
+    }
+  }
+  return 0;
+}
 }  // namespace
 
 int generators_trunk(GeneratorEngine* const* gs, int n, int bwd, int update_running, cudaStream_t st) {
   if (n < 1 || n > kTrunkMaxGen) { set_error("generators_trunk: 1..%d engines", kTrunkMaxGen); return -62; }
   EngineImpl* es[kTrunkMaxGen];
+  bool fused = true;
   for (int i = 0; i < n; ++i) {
     es[i] = static_cast<EngineImpl*>(gs[i]);
-    if (!es[i]->ws || !es[i]->ws_training || !use_trunk_fused(*es[i]) || (bwd && !es[i]->wgrad_batched)) {
-      set_error("generators_trunk: engine %d is not bound for training on the fused trunk path", i);
+    if (!es[i]->ws || !es[i]->ws_training || !use_trunk_fused(*es[i]) || (bwd && !es[i]->wgrad_batched)) fused = false;
+  }
+  if (fused) return run_trunk_multi(es, n, bwd, update_running, st);
+  for (int i = 0; i < n; ++i)
+    if (!use_trunk_grouped(*es[i])) {
+      set_error("generators_trunk: engine %d is not bound for training on the fused or the grouped per-layer trunk path", i);
       return -66;
     }
+  // grouped per-layer launches, at most kIlMaxGroups generators per launch (4 generators: 2 + 2)
+  const int chunks = (n + kIlMaxGroups - 1) / kIlMaxGroups;
+  for (int c = 0, i0 = 0; c < chunks; ++c) {
+    const int m = (n - i0 + (chunks - c) - 1) / (chunks - c);
+    RC(bwd ? trunk_layers_backward_multi(es + i0, m, st) : trunk_layers_forward_multi(es + i0, m, update_running, st));
+    i0 += m;
   }
-  return run_trunk_multi(es, n, bwd, update_running, st);
+  return 0;
 }
 
 int generator_trunk_error(GeneratorEngine* g) {
@@ -756,10 +1013,12 @@ int generator_forward_phases(GeneratorEngine* g, const float* lr, float* sr, int
   const int64_t P = int64_t(N) * H * W;
   char nm[96];
 
-  if (phases != kPhaseAll && !(training && use_trunk_fused(*e))) {
-    set_error("generator_forward_phases: split execution needs the fused trunk path (training, supported configuration)");
+  if (phases != kPhaseAll && !(training && (use_trunk_fused(*e) || use_trunk_grouped(*e)))) {
+    set_error("generator_forward_phases: split execution needs the fused or the grouped per-layer trunk path (training, supported configuration)");
     return -31;
   }
+  // split execution on the per-layer path: the TRUNK phase belongs to generators_trunk() (grouped launches)
+  const bool layers_here = phases == kPhaseAll;
   if (!training && e->n_res > 0) {
     // eval: every BatchNorm's folded coefficients in one launch, two kernels ahead of the first conv that reads them
     RC(launch_bn_eval_coeffs_all(e->master, e->bn_buffers, ws + L.trunk_tab, 2 * e->n_res, kBnEps,
@@ -858,7 +1117,7 @@ int generator_forward_phases(GeneratorEngine* g, const float* lr, float* sr, int
   const bool fused = training && use_trunk_fused(*e);
   e->prof_layers = 1;
   if (fused && (phases & kPhaseTrunk)) RC(run_trunk(e, 0, update_running, st));
-  for (int b = 0; b < e->n_res && !fused; ++b) {
+  for (int b = 0; b < e->n_res && !fused && layers_here; ++b) {
     const float* coef1 = reinterpret_cast<const float*>(ws + L.bncoef) + size_t(2 * b) * 256;
     const float* coef2 = coef1 + 256;
     if (!training) {
@@ -877,7 +1136,7 @@ int generator_forward_phases(GeneratorEngine* g, const float* lr, float* sr, int
     x = ws + L.out[b];
   }
   // conv2 + global skip (src/models.py:83-84)
-  if (!fused) RC(conv3x3(x, po.conv2_f, e->master + poff(*e, "conv2.bias"), ws + L.out1, ws + L.trunk, false));
+  if (!fused && layers_here) RC(conv3x3(x, po.conv2_f, e->master + poff(*e, "conv2.bias"), ws + L.out1, ws + L.trunk, false));
   if (!(phases & kPhasePost)) return 0;
   // upsample stages: conv 64->256, PixelShuffle(2), ReLU (src/models.py:69-75,85)
   const void* in = ws + L.trunk;
@@ -1069,10 +1328,17 @@ int generator_backward_phases(GeneratorEngine* g, const float* dsr, int phases, 
   void* dmid = ws + L.g[2];
   // the whole dgrad chain of the trunk (conv2, then every block's BatchNorm / ReLU / conv backward) in one launch
   const bool fused = batched && use_trunk_fused(*e);
-  if (phases != kPhaseAll && !fused) { set_error("generator_backward_phases: split execution needs the fused trunk path"); return -31; }
+  const bool layers_here = !fused && phases == kPhaseAll;
+  if (phases != kPhaseAll && !fused && !(batched && use_trunk_grouped(*e))) {
+    set_error("generator_backward_phases: split execution needs the fused or the grouped per-layer trunk path");
+    return -31;
+  }
   if (fused) {
     if (mid) RC(run_trunk(e, 1, 0, st));
     dout = ws + L.g[0] + L.slot * size_t(e->trunk_dout_idx);
+  } else if (!layers_here) {
+    // split execution on the per-layer path: generators_trunk() ran (or will run) the dgrad chain as grouped launches
+    dout = layers_dout(*e);
   } else {
     RC(dgrad3x3(d_trunk, H, W, false, po.conv2_d, nullptr, nullptr, dout, e->n_res > 0 ? ws + L.y2[e->n_res - 1] : nullptr));
   }
@@ -1120,7 +1386,7 @@ int generator_backward_phases(GeneratorEngine* g, const float* dsr, int phases, 
     }
     return launch_bn_bwd_apply(dz, y, bwd, bwd + 64, bwd + 128, dy, P, st);
   };
-  for (int b = e->n_res - 1; b >= 0 && !fused; --b) {
+  for (int b = e->n_res - 1; b >= 0 && layers_here; --b) {
     const void* x_in = b > 0 ? ws + L.out[b - 1] : ws + L.out1;
     void* d_y2 = ws + L.dyall + L.slot * size_t(2 * b + 1);
     void* d_p1 = keep ? ws + L.kd_p1[b] : dother;

@@ -579,6 +579,16 @@ class MultiGeneratorGAN:
                 self.loss_allreduce(out)
             self._pending.append((gids, out))
             return out
+        if not any_gan and self._multi is not None and self._multi.joint and self._multi.lr.shape == lr_imgs.shape:
+            # eager replay of the step the graph captured (same joint launches; used for per-launch event timing)
+            by_id = joint_pixel_generator_steps(self.generators, self.criterion, self.g_optimizers, lr_imgs, hr_imgs,
+                                                self._multi.streams)
+            gids = [gid for gid, _ in plan]
+            out = by_id[gids].clone() if gids != list(range(len(gids))) else by_id
+            if self.loss_allreduce is not None:
+                self.loss_allreduce(out)
+            self._pending.append((gids, out))
+            return out
         rows = []
         for gid, mode in plan:
             if self.use_cuda_graphs:

@@ -1,7 +1,7 @@
 """Developer tool (GPU box): the joint multi-generator step (trunks of all K generators in one interleaved launch per
 direction, train.joint_pixel_generator_steps) against K independent per-generator graph branches: same initial weights,
 same batches -> losses and updated parameters must agree to bf16 noise; both graphs are timed.
-Usage: python tools/check_joint.py [K N H W]"""
+Usage: python tools/check_joint.py [K N H W] [--grouped] [--joint-only]"""
 import os
 import sys
 
@@ -28,7 +28,9 @@ def main():
     joint_only = "--joint-only" in sys.argv
     a = [int(x) for x in sys.argv[1:] if not x.startswith("--")]
     K, N, H, W = (a + [3, 16, 96, 96])[:4] if len(a) >= 4 else (3, 16, 96, 96)
-    S.lib().srg_set_trunk_fused(1)          # force the fused trunk kernel (automatic mode picks it for small geometries only)
+    grouped = "--grouped" in sys.argv       # joint step on the grouped per-layer path (one conv3_il launch per layer for all K)
+    # otherwise force the fused trunk kernel (automatic mode picks it for small geometries only)
+    S.lib().srg_set_trunk_fused(0 if grouped else 1)
     crit = S.ReconstructionLoss()
     gen = torch.Generator(device="cpu").manual_seed(7)
     batches = [(torch.rand(N, 3, H, W, generator=gen).cuda(), torch.rand(N, 3, 4 * H, 4 * W, generator=gen).cuda()) for _ in range(3)]
@@ -55,7 +57,7 @@ def main():
         out[joint] = (losses, flats, e0.elapsed_time(e1) / 20, step.launches_per_replay, errs)
         print(f"joint={joint}: {out[joint][2]:.3f} ms per {K}-generator step, {out[joint][3]} launches per replay, error words {errs}",
               flush=True)
-        if joint:
+        if joint and not grouped:
             prof_dump("joint", K)
     if joint_only:
         sys.exit(1 if any(out[True][4]) else 0)
