@@ -539,8 +539,12 @@ constexpr uint32_t kIlWideStage = 22 * 1024;    // 17 x 1280 = 21760 B, rounded 
 #endif
 // YS: the statistics' second factor comes from a global tensor (p.stats_y, BatchNorm-backward product sums); a separate
 // instantiation so that its 16 prefetch registers do not push the common form over the 96-register budget.
-template <bool WIDE, bool YS, bool GROUPED = false>
-__global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKParams p) {
+// GRP < 0: plain launch.  GRP >= 0: the body of group GRP of a grouped launch -- the group index is a compile-time constant so
+// that every per-group tensor map / pointer stays an immediate offset into the parameter space (a run-time index costs live
+// registers in the epilogue warps and spills the 96-register kernel).
+template <bool WIDE, bool YS, int GRP>
+__device__ __forceinline__ void conv3_il_body(const IlKParams& p) {
+  constexpr bool GROUPED = GRP >= 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __builtin_assume(__isShared(smem));      // the integer round-up hides the state space: keep LDS / STS instead of generic accesses
@@ -568,7 +572,7 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
   float* s_stats = reinterpret_cast<float*>(tail + 768);                  // [16][128] floats (p.stats only)
 
   // n_groups > 1 implies n_blocks == 1 (OUT_NHWC, 64 output channels)
-  const int grp = GROUPED ? int(blockIdx.x) % p.n_groups : 0;
+  constexpr int grp = GROUPED ? GRP : 0;
   const int nblk = GROUPED ? 0 : int(blockIdx.x) % p.n_blocks;
   const int tile0 = int(blockIdx.x) / (GROUPED ? p.n_groups : p.n_blocks);
   const CUtensorMap* const in_map = &p.in_map[2 * grp];
@@ -1010,6 +1014,19 @@ __global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKPara
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+template <bool WIDE, bool YS, bool GROUPED = false>
+__global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKParams p) {
+  if constexpr (!GROUPED) {
+    conv3_il_body<WIDE, YS, -1>(p);
+  } else {
+    static_assert(kIlMaxGroups == 3, "one body per group");
+    const int g = int(blockIdx.x) % p.n_groups;      // CTA-uniform
+    if (g == 0) conv3_il_body<WIDE, YS, 0>(p);
+    else if (g == 1) conv3_il_body<WIDE, YS, 1>(p);
+    else conv3_il_body<WIDE, YS, 2>(p);
+  }
 }
 
 // =====================================================================================================================
@@ -1478,14 +1495,16 @@ static int launch_conv3_il(const ConvGemmArgs* as, int n, cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     attr_set = true;
   }
   const dim3 grid(p.ctas_per_block * p.n_blocks * n);
   const bool pdl = a.exclusive || pdl_conv();
   const bool ys = a.stats != nullptr && a.stats_y != nullptr;
-  if (n > 1 && ys) { set_error("conv3_il: a grouped launch takes no second statistics factor"); return -18; }
-  cudaError_t e = n > 1 ? (wide ? launch_opt_pdl(pdl, conv3_il_kernel<true, false, true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
+  if (n > 1 && ys && !wide) { set_error("conv3_il: a grouped launch with a second statistics factor needs the wide form"); return -18; }
+  cudaError_t e = n > 1 ? (wide ? (ys ? launch_opt_pdl(pdl, conv3_il_kernel<true, true, true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
+                                      : launch_opt_pdl(pdl, conv3_il_kernel<true, false, true>, grid, dim3(kIlThreads), smem_bytes, stream, p))
                                 : launch_opt_pdl(pdl, conv3_il_kernel<false, false, true>, grid, dim3(kIlThreads), smem_bytes, stream, p))
                   : wide ? (ys ? launch_opt_pdl(pdl, conv3_il_kernel<true, true>, grid, dim3(kIlThreads), smem_bytes, stream, p)
                              : launch_opt_pdl(pdl, conv3_il_kernel<true, false>, grid, dim3(kIlThreads), smem_bytes, stream, p))

@@ -475,6 +475,14 @@ bool use_trunk_grouped(const EngineImpl& e) {
   return wgrad_layout_batched(e);
 }
 
+// SRG_GROUPED_OPT bits: 1 = the statistics finalize runs inside the apply / backward-apply pass (single GPU; the grouped launch
+// leaves 49 partial rows per generator instead of 148, so the re-reduction per CTA is cheap), 2 = the BatchNorm-backward sums
+// are accumulated by the grouped dgrad launch's epilogue instead of a separate reduction pass
+int grouped_opt() {
+  static const int v = [] { const char* e = getenv("SRG_GROUPED_OPT"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
 struct ForkJoin {
   cudaStream_t side[kIlMaxGroups] = {};
   cudaEvent_t fork = nullptr, join[kIlMaxGroups] = {};
@@ -528,7 +536,7 @@ BnNames bn_offsets(const EngineImpl& e, int b, int k) {
 // one grouped 3x3 64 -> 64 launch: problem g reads in[g], writes out[g]
 int grouped_conv3x3(EngineImpl* const* es, int n, const void* const* in, const int64_t* w_off, const float* const* bias,
                     const void* const* residual, const void* const* mask, void* const* out, bool stats, int* stats_rows,
-                    cudaStream_t st) {
+                    cudaStream_t st, const void* const* stats_y = nullptr) {
   ConvGemmArgs as[kIlMaxGroups];
   for (int g = 0; g < n; ++g) {
     EngineImpl* e = es[g];
@@ -541,6 +549,7 @@ int grouped_conv3x3(EngineImpl* const* es, int n, const void* const* in, const i
     a.residual = residual ? residual[g] : nullptr; a.mask_src = mask ? mask[g] : nullptr;
     a.out = out[g]; a.out_mode = OUT_NHWC;
     if (stats) a.stats = reinterpret_cast<float*>(e->ws + e->L.partials);
+    if (stats && stats_y) a.stats_y = stats_y[g];
   }
   if (stats) *stats_rows = n > 1 ? conv_gemm_grouped_rows(as[0], n) : conv_gemm_grid(as[0]);
   es[0]->launches += 1;
@@ -587,10 +596,15 @@ int trunk_layers_forward_multi(EngineImpl* const* es, int n, int update_running,
       f.running_var = update_running ? e->bn_buffers + o.rm + 64 : nullptr;
       f.out0 = coef; f.out1 = coef + 64; f.out2 = coef + 128; f.out3 = coef + 192;
       float* partials = reinterpret_cast<float*>(e->ws + L.partials);
-      if (e->peer) RC(launch_peer_finalize(e->peer, partials, rows, f, sg));
-      else RC(launch_partials_finalize(partials, rows, f, sg));
       const void* y = e->ws + (k == 0 ? L.y1[b] : L.y2[b]);
       void* dst = e->ws + (k == 0 ? L.z1[b] : L.out[b]);
+      if (!e->peer && (grouped_opt() & 1)) {
+        RC(launch_bn_apply_fin(y, partials, rows, f, k == 0 ? nullptr : x[g], k == 0 ? 1 : 0, dst, P, sg));
+        e->launches += 1;
+        continue;
+      }
+      if (e->peer) RC(launch_peer_finalize(e->peer, partials, rows, f, sg));
+      else RC(launch_partials_finalize(partials, rows, f, sg));
       RC(launch_bn_apply(y, coef, coef + 64, k == 0 ? nullptr : x[g], k == 0 ? 1 : 0, dst, P, sg));
       e->launches += 2;
     }
@@ -641,7 +655,11 @@ int trunk_layers_backward_multi(EngineImpl* const* es, int n, cudaStream_t st) {
     dother[g] = es[g]->ws + L.g[1];
     in[g] = es[g]->ws + L.g[3]; out[g] = dout[g]; woff[g] = es[g]->po.conv2_d;
   }
-  RC(grouped_conv3x3(es, n, in, woff, nullptr, nullptr, nullptr, out, false, nullptr, st));
+  const bool epi_sums = (grouped_opt() & 2) != 0;
+  const void* sy[kIlMaxGroups];
+  int rows = 0;
+  for (int g = 0; g < n; ++g) sy[g] = es[g]->ws + es[g]->L.y2[R - 1];
+  RC(grouped_conv3x3(es, n, in, woff, nullptr, nullptr, nullptr, out, epi_sums, &rows, st, sy));
   // BatchNorm backward of every generator (sums of dz and dz*y, coefficients, apply) on forked streams
   auto bn_bwd_stage = [&](int b, int k, void* const* dz, void* const* dy) -> int {
     RC(fj_fork(fj, n, st));
@@ -654,14 +672,24 @@ int trunk_layers_backward_multi(EngineImpl* const* es, int n, cudaStream_t st) {
       float* partials = reinterpret_cast<float*>(e->ws + L.partials);
       const BnNames o = bn_offsets(*e, b, k);
       const void* y = e->ws + (k == 0 ? L.y1[b] : L.y2[b]);
-      RC(launch_chan_reduce(dz[g], y, P, partials, sg));
+      int r = rows;
+      if (!epi_sums) {
+        RC(launch_chan_reduce(dz[g], y, P, partials, sg));
+        r = reduce_blocks(P);
+        e->launches += 1;
+      }
       ReduceFinalize f; memset(&f, 0, sizeof(f));
       f.mode = RF_BN_BWD; f.count = double(P) * e->world; f.gamma = e->master + o.gamma; f.save_mean = coef + 128; f.save_inv = coef + 192;
       f.dgamma = e->grads + o.gamma; f.dbeta = e->grads + o.beta; f.out0 = bwd; f.out1 = bwd + 64; f.out2 = bwd + 128;
-      if (e->peer) RC(launch_peer_finalize(e->peer, partials, reduce_blocks(P), f, sg));
-      else RC(launch_partials_finalize(partials, reduce_blocks(P), f, sg));
+      if (!e->peer && (grouped_opt() & 1)) {
+        RC(launch_bn_bwd_apply_fin(dz[g], y, partials, r, f, dy[g], P, sg));
+        e->launches += 1;
+        continue;
+      }
+      if (e->peer) RC(launch_peer_finalize(e->peer, partials, r, f, sg));
+      else RC(launch_partials_finalize(partials, r, f, sg));
       RC(launch_bn_bwd_apply(dz[g], y, bwd, bwd + 64, bwd + 128, dy[g], P, sg));
-      e->launches += 3;
+      e->launches += 2;
     }
     return fj_join(fj, n, st);
   };
@@ -674,8 +702,9 @@ int trunk_layers_backward_multi(EngineImpl* const* es, int n, cudaStream_t st) {
       const Layout& L = es[g]->L;
       d_p1[g] = es[g]->keep_grads ? es[g]->ws + L.kd_p1[b] : dother[g];
       in[g] = d_y[g]; out[g] = d_p1[g]; mask[g] = es[g]->ws + L.z1[b]; woff[g] = es[g]->po.rb_d[1][b];   // ReLU backward via mask
+      sy[g] = es[g]->ws + L.y1[b];
     }
-    RC(grouped_conv3x3(es, n, in, woff, nullptr, nullptr, mask, out, false, nullptr, st));
+    RC(grouped_conv3x3(es, n, in, woff, nullptr, nullptr, mask, out, epi_sums, &rows, st, sy));
     // z1 = relu(bn1(y1))
     for (int g = 0; g < n; ++g) d_y[g] = es[g]->ws + es[g]->L.dyall + es[g]->L.slot * size_t(2 * b);
     RC(bn_bwd_stage(b, 0, d_p1, d_y));
@@ -683,8 +712,9 @@ int trunk_layers_backward_multi(EngineImpl* const* es, int n, cudaStream_t st) {
       const Layout& L = es[g]->L;
       d_in[g] = es[g]->keep_grads ? es[g]->ws + L.kd_in[b] : dother[g];
       in[g] = d_y[g]; out[g] = d_in[g]; res[g] = dout[g]; woff[g] = es[g]->po.rb_d[0][b];               // + skip gradient
+      if (b > 0) sy[g] = es[g]->ws + L.y2[b - 1];
     }
-    RC(grouped_conv3x3(es, n, in, woff, nullptr, res, nullptr, out, false, nullptr, st));
+    RC(grouped_conv3x3(es, n, in, woff, nullptr, res, nullptr, out, epi_sums && b > 0, &rows, st, sy));
     for (int g = 0; g < n; ++g) {
       if (es[g]->keep_grads) { dout[g] = d_in[g]; } else { void* t = dout[g]; dout[g] = dother[g]; dother[g] = t; }
     }

@@ -481,6 +481,45 @@ def test_parallel_branch_graph_of_three_generators_matches_sequential(S):
     assert t_b.end_epoch() == t_a.end_epoch()
 
 
+@pytest.mark.parametrize("K", [2, 3, 4])
+def test_grouped_trunk_launches_match_per_generator_branches(S, K):
+    """Joint step on the grouped per-layer path (csrc/generator.cu trunk_layers_*_multi: the same trunk layer of up to three
+    generators in ONE conv3_il launch, BatchNorm passes on forked streams) against K independent graph branches.  Same
+    kernels and arithmetic per generator; only the per-CTA order of the BatchNorm partial sums differs, so losses agree to
+    fp32 summation noise and the Adam-updated weights to a fraction of the learning rate."""
+    L = S.lib()
+    old = L.srg_set_trunk_fused(0)           # per-layer launches (automatic mode would pick the fused trunk kernel at this size)
+    try:
+        crit = S.ReconstructionLoss()
+        torch.manual_seed(5)
+        batches = [(torch.rand(2, 3, 40, 24).cuda(), torch.rand(2, 3, 160, 96).cuda()) for _ in range(2)]
+        res = {}
+        for joint in (False, True):
+            gens, opts = [], []
+            for s_ in range(K):
+                torch.manual_seed(70 + s_)
+                g = S.SRResNet(num_residuals=2).cuda()
+                g.flat_parameters()
+                gens.append(g)
+                opts.append(S.Adam(g.parameters(), lr=1e-4, capturable=True))
+            step = S.GraphedMultiGeneratorStep(gens, crit, opts, batches[0][0], batches[0][1], joint=joint)
+            assert step.joint == joint
+            losses = [step(lr, hr).clone() for lr, hr in batches]
+            torch.cuda.synchronize()
+            res[joint] = (losses, [g.flat_parameters().clone() for g in gens], step.launches_per_replay,
+                          [g.state_dict()["residual_blocks.1.bn2.running_var"].clone() for g in gens])
+        for la, lb in zip(res[False][0], res[True][0]):
+            assert torch.allclose(la, lb, rtol=2e-4, atol=1e-6), (la, lb)
+        for fa, fb in zip(res[False][1], res[True][1]):
+            d = (fa - fb).abs()
+            assert d.max().item() <= 4.1e-4 and d.mean().item() < 2e-5, (d.max().item(), d.mean().item())   # 2 steps x lr 1e-4
+        for va, vb in zip(res[False][3], res[True][3]):
+            assert torch.allclose(va, vb, rtol=1e-4, atol=1e-7)
+        assert res[True][2] < res[False][2]       # K x 5 trunk conv launches per direction became ceil(K / 3) x 5
+    finally:
+        L.srg_set_trunk_fused(old)
+
+
 def test_peer_sync_kernel_world1_matches_local_finalize(S):
     """The fused reduce + NVLink exchange + finalize kernel (csrc/peer_sync.cu) with a single rank (its own buffer is
     the only peer) must reproduce the local finalize path bit for bit; the multi-rank behaviour is covered by
