@@ -487,20 +487,27 @@ def run_ours(a):
         n_layers = max(1, int(S.lib().srg_generator_trunk_layers(gens[0].last_engine().handle)))
     except Exception:
         pass
-    flop_per_launch *= n_layers            # a fused trunk launch covers 2*n_res+1 layers
+    flop_per_launch *= n_layers            # a fused trunk launch covers 2*n_res+1 layers, a grouped launch one layer of <= 3 generators
     achieved *= n_layers
+    grouped = 1 < n_layers <= 4
     traffic = None
     try:
         if not (a.workload == "cfg2" and B == 16 and LH == 96 and LW == 96):
             raise ValueError("ncu capture was taken at the cfg2 geometry")
-        if n_layers != 1:
-            raise ValueError("capture is of the per-layer kernel")
-        with open(os.path.join(ROOT, "profiles", "r02_conv3_il_traffic.json")) as f:
+        if n_layers != 1 and not (grouped and n_layers == 3):
+            raise ValueError("captures are of the per-layer kernel and of the 3-generator grouped launch")
+        fname = "r02_conv3_il_grouped_traffic.json" if grouped else "r02_conv3_il_traffic.json"
+        with open(os.path.join(ROOT, "profiles", fname)) as f:
             traffic = json.load(f)["dram_bytes_per_launch"]       # dram__bytes_read.sum + dram__bytes_write.sum (ncu)
     except Exception:
         pass
-    kname = ("conv3_il_kernel (3x3 64->64 fprop/dgrad implicit GEMM, row-interleaved N=128 tcgen05 MMAs)" if n_layers == 1 else
-             f"trunk_kernel (fused: {n_layers} 3x3 64->64 conv layers of one direction + their BatchNorm steps per launch)")
+    if n_layers == 1:
+        kname = "conv3_il_kernel (3x3 64->64 fprop/dgrad implicit GEMM, row-interleaved N=128 tcgen05 MMAs)"
+    elif grouped:
+        kname = (f"conv3_il_kernel, grouped launch (the same 3x3 64->64 fprop/dgrad layer of {n_layers} generators in one launch, "
+                 "row-interleaved N=128 tcgen05 MMAs)")
+    else:
+        kname = f"trunk_kernel (fused: {n_layers} 3x3 64->64 conv layers of one direction + their BatchNorm steps per launch)"
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "frac_of_burst_peak": achieved / peak_burst, "peak_burst": peak_burst,
                 "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, cfg2 geometry)", "kernel": kname,
@@ -564,7 +571,9 @@ def run_ours(a):
                        "whole_job_algorithmic_tflops": whole_step_tflops * world,
                        "whole_step_frac_of_bf16_sustained_peak": whole_step_tflops / peak,
                        "whole_step_frac_of_bf16_burst_peak": whole_step_tflops / peak_burst,
-                       "trunk_path": ("fused trunk kernel" if n_layers > 1 else "per-layer launches"), "last_losses": last},
+                       "trunk_path": ("per-layer launches" if n_layers == 1 else
+                                      "grouped per-layer launches (one conv launch per layer for all generators)" if grouped else
+                                      "fused trunk kernel"), "last_losses": last},
             "roofline": roofline, "roofline_hbm": hbm, "weak16": weak16, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples", "power_w_max")},

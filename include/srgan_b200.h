@@ -107,9 +107,15 @@ int srg_set_trunk_fused(int on);
  * stages), 2 = TRUNK (the 16 residual blocks + conv2, src/models.py:82-84, forward or backward), 4 = POST (forward:
  * upsample + conv3, src/models.py:85-86; backward: conv1 gradients and the batched trunk weight gradients); 7 = the whole
  * pass (= srg_generator_forward / srg_generator_backward).  srg_generators_trunk runs the TRUNK phase of n <= 4 engines of
- * identical geometry as ONE launch that interleaves their layers, so the BatchNorm barrier latency of one generator is
- * hidden behind the tensor work of the others.  Engines must be bound for training; split execution is only available
- * where the fused trunk kernel applies (otherwise these return an error and the caller uses the whole-pass entry points). */
+ * identical geometry jointly: where the fused trunk kernel is preferred, as ONE launch that interleaves their layers (the
+ * BatchNorm barrier latency of one generator hides behind the tensor work of the others); otherwise layer by layer with ONE
+ * grouped convolution launch per layer for up to three engines (csrc/conv_gemm.cu launch_conv_gemm_grouped: 49 CTAs per
+ * engine, 3x the tiles per CTA) and each engine's BatchNorm passes on forked streams between two launches (internal side
+ * streams that join `stream` again before the call returns; capturable).  srg_generator_trunk_layers reports 33 / n / 1 for
+ * the fused / grouped / per-layer form of the last profiled launch.  Engines must be bound for training; split execution
+ * needs the fused trunk kernel or the grouped path (batched trunk weight gradients, single GPU or the peer-memory
+ * SyncBatchNorm transport, SRG_TRUNK_GROUPED != 0) -- otherwise these return an error and the caller uses the whole-pass
+ * entry points. */
 int srg_generator_forward_phases(srg_generator_t* g, const float* lr_nchw, float* sr_nchw, int training, int update_running,
                                  int phases, void* stream);
 int srg_generator_backward_phases(srg_generator_t* g, const float* dsr_nchw, int phases, void* stream);

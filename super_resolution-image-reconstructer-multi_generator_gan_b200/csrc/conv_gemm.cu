@@ -539,12 +539,11 @@ constexpr uint32_t kIlWideStage = 22 * 1024;    // 17 x 1280 = 21760 B, rounded 
 #endif
 // YS: the statistics' second factor comes from a global tensor (p.stats_y, BatchNorm-backward product sums); a separate
 // instantiation so that its 16 prefetch registers do not push the common form over the 96-register budget.
-// GRP < 0: plain launch.  GRP >= 0: the body of group GRP of a grouped launch -- the group index is a compile-time constant so
-// that every per-group tensor map / pointer stays an immediate offset into the parameter space (a run-time index costs live
-// registers in the epilogue warps and spills the 96-register kernel).
-template <bool WIDE, bool YS, int GRP>
-__device__ __forceinline__ void conv3_il_body(const IlKParams& p) {
-  constexpr bool GROUPED = GRP >= 0;
+// GROUPED: CTA c works for group c % n_groups (a run-time index into the per-group tensor maps / pointers).  Measured on one
+// box: one body per group with a compile-time index (no spills, 3x the code) runs the grouped trunk launch in 38.5-40.9 us, the
+// run-time index (8 bytes of spills) in 33.2 us (profiles/r02_ab_grouped.log), so the run-time index stays.
+template <bool WIDE, bool YS, bool GROUPED = false>
+__global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __builtin_assume(__isShared(smem));      // the integer round-up hides the state space: keep LDS / STS instead of generic accesses
@@ -572,7 +571,7 @@ __device__ __forceinline__ void conv3_il_body(const IlKParams& p) {
   float* s_stats = reinterpret_cast<float*>(tail + 768);                  // [16][128] floats (p.stats only)
 
   // n_groups > 1 implies n_blocks == 1 (OUT_NHWC, 64 output channels)
-  constexpr int grp = GROUPED ? GRP : 0;
+  const int grp = GROUPED ? int(blockIdx.x) % p.n_groups : 0;
   const int nblk = GROUPED ? 0 : int(blockIdx.x) % p.n_blocks;
   const int tile0 = int(blockIdx.x) / (GROUPED ? p.n_groups : p.n_blocks);
   const CUtensorMap* const in_map = &p.in_map[2 * grp];
@@ -1014,19 +1013,6 @@ __device__ __forceinline__ void conv3_il_body(const IlKParams& p) {
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 256);
-}
-
-template <bool WIDE, bool YS, bool GROUPED = false>
-__global__ void IL_KERNEL_BOUNDS conv3_il_kernel(const __grid_constant__ IlKParams p) {
-  if constexpr (!GROUPED) {
-    conv3_il_body<WIDE, YS, -1>(p);
-  } else {
-    static_assert(kIlMaxGroups == 3, "one body per group");
-    const int g = int(blockIdx.x) % p.n_groups;      // CTA-uniform
-    if (g == 0) conv3_il_body<WIDE, YS, 0>(p);
-    else if (g == 1) conv3_il_body<WIDE, YS, 1>(p);
-    else conv3_il_body<WIDE, YS, 2>(p);
-  }
 }
 
 // =====================================================================================================================

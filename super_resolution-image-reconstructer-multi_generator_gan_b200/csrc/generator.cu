@@ -477,7 +477,8 @@ bool use_trunk_grouped(const EngineImpl& e) {
 
 // SRG_GROUPED_OPT bits: 1 = the statistics finalize runs inside the apply / backward-apply pass (single GPU; the grouped launch
 // leaves 49 partial rows per generator instead of 148, so the re-reduction per CTA is cheap), 2 = the BatchNorm-backward sums
-// are accumulated by the grouped dgrad launch's epilogue instead of a separate reduction pass
+// are accumulated by the grouped dgrad launch's epilogue instead of a separate reduction pass, 4 = the backward reduction's last
+// block finalizes the coefficients (single GPU)
 int grouped_opt() {
   static const int v = [] { const char* e = getenv("SRG_GROUPED_OPT"); return e ? atoi(e) : 0; }();
   return v;
@@ -673,6 +674,16 @@ int trunk_layers_backward_multi(EngineImpl* const* es, int n, cudaStream_t st) {
       const BnNames o = bn_offsets(*e, b, k);
       const void* y = e->ws + (k == 0 ? L.y1[b] : L.y2[b]);
       int r = rows;
+      if (!epi_sums && !e->peer && (grouped_opt() & 4)) {
+        // the reduction's last block finalizes (atomic ticket): no single-block finalize launch on the backward chain
+        ReduceFinalize f; memset(&f, 0, sizeof(f));
+        f.mode = RF_BN_BWD; f.count = double(P); f.gamma = e->master + o.gamma; f.save_mean = coef + 128; f.save_inv = coef + 192;
+        f.dgamma = e->grads + o.gamma; f.dbeta = e->grads + o.beta; f.out0 = bwd; f.out1 = bwd + 64; f.out2 = bwd + 128;
+        RC(launch_chan_reduce_final(dz[g], y, P, partials, reinterpret_cast<unsigned int*>(e->ws + L.ticket), f, sg));
+        RC(launch_bn_bwd_apply(dz[g], y, bwd, bwd + 64, bwd + 128, dy[g], P, sg));
+        e->launches += 2;
+        continue;
+      }
       if (!epi_sums) {
         RC(launch_chan_reduce(dz[g], y, P, partials, sg));
         r = reduce_blocks(P);
