@@ -1486,7 +1486,7 @@ static int launch_conv3_il(const ConvGemmArgs* as, int n, cudaStream_t stream) {
     attr_set = true;
   }
   const dim3 grid(p.ctas_per_block * p.n_blocks * n);
-  const bool pdl = a.exclusive || pdl_conv();
+  const int pdl = a.exclusive ? 2 : (pdl_conv() ? 1 : 0);
   const bool ys = a.stats != nullptr && a.stats_y != nullptr;
   if (n > 1 && ys && !wide) { set_error("conv3_il: a grouped launch with a second statistics factor needs the wide form"); return -18; }
   cudaError_t e = n > 1 ? (wide ? (ys ? launch_opt_pdl(pdl, conv3_il_kernel<true, true, true>, grid, dim3(kIlThreads), smem_bytes, stream, p)

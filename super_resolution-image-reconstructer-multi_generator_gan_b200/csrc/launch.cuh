@@ -18,8 +18,20 @@ namespace srg {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// SRG_PDL (read once): 0 = plain stream-order launches everywhere (a kernel timeline then shows each kernel's own duration
+// instead of one that starts while the predecessor is still running); 1 = every launch_pdl() kernel may start early; 2
+// (default) = only grids of at most 8 blocks (the single-block finalize kernels) and inference (`exclusive`) convolutions start
+// early: a big grid parked at griddepcontrol.wait holds registers / shared memory that a ready kernel of another stream could
+// use.  Measured on the cfg2 training step (profiles/r02_ab_pdl_grouped.log): 9.61-9.64 ms (2) vs 9.69-9.74 ms (1).
+inline int pdl_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SRG_PDL"); v = e ? atoi(e) : 2; }
+  return v;
+}
+
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline cudaError_t launch_with_pdl_attr(bool early, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args&&... args) {
   cudaLaunchConfig_t cfg;
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -29,14 +41,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  // SRG_PDL=0 (developer switch): plain stream-order launches everywhere, so that a kernel timeline shows each kernel's own
-  // duration instead of a duration that starts while the predecessor is still running
-  // SRG_PDL=2: only grids of at most 8 blocks (the single-block finalize kernels) start early: a big grid that is parked at
-  // griddepcontrol.wait holds registers that another graph branch's ready kernel could use
-  static int pdl_on = -1;
-  if (pdl_on < 0) { const char* e = getenv("SRG_PDL"); pdl_on = e ? atoi(e) : 1; }
-  cfg.numAttrs = (pdl_on == 1 || (pdl_on == 2 && grid.x * grid.y * grid.z <= 8)) ? 1 : 0;
+  cfg.numAttrs = early ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  const int mode = pdl_mode();
+  const bool early = mode == 1 || (mode == 2 && grid.x * grid.y * grid.z <= 8);
+  return launch_with_pdl_attr(early, kernel, grid, block, smem, st, std::forward<Args>(args)...);
+}
+// inference launches: a chain of SM-exclusive convolutions on one stream with nothing else to schedule -- early start pays
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_exclusive(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return launch_with_pdl_attr(pdl_mode() != 0, kernel, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
 // A/B switches (read once): SRG_PDL_CONV=0 launches the SM-exclusive convolution kernels WITHOUT the attribute (a CTA that
@@ -46,18 +64,13 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 inline bool pdl_conv() { static int v = -1; if (v < 0) { const char* e = getenv("SRG_PDL_CONV"); v = (e && e[0] == '0') ? 0 : 1; } return v != 0; }
 inline int pdl_ew_late() { static int v = -1; if (v < 0) { const char* e = getenv("SRG_PDL_EW_LATE"); v = (e && e[0] == '1') ? 1 : 0; } return v; }
 
+// pdl: 0 = never early, 1 = as launch_pdl() decides, 2 = inference launch (launch_pdl_exclusive)
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_opt_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+inline cudaError_t launch_opt_pdl(int pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                   Args&&... args) {
-  if (pdl) return launch_pdl(kernel, grid, block, smem, st, std::forward<Args>(args)...);
-  cudaLaunchConfig_t cfg;
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cfg.attrs = nullptr;
-  cfg.numAttrs = 0;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+  if (pdl == 2) return launch_pdl_exclusive(kernel, grid, block, smem, st, std::forward<Args>(args)...);
+  if (pdl == 1) return launch_pdl(kernel, grid, block, smem, st, std::forward<Args>(args)...);
+  return launch_with_pdl_attr(false, kernel, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
 }  // namespace srg
