@@ -276,10 +276,14 @@ def run_infer(a):
 def hbm_roofline(S, torch, dev, B, LH, LW, pk):
     """Achieved HBM GB/s of the memory-bound kernels of the step, each timed ALONE with CUDA events on cfg-shaped
     tensors through its per-operator C-ABI entry point.  Every launch works on a different one of `nbuf` buffer sets
-    (together far larger than the 126 MB L2), so the algorithmic bytes really come from / go to HBM."""
+    (together far larger than the 126 MB L2), so the algorithmic bytes really come from / go to HBM.  The `reps` launches
+    are captured into a CUDA graph and the replay is timed (the way the step runs them): host enqueue time per launch
+    through ctypes is of the order of these kernels' durations and would otherwise be part of the figure."""
     from ctypes import c_void_p
     L = S.lib()
-    st = c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def stp():                                            # the CURRENT stream (the capture stream inside torch.cuda.graph)
+        return c_void_p(torch.cuda.current_stream().cuda_stream)
     P = B * LH * LW
     act_bytes = P * 128                                     # one [P][64] bf16 tensor
     nbuf = max(4, int(600e6 // (3 * act_bytes)) + 1)
@@ -299,24 +303,24 @@ def hbm_roofline(S, torch, dev, B, LH, LW, pk):
 
     def k_apply_relu(i):
         a_, b_, c_ = bufs[i % nbuf]
-        L.srg_bn_apply(p(a_), p(coef[0]), p(coef[1]), None, 1, p(c_), P, st)
+        L.srg_bn_apply(p(a_), p(coef[0]), p(coef[1]), None, 1, p(c_), P, stp())
 
     def k_apply_skip(i):
         a_, b_, c_ = bufs[i % nbuf]
-        L.srg_bn_apply(p(a_), p(coef[0]), p(coef[1]), p(b_), 0, p(c_), P, st)
+        L.srg_bn_apply(p(a_), p(coef[0]), p(coef[1]), p(b_), 0, p(c_), P, stp())
 
     def k_stats2(i):
         a_, b_, c_ = bufs[i % nbuf]
-        L.srg_bn_stats(p(a_), p(b_), P, p(partials), st)
+        L.srg_bn_stats(p(a_), p(b_), P, p(partials), stp())
 
     def k_bwd_apply(i):
         a_, b_, c_ = bufs[i % nbuf]
-        L.srg_bn_backward_apply(p(a_), p(b_), p(coef[2]), p(coef[3]), p(coef[4]), p(c_), P, st)
+        L.srg_bn_backward_apply(p(a_), p(b_), p(coef[2]), p(coef[3]), p(coef[4]), p(c_), P, stp())
 
     def k_loss(i):
         h_, s_ = hr[i % 2], sr[i % 2]
-        L.srg_recon_loss_forward(p(h_), p(s_), B, 3, 4 * LH, 4 * LW, p(scratch), scratch.numel(), p(e_buf), p(g_buf), p(losses), st)
-        L.srg_recon_loss_backward(p(h_), p(s_), B, 3, 4 * LH, 4 * LW, p(scratch), p(e_buf), p(g_buf), None, None, p(dsr), 1.0, st)
+        L.srg_recon_loss_forward(p(h_), p(s_), B, 3, 4 * LH, 4 * LW, p(scratch), scratch.numel(), p(e_buf), p(g_buf), p(losses), stp())
+        L.srg_recon_loss_backward(p(h_), p(s_), B, 3, 4 * LH, 4 * LW, p(scratch), p(e_buf), p(g_buf), None, None, p(dsr), 1.0, stp())
 
     cases = [
         ("bn_apply_kernel<relu> (BatchNorm apply + ReLU, src/models.py:23)", k_apply_relu, 2 * act_bytes),
@@ -333,13 +337,19 @@ def hbm_roofline(S, torch, dev, B, LH, LW, pk):
         for i in range(4):
             fn(i)
         torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(reps):
+                fn(i)
+        graph.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(reps):
-            fn(i)
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / reps
+        del graph
         gbs = nbytes / (us * 1e-6) / 1e9
         out.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                     "algorithmic_bytes_per_launch": nbytes, "avg_us": us})
