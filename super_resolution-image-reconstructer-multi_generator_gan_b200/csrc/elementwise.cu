@@ -274,16 +274,7 @@ __global__ void __launch_bounds__(1024) partials_finalize_kernel(const float* __
   pdl_trigger();
   pdl_wait();
   const int col = threadIdx.x & 127, rl = threadIdx.x >> 7;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int b = rl;
-  for (; b + 24 < rows; b += 32) {
-    a0 += double(partials[size_t(b) * 128 + col]);
-    a1 += double(partials[size_t(b + 8) * 128 + col]);
-    a2 += double(partials[size_t(b + 16) * 128 + col]);
-    a3 += double(partials[size_t(b + 24) * 128 + col]);
-  }
-  for (; b < rows; b += 8) a0 += double(partials[size_t(b) * 128 + col]);
-  red[rl][col] = (a0 + a1) + (a2 + a3);
+  red[rl][col] = partials_lane_sum(partials, rows, col, rl);
   __syncthreads();
   if (rl == 0) {
     double t = 0.0;

@@ -73,4 +73,32 @@ inline cudaError_t launch_opt_pdl(int pdl, void (*kernel)(KArgs...), dim3 grid, 
   return launch_with_pdl_attr(false, kernel, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
+// Column sum of a [rows][128] fp32 partial-sum table for row lane rl of 8 (rows rl, rl+8, ...), fp64, FIXED order: four
+// accumulators take rows b, b+8, b+16, b+24 of every group of 32 rows in turn.  Shared by the local finalize
+// (elementwise.cu) and the peer-memory finalize (peer_sync.cu), which must agree bit for bit.  Up to 12 independent loads are
+// in flight per thread (the additions keep the 4-per-group order): the one-block finalize kernels sit on the dependency chain
+// between a convolution and the BatchNorm pass behind it, and with 4 loads per round 288 rows were 9 L2 round trips.
+__device__ __forceinline__ double partials_lane_sum(const float* __restrict__ partials, int rows, int col, int rl) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  const float* p = partials + col;
+  int b = rl;
+  for (; b + 88 < rows; b += 96) {
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = p[size_t(b + 8 * k) * 128];
+#pragma unroll
+    for (int k = 0; k < 12; k += 4) { a0 += double(v[k]); a1 += double(v[k + 1]); a2 += double(v[k + 2]); a3 += double(v[k + 3]); }
+  }
+  for (; b + 24 < rows; b += 32) {
+    const float v0 = p[size_t(b) * 128], v1 = p[size_t(b + 8) * 128], v2 = p[size_t(b + 16) * 128], v3 = p[size_t(b + 24) * 128];
+    a0 += double(v0); a1 += double(v1); a2 += double(v2); a3 += double(v3);
+  }
+  // at most three rows are left: load them together (a missing row adds +0.0)
+  const float t0 = b < rows ? p[size_t(b) * 128] : 0.f;
+  const float t1 = b + 8 < rows ? p[size_t(b + 8) * 128] : 0.f;
+  const float t2 = b + 16 < rows ? p[size_t(b + 16) * 128] : 0.f;
+  a0 += double(t0); a0 += double(t1); a0 += double(t2);
+  return (a0 + a1) + (a2 + a3);
+}
+
 }  // namespace srg
