@@ -167,13 +167,16 @@ __device__ __forceinline__ void finalize_channels(const ReduceFinalize& f, int c
   }
 }
 
-template <bool TWO>
-__global__ void __launch_bounds__(256) chan_reduce_final_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+template <bool TWO, int T>
+__global__ void __launch_bounds__(T) chan_reduce_final_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
                                                                 int64_t pixels, float* __restrict__ partials,
                                                                 unsigned int* __restrict__ ticket, const ReduceFinalize f,
                                                                 uint64_t pol) {
-  __shared__ float red[32][129];
+  constexpr int PR = T / 8;       // pixels per round-slot (as chan_reduce_kernel)
+  constexpr int RL = T / 32;      // row lanes of the last block's fixed-order sum
+  __shared__ float red[PR][129];
   __shared__ bool is_last;
+  static_assert(sizeof(float) * PR * 129 >= sizeof(double) * RL * 128, "the fp64 staging reuses the float rows");
   pdl_trigger();
   pdl_wait();
   const int cg = threadIdx.x & 7;
@@ -181,8 +184,8 @@ __global__ void __launch_bounds__(256) chan_reduce_final_kernel(const uint4* __r
   float s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
-  const int64_t stride = int64_t(gridDim.x) * 32;
-  int64_t p = int64_t(blockIdx.x) * 32 + lane_p;
+  const int64_t stride = int64_t(gridDim.x) * PR;
+  int64_t p = int64_t(blockIdx.x) * PR + lane_p;
   for (; p + 3 * stride < pixels; p += 4 * stride) {      // same loop (and per-thread accumulation order) as chan_reduce_kernel
     uint4 ra[4], rb[4];
 #pragma unroll
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(256) chan_reduce_final_kernel(const uint4* __r
   if (threadIdx.x < 128) {
     float acc = 0.f;
 #pragma unroll 8
-    for (int l = 0; l < 32; ++l) acc += red[l][threadIdx.x];
+    for (int l = 0; l < PR; ++l) acc += red[l][threadIdx.x];
     partials[size_t(blockIdx.x) * 128 + threadIdx.x] = acc;
   }
   __threadfence();
@@ -229,24 +232,24 @@ __global__ void __launch_bounds__(256) chan_reduce_final_kernel(const uint4* __r
   if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!is_last) return;
-  // the last block to finish: fixed-order fp64 sum of every block's row (8 row lanes x 32 column quads), then the finalize
+  // the last block to finish: fixed-order fp64 sum of every block's row (RL row lanes x 32 column quads), then the finalize
   __threadfence();
-  double* dred = reinterpret_cast<double*>(&red[0][0]);        // [8][128] doubles over the dead float rows (16.5 KB)
+  double* dred = reinterpret_cast<double*>(&red[0][0]);        // [RL][128] doubles over the dead float rows
   const int c4 = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const float4* src = reinterpret_cast<const float4*>(partials) + c4;
   const int rows = int(gridDim.x);
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int r = rl;
-  for (; r + 32 < rows; r += 40) {
-    const float4 v0 = __ldcg(src + size_t(r) * 32), v1 = __ldcg(src + size_t(r + 8) * 32), v2 = __ldcg(src + size_t(r + 16) * 32);
-    const float4 v3 = __ldcg(src + size_t(r + 24) * 32), v4 = __ldcg(src + size_t(r + 32) * 32);
+  for (; r + 4 * RL < rows; r += 5 * RL) {
+    const float4 v0 = __ldcg(src + size_t(r) * 32), v1 = __ldcg(src + size_t(r + RL) * 32), v2 = __ldcg(src + size_t(r + 2 * RL) * 32);
+    const float4 v3 = __ldcg(src + size_t(r + 3 * RL) * 32), v4 = __ldcg(src + size_t(r + 4 * RL) * 32);
     a0 += double(v0.x); a1 += double(v0.y); a2 += double(v0.z); a3 += double(v0.w);
     a0 += double(v1.x); a1 += double(v1.y); a2 += double(v1.z); a3 += double(v1.w);
     a0 += double(v2.x); a1 += double(v2.y); a2 += double(v2.z); a3 += double(v2.w);
     a0 += double(v3.x); a1 += double(v3.y); a2 += double(v3.z); a3 += double(v3.w);
     a0 += double(v4.x); a1 += double(v4.y); a2 += double(v4.z); a3 += double(v4.w);
   }
-  for (; r < rows; r += 8) {
+  for (; r < rows; r += RL) {
     const float4 v = __ldcg(src + size_t(r) * 32);
     a0 += double(v.x); a1 += double(v.y); a2 += double(v.z); a3 += double(v.w);
   }
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(256) chan_reduce_final_kernel(const uint4* __r
   double t = 0.0;
   if (threadIdx.x < 128) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += dred[i * 128 + threadIdx.x];
+    for (int i = 0; i < RL; ++i) t += dred[i * 128 + threadIdx.x];
   }
   __syncthreads();
   if (threadIdx.x < 128) dred[threadIdx.x] = t;
@@ -303,12 +306,15 @@ int launch_chan_reduce_final(const void* a, const void* b, int64_t pixels, float
                              const ReduceFinalize& f, cudaStream_t st) {
   const int blocks = reduce_blocks(pixels);
   const uint64_t pol = (b && l2_hints()) ? kL2EvictLast : kL2EvictNormal;
-  if (b)
-    launch_pdl(chan_reduce_final_kernel<true>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint4*>(a),
-               reinterpret_cast<const uint4*>(b), pixels, partials, ticket, f, pol);
-  else
-    launch_pdl(chan_reduce_final_kernel<false>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint4*>(a),
-               static_cast<const uint4*>(nullptr), pixels, partials, ticket, f, pol);
+  const uint4* aa = reinterpret_cast<const uint4*>(a);
+  const uint4* bb = reinterpret_cast<const uint4*>(b);
+  if (red_threads() == 512) {
+    if (b) launch_pdl(chan_reduce_final_kernel<true, 512>, dim3(blocks), dim3(512), 0, st, aa, bb, pixels, partials, ticket, f, pol);
+    else launch_pdl(chan_reduce_final_kernel<false, 512>, dim3(blocks), dim3(512), 0, st, aa, bb, pixels, partials, ticket, f, pol);
+  } else {
+    if (b) launch_pdl(chan_reduce_final_kernel<true, 256>, dim3(blocks), dim3(256), 0, st, aa, bb, pixels, partials, ticket, f, pol);
+    else launch_pdl(chan_reduce_final_kernel<false, 256>, dim3(blocks), dim3(256), 0, st, aa, bb, pixels, partials, ticket, f, pol);
+  }
   SRG_LAUNCH_CHECK("chan_reduce_final");
   return 0;
 }

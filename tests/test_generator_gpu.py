@@ -851,15 +851,17 @@ def test_eval_forward_streams_frames_bit_identically(S):
     assert g.last_engine().N == 5
 
 
-def test_finalize_fused_batchnorm_passes_match_separate_finalize(S, monkeypatch):
+@pytest.mark.parametrize("switch", ["SRG_FIN_FUSED", "SRG_REDUCE_FINAL"])
+def test_finalize_fused_batchnorm_passes_match_separate_finalize(S, monkeypatch, switch):
     """SRG_FIN_FUSED=1 (BatchNorm statistics finalize inside the apply / backward-apply pass, csrc/elementwise.cu
-    bn_apply_fin / bn_bwd_apply_fin) against the default two-launch form on the same weights and inputs: same partial
+    bn_apply_fin / bn_bwd_apply_fin) and SRG_REDUCE_FINAL=1 (the BatchNorm-backward reduction's last block finalizes,
+    chan_reduce_final_kernel) against the default two-launch form on the same weights and inputs: same partial
     sums, summed in fp64 in a different fixed order, so intermediates agree to a bf16 ulp in the first block and the
     parameter gradients to rounding noise through the chain."""
     res = []
     old_mode = S.lib().srg_set_trunk_fused(0)             # per-layer launches (the tiny geometry would pick the fused trunk)
     for flag in ("0", "1"):
-        monkeypatch.setenv("SRG_FIN_FUSED", flag)         # read at engine creation
+        monkeypatch.setenv(switch, flag)                  # read at engine creation
         torch.manual_seed(11)
         g = S.SRResNet().cuda().train()
         torch.manual_seed(12)
@@ -873,7 +875,7 @@ def test_finalize_fused_batchnorm_passes_match_separate_finalize(S, monkeypatch)
                     {k: v.clone() for k, v in g.state_dict().items() if "running" in k}, S.lib().srg_generator_launch_count(eng.handle)))
     S.lib().srg_set_trunk_fused(old_mode)
     (y0, T0, G0, R0, n0), (y1, T1, G1, R1, n1) = res
-    assert n1 < n0                                        # 64 fewer launches per forward + backward
+    assert n1 < n0                                        # 64 (32 with SRG_REDUCE_FINAL) fewer launches per forward + backward
     for n in ("rb0.y1", "rb0.z1", "rb0.out"):
         assert maxrel(T1[n], T0[n]) < 4e-3, n
     assert maxrel(y1, y0) < 5e-2
