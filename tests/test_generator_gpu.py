@@ -481,7 +481,7 @@ def test_parallel_branch_graph_of_three_generators_matches_sequential(S):
     assert t_b.end_epoch() == t_a.end_epoch()
 
 
-@pytest.mark.parametrize("K", [2, 3, 4])
+@pytest.mark.parametrize("K", [1, 2, 3, 4])
 def test_grouped_trunk_launches_match_per_generator_branches(S, K):
     """Joint step on the grouped per-layer path (csrc/generator.cu trunk_layers_*_multi: the same trunk layer of up to three
     generators in ONE conv3_il launch, BatchNorm passes on forked streams) against K independent graph branches.  Same
@@ -515,7 +515,7 @@ def test_grouped_trunk_launches_match_per_generator_branches(S, K):
             assert d.max().item() <= 4.1e-4 and d.mean().item() < 2e-5, (d.max().item(), d.mean().item())   # 2 steps x lr 1e-4
         for va, vb in zip(res[False][3], res[True][3]):
             assert torch.allclose(va, vb, rtol=1e-4, atol=1e-7)
-        assert res[True][2] < res[False][2]       # K x 5 trunk conv launches per direction became ceil(K / 3) x 5
+        assert res[True][2] < res[False][2] or K == 1       # K x 5 trunk conv launches per direction became ceil(K / 3) x 5
     finally:
         L.srg_set_trunk_fused(old)
 
