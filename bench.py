@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-sync-each-step", action="store_true", help="e2e leg: wait for every step's losses before "
                     "enqueuing the next step (default: read them one step late)")
-    ap.add_argument("--syncbn", default="peer", choices=["peer", "nccl"], help="SyncBatchNorm transport for N > 1: fused "
+    ap.add_argument("--syncbn", default="peer", choices=["peer", "nccl", "none"], help="SyncBatchNorm transport for N > 1: fused "
                     "NVLink peer-memory exchange kernel (default) or ncclAllReduce between reduce and finalize kernels")
     ap.add_argument("--no-stream", action="store_true", help="infer-1080p: one engine call for the whole batch instead of "
                     "streaming chunks of frames (A/B; materialises every frame's activations)")
@@ -389,7 +389,8 @@ def run_ours(a):
         d_opt = S.Adam(disc.parameters(), lr=5e-5, capturable=True)
     loss_ar = None
     if world > 1:
-        S.parallel.data_parallel(gens + ([disc] if disc is not None else []), sync_batchnorm=True, sync_bn_transport=a.syncbn)
+        S.parallel.data_parallel(gens + ([disc] if disc is not None else []), sync_batchnorm=(a.syncbn != "none"),
+                                 sync_bn_transport=a.syncbn)      # "none": per-rank statistics (apportioning runs only)
         loss_ar = S.parallel.mean_over_ranks()
     policy = S.MultiGeneratorPolicy(S.PolicyConfig(num_generators=K, force=S.GAN if disc is not None else S.PIXEL, seed=0))
     use_graphs = not a.no_graphs

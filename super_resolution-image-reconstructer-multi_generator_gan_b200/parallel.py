@@ -13,6 +13,7 @@ kernels, the collectives are captured into the step's CUDA graph, and the K gene
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_void_p
 from typing import Iterable, Optional
 
@@ -111,6 +112,8 @@ def average_gradients_hook(group: Optional[dist.ProcessGroup] = None, comm: Opti
         world = dist.get_world_size(group)
         if world == 1:
             return
+        if os.environ.get("SRG_DP_NO_ALLREDUCE") == "1":
+            return          # MEASUREMENT ONLY (bench.py apportions the multi-GPU step): ranks drift apart, never train like this
         if comm is not None:
             # ncclAvg: sum and 1/world in the collective itself, no extra pass over the gradients
             check(_lib.lib().srg_nccl_allreduce_mean_f32(comm, c_void_p(flat_grads.data_ptr()), flat_grads.numel(),
