@@ -8,6 +8,7 @@
 // sit on the critical path of every generator forward+backward).  The collective sequence number lives in device memory
 // and is advanced by the kernel itself, so the launch is CUDA-graph capturable.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_gemm.cuh"
@@ -30,7 +31,23 @@ struct PeerParams {
   int world, rank;
   unsigned long long* seq;    // device counter of collectives issued on this communicator
   int* err;                   // set to 1 if a wait timed out
+  int ll;                     // 1: data and sequence number travel in the same 8-byte words (no fence, no separate flag)
 };
+
+// "LL" exchange region behind the flag-protocol region of every rank's buffer: per (slot, source rank) 128 doubles as 256
+// words {u32 half of the double, u32 sequence number}.  An aligned 8-byte store is single-copy atomic, so a word whose
+// sequence half matches carries valid data: the sender needs no system-scope fence and no separate flag store, the receiver no
+// second round trip (the scheme of NCCL's low-latency protocol).
+constexpr int kLLWords = 256;
+__device__ __forceinline__ unsigned long long* ll_region(double* base, int world) {
+  return reinterpret_cast<unsigned long long*>(base + size_t(kSlots) * world * kSlotDoubles);
+}
+__device__ __forceinline__ void st_volatile_v2(unsigned long long* p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_volatile_v2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -90,37 +107,70 @@ __global__ void __launch_bounds__(1024) peer_finalize_kernel(const float* __rest
   __syncthreads();
   const unsigned long long seq = seq_s;
   const int slot = int(seq % kSlots);
-  // (2) my 128 sums -> every rank's buffer, slot [slot][my rank]
-  if (rl == 0) {
-    double t = 0.0;
+  if (pp.ll) {
+    // (2)-(4) in one round: every column thread sends its sum to every rank as two self-validating words and collects the
+    // ranks' words for its column from the local buffer, in rank order
+    if (rl == 0) {
+      double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][col];
-    for (int r = 0; r < pp.world; ++r) pp.peers[r][(size_t(slot) * pp.world + pp.rank) * kSlotDoubles + col] = t;
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (threadIdx.x < pp.world) {
-    const int r = threadIdx.x;
-    st_release_sys(reinterpret_cast<unsigned long long*>(pp.peers[r] + (size_t(slot) * pp.world + pp.rank) * kSlotDoubles + 128), seq);
-    // (3) wait for rank r's contribution in my own buffer
-    const unsigned long long* flag =
-        reinterpret_cast<const unsigned long long*>(pp.peers[pp.rank] + (size_t(slot) * pp.world + r) * kSlotDoubles + 128);
-    long long spins = 0;
-    while (ld_acquire_sys(flag) != seq) {
-      // a lost / stalled peer must never hang the GPU -- but it must not go unnoticed either: the statistics are
-      // poisoned below (NaN losses on every rank that missed a contribution) and *err makes the host raise
-      if (++spins > kPeerWaitSpins) { *pp.err = 1; timed_out = 1; break; }
-      __nanosleep(64);
+      for (int i = 0; i < 8; ++i) t += red[i][col];
+      const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(t));
+      const unsigned long long tag = (seq & 0xffffffffull) << 32;
+      const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+      const size_t mine = (size_t(slot) * pp.world + pp.rank) * kLLWords + 2 * col;
+      for (int r = 0; r < pp.world; ++r) st_volatile_v2(ll_region(pp.peers[r], pp.world) + mine, w0, w1);
+      double total = 0.0;
+      bool lost = false;
+      const unsigned long long* in = ll_region(pp.peers[pp.rank], pp.world) + size_t(slot) * pp.world * kLLWords + 2 * col;
+      for (int r = 0; r < pp.world; ++r) {
+        unsigned long long a, b;
+        long long spins = 0;
+        for (;;) {
+          ld_volatile_v2(in + size_t(r) * kLLWords, a, b);
+          if ((a >> 32) == (tag >> 32) && (b >> 32) == (tag >> 32)) break;
+          if (++spins > kPeerWaitSpins) { lost = true; break; }
+          if (spins > 64) __nanosleep(32);
+        }
+        total += __longlong_as_double(static_cast<long long>((a & 0xffffffffull) | (b << 32)));
+      }
+      if (lost) { *pp.err = 1; total = __longlong_as_double(0x7ff8000000000000ll); }   // NaN: never silently use a missing contribution
+      red[0][col] = total;     // (red[0][col] was read above by this thread only)
     }
-  }
-  __syncthreads();
-  pdl_trigger();
-  // (4) rank-ordered total, (5) finalize
-  if (rl == 0) {
-    double t = 0.0;
-    for (int r = 0; r < pp.world; ++r) t += ld_volatile_f64(pp.peers[pp.rank] + (size_t(slot) * pp.world + r) * kSlotDoubles + col);
-    if (timed_out) t = __longlong_as_double(0x7ff8000000000000ll);      // NaN: a missing contribution is never silently used
-    red[0][col] = t;
+    __syncthreads();
+    pdl_trigger();
+  } else {
+  // (2) my 128 sums -> every rank's buffer, slot [slot][my rank]
+    if (rl == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][col];
+      for (int r = 0; r < pp.world; ++r) pp.peers[r][(size_t(slot) * pp.world + pp.rank) * kSlotDoubles + col] = t;
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < pp.world) {
+      const int r = threadIdx.x;
+      st_release_sys(reinterpret_cast<unsigned long long*>(pp.peers[r] + (size_t(slot) * pp.world + pp.rank) * kSlotDoubles + 128), seq);
+      // (3) wait for rank r's contribution in my own buffer
+      const unsigned long long* flag =
+          reinterpret_cast<const unsigned long long*>(pp.peers[pp.rank] + (size_t(slot) * pp.world + r) * kSlotDoubles + 128);
+      long long spins = 0;
+      while (ld_acquire_sys(flag) != seq) {
+        // a lost / stalled peer must never hang the GPU -- but it must not go unnoticed either: the statistics are
+        // poisoned below (NaN losses on every rank that missed a contribution) and *err makes the host raise
+        if (++spins > kPeerWaitSpins) { *pp.err = 1; timed_out = 1; break; }
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+    pdl_trigger();
+    // (4) rank-ordered total, (5) finalize
+    if (rl == 0) {
+      double t = 0.0;
+      for (int r = 0; r < pp.world; ++r) t += ld_volatile_f64(pp.peers[pp.rank] + (size_t(slot) * pp.world + r) * kSlotDoubles + col);
+      if (timed_out) t = __longlong_as_double(0x7ff8000000000000ll);      // NaN: a missing contribution is never silently used
+      red[0][col] = t;
+    }
   }
   __syncthreads();
   if (threadIdx.x < 64) finalize_channels_peer(f, threadIdx.x, red[0][threadIdx.x], red[0][64 + threadIdx.x], 1.f / float(pp.world));
@@ -141,7 +191,8 @@ PeerSync* peer_sync_create(int world, int rank) {
   if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world) { set_error("peer_sync_create: bad world/rank"); return nullptr; }
   PeerSync* ps = new PeerSync();
   ps->world = world; ps->rank = rank;
-  const size_t bytes = size_t(kSlots) * world * kSlotDoubles * sizeof(double);
+  // flag-protocol region (also used by the fused trunk kernel's in-kernel exchange) + LL region (peer_finalize_kernel)
+  const size_t bytes = size_t(kSlots) * world * kSlotDoubles * sizeof(double) + size_t(kSlots) * world * kLLWords * 8;
   if (cudaMalloc(&ps->local, bytes) != cudaSuccess || cudaMalloc(&ps->d_seq, 8) != cudaSuccess ||
       cudaMalloc(&ps->d_err, 4) != cudaSuccess) {
     set_error("peer_sync_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -207,6 +258,9 @@ int launch_peer_finalize(PeerSync* ps, const float* partials, int rows, const Re
     pp.peers[r] = ps->peers[r];
   }
   pp.world = ps->world; pp.rank = ps->rank; pp.seq = ps->d_seq; pp.err = ps->d_err;
+  // SRG_PEER_LL=0: the round-1 protocol (data, system-scope fence, flag store, flag poll, data read) for A/B runs
+  static const int ll = [] { const char* v = getenv("SRG_PEER_LL"); return (v != nullptr && v[0] == '0') ? 0 : 1; }();
+  pp.ll = ll;
   cudaError_t e = launch_pdl(peer_finalize_kernel, dim3(1), dim3(1024), 0, st, partials, rows, f, pp);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("peer_finalize launch: %s", cudaGetErrorString(e)); return int(e); }
