@@ -1289,7 +1289,7 @@ static int num_sms() {
 
 template <int BLOCK_N, int NT>
 static int launch_instance(const ConvKParams& p, dim3 grid, size_t smem_bytes, cudaStream_t stream) {
-  static bool attr_set = false;
+  static DeviceOnce attr_set;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
@@ -1473,7 +1473,7 @@ static int launch_conv3_il(const ConvGemmArgs* as, int n, cudaStream_t stream) {
   static int il_opt = -1;
   if (il_opt < 0) { const char* ev = getenv("SRG_IL_OPT"); il_opt = ev ? atoi(ev) : 1; }
   p.opt = a.exclusive ? (il_opt & ~1) : il_opt;
-  static bool attr_set = false;
+  static DeviceOnce attr_set;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv3_il_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_il_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1546,7 +1546,7 @@ static int launch_conv9_rows(const ConvGemmArgs& a, cudaStream_t stream) {
   p.bias = a.bias;
   p.out = reinterpret_cast<float*>(a.out);
   p.prof = reinterpret_cast<long long*>(a.prof);
-  static bool attr_set = false;
+  static DeviceOnce attr_set;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv9_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }

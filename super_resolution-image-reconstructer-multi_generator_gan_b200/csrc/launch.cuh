@@ -11,12 +11,30 @@
 
 #include <stdlib.h>
 
+#include <atomic>
 #include <utility>
 
 namespace srg {
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// cudaFuncSetAttribute() applies to the CURRENT device only, so "done once" is remembered per device ordinal (one bit
+// each) and not per process: a process that drives a second GPU sets the attribute there too.  Used as
+//   static DeviceOnce attr_set;  if (!attr_set) { ...cudaFuncSetAttribute...;  attr_set = true; }
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  static unsigned long long bit() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return 1ull << (d & 63);
+  }
+  bool operator!() const { return (mask.load(std::memory_order_acquire) & bit()) == 0; }
+  DeviceOnce& operator=(bool done) {
+    if (done) mask.fetch_or(bit(), std::memory_order_release);
+    return *this;
+  }
+};
 
 // SRG_PDL (read once): 0 = plain stream-order launches everywhere (a kernel timeline then shows each kernel's own duration
 // instead of one that starts while the predecessor is still running); 1 = every launch_pdl() kernel may start early; 2

@@ -40,6 +40,7 @@
 #include <string.h>
 
 #include "conv_gemm.cuh"
+#include "launch.cuh"
 #include "peer_sync.cuh"
 #include "ptx.cuh"
 
@@ -1044,7 +1045,7 @@ int launch_trunk(const TrunkArgs& a, cudaStream_t stream) {
     if (cudaMemsetAsync(src.sync, 0, sync_words * 4, stream) != cudaSuccess) { set_error("trunk_fused: memset failed"); return -61; }
   }
   const size_t smem_bytes = a.bwd ? tr_smem_bytes<true>() : tr_smem_bytes<false>();
-  static bool attr_set = false;
+  static DeviceOnce attr_set;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tr_smem_bytes<false>()));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tr_smem_bytes<true>()));

@@ -392,7 +392,7 @@ int launch_wgrad3x3(const WgradArgs& a, cudaStream_t stream) {
     int rc = encode_map_bf16(&p.dy_map[v], dv.ptr, 4, dims, strides, box);
     if (rc) return rc;
   }
-  static bool attr = false;
+  static DeviceOnce attr;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
@@ -649,7 +649,7 @@ int launch_wgrad3x3_batched(const WgradBatchArgs& a, cudaStream_t stream) {
     rc = encode_map_bf16(&p.dy_map, a.dy_base, 5, dims, ds, dbox);
     if (rc) return rc;
   }
-  static bool attr = false;
+  static DeviceOnce attr;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(wgrad3_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
@@ -730,7 +730,7 @@ int launch_wgrad_gemm(const WgradArgs& a, cudaStream_t stream) {
     int rc = encode_map_bf16(&p.dy_map[v], dv.ptr, 4, dims, strides, box);
     if (rc) return rc;
   }
-  static bool attr = false;
+  static DeviceOnce attr;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }

@@ -13,6 +13,7 @@ Parameter storage: every ``nn.Parameter`` is a view into ONE flat fp32 buffer la
 from __future__ import annotations
 
 import ctypes
+import itertools
 import math
 import weakref
 from ctypes import byref, c_char_p, c_int, c_int64, c_void_p, create_string_buffer
@@ -89,6 +90,29 @@ class ResidualBlock(_Holder):
         self.relu = _Stateless("ReLU(inplace=True)")
         self.conv2 = ConvParams(num_features, num_features, 3, padding=1)
         self.bn2 = BatchNormParams(num_features)
+
+
+# ---- engine ownership -----------------------------------------------------------------------------------------
+# A grad-enabled forward marks its engine busy until backward has run.  A forward whose output is dropped WITHOUT a
+# backward would otherwise keep the engine (and its multi-GB training workspace) for ever and make every such call
+# allocate a new one: the autograd node's death releases it.  The token keeps a late finalizer of an OLD node (nodes
+# also die after their backward) from releasing an engine that a newer forward has already re-acquired.
+_busy_tokens = itertools.count(2)          # never 1: `True == 1`, and train.py marks engines with plain True
+
+
+def _acquire(eng) -> int:
+    eng.busy = next(_busy_tokens)
+    return eng.busy
+
+
+def _release_if(eng, token: int) -> None:
+    if eng.busy == token:
+        eng.busy = False
+
+
+def _release_on_death(ctx, eng) -> None:
+    ctx.busy_token = eng.busy
+    weakref.finalize(ctx, _release_if, eng, eng.busy)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -188,6 +212,7 @@ class _GeneratorFn(torch.autograd.Function):
               "srg_generator_forward")
         ctx.module_ref = weakref.ref(module)
         ctx.eng = eng
+        _release_on_death(ctx, eng)
         ctx.n_params = len(params)
         ctx.set_materialize_grads(False)
         return sr
@@ -197,7 +222,7 @@ class _GeneratorFn(torch.autograd.Function):
         module = ctx.module_ref()
         eng = ctx.eng
         if dsr is None or module is None:
-            eng.busy = False
+            _release_if(eng, ctx.busy_token)
             return (None,) * (3 + ctx.n_params)
         L = _lib.lib()
         dsr = dsr.contiguous()
@@ -206,7 +231,7 @@ class _GeneratorFn(torch.autograd.Function):
         flat_g = module._grad_buffer_for_backward(eng)
         check(L.srg_generator_set_grads(eng.handle, c_void_p(flat_g.data_ptr())))
         check(L.srg_generator_backward(eng.handle, c_void_p(dsr.data_ptr()), stream_ptr()), "srg_generator_backward")
-        eng.busy = False
+        _release_if(eng, ctx.busy_token)
         module._after_backward(flat_g)
         grads = tuple(flat_g[off:off + n].view(shape) for (_, off, n, shape) in module._ptable)
         return (None, None, None) + grads
@@ -367,7 +392,7 @@ class SRResNet(_FlatModule):
         if self.training and rt["nbt"] is not None and self.num_residuals > 0:
             rt["nbt"] += 1
         if need_grad:
-            eng.busy = True
+            _acquire(eng)
             return _GeneratorFn.apply(self, eng, x, *rt["plist"])
         # eval mode (running statistics) or no_grad: no autograd graph.  The reference keeps a graph through an
         # eval-mode generator in train_discriminator (src/train.py:212) but discards those gradients.
@@ -481,6 +506,7 @@ class _DiscriminatorFn(torch.autograd.Function):
               "srg_discriminator_forward")
         ctx.module_ref = weakref.ref(module)
         ctx.eng = eng
+        _release_on_death(ctx, eng)
         ctx.n_params = len(params)
         ctx.x_shape = tuple(x.shape)
         ctx.param_grads = module._rt.get("param_grads", True)
@@ -492,7 +518,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         module = ctx.module_ref()
         eng = ctx.eng
         if dout is None or module is None:
-            eng.busy = False
+            _release_if(eng, ctx.busy_token)
             return (None,) * (3 + ctx.n_params)
         L = _lib.lib()
         dout = dout.contiguous()
@@ -508,7 +534,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         check(L.srg_discriminator_backward(eng.handle, c_void_p(dout.data_ptr()), 1 if want_pg else 0,
                                            c_void_p(dx.data_ptr()) if dx is not None else None, stream_ptr()),
               "srg_discriminator_backward")
-        eng.busy = False
+        _release_if(eng, ctx.busy_token)
         if want_pg:
             module._after_backward(flat_g)
             grads = tuple(flat_g[off:off + n].view(shape) for (_, off, n, shape) in module._ptable)
@@ -593,7 +619,7 @@ class Discriminator(_FlatModule):
         check(L.srg_discriminator_pack(eng.handle, stream_ptr()), "srg_discriminator_pack")
         rt["last_engine"] = eng
         if need_grad:
-            eng.busy = True
+            _acquire(eng)
             return _DiscriminatorFn.apply(self, eng, xc, *rt["plist"])
         out = torch.empty(N, 512, eng.out_hw[0], eng.out_hw[1], dtype=torch.float32, device=xc.device)
         check(L.srg_discriminator_forward(eng.handle, c_void_p(xc.data_ptr()), c_void_p(out.data_ptr()), stream_ptr()),

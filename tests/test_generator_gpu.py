@@ -405,6 +405,33 @@ def test_errors_are_python_exceptions(S):
         S.SRResNet(num_features=32)
 
 
+def test_dropped_training_forward_releases_its_engine(S):
+    """A train-mode forward whose output is dropped without backward must not leak its engine (and workspace): the next
+    forward of the same geometry reuses it; two LIVE forwards still get two engines."""
+    import gc
+    torch.manual_seed(0)
+    g = S.SRResNet().cuda().train()
+    x = torch.rand(2, 3, 16, 24, device="cuda")
+    for _ in range(3):
+        y = g(x)
+        del y
+        gc.collect()
+    pools = g._rt["engines"]
+    assert sum(len(p) for p in pools.values()) == 1 and not any(e.busy for p in pools.values() for e in p)
+    y1, y2 = g(x), g(x)
+    assert sum(len(p) for p in pools.values()) == 2
+    (y1.sum() + y2.sum()).backward()
+    assert not any(e.busy for p in pools.values() for e in p)
+    d = S.Discriminator().cuda().train()
+    h = torch.rand(1, 3, 428, 684, device="cuda")
+    for _ in range(2):
+        o = d(h)
+        del o
+        gc.collect()
+    assert sum(len(p) for p in d._rt["engines"].values()) == 1
+    torch.cuda.synchronize()
+
+
 def test_train_generator_step_matches_oracle_sequence(S, O, golden_dir):
     """Two consecutive train_generator steps (forward, loss, backward, Adam) against the oracle's steps."""
     torch.manual_seed(1)

@@ -200,3 +200,48 @@ def test_reference_written_checkpoint_fixture_loads_on_cpu(golden_dir):
     assert set(mine) == {k[len("module."):] for k in sd}
     for k, v in sd.items():
         assert torch.equal(mine[k[len("module."):]].cpu(), v), k
+
+
+def test_engine_is_released_when_the_autograd_node_dies_without_backward():
+    """models._release_on_death: a grad-enabled forward whose output is dropped frees its engine; the finalizer of an
+    OLD node (nodes also die after backward) must not release an engine a newer forward has re-acquired; the plain
+    True that train.py's phase-split step writes is never mistaken for a token."""
+    import gc
+    M = S.models
+
+    class Eng:
+        busy = False
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, eng_box, x):
+            ctx.eng = eng_box[0]
+            M._release_on_death(ctx, eng_box[0])
+            return x * 2
+
+        @staticmethod
+        def backward(ctx, g):
+            M._release_if(ctx.eng, ctx.busy_token)
+            return None, g * 2
+
+    eng = Eng()
+    x = torch.ones(3, requires_grad=True)
+    t1 = M._acquire(eng)
+    y = Fn.apply([eng], x)
+    assert eng.busy == t1 and t1 >= 2
+    del y
+    gc.collect()
+    assert eng.busy is False                           # dropped without backward: released
+    M._acquire(eng)
+    y1 = Fn.apply([eng], x)
+    y1.sum().backward()
+    assert eng.busy is False                           # released by backward, node y1 still alive
+    t3 = M._acquire(eng)
+    y2 = Fn.apply([eng], x)
+    del y1
+    gc.collect()
+    assert eng.busy == t3                              # the old node's death leaves the new owner alone
+    eng.busy = True                                    # train.joint_pixel_generator_steps marks engines like this
+    del y2
+    gc.collect()
+    assert eng.busy is True
