@@ -252,6 +252,23 @@ def test_reconstruction_loss_weighted_backward(S, O):
     assert maxrel(sr.grad, src.grad) < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 5, 8), (1, 3, 7, 12), (2, 1, 6, 516), (1, 3, 1, 4), (2, 3, 9, 1028)])
+def test_reconstruction_loss_row_strips_at_ragged_heights(S, O, shape):
+    """W % 4 == 0 takes the row-strip form of passes 1 / 2 (4 / 2 rows per iteration): heights that are not multiples of the
+    strip, single-row planes and widths beyond one 512-column round must match the oracle like the row-by-row form."""
+    torch.manual_seed(11)
+    hr = torch.rand(*shape)
+    sr0 = hr + 0.05 * torch.randn_like(hr)
+    sr = sr0.clone().cuda().requires_grad_(True)
+    e, t = S.ReconstructionLoss()(hr.cuda(), sr)
+    (e + t).backward()
+    src = sr0.clone().requires_grad_(True)
+    e_r, t_r = O.reconstruction_loss(hr, src)
+    (e_r + t_r).backward()
+    assert abs(float(e) - float(e_r)) < 2e-6 * max(1.0, abs(float(e_r))) and abs(float(t) - float(t_r)) < 1e-6
+    assert maxrel(sr.grad, src.grad) < 1e-5
+
+
 def test_adam_matches_oracle_three_steps(S, O):
     torch.manual_seed(3)
     g = S.SRResNet(num_residuals=1, upscale_factor=2).cuda()
