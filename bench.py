@@ -220,7 +220,11 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "generators": a.generators, "sample_batch": b,
+        # the same workload keys as the GPU arm prints (the arm times a bounded sample of that workload: cpu_baseline.sample)
+        "config": {"workload": workload_name(a), "generators": a.generators, "batch_per_gpu": geometry(a)[0],
+                   "global_batch": geometry(a)[0] * int(os.environ.get("WORLD_SIZE", "1")),
+                   "lr_hw": [geometry(a)[1], geometry(a)[2]], "upscale": 4,
+                   "parallelism": f"dp{int(os.environ.get('WORLD_SIZE', '1'))}", "sample_batch": b,
                    "note": ("the unmodified reference sources run from oracle/_ref (copied verbatim by oracle/make_ref.py, "
                             "git-ignored)" if kind == "reference" else
                             "oracle/_ref did not travel: reference arithmetic restated on torch CPU kernels (oracle/srgan_oracle.py)")},
