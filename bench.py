@@ -218,8 +218,9 @@ def run_reference(a):
     val, dt, cores, sample, kind, b = cpu_reference_steps(a, a.steps, a.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": ("strong" if (int(os.environ.get("WORLD_SIZE", "1")) > 1 and a.batch is None and a.workload == "cfg2") else "weak"),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         # the same workload keys as the GPU arm prints (the arm times a bounded sample of that workload: cpu_baseline.sample)
         "config": {"workload": workload_name(a), "generators": a.generators, "batch_per_gpu": geometry(a)[0],
                    "global_batch": geometry(a)[0] * int(os.environ.get("WORLD_SIZE", "1")),
